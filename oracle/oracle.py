@@ -1,0 +1,386 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+The oracle restates the reference's Eigen path (see oracle/lq_oracle.h); it is never used by ocs2_b200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblq_oracle.so")
+
+ALG_ILQR, ALG_SLQ = 0, 1
+STRATEGY_LINE_SEARCH, STRATEGY_LM = 0, 1
+HC_DIAGONAL_SHIFT, HC_CHOLESKY_MODIFICATION, HC_EIGENVALUE_MODIFICATION, HC_GERSHGORIN_MODIFICATION = 0, 1, 2, 3
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class Settings(C.Structure):
+    _fields_ = [
+        ("algorithm", C.c_int32),
+        ("reduced_form", C.c_int32),
+        ("strategy", C.c_int32),
+        ("hessian_correction", C.c_int32),
+        ("hessian_multiple", C.c_double),
+        ("lm_riccati_multiple", C.c_double),
+        ("time_step", C.c_double),
+    ]
+
+
+class _Problem(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("nu", C.c_int32), ("nc_max", C.c_int32), ("N", C.c_int32)] + [
+        (name, _dp) for name in ("A", "B", "Hv", "Q", "P", "R", "q", "r", "c", "C", "D", "e")
+    ] + [("nc", _ip)] + [(name, _dp) for name in ("Qf", "qf", "cf", "x_nom", "u_nom", "time")]
+
+
+class _Solution(C.Structure):
+    _fields_ = [(name, _dp) for name in ("K", "dbias", "bias", "Sm", "Sv", "s")] + [("status", C.c_int32)]
+
+
+class _Projected(C.Structure):
+    _fields_ = [(name, _dp) for name in
+                ("At", "Bt", "Hvt", "Qt", "Pt", "Rt", "qt", "rt", "ct", "Cmt", "Evt", "Pu", "dQ", "dGm", "dGv")]
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/liblq_oracle.so with the committed Makefile (g++ only, no reference sources involved)."""
+    src = os.path.join(_HERE, "lq_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B", "liblq_oracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_inverse_uut.restype = C.c_int
+        _lib.orc_shift_hessian.restype = C.c_int
+        _lib.orc_project_stage.restype = C.c_int
+        _lib.orc_backward.restype = C.c_int
+        _lib.orc_rollout.restype = C.c_int
+        _lib.orc_discrete_lq_cost.restype = C.c_double
+        _lib.orc_baseline_run.restype = C.c_double
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp) if a is not None else _dp()
+
+
+def _f(a):
+    """Column-major (Fortran) contiguous float64 copy."""
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def make_settings(algorithm=ALG_ILQR, reduced_form=True, strategy=STRATEGY_LINE_SEARCH, hessian_correction=HC_DIAGONAL_SHIFT,
+                  hessian_multiple=1e-6, lm_riccati_multiple=0.0, time_step=1e-2) -> Settings:
+    return Settings(algorithm, int(reduced_form), strategy, hessian_correction, hessian_multiple, lm_riccati_multiple, time_step)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# single building blocks
+# --------------------------------------------------------------------------------------------------------------------
+def inverse_uut(H):
+    H = _f(H)
+    m = H.shape[0]
+    Ui = np.zeros((m, m), order="F")
+    rc = lib().orc_inverse_uut(m, _p(H), _p(Ui))
+    return Ui, rc
+
+
+def constraint_projection(D, Ui):
+    D = _f(D)
+    Ui = _f(Ui)
+    nc, m = D.shape
+    Dd = np.zeros((m, nc), order="F")
+    RcInv = np.zeros((nc, nc), order="F")
+    Pu = np.zeros((m, m - nc), order="F")
+    lib().orc_constraint_projection(m, nc, _p(D), nc, _p(Ui), _p(Dd), _p(RcInv), _p(Pu))
+    return Dd, RcInv, Pu
+
+
+def shift_hessian(strategy, M, eps):
+    M = _f(M).copy(order="F")
+    rc = lib().orc_shift_hessian(strategy, M.shape[0], _p(M), C.c_double(eps))
+    return M, rc
+
+
+def flatten(Sm, Sv, s):
+    Sm = _f(Sm)
+    n = Sm.shape[0]
+    out = np.zeros(n * (n + 1) // 2 + n + 1)
+    lib().orc_flatten(n, _p(Sm), _p(np.ascontiguousarray(Sv, dtype=np.float64)), C.c_double(s), _p(out))
+    return out
+
+
+def unflatten(n, allSs):
+    allSs = np.ascontiguousarray(allSs, dtype=np.float64)
+    Sm = np.zeros((n, n), order="F")
+    Sv = np.zeros(n)
+    s = C.c_double(0)
+    lib().orc_unflatten(n, _p(allSs), _p(Sm), _p(Sv), C.byref(s))
+    return Sm, Sv, s.value
+
+
+def time_segment(t, time):
+    time = np.ascontiguousarray(time, dtype=np.float64)
+    idx = C.c_int(0)
+    alpha = C.c_double(0)
+    lib().orc_time_segment(C.c_double(t), _p(time), len(time), C.byref(idx), C.byref(alpha))
+    return idx.value, alpha.value
+
+
+@dataclass
+class ProjectedStage:
+    p: int
+    status: int
+    At: np.ndarray
+    Bt: np.ndarray
+    Hvt: np.ndarray
+    Qt: np.ndarray
+    Pt: np.ndarray
+    Rt: np.ndarray
+    qt: np.ndarray
+    rt: np.ndarray
+    ct: float
+    Cmt: np.ndarray
+    Evt: np.ndarray
+    Pu: np.ndarray
+    dQ: np.ndarray
+    dGm: np.ndarray
+    dGv: np.ndarray
+    _keep: list = field(default_factory=list, repr=False)
+
+    def c_struct(self):
+        ct = np.array([self.ct])
+        self._keep = [ct]
+        return _Projected(_p(self.At), _p(self.Bt), _p(self.Hvt), _p(self.Qt), _p(self.Pt), _p(self.Rt), _p(self.qt), _p(self.rt),
+                          _p(ct), _p(self.Cmt), _p(self.Evt), _p(self.Pu), _p(self.dQ), _p(self.dGm), _p(self.dGv))
+
+
+def project_stage(st: Settings, A, B, Hv, Q, P, R, q, r, c, Cm=None, Dm=None, e=None, Sm=None) -> ProjectedStage:
+    A, B, Q, P, R = map(_f, (A, B, Q, P, R))
+    Hv, q, r = (np.ascontiguousarray(v, dtype=np.float64) for v in (Hv, q, r))
+    n, m = B.shape
+    nc = 0 if Dm is None else np.asarray(Dm).shape[0]
+    if nc:
+        Cm, Dm = _f(Cm), _f(Dm)
+        e = np.ascontiguousarray(e, dtype=np.float64)
+    p = m - nc
+    bufs = dict(At=np.zeros((n, n), order="F"), Bt=np.zeros((n, p), order="F"), Hvt=np.zeros(n), Qt=np.zeros((n, n), order="F"),
+                Pt=np.zeros((p, n), order="F"), Rt=np.zeros((p, p), order="F"), qt=np.zeros(n), rt=np.zeros(p), ct=np.zeros(1),
+                Cmt=np.zeros((m, n), order="F"), Evt=np.zeros(m), Pu=np.zeros((m, p), order="F"), dQ=np.zeros((n, n), order="F"),
+                dGm=np.zeros((p, n), order="F"), dGv=np.zeros(p))
+    out = _Projected(*[_p(bufs[k]) for k in ("At", "Bt", "Hvt", "Qt", "Pt", "Rt", "qt", "rt", "ct", "Cmt", "Evt", "Pu", "dQ", "dGm", "dGv")])
+    status = C.c_int(0)
+    SmF = _f(Sm) if Sm is not None else None
+    pp = lib().orc_project_stage(C.byref(st), n, m, nc, max(nc, 1), _p(A), _p(B), _p(Hv), _p(Q), _p(P), _p(R), _p(q), _p(r),
+                                 C.c_double(c), _p(Cm) if nc else _dp(), _p(Dm) if nc else _dp(), _p(e) if nc else _dp(),
+                                 _p(SmF), C.byref(out), C.byref(status))
+    assert pp == p
+    bufs["ct"] = float(bufs["ct"][0])
+    return ProjectedStage(p=p, status=status.value, **bufs)
+
+
+def compute_map(reduced, pr: ProjectedStage, SmNext, SvNext, sNext):
+    n = pr.At.shape[0]
+    p = pr.p
+    SmNext = _f(SmNext)
+    SvNext = np.ascontiguousarray(SvNext, dtype=np.float64)
+    Km = np.zeros((p, n), order="F")
+    Lv = np.zeros(p)
+    Sm = np.zeros((n, n), order="F")
+    Sv = np.zeros(n)
+    s = C.c_double(0)
+    cs = pr.c_struct()
+    lib().orc_compute_map(int(reduced), n, p, C.byref(cs), _p(SmNext), _p(SvNext), C.c_double(sNext), _p(Km), _p(Lv), _p(Sm), _p(Sv),
+                          C.byref(s))
+    return Km, Lv, Sm, Sv, s.value
+
+
+def flow_map_slq(reduced, pr: ProjectedStage, allSs):
+    n = pr.At.shape[0]
+    allSs = np.ascontiguousarray(allSs, dtype=np.float64)
+    out = np.zeros_like(allSs)
+    cs = pr.c_struct()
+    lib().orc_flow_map_slq(int(reduced), n, pr.p, C.byref(cs), _p(allSs), _p(out))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# whole problems. Python-side layout: arrays indexed [node, row, col] (C-order over nodes, each block stored column-major,
+# i.e. arr[k] is the transposed view of a Fortran block). To keep this simple every per-node matrix field is held as
+# an ndarray of shape (nodes, cols, rows): arr[k].T is the matrix.  Helpers below convert from natural (nodes, rows, cols).
+# --------------------------------------------------------------------------------------------------------------------
+def to_colmajor_nodes(a):
+    """(nodes, rows, cols) natural -> contiguous (nodes, cols, rows) buffer whose per-node block is column-major."""
+    a = np.asarray(a, dtype=np.float64)
+    return np.ascontiguousarray(np.swapaxes(a, -1, -2))
+
+
+def from_colmajor_nodes(a):
+    return np.swapaxes(a, -1, -2)
+
+
+@dataclass
+class Problem:
+    """One LQ problem in natural numpy layout: A (nodes,n,n), B (nodes,n,m), Hv (nodes,n), Q (nodes,n,n), P (nodes,m,n),
+    R (nodes,m,m), q (nodes,n), r (nodes,m), c (nodes,), C (nodes,ncmax,n), D (nodes,ncmax,m), e (nodes,ncmax), nc (nodes,) int32,
+    Qf (n,n), qf (n,), cf float, x_nom (N+1,n), u_nom (N+1,m), time (N+1,). nodes = N for ILQR, N+1 for SLQ."""
+    N: int
+    A: np.ndarray
+    B: np.ndarray
+    Hv: np.ndarray
+    Q: np.ndarray
+    P: np.ndarray
+    R: np.ndarray
+    q: np.ndarray
+    r: np.ndarray
+    c: np.ndarray
+    Qf: np.ndarray
+    qf: np.ndarray
+    cf: float
+    C: np.ndarray | None = None
+    D: np.ndarray | None = None
+    e: np.ndarray | None = None
+    nc: np.ndarray | None = None
+    x_nom: np.ndarray | None = None
+    u_nom: np.ndarray | None = None
+    time: np.ndarray | None = None
+
+    @property
+    def nx(self):
+        return self.A.shape[1]
+
+    @property
+    def nu(self):
+        return self.B.shape[2]
+
+    @property
+    def nc_max(self):
+        return 0 if self.D is None else self.D.shape[1]
+
+    def c_struct(self):
+        keep = {}
+        for name in ("A", "B", "Q", "P", "R", "C", "D"):
+            v = getattr(self, name)
+            keep[name] = to_colmajor_nodes(v) if v is not None else None
+        for name in ("Hv", "q", "r", "c", "e", "qf", "x_nom", "u_nom", "time"):
+            v = getattr(self, name)
+            keep[name] = np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
+        keep["Qf"] = np.ascontiguousarray(np.asarray(self.Qf, dtype=np.float64).T)
+        keep["cf"] = np.array([self.cf], dtype=np.float64)
+        keep["nc"] = np.ascontiguousarray(self.nc, dtype=np.int32) if self.nc is not None else None
+        if keep["time"] is None:
+            keep["time"] = np.arange(self.N + 1, dtype=np.float64)
+        pb = _Problem(self.nx, self.nu, self.nc_max, self.N, _p(keep["A"]), _p(keep["B"]), _p(keep["Hv"]), _p(keep["Q"]), _p(keep["P"]),
+                      _p(keep["R"]), _p(keep["q"]), _p(keep["r"]), _p(keep["c"]), _p(keep["C"]), _p(keep["D"]), _p(keep["e"]),
+                      keep["nc"].ctypes.data_as(_ip) if keep["nc"] is not None else _ip(), _p(keep["Qf"]), _p(keep["qf"]), _p(keep["cf"]),
+                      _p(keep["x_nom"]), _p(keep["u_nom"]), _p(keep["time"]))
+        return pb, keep
+
+
+@dataclass
+class Solution:
+    """K (N+1,m,n), dbias (N+1,m), bias (N+1,m), Sm (N+1,n,n), Sv (N+1,n), s (N+1,), status."""
+    K: np.ndarray
+    dbias: np.ndarray
+    bias: np.ndarray
+    Sm: np.ndarray
+    Sv: np.ndarray
+    s: np.ndarray
+    status: int = 0
+
+
+def backward(st: Settings, pb: Problem) -> Solution:
+    n, m, N = pb.nx, pb.nu, pb.N
+    Kc = np.zeros((N + 1, n, m))  # column-major blocks of m x n
+    db = np.zeros((N + 1, m))
+    bias = np.zeros((N + 1, m))
+    Smc = np.zeros((N + 1, n, n))
+    Sv = np.zeros((N + 1, n))
+    s = np.zeros(N + 1)
+    cp, keep = pb.c_struct()
+    sol = _Solution(_p(Kc), _p(db), _p(bias), _p(Smc), _p(Sv), _p(s), 0)
+    status = lib().orc_backward(C.byref(st), C.byref(cp), C.byref(sol))
+    del keep
+    return Solution(K=from_colmajor_nodes(Kc).copy(), dbias=db, bias=bias, Sm=from_colmajor_nodes(Smc).copy(), Sv=Sv, s=s, status=status)
+
+
+def rollout(st: Settings, pb: Problem, sol: Solution, x0, alpha=1.0, max_out=None):
+    n, m, N = pb.nx, pb.nu, pb.N
+    if max_out is None:
+        max_out = N + 1 if st.algorithm == ALG_ILQR else int(np.ceil((pb.time[-1] - pb.time[0]) / st.time_step)) + 4
+    x = np.zeros((max_out, n))
+    u = np.zeros((max_out, m))
+    t = np.zeros(max_out)
+    cp, keep = pb.c_struct()
+    Kc = to_colmajor_nodes(sol.K)
+    Smc = to_colmajor_nodes(sol.Sm)
+    csol = _Solution(_p(Kc), _p(np.ascontiguousarray(sol.dbias)), _p(np.ascontiguousarray(sol.bias)), _p(Smc), _p(sol.Sv), _p(sol.s), 0)
+    n_out = C.c_int(0)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    status = lib().orc_rollout(C.byref(st), C.byref(cp), C.byref(csol), _p(x0), C.c_double(alpha), _p(x), _p(u), _p(t), max_out,
+                               C.byref(n_out))
+    del keep
+    assert status >= 0, "rollout output capacity too small"
+    k = n_out.value
+    return x[:k], u[:k], t[:k], status
+
+
+def discrete_lq_cost(pb: Problem, x, u) -> float:
+    cp, keep = pb.c_struct()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    val = lib().orc_discrete_lq_cost(C.byref(cp), _p(x), _p(u))
+    del keep
+    return val
+
+
+def generate_problem(seed, problem, algorithm, n, m, nc, N, dt):
+    """One problem of the seeded synthetic family (bit-identical to the CUDA generator). Returns (Problem, x0)."""
+    nodes = N if algorithm == ALG_ILQR else N + 1
+    A = np.zeros((nodes, n, n))
+    B = np.zeros((nodes, m, n))
+    Hv = np.zeros((nodes, n))
+    Q = np.zeros((nodes, n, n))
+    P = np.zeros((nodes, n, m))
+    R = np.zeros((nodes, m, m))
+    q = np.zeros((nodes, n))
+    r = np.zeros((nodes, m))
+    c = np.zeros(nodes)
+    ncm = max(nc, 1)
+    Cm = np.zeros((nodes, n, ncm))
+    Dm = np.zeros((nodes, m, ncm))
+    e = np.zeros((nodes, ncm))
+    Qf = np.zeros((n, n))
+    qf = np.zeros(n)
+    cf = np.zeros(1)
+    x0 = np.zeros(n)
+    lib().orc_generate_problem(C.c_uint64(seed), C.c_int64(problem), algorithm, n, m, nc, N, C.c_double(dt), _p(A), _p(B), _p(Hv), _p(Q),
+                               _p(P), _p(R), _p(q), _p(r), _p(c), _p(Cm), _p(Dm), _p(e), _p(Qf), _p(qf), _p(cf), _p(x0))
+    sw = from_colmajor_nodes
+    pb = Problem(N=N, A=sw(A), B=sw(B), Hv=Hv, Q=sw(Q), P=sw(P), R=sw(R), q=q, r=r, c=c, Qf=Qf.T, qf=qf, cf=float(cf[0]),
+                 C=sw(Cm) if nc else None, D=sw(Dm) if nc else None, e=e if nc else None, time=dt * np.arange(N + 1))
+    return pb, x0
+
+
+def baseline_run(st: Settings, seed, first, count, n, m, nc, N, dt, threads):
+    """Timed CPU baseline on `count` generated problems (backward + rollout). Returns (seconds, checksum)."""
+    chk = C.c_double(0)
+    secs = lib().orc_baseline_run(C.byref(st), C.c_uint64(seed), C.c_int64(first), C.c_int64(count), n, m, nc, N, C.c_double(dt), threads,
+                                  C.byref(chk))
+    return secs, chk.value

@@ -1,0 +1,326 @@
+"""Pins the CPU oracle against the reference's own golden vectors / known-answer tests / identities (CPU only).
+
+Each test cites the reference test it transfers (paths relative to /root/reference). Eigen's Random() fixtures are not
+reproducible without Eigen, so the *properties* and tolerances are transferred with numpy-seeded inputs.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import kkt_oracle
+from oracle import oracle as orc
+
+RNG = np.random.default_rng(0)
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def spd(n, rng=RNG):
+    """generateSPDmatrix (ocs2_core/include/ocs2_core/misc/randomMatrices.h): symmetric, diagonally dominant."""
+    A = rng.uniform(-1, 1, (n, n))
+    A = 0.5 * (A + A.T)
+    return A + n * np.eye(n)
+
+
+def random_cost(n, m, rng):
+    """getRandomCost (ocs2_oc/test/include/ocs2_oc/test/testProblemsGeneration.h:45-58): joint PSD M^T M."""
+    M = rng.uniform(-1, 1, (n + m, n + m))
+    W = M.T @ M
+    return W[:n, :n], W[n:, :n], W[n:, n:], rng.uniform(-1, 1, n), rng.uniform(-1, 1, m), float(rng.uniform(-1, 1))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_flatten_golden_order():
+    """ocs2_ddp/test/RiccatiTest.cpp:107-131 (testFlattenSMatrix): exact golden vector."""
+    Sm = np.array([[1, 2, 4, 7], [2, 3, 5, 8], [4, 5, 6, 9], [7, 8, 9, 10]], dtype=float)
+    allSs = orc.flatten(Sm, np.array([11.0, 12, 13, 14]), 15.0)
+    assert np.array_equal(allSs, np.arange(1.0, 16.0))
+
+
+def test_flatten_unflatten_roundtrip():
+    """ocs2_ddp/test/RiccatiTest.cpp:133-157 (stateDim = 42)."""
+    n = 42
+    Sm = RNG.uniform(-1, 1, (n, n))
+    Sm = Sm + Sm.T
+    Sv = RNG.uniform(-1, 1, n)
+    s = float(RNG.uniform(-1, 1))
+    Sm2, Sv2, s2 = orc.unflatten(n, orc.flatten(Sm, Sv, s))
+    assert s2 == s and np.array_equal(Sv2, Sv) and np.array_equal(Sm2, Sm)
+
+
+def test_llt_of_inverse():
+    """ocs2_core/test/misc/testLinearAlgebra.cpp:111-125 (LLTofInverse, n = 10, tol 1e-9)."""
+    A = spd(10)
+    Ui, rc = orc.inverse_uut(A)
+    assert rc == 0
+    assert np.allclose(np.tril(Ui, -1), 0.0)  # upper triangular
+    assert np.abs(np.linalg.inv(A) - Ui @ Ui.T).max() < 1e-9
+
+
+def test_llt_reports_indefinite():
+    _, rc = orc.inverse_uut(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    assert rc == 1
+
+
+def test_constraint_projection_against_full_computation():
+    """ocs2_core/test/misc/testLinearAlgebra.cpp:127-165 (m = 4 constraints, n = 15 inputs, tol 1e-9)."""
+    nc, m = 4, 15
+    D = RNG.uniform(-1, 1, (nc, m))
+    R = spd(m)
+    Ui, _ = orc.inverse_uut(R)
+    Rinv = Ui @ Ui.T
+    Dd, RcInv, Pu = orc.constraint_projection(D, Ui)
+    RmProjected = np.linalg.inv(D @ Rinv @ D.T)
+    Dd_check = Rinv @ D.T @ RmProjected
+    assert np.abs(Dd - Dd_check).max() < 1e-9
+    assert np.abs(RcInv @ RcInv.T - Dd_check.T @ R @ Dd_check).max() < 1e-9
+    nullProj = np.eye(m) - Dd_check @ D
+    assert np.abs(Pu @ Pu.T - Rinv.T @ nullProj.T @ R @ nullProj @ Rinv).max() < 1e-9
+    # invariants listed in SURVEY.md appendix A.3
+    assert np.abs(D @ Dd - np.eye(nc)).max() < 1e-12
+    assert np.abs(D @ Pu).max() < 1e-12
+    assert np.abs(Pu.T @ R @ Pu - np.eye(m - nc)).max() < 1e-12
+
+
+def test_make_psd_gershgorin():
+    """ocs2_core/test/misc/testLinearAlgebra.cpp:167-189."""
+    n = 10
+    dd = spd(n)
+    corr, rc = orc.shift_hessian(orc.HC_GERSHGORIN_MODIFICATION, dd, 1e-6)
+    assert rc == 0 and np.allclose(dd, corr, rtol=1e-9)
+    lam_min = np.linalg.eigvalsh(dd).min()
+    nd = dd - (lam_min + 1e-2) * np.eye(n)
+    corr, _ = orc.shift_hessian(orc.HC_GERSHGORIN_MODIFICATION, nd, 1e-3)
+    assert np.linalg.eigvalsh(corr).min() >= 1e-3
+
+
+def test_diagonal_shift_and_unsupported():
+    M = spd(5)
+    out, rc = orc.shift_hessian(orc.HC_DIAGONAL_SHIFT, M, 1e-3)
+    assert rc == 0 and np.array_equal(out, M + 1e-3 * np.eye(5))
+    _, rc = orc.shift_hessian(orc.HC_EIGENVALUE_MODIFICATION, M, 1e-3)
+    assert rc == 1
+
+
+@pytest.mark.parametrize("nc", [0, 2])
+def test_change_of_input_variables_equivalence(nc):
+    """ocs2_oc/test/testChangeOfInputVariables.cpp: projected model evaluated at u~ == original at u = Pu u~ + Px x + u0."""
+    rng = np.random.default_rng(5 + nc)
+    n, m = 4, 5
+    Q, P, R, q, r, c = random_cost(n, m, rng)
+    R = R + np.eye(m)
+    A, B, Hv = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, m)), rng.uniform(-1, 1, n)
+    Cm = rng.uniform(-1, 1, (nc, n)) if nc else None
+    Dm = rng.uniform(-1, 1, (nc, m)) if nc else None
+    e = rng.uniform(-1, 1, nc) if nc else None
+    st = orc.make_settings(hessian_multiple=0.0)
+    S = spd(n, rng)
+    pr = orc.project_stage(st, A, B, Hv, Q, P, R, q, r, c, Cm, Dm, e, Sm=S)
+    assert pr.p == m - nc
+    dx = rng.uniform(-1, 1, n)
+    ut = rng.uniform(-1, 1, m - nc)
+    u = pr.Pu @ ut - pr.Cmt @ dx - pr.Evt
+
+    def cost(Q, P, R, q, r, c, x, u):
+        return c + q @ x + r @ u + 0.5 * x @ Q @ x + u @ P @ x + 0.5 * u @ R @ u
+
+    assert cost(pr.Qt, pr.Pt, pr.Rt, pr.qt, pr.rt, pr.ct, dx, ut) == pytest.approx(cost(Q, P, R, q, r, c, dx, u), rel=1e-12)
+    assert np.allclose(pr.At @ dx + pr.Bt @ ut + pr.Hvt, A @ dx + B @ u + Hv, rtol=1e-12, atol=1e-13)
+    if nc:
+        assert np.allclose(Cm @ dx + Dm @ u + e, 0.0, atol=1e-12)  # constraint satisfied for every u~
+    # Hm = R + B'SB; Pu' Hm Pu = I (GaussNewtonDDP.cpp:774-781)
+    Hm = R + B.T @ S @ B
+    assert np.allclose(pr.Pu.T @ Hm @ pr.Pu, np.eye(m - nc), atol=1e-10)
+
+
+def test_flow_map_reduced_equals_full():
+    """ocs2_ddp/test/RiccatiTest.cpp:87-105 (STATE_DIM 48, INPUT_DIM 10, projected data with R~ = I, tol 1e-9)."""
+    rng = np.random.default_rng(3)
+    n, m = 48, 10
+    st = orc.make_settings(algorithm=orc.ALG_SLQ, hessian_multiple=0.0)
+    pr = orc.project_stage(st, rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, m)), rng.uniform(-1, 1, n), spd(n, rng),
+                           rng.uniform(-1, 1, (m, n)), np.eye(m), rng.uniform(-1, 1, n), rng.uniform(-1, 1, m), 0.3)
+    assert np.allclose(pr.Rt, np.eye(m))
+    pr.dQ = np.asfortranarray(0.1 * spd(n, rng))
+    allSs = rng.uniform(-1, 1, n * (n + 1) // 2 + n + 1)
+    d_red = orc.flow_map_slq(True, pr, allSs)
+    d_full = orc.flow_map_slq(False, pr, allSs)
+    assert np.abs(d_red - d_full).max() < 1e-9
+
+
+def test_discrete_map_reduced_equals_full():
+    """Same identity for DiscreteTimeRiccatiEquations (reduced form is exact when projected Hm = I)."""
+    rng = np.random.default_rng(4)
+    n, m = 12, 5
+    st = orc.make_settings(hessian_multiple=1e-5)
+    Q, P, R, q, r, c = random_cost(n, m, rng)
+    R = R + np.eye(m)
+    S = spd(n, rng)
+    pr = orc.project_stage(st, np.eye(n) + 0.1 * rng.uniform(-1, 1, (n, n)), 0.1 * rng.uniform(-1, 1, (n, m)), 0.01 * rng.uniform(-1, 1, n),
+                           Q, P, R, q, r, c, Sm=S)
+    Sv = rng.uniform(-1, 1, n)
+    a = orc.compute_map(True, pr, S, Sv, 0.7)
+    b = orc.compute_map(False, pr, S, Sv, 0.7)
+    for x, y in zip(a, b):
+        assert np.allclose(x, y, rtol=1e-9, atol=1e-9)
+
+
+def test_time_segment_rules():
+    """implementation/LinearInterpolation.h:69-107 and ocs2_core/test/misc/testInterpolation.cpp semantics."""
+    t = np.array([0.0, 1.0, 2.0, 3.0])
+    assert orc.time_segment(-1.0, t) == (0, 1.0)
+    assert orc.time_segment(0.0, t) == (0, 1.0)  # lower_bound: t == t0 -> interval -1 -> clamp
+    assert orc.time_segment(0.25, t) == (0, 0.75)
+    assert orc.time_segment(1.0, t) == (0, 0.0)  # exact node j >= 1 -> (j-1, alpha = 0)
+    assert orc.time_segment(2.5, t) == (2, 0.5)
+    assert orc.time_segment(3.0, t) == (2, 0.0)
+    assert orc.time_segment(9.0, t) == (2, 0.0)
+    short = np.array([0.0, 1.0, 1.0 + 1e-9, 2.0])
+    assert orc.time_segment(1.0 + 0.2e-9, short) == (1, 1.0)
+    assert orc.time_segment(1.0 + 0.8e-9, short) == (1, 0.0)
+
+
+def test_slq_rk4_converges_to_matlab_care():
+    """ocs2_ddp/test/testContinuousTimeLqr.cpp:41-72: MATLAB golden K and S (tol 1e-9) for A=[1 2;3 4], B=[5;6],
+    Q=[3 2;2 4], R=5, P=[0.1 0.2]. The SLQ Riccati flow map integrated backwards with RK4 (h = 1e-3, T = 20) must converge to it."""
+    h, T = 1e-3, 20.0
+    N = int(round(T / h))
+    nodes = N + 1
+    rep = lambda M: np.repeat(np.asarray(M, dtype=float)[None], nodes, 0)  # noqa: E731
+    pb = orc.Problem(N=N, A=rep([[1.0, 2.0], [3.0, 4.0]]), B=rep([[5.0], [6.0]]), Hv=np.zeros((nodes, 2)), Q=rep([[3.0, 2.0], [2.0, 4.0]]),
+                     P=rep([[0.1, 0.2]]), R=rep([[5.0]]), q=np.zeros((nodes, 2)), r=np.zeros((nodes, 1)), c=np.zeros(nodes),
+                     Qf=np.zeros((2, 2)), qf=np.zeros(2), cf=0.0, time=h * np.arange(nodes))
+    st = orc.make_settings(algorithm=orc.ALG_SLQ, reduced_form=True, hessian_multiple=0.0, time_step=h)
+    sol = orc.backward(st, pb)
+    assert sol.status == 0
+    K_check = np.array([[-0.905054653909129, -1.802904101100247]])
+    S_check = np.array([[1.109884545577592, -0.187358243057052], [-0.187358243057052, 1.625218620131083]])
+    assert np.allclose(sol.K[0], K_check, rtol=1e-9, atol=0)
+    assert np.allclose(sol.Sm[0], S_check, rtol=1e-9, atol=0)
+    # full-form Riccati gives the same answer
+    st_full = orc.make_settings(algorithm=orc.ALG_SLQ, reduced_form=False, hessian_multiple=0.0, time_step=h)
+    sol_full = orc.backward(st_full, pb)
+    assert np.allclose(sol_full.Sm[0], S_check, rtol=1e-9, atol=0)
+
+
+def random_lq(rng, n, m, N, nc=0, dt=0.05):
+    A = np.stack([np.eye(n) + dt * rng.uniform(-1, 1, (n, n)) for _ in range(N)])
+    B = np.stack([dt * rng.uniform(-1, 1, (n, m)) * 3 for _ in range(N)])
+    Q, P, R, q, r, c = (np.zeros((N, n, n)), np.zeros((N, m, n)), np.zeros((N, m, m)), np.zeros((N, n)), np.zeros((N, m)), np.zeros(N))
+    for k in range(N):
+        Qk, Pk, Rk, qk, rk, ck = random_cost(n, m, rng)
+        Q[k], P[k], R[k], q[k], r[k], c[k] = dt * Qk, dt * Pk, dt * (Rk + 0.1 * np.eye(m)), dt * qk, dt * rk, dt * ck
+    Qf, _, _, qf, _, cf = random_cost(n, m, rng)
+    kw = {}
+    if nc:
+        D = rng.uniform(-1, 1, (N, nc, m))
+        D[:, :, :nc] += 2 * np.eye(nc)
+        kw = dict(C=rng.uniform(-1, 1, (N, nc, n)), D=D, e=0.1 * rng.uniform(-1, 1, (N, nc)))
+    return orc.Problem(N=N, A=A, B=B, Hv=0.01 * rng.uniform(-1, 1, (N, n)), Q=Q, P=P, R=R, q=q, r=r, c=c, Qf=Qf, qf=qf, cf=cf,
+                       time=dt * np.arange(N + 1), **kw)
+
+
+@pytest.mark.parametrize("n,m,nc,N", [(3, 2, 0, 50), (3, 2, 2, 50), (9, 9, 3, 100), (4, 1, 0, 30)])
+@pytest.mark.parametrize("reduced", [True, False])
+def test_ilqr_sweep_matches_dense_kkt(n, m, nc, N, reduced):
+    """ocs2_ddp/test/CorrectnessTest.cpp:51-306 (random LQ, +-state-input constraints, DDP vs dense KKT; the reference uses
+    5e-3/1e-2 after several DDP iterations — a single exact LQ solve must agree to round-off)."""
+    rng = np.random.default_rng(100 * n + 10 * m + nc)
+    pb = random_lq(rng, n, m, N, nc)
+    st = orc.make_settings(algorithm=orc.ALG_ILQR, reduced_form=reduced, hessian_multiple=0.0)
+    sol = orc.backward(st, pb)
+    assert sol.status == 0
+    x0 = rng.uniform(-1, 1, n)
+    x, u, _, status = orc.rollout(st, pb, sol, x0, alpha=1.0)
+    assert status == 0
+    xk, uk, cost = kkt_oracle.solve_discrete_lq(pb, x0)
+    assert np.abs(x - xk).max() < 1e-9 * max(1.0, np.abs(xk).max())
+    assert np.abs(u[:N] - uk).max() < 1e-9 * max(1.0, np.abs(uk).max())
+    # V(x0) = 1/2 x0'S0x0 + Sv0'x0 + s0 equals the rolled-out cost
+    V = 0.5 * x0 @ sol.Sm[0] @ x0 + sol.Sv[0] @ x0 + sol.s[0]
+    assert V == pytest.approx(cost, rel=1e-9, abs=1e-10)
+    assert orc.discrete_lq_cost(pb, x, u) == pytest.approx(cost, rel=1e-9, abs=1e-10)
+
+
+def test_ilqr_lm_strategy_zero_multiple_equals_line_search():
+    rng = np.random.default_rng(77)
+    pb = random_lq(rng, 5, 3, 40)
+    a = orc.backward(orc.make_settings(strategy=orc.STRATEGY_LINE_SEARCH, hessian_multiple=0.0, reduced_form=False), pb)
+    b = orc.backward(orc.make_settings(strategy=orc.STRATEGY_LM, lm_riccati_multiple=0.0, reduced_form=False), pb)
+    assert np.allclose(a.K, b.K, rtol=1e-10, atol=1e-12) and np.allclose(a.Sm, b.Sm, rtol=1e-10, atol=1e-12)
+
+
+def test_slq_matches_ilqr_in_the_small_step_limit():
+    """SLQ (continuous flow map, RK4) and ILQR (discrete sweep) solve the same problem as dt -> 0: consistency of the two paths."""
+    rng = np.random.default_rng(9)
+    n, m, N, dt = 3, 2, 400, 2.5e-3
+    nodes = N + 1
+    Ac = rng.uniform(-1, 1, (n, n))
+    Bc = rng.uniform(-1, 1, (n, m))
+    Qc, Pc, Rc, _, _, _ = random_cost(n, m, rng)
+    Rc = Rc + np.eye(m)
+    Qf = spd(n, rng) / n
+    rep = lambda M, k: np.repeat(np.asarray(M, dtype=float)[None], k, 0)  # noqa: E731
+    cont = orc.Problem(N=N, A=rep(Ac, nodes), B=rep(Bc, nodes), Hv=np.zeros((nodes, n)), Q=rep(Qc, nodes), P=rep(Pc, nodes), R=rep(Rc, nodes),
+                       q=np.zeros((nodes, n)), r=np.zeros((nodes, m)), c=np.zeros(nodes), Qf=Qf, qf=np.zeros(n), cf=0.0,
+                       time=dt * np.arange(nodes))
+    import scipy.linalg
+
+    Md = scipy.linalg.expm(np.block([[Ac, Bc], [np.zeros((m, n + m))]]) * dt)
+    disc = orc.Problem(N=N, A=rep(Md[:n, :n], N), B=rep(Md[:n, n:], N), Hv=np.zeros((N, n)), Q=rep(Qc * dt, N), P=rep(Pc * dt, N),
+                       R=rep(Rc * dt, N), q=np.zeros((N, n)), r=np.zeros((N, m)), c=np.zeros(N), Qf=Qf, qf=np.zeros(n), cf=0.0,
+                       time=dt * np.arange(nodes))
+    s_slq = orc.backward(orc.make_settings(algorithm=orc.ALG_SLQ, hessian_multiple=0.0, time_step=dt), cont)
+    s_ilqr = orc.backward(orc.make_settings(algorithm=orc.ALG_ILQR, hessian_multiple=0.0), disc)
+    assert np.allclose(s_slq.Sm[0], s_ilqr.Sm[0], rtol=2e-2)
+    assert np.allclose(s_slq.K[0], s_ilqr.K[0], rtol=5e-2, atol=5e-2)
+    # continuous rollout with node-aligned steps lands on N+1 outputs and ends at tf
+    x0 = rng.uniform(-1, 1, n)
+    st = orc.make_settings(algorithm=orc.ALG_SLQ, hessian_multiple=0.0, time_step=dt)
+    x, u, t, status = orc.rollout(st, cont, s_slq, x0)
+    assert status == 0 and len(t) == N + 1 and t[-1] == cont.time[-1] and t[0] == pytest.approx(1e-9)
+
+
+def test_cartpole_fixture_regenerates_and_matches_kkt():
+    """config[0] anchor: the committed fixture equals a fresh oracle run, and the oracle equals the dense KKT solution."""
+    g = np.load(os.path.join(GOLDEN, "cartpole_ilqr.npz"))
+    N = int(g["N"])
+    pb = orc.Problem(N=N, A=g["A"], B=g["B"], Hv=np.zeros((N, 4)), Q=g["Q"], P=g["P"], R=g["R"], q=g["q"], r=g["r"], c=g["c"], Qf=g["Qf"],
+                     qf=g["qf"], cf=float(g["cf"]), x_nom=g["x_nom"], u_nom=g["u_nom"], time=float(g["dt"]) * np.arange(N + 1))
+    st = orc.make_settings(hessian_multiple=float(g["eps"]), time_step=float(g["dt"]))
+    sol = orc.backward(st, pb)
+    for name in ("K", "dbias", "bias", "Sm", "Sv", "s"):
+        assert np.allclose(getattr(sol, name), g[name], rtol=1e-12, atol=1e-12), name
+    x, u, _, _ = orc.rollout(st, pb, sol, g["x0"])
+    assert np.allclose(x, g["x"], rtol=1e-12, atol=1e-12) and np.allclose(u, g["u"], rtol=1e-12, atol=1e-12)
+    # KKT in deviation coordinates (nominal removed): dx_{k+1} = A dx + B du, cost around the nominal
+    dev = orc.Problem(N=N, A=g["A"], B=g["B"], Hv=np.zeros((N, 4)), Q=g["Q"], P=g["P"], R=g["R"], q=g["q"], r=g["r"], c=g["c"], Qf=g["Qf"],
+                      qf=g["qf"], cf=float(g["cf"]))
+    st0 = orc.make_settings(hessian_multiple=0.0)
+    sol0 = orc.backward(st0, dev)
+    dx0 = g["x0"] - g["x_nom"][0]
+    xk, uk, _ = kkt_oracle.solve_discrete_lq(dev, dx0)
+    xd, ud, _, _ = orc.rollout(st0, dev, sol0, dx0)
+    assert np.abs(xd - xk).max() < 1e-9 and np.abs(ud[:N] - uk).max() < 1e-9
+    # eps = 1e-6 shift perturbs the solution only slightly
+    assert np.abs((x - g["x_nom"]) - xk).max() < 1e-3
+
+
+def test_generator_is_deterministic_and_well_posed():
+    pb, x0 = orc.generate_problem(0, 5, orc.ALG_ILQR, 9, 9, 3, 20, 0.01)
+    pb2, x02 = orc.generate_problem(0, 5, orc.ALG_ILQR, 9, 9, 3, 20, 0.01)
+    assert np.array_equal(pb.A, pb2.A) and np.array_equal(x0, x02)
+    pb3, _ = orc.generate_problem(0, 6, orc.ALG_ILQR, 9, 9, 3, 20, 0.01)
+    assert not np.array_equal(pb.A, pb3.A)
+    assert np.allclose(pb.Q, np.swapaxes(pb.Q, 1, 2)) and np.allclose(pb.R, np.swapaxes(pb.R, 1, 2))
+    W = np.block([[pb.Q[3], pb.P[3].T], [pb.P[3], pb.R[3]]])
+    assert np.linalg.eigvalsh(W).min() > 0
+    assert np.allclose(pb.D[0][:, :3], np.eye(3))
+    st = orc.make_settings(hessian_multiple=1e-3)
+    sol = orc.backward(st, pb)
+    assert sol.status == 0
+    x, u, _, status = orc.rollout(st, pb, sol, x0)
+    assert status == 0 and np.isfinite(x).all()
+    # constraints hold along the rollout: C x + D u + e = 0
+    for k in range(pb.N):
+        assert np.abs(pb.C[k] @ x[k] + pb.D[k] @ u[k] + pb.e[k]).max() < 1e-10
