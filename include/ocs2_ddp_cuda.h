@@ -1,0 +1,184 @@
+/*
+ * ocs2_ddp_cuda.h — C ABI of the B200-native batched LQ solver (libocs2_ddp_cuda.so).
+ *
+ * This is the drop-in boundary for ONE hot path of RIVeR-Lab/ocs2: the LQ sub-problem of the DDP inner loop, applied to
+ * `batch` independent optimal control problems at once, FP64, on one CUDA device (sm_100a):
+ *
+ *   o2c_backward  replaces, per problem,
+ *       ILQR::solveSequentialRiccatiEquations / riccatiEquationsWorker      ocs2_ddp/src/ILQR.cpp:186-299
+ *       SLQ::solveSequentialRiccatiEquations / riccatiEquationsWorker       ocs2_ddp/src/SLQ.cpp:174-302
+ *       GaussNewtonDDP::computeProjectionAndRiccatiModification             ocs2_ddp/src/GaussNewtonDDP.cpp:734-782
+ *       DiscreteTimeRiccatiEquations::computeMap                            ocs2_ddp/src/riccati_equations/DiscreteTimeRiccatiEquations.cpp:50-154
+ *       ContinuousTimeRiccatiEquations::computeFlowMap (+ RK4 integrate_times) .../ContinuousTimeRiccatiEquations.cpp:152-292
+ *       GaussNewtonDDP::calculateController + ILQR/SLQ::calculateControllerWorker  GaussNewtonDDP.cpp:588-642, ILQR.cpp:162-181, SLQ.cpp:127-169
+ *   o2c_rollout   replaces incrementController + rolloutTrajectory of the LQ model with the LinearController
+ *       ocs2_ddp/src/DDP_HelperFunctions.cpp:125-138, 296-304; ocs2_core/src/control/LinearController.cpp:79-87;
+ *       ocs2_oc/src/rollout/TimeTriggeredRollout.cpp:46-115
+ *
+ * The reference has no FFI for this path (the seam is C++ virtual dispatch inside GaussNewtonDDP, see
+ * ocs2_ddp/include/ocs2_ddp/GaussNewtonDDP.h:149-193); INTEGRATION.md shows the ILQR/SLQ subclass a maintainer would add to
+ * call this ABI. Inputs are the ModelData fields (ocs2_core/include/ocs2_core/model_data/ModelData.h:43-60) of every time node
+ * in a struct-of-arrays batch layout; every matrix block is column-major (Eigen default) and contiguous.
+ *
+ * Conventions: all functions return an o2c_error (0 = success) and never throw; o2c_last_error() gives the message of the
+ * last failure on the calling thread. Calls on one handle must be serialised by the caller; different handles are independent.
+ * There is NO CPU fallback: without a CUDA device o2c_create fails with O2C_ERR_CUDA.
+ */
+#ifndef OCS2_DDP_CUDA_H_
+#define OCS2_DDP_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O2C_ABI_VERSION 1
+
+typedef enum o2c_error {
+  O2C_OK = 0,
+  O2C_ERR_INVALID_ARGUMENT = 1,
+  O2C_ERR_UNSUPPORTED = 2, /* e.g. CHOLESKY_MODIFICATION / EIGENVALUE_MODIFICATION hessian correction */
+  O2C_ERR_CUDA = 3,
+  O2C_ERR_OUT_OF_MEMORY = 4,
+  O2C_ERR_NOT_READY = 5 /* rollout before backward, download before compute, ... */
+} o2c_error;
+
+/* values mirror the reference enums */
+enum { O2C_ALG_ILQR = 0, O2C_ALG_SLQ = 1 };                 /* ddp::Algorithm (ocs2_ddp/include/ocs2_ddp/DDP_Settings.h) */
+enum { O2C_FORM_FULL = 0, O2C_FORM_REDUCED = 1 };           /* ddp preComputeRiccatiTerms (ILQR.cpp:68, SLQ.cpp:65) */
+enum { O2C_STRATEGY_LINE_SEARCH = 0, O2C_STRATEGY_LEVENBERG_MARQUARDT = 1 }; /* search_strategy::Type */
+enum {                                                      /* hessian_correction::Strategy (HessianCorrection.h:44-49) */
+  O2C_HC_DIAGONAL_SHIFT = 0,
+  O2C_HC_CHOLESKY_MODIFICATION = 1,   /* unsupported */
+  O2C_HC_EIGENVALUE_MODIFICATION = 2, /* unsupported */
+  O2C_HC_GERSHGORIN_MODIFICATION = 3
+};
+
+/* per-problem status bits (replace the reference's exceptions, SURVEY.md §5 "failure detection") */
+enum {
+  O2C_STATUS_OK = 0,
+  O2C_STATUS_CHOL_NOT_PD = 1,    /* Hm = R + B'SB not positive definite (LinearAlgebra.cpp:119-124 would silently continue) */
+  O2C_STATUS_NONFINITE = 2,      /* non-finite gains / value function / rollout (GaussNewtonDDP.cpp:621-636, DDP_HelperFunctions.cpp:132-134) */
+  O2C_STATUS_CONSTRAINT_RANK = 4 /* |Rc_ii| clamped to 1e-9 in the constraint QR (LinearAlgebra.cpp:38-47) */
+};
+
+typedef struct o2c_config {
+  int32_t nx;                 /* state dimension n */
+  int32_t nu;                 /* input dimension m */
+  int32_t nc_max;             /* max number of state-input equality constraints per node (0 = unconstrained) */
+  int32_t num_stages;         /* N: time nodes 0..N; ILQR consumes stage data of nodes 0..N-1, SLQ of nodes 0..N */
+  int32_t batch;              /* number of independent problems held by the handle */
+  int32_t algorithm;          /* O2C_ALG_* */
+  int32_t riccati_form;       /* O2C_FORM_* */
+  int32_t strategy;           /* O2C_STRATEGY_* */
+  int32_t hessian_correction; /* O2C_HC_* (lineSearch.hessianCorrectionStrategy) */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t max_alphas;         /* capacity for simultaneous rollout step lengths (line search), >= 1 */
+  int32_t has_nominal;        /* 1: x_nom/u_nom are provided; 0: nominal trajectories are zero (deviation coordinates) */
+  double hessian_multiple;    /* lineSearch.hessianCorrectionMultiple */
+  double lm_riccati_multiple; /* levenbergMarquardt riccatiMultiple */
+  double time_step;           /* ddp timeStep (SLQ RK4 integrate_times) and rollout timeStep (continuous rollout) */
+} o2c_config;
+
+/* One field of a batch: block(problem, node) starts at ptr + problem*problem_stride + node*node_stride (strides in doubles).
+ * ptr == NULL means "absent". */
+typedef struct o2c_field {
+  double* ptr;
+  int64_t problem_stride;
+  int64_t node_stride;
+} o2c_field;
+
+/* Struct-of-arrays view of the LQ data (host or device memory, as stated by the function taking it). Field names follow
+ * ModelData: dynamics.dfdx/dfdu, dynamicsBias, cost.dfdxx/dfdux/dfduu/dfdx/dfdu/f, stateInputEqConstraint.dfdx/dfdu/f. */
+typedef struct o2c_lq_view {
+  o2c_field A, B, Hv;          /* n*n, n*m, n */
+  o2c_field Q, P, R, q, r, c;  /* n*n, m*n, m*m, n, m, 1 */
+  o2c_field C, D, e;           /* nc_max*n, nc_max*m, nc_max; column-major with leading dimension nc_max */
+  const int32_t* nc;           /* active constraints per (problem, node); NULL => nc_max everywhere */
+  int64_t nc_problem_stride, nc_node_stride;
+  o2c_field Qf, qf, cf;        /* terminal value function (already Hessian-corrected); node_stride ignored */
+  o2c_field x_nom, u_nom;      /* nominal trajectories, N+1 nodes of n / m (only read when has_nominal) */
+  o2c_field x0;                /* initial state for the rollout, n per problem; node_stride ignored */
+  const double* time;          /* N+1 node times shared by the batch (required for SLQ; ILQR: optional) */
+} o2c_lq_view;
+
+/* Struct-of-arrays view of the solution. Controller and value function have N+1 nodes (node N of the controller is the copy of
+ * node N-1, GaussNewtonDDP.cpp:609-618; node N of the value function is the terminal condition, :526). */
+typedef struct o2c_solution_view {
+  o2c_field K, dbias, bias;  /* LinearController gainArray_ (m*n), deltaBiasArray_ (m), biasArray_ (m) */
+  o2c_field Sm, Sv, s;       /* valueFunctionTrajectory dfdxx (n*n), dfdx (n), f (1) */
+  o2c_field x, u;            /* rollout: out_nodes nodes of n / m per (alpha, problem); see alpha_stride */
+  int64_t x_alpha_stride, u_alpha_stride; /* stride (doubles) between rollouts of consecutive step lengths */
+  int32_t* status;           /* per-problem O2C_STATUS_* bits */
+} o2c_solution_view;
+
+typedef struct o2c_handle o2c_handle;
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this ABI is exported */
+#endif
+
+/* ---- life cycle ---- */
+int o2c_abi_version(void);
+const char* o2c_last_error(void);
+o2c_error o2c_create(const o2c_config* config, o2c_handle** handle);
+o2c_error o2c_destroy(o2c_handle* handle);
+o2c_error o2c_get_config(const o2c_handle* handle, o2c_config* config);
+o2c_error o2c_sync(o2c_handle* handle);
+/* the CUDA stream (cudaStream_t) all compute of this handle is enqueued on; time it with CUDA events on this stream */
+o2c_error o2c_compute_stream(o2c_handle* handle, void** stream);
+
+/* ---- data movement ---- */
+/* Library-owned, device-resident views (the layout the kernels consume: one interleaved record per (problem, node)).
+ * Producers that already live on the device (an LQ approximator, the synthetic generator) write through these. */
+o2c_error o2c_device_lq_view(o2c_handle* handle, o2c_lq_view* view);
+o2c_error o2c_device_solution_view(o2c_handle* handle, o2c_solution_view* view);
+/* number of output nodes of a rollout (N+1 for ILQR; the RK4 step schedule of the continuous rollout for SLQ) */
+o2c_error o2c_rollout_num_nodes(o2c_handle* handle, int32_t* out_nodes);
+/* rollout output times (out_nodes doubles, host memory) */
+o2c_error o2c_rollout_times(o2c_handle* handle, double* times);
+
+/* host SoA -> device for problems [problem_begin, problem_begin+problem_count); the view is indexed from problem 0 of the
+ * host arrays (block of handle problem p is read at host index p - problem_begin). Asynchronous w.r.t. the host only when
+ * the host memory is pinned; ordered before subsequent compute calls. */
+o2c_error o2c_upload(o2c_handle* handle, const o2c_lq_view* host_view, int32_t problem_begin, int32_t problem_count);
+/* same, from device memory in an arbitrary strided SoA layout */
+o2c_error o2c_import_device(o2c_handle* handle, const o2c_lq_view* device_view, int32_t problem_begin, int32_t problem_count);
+/* device -> host SoA; fields with ptr == NULL are skipped; n_alpha rollouts are copied */
+o2c_error o2c_download(o2c_handle* handle, const o2c_solution_view* host_view, int32_t problem_begin, int32_t problem_count,
+                       int32_t n_alpha);
+o2c_error o2c_set_time(o2c_handle* handle, const double* host_time /* N+1 */);
+
+/* ---- compute (asynchronous, enqueued on the compute stream) ---- */
+/* backward pass + controller for problems [begin, begin+count) */
+o2c_error o2c_backward(o2c_handle* handle, int32_t problem_begin, int32_t problem_count);
+/* forward rollouts of the LQ model for n_alpha step lengths (host array `alphas`) from the resident x0 */
+o2c_error o2c_rollout(o2c_handle* handle, const double* alphas, int32_t n_alpha, int32_t problem_begin, int32_t problem_count);
+/* backward + one rollout with step length alpha (one "LQ solve" of the benchmark metric) */
+o2c_error o2c_solve(o2c_handle* handle, double alpha, int32_t problem_begin, int32_t problem_count);
+/* number of kernel launches enqueued by this handle so far (bench.py's gpu_launches) */
+o2c_error o2c_launch_count(const o2c_handle* handle, int64_t* launches);
+/* name of the sweep kernel variant that o2c_backward dispatches to for this config (diagnostics / profiles) */
+const char* o2c_kernel_variant(const o2c_handle* handle);
+
+/* ---- end-to-end convenience: host buffers in, host buffers out, chunked H2D / compute / D2H pipeline ---- */
+o2c_error o2c_solve_host(o2c_handle* handle, const o2c_lq_view* host_lq, const o2c_solution_view* host_solution, double alpha,
+                         int32_t problem_count, int32_t chunk);
+
+/* ---- synthetic data (benchmarks / parity tests): seeded counter-based generator, bit-identical to oracle's
+ * orc_generate_problem; problem p of the handle gets global problem index first_problem_index + p ---- */
+o2c_error o2c_generate_synthetic(o2c_handle* handle, uint64_t seed, int64_t first_problem_index, double dt);
+
+/* pinned host memory helpers for callers without a CUDA runtime of their own */
+o2c_error o2c_host_alloc(void** ptr, uint64_t bytes);
+o2c_error o2c_host_free(void* ptr);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCS2_DDP_CUDA_H_ */

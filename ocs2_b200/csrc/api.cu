@@ -1,0 +1,909 @@
+// api.cu — C ABI of libocs2_ddp_cuda (see include/ocs2_ddp_cuda.h). Host-side plumbing only: handle life cycle, device buffers,
+// strided-SoA <-> record conversion, RK4 step schedules (boost::odeint integrate_times / integrate_adaptive semantics), kernel dispatch,
+// and the chunked H2D / compute / D2H pipeline of o2c_solve_host. No CPU arithmetic fallback exists: every compute call launches CUDA kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "o2c_common.cuh"
+
+using namespace o2c;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+o2c_error fail(o2c_error code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define O2C_CUDA(expr)                                                                                             \
+  do {                                                                                                             \
+    cudaError_t _e = (expr);                                                                                       \
+    if (_e != cudaSuccess) {                                                                                       \
+      return fail(_e == cudaErrorMemoryAllocation ? O2C_ERR_OUT_OF_MEMORY : O2C_ERR_CUDA,                          \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                                             \
+    }                                                                                                              \
+  } while (0)
+
+constexpr int kLanes = 3;
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  double* stage_in = nullptr;
+  double* stage_out = nullptr;
+  size_t stage_in_doubles = 0, stage_out_doubles = 0;
+  std::vector<double> bounce;  // host bounce buffer for irregular strides
+};
+
+}  // namespace
+
+struct o2c_handle {
+  o2c_config cfg{};
+  Layout L{};
+  SolverSettings st{};
+  Lane lanes[kLanes];
+  double *d_lq = nullptr, *d_term = nullptr, *d_xnom = nullptr, *d_unom = nullptr, *d_x0 = nullptr, *d_time = nullptr;
+  double *d_sol = nullptr, *d_xs = nullptr, *d_us = nullptr, *d_alphas = nullptr;
+  int *d_nc = nullptr, *d_status = nullptr;
+  SlqStep* d_slq_steps = nullptr;
+  int n_slq_steps = 0;
+  RolloutStep* d_ro_steps = nullptr;
+  int n_ro_steps = 0, ro_first_idx = 0;
+  double ro_first_alpha = 1.0;
+  int out_nodes = 0;
+  std::vector<double> time, ro_times;
+  bool time_set = false;
+  bool use_fast = false;
+  int64_t launches = 0;
+  int stage_chunk = 0;
+
+  DeviceBuffers buffers() const {
+    DeviceBuffers b{};
+    b.lq = d_lq;
+    b.term = d_term;
+    b.x_nom = d_xnom;
+    b.u_nom = d_unom;
+    b.nc = d_nc;
+    b.x0 = d_x0;
+    b.time = d_time;
+    b.sol = d_sol;
+    b.xs = d_xs;
+    b.us = d_us;
+    b.status = d_status;
+    return b;
+  }
+};
+
+namespace {
+
+__global__ void fill_int_kernel(int* p, int v, size_t count) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) p[i] = v;
+}
+
+// LinearInterpolation::timeSegment (ocs2_core/include/ocs2_core/misc/implementation/LinearInterpolation.h:69-107)
+void time_segment(double t, const std::vector<double>& time, int& index, double& alpha) {
+  const int count = (int)time.size();
+  if (count <= 1) {
+    index = 0;
+    alpha = 1.0;
+    return;
+  }
+  const int idx = (int)(std::lower_bound(time.begin(), time.end(), t) - time.begin()) - 1;
+  const int lastInterval = count - 1;
+  if (idx >= 0) {
+    if (idx < lastInterval) {
+      const double len = time[idx + 1] - time[idx];
+      const double till = time[idx + 1] - t;
+      index = idx;
+      if (len > 2.0 * 1e-9) {
+        alpha = till / len;
+      } else {
+        alpha = (till < 0.5 * len) ? 0.0 : 1.0;
+      }
+      return;
+    }
+    index = std::max(lastInterval - 1, 0);
+    alpha = 0.0;
+    return;
+  }
+  index = 0;
+  alpha = 1.0;
+}
+inline bool less_with_sign(double t1, double t2) { return (t2 - t1) > std::numeric_limits<double>::epsilon(); }
+inline bool less_eq_with_sign(double t1, double t2) { return (t1 - t2) <= std::numeric_limits<double>::epsilon(); }
+
+// SLQ backward schedule: boost::numeric::odeint::integrate_times with a plain RK4 stepper over z = -t reversed
+// (SLQ.cpp:256-302, DDP_HelperFunctions.cpp:309-328, implementation/Integrator.h:298-311)
+o2c_error build_slq_schedule(o2c_handle* h, std::vector<SlqStep>& steps) {
+  const int N = h->L.N;
+  const double dt = h->st.time_step;
+  if (!(dt > 0.0)) return fail(O2C_ERR_INVALID_ARGUMENT, "time_step must be positive for SLQ");
+  std::vector<double> z(N + 1);
+  for (int j = 0; j <= N; ++j) z[j] = -h->time[N - j];
+  steps.clear();
+  const double cs[4] = {0.0, 0.5, 0.5, 1.0};
+  for (int j = 0; j < N; ++j) {
+    const int i0 = N - 1 - j;
+    double current_time = z[j];
+    double current_dt = dt;
+    const size_t first = steps.size();
+    while (less_with_sign(current_time, z[j + 1])) {
+      current_dt = std::min(dt, z[j + 1] - current_time);
+      SlqStep s{};
+      s.interval = i0;
+      s.observe_node = -1;
+      s.h = current_dt;
+      for (int c = 0; c < 4; ++c) {
+        const double zt = current_time + current_dt * cs[c];
+        int idx;
+        double a;
+        time_segment(-zt, h->time, idx, a);
+        if (idx == i0) {
+          s.alpha[c] = a;
+        } else if (idx == i0 - 1 && a == 0.0) {
+          s.alpha[c] = 1.0;
+        } else if (idx == i0 + 1 && a == 1.0) {
+          s.alpha[c] = 0.0;
+        } else {
+          return fail(O2C_ERR_UNSUPPORTED, "SLQ step leaves its time interval (non-monotone or degenerate time grid)");
+        }
+      }
+      steps.push_back(s);
+      current_time += current_dt;
+      current_dt = std::max(dt, current_dt);
+      if (steps.size() > 50000000) return fail(O2C_ERR_INVALID_ARGUMENT, "SLQ schedule too long (time_step too small)");
+    }
+    if (steps.size() == first) {
+      // zero-length interval: the observer still records the unchanged state; emit a zero step so the kernel writes node i0
+      SlqStep s{};
+      s.interval = i0;
+      s.h = 0.0;
+      for (int c = 0; c < 4; ++c) s.alpha[c] = 0.0;
+      steps.push_back(s);
+    }
+    steps.back().observe_node = i0;
+  }
+  return O2C_OK;
+}
+
+// continuous rollout schedule: TimeTriggeredRollout::run -> integrateAdaptive with a plain stepper = integrate_const steps of
+// timeStep + one truncated last step; start nudged by weakEpsilon (RolloutBase.cpp:62-64)
+o2c_error build_rollout_schedule(o2c_handle* h, std::vector<RolloutStep>& steps) {
+  const int N = h->L.N;
+  const double dt = h->st.time_step;
+  if (!(dt > 0.0)) return fail(O2C_ERR_INVALID_ARGUMENT, "time_step must be positive for the continuous rollout");
+  const double t0 = h->time[0], tf = h->time[N];
+  const double tStart = std::min(t0 + 1e-9, tf);
+  steps.clear();
+  h->ro_times.clear();
+  time_segment(tStart, h->time, h->ro_first_idx, h->ro_first_alpha);
+  h->ro_times.push_back(tStart);
+  auto add = [&](double t, double hh, double tnext) {
+    RolloutStep s{};
+    s.h = hh;
+    const double cs[4] = {0.0, 0.5, 0.5, 1.0};
+    for (int c = 0; c < 4; ++c) time_segment(t + hh * cs[c], h->time, s.idx[c], s.alpha[c]);
+    time_segment(tnext, h->time, s.obs_idx, s.obs_alpha);
+    steps.push_back(s);
+    h->ro_times.push_back(tnext);
+  };
+  if (tStart < tf) {
+    double t = tStart;
+    int step = 0;
+    while (less_eq_with_sign(t + dt, tf)) {
+      ++step;
+      const double tn = tStart + (double)step * dt;
+      add(t, dt, tn);
+      t = tn;
+      if (step > 50000000) return fail(O2C_ERR_INVALID_ARGUMENT, "rollout schedule too long (time_step too small)");
+    }
+    const double end = tStart + dt * (double)step;
+    if (less_with_sign(end, tf)) add(end, tf - end, tf);
+  }
+  return O2C_OK;
+}
+
+o2c_error install_time(o2c_handle* h, const double* host_time) {
+  const int N = h->L.N;
+  h->time.assign(host_time, host_time + N + 1);
+  for (int k = 0; k < N; ++k)
+    if (!(h->time[k + 1] >= h->time[k])) return fail(O2C_ERR_INVALID_ARGUMENT, "time nodes must be non-decreasing");
+  O2C_CUDA(cudaMemcpyAsync(h->d_time, h->time.data(), sizeof(double) * (N + 1), cudaMemcpyHostToDevice, h->lanes[0].stream));
+  O2C_CUDA(cudaStreamSynchronize(h->lanes[0].stream));
+  if (h->st.algorithm == O2C_ALG_SLQ) {
+    std::vector<SlqStep> steps;
+    o2c_error e = build_slq_schedule(h, steps);
+    if (e != O2C_OK) return e;
+    if (h->d_slq_steps) cudaFree(h->d_slq_steps);
+    h->d_slq_steps = nullptr;
+    h->n_slq_steps = (int)steps.size();
+    if (!steps.empty()) {
+      O2C_CUDA(cudaMalloc(&h->d_slq_steps, sizeof(SlqStep) * steps.size()));
+      O2C_CUDA(cudaMemcpy(h->d_slq_steps, steps.data(), sizeof(SlqStep) * steps.size(), cudaMemcpyHostToDevice));
+    }
+    std::vector<RolloutStep> rs;
+    e = build_rollout_schedule(h, rs);
+    if (e != O2C_OK) return e;
+    const int out_nodes = (int)rs.size() + 1;
+    if (h->d_ro_steps) cudaFree(h->d_ro_steps);
+    h->d_ro_steps = nullptr;
+    h->n_ro_steps = (int)rs.size();
+    if (!rs.empty()) {
+      O2C_CUDA(cudaMalloc(&h->d_ro_steps, sizeof(RolloutStep) * rs.size()));
+      O2C_CUDA(cudaMemcpy(h->d_ro_steps, rs.data(), sizeof(RolloutStep) * rs.size(), cudaMemcpyHostToDevice));
+    }
+    if (out_nodes != h->out_nodes) {
+      if (h->d_xs) cudaFree(h->d_xs);
+      if (h->d_us) cudaFree(h->d_us);
+      h->d_xs = h->d_us = nullptr;
+      h->out_nodes = out_nodes;
+      const size_t tasks = (size_t)h->cfg.max_alphas * h->cfg.batch * out_nodes;
+      O2C_CUDA(cudaMalloc(&h->d_xs, sizeof(double) * tasks * h->L.n));
+      O2C_CUDA(cudaMalloc(&h->d_us, sizeof(double) * tasks * h->L.m));
+    }
+  } else {
+    h->ro_times = h->time;
+  }
+  h->time_set = true;
+  return O2C_OK;
+}
+
+struct FieldSpec {
+  const o2c_field* f;
+  int block;
+  int nodes;  // 1 for per-problem fields
+};
+
+// size of the dense staging area (doubles) one problem needs on the way in / out
+size_t stage_in_per_problem(const Layout& L, bool nominal) {
+  size_t t = (size_t)L.nodes * L.rec + L.trec + L.n;
+  if (nominal) t += (size_t)(L.N + 1) * (L.n + L.m);
+  t += (size_t)(L.nodes + 1) / 2 + 2;  // int32 nc per node
+  return t + 64;
+}
+size_t stage_out_per_problem(const Layout& L, int out_nodes, int n_alpha) {
+  return (size_t)(L.N + 1) * L.orec + (size_t)n_alpha * out_nodes * (L.n + L.m) + 64;
+}
+
+o2c_error ensure_stage(Lane& lane, size_t in_doubles, size_t out_doubles) {
+  if (in_doubles > lane.stage_in_doubles) {
+    if (lane.stage_in) cudaFree(lane.stage_in);
+    lane.stage_in = nullptr;
+    lane.stage_in_doubles = 0;
+    O2C_CUDA(cudaMalloc(&lane.stage_in, in_doubles * sizeof(double)));
+    lane.stage_in_doubles = in_doubles;
+  }
+  if (out_doubles > lane.stage_out_doubles) {
+    if (lane.stage_out) cudaFree(lane.stage_out);
+    lane.stage_out = nullptr;
+    lane.stage_out_doubles = 0;
+    O2C_CUDA(cudaMalloc(&lane.stage_out, out_doubles * sizeof(double)));
+    lane.stage_out_doubles = out_doubles;
+  }
+  return O2C_OK;
+}
+
+// copies one host field (count problems x nodes blocks) into dense device staging and returns the device-side strided view
+o2c_error field_h2d(Lane& lane, const o2c_field& f, int block, int nodes, int count, double*& cursor, FieldDev& out) {
+  out = FieldDev{nullptr, 0, 0};
+  if (f.ptr == nullptr || count == 0) return O2C_OK;
+  double* dst = cursor;
+  const size_t total = (size_t)count * nodes * block;
+  cursor += (total + 1) & ~(size_t)1;
+  const long long ps = f.problem_stride, ns = (nodes > 1) ? f.node_stride : block;
+  if (ns == block && (count == 1 || ps == (long long)nodes * block)) {
+    O2C_CUDA(cudaMemcpyAsync(dst, f.ptr, total * sizeof(double), cudaMemcpyHostToDevice, lane.stream));
+    out = FieldDev{dst, (long long)nodes * block, block};
+  } else if (ns == block && ps >= (long long)nodes * block) {
+    O2C_CUDA(cudaMemcpy2DAsync(dst, (size_t)nodes * block * sizeof(double), f.ptr, (size_t)ps * sizeof(double),
+                               (size_t)nodes * block * sizeof(double), count, cudaMemcpyHostToDevice, lane.stream));
+    out = FieldDev{dst, (long long)nodes * block, block};
+  } else if (ps == block && ns >= (long long)count * block) {
+    // [node][problem] order: rows are nodes
+    O2C_CUDA(cudaMemcpy2DAsync(dst, (size_t)count * block * sizeof(double), f.ptr, (size_t)ns * sizeof(double),
+                               (size_t)count * block * sizeof(double), nodes, cudaMemcpyHostToDevice, lane.stream));
+    out = FieldDev{dst, block, (long long)count * block};
+  } else {
+    // irregular strides: gather on the host (synchronous)
+    lane.bounce.resize(total);
+    for (int p = 0; p < count; ++p)
+      for (int k = 0; k < nodes; ++k)
+        std::memcpy(lane.bounce.data() + ((size_t)p * nodes + k) * block, f.ptr + p * ps + k * ns, sizeof(double) * block);
+    O2C_CUDA(cudaMemcpyAsync(dst, lane.bounce.data(), total * sizeof(double), cudaMemcpyHostToDevice, lane.stream));
+    O2C_CUDA(cudaStreamSynchronize(lane.stream));
+    out = FieldDev{dst, (long long)nodes * block, block};
+  }
+  return O2C_OK;
+}
+
+o2c_error field_d2h(Lane& lane, const o2c_field& f, int block, int nodes, int count, const double* src) {
+  if (f.ptr == nullptr || count == 0) return O2C_OK;
+  const size_t total = (size_t)count * nodes * block;
+  const long long ps = f.problem_stride, ns = (nodes > 1) ? f.node_stride : block;
+  if (ns == block && (count == 1 || ps == (long long)nodes * block)) {
+    O2C_CUDA(cudaMemcpyAsync(f.ptr, src, total * sizeof(double), cudaMemcpyDeviceToHost, lane.stream));
+  } else if (ns == block && ps >= (long long)nodes * block) {
+    O2C_CUDA(cudaMemcpy2DAsync(f.ptr, (size_t)ps * sizeof(double), src, (size_t)nodes * block * sizeof(double),
+                               (size_t)nodes * block * sizeof(double), count, cudaMemcpyDeviceToHost, lane.stream));
+  } else {
+    lane.bounce.resize(total);
+    O2C_CUDA(cudaMemcpyAsync(lane.bounce.data(), src, total * sizeof(double), cudaMemcpyDeviceToHost, lane.stream));
+    O2C_CUDA(cudaStreamSynchronize(lane.stream));
+    for (int p = 0; p < count; ++p)
+      for (int k = 0; k < nodes; ++k)
+        std::memcpy(f.ptr + p * ps + k * ns, lane.bounce.data() + ((size_t)p * nodes + k) * block, sizeof(double) * block);
+  }
+  return O2C_OK;
+}
+
+o2c_field offset_field(const o2c_field& f, long long problems) {
+  o2c_field g = f;
+  if (g.ptr) g.ptr += problems * f.problem_stride;
+  return g;
+}
+
+o2c_error check_range(const o2c_handle* h, int begin, int count) {
+  if (!h) return fail(O2C_ERR_INVALID_ARGUMENT, "null handle");
+  if (begin < 0 || count < 0 || (long long)begin + count > h->cfg.batch) return fail(O2C_ERR_INVALID_ARGUMENT, "problem range outside the batch");
+  return O2C_OK;
+}
+
+// host view (already offset so that index 0 is the first problem of the chunk) -> records of problems [begin, begin+count)
+o2c_error upload_chunk(o2c_handle* h, Lane& lane, const o2c_lq_view& v, int begin, int count) {
+  const Layout& L = h->L;
+  const bool nominal = h->cfg.has_nominal != 0;
+  o2c_error e = ensure_stage(lane, stage_in_per_problem(L, nominal) * (size_t)count, 0);
+  if (e != O2C_OK) return e;
+  double* cur = lane.stage_in;
+  LqViewDev d{};
+  const int n = L.n, m = L.m, ncm = L.ncmax, nodes = L.nodes;
+#define H2D(field, block, nn)                                                   \
+  if ((e = field_h2d(lane, v.field, block, nn, count, cur, d.field)) != O2C_OK) return e;
+  H2D(A, n * n, nodes) H2D(B, n * m, nodes) H2D(Hv, n, nodes) H2D(Q, n * n, nodes) H2D(P, m * n, nodes) H2D(R, m * m, nodes)
+  H2D(q, n, nodes) H2D(r, m, nodes) H2D(c, 1, nodes)
+  if (ncm > 0) {
+    H2D(C, ncm * n, nodes) H2D(D, ncm * m, nodes) H2D(e, ncm, nodes)
+  }
+  H2D(Qf, n * n, 1) H2D(qf, n, 1) H2D(cf, 1, 1) H2D(x0, n, 1)
+  if (nominal) {
+    H2D(x_nom, n, L.N + 1) H2D(u_nom, m, L.N + 1)
+  }
+#undef H2D
+  int* nc_stage = nullptr;
+  if (ncm > 0 && v.nc != nullptr) {
+    // int32 per (problem, node): gathered densely on the host, staged after the doubles
+    std::vector<int> tmp((size_t)count * nodes);
+    for (int p = 0; p < count; ++p)
+      for (int k = 0; k < nodes; ++k) tmp[(size_t)p * nodes + k] = v.nc[p * v.nc_problem_stride + k * v.nc_node_stride];
+    nc_stage = reinterpret_cast<int*>(cur);
+    O2C_CUDA(cudaMemcpyAsync(nc_stage, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, lane.stream));
+    O2C_CUDA(cudaStreamSynchronize(lane.stream));
+    d.nc = nc_stage;
+    d.nc_ps = nodes;
+    d.nc_ns = 1;
+  }
+  O2C_CUDA(launch_pack(L, d, h->d_lq, h->d_term, h->d_xnom, h->d_unom, h->d_nc, h->d_x0, begin, count, lane.stream));
+  h->launches += 1;
+  return O2C_OK;
+}
+
+o2c_error download_chunk(o2c_handle* h, Lane& lane, const o2c_solution_view& v, int begin, int count, int n_alpha) {
+  const Layout& L = h->L;
+  const int n = L.n, m = L.m, N = L.N, on = h->out_nodes;
+  o2c_error e = ensure_stage(lane, 0, stage_out_per_problem(L, on, std::max(n_alpha, 1)) * (size_t)count);
+  if (e != O2C_OK) return e;
+  double* cur = lane.stage_out;
+  SolViewDev d{};
+  auto take = [&](const o2c_field& f, int block, int nodes, FieldDev& out) {
+    out = FieldDev{nullptr, 0, 0};
+    if (!f.ptr) return;
+    out = FieldDev{cur, (long long)nodes * block, block};
+    cur += ((size_t)count * nodes * block + 1) & ~(size_t)1;
+  };
+  take(v.K, m * n, N + 1, d.K);
+  take(v.dbias, m, N + 1, d.dbias);
+  take(v.bias, m, N + 1, d.bias);
+  take(v.Sm, n * n, N + 1, d.Sm);
+  take(v.Sv, n, N + 1, d.Sv);
+  take(v.s, 1, N + 1, d.s);
+  double* xbase = nullptr;
+  double* ubase = nullptr;
+  if (v.x.ptr && n_alpha > 0) {
+    xbase = cur;
+    d.x = FieldDev{cur, (long long)on * n, n};
+    d.x_as = (long long)count * on * n;
+    cur += (size_t)n_alpha * count * on * n;
+  }
+  if (v.u.ptr && n_alpha > 0) {
+    ubase = cur;
+    d.u = FieldDev{cur, (long long)on * m, m};
+    d.u_as = (long long)count * on * m;
+    cur += (size_t)n_alpha * count * on * m;
+  }
+  cur = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(cur) + 15) & ~(uintptr_t)15);
+  int* status_stage = nullptr;
+  if (v.status) {
+    status_stage = reinterpret_cast<int*>(cur);
+    d.status = status_stage;
+  }
+  O2C_CUDA(launch_unpack(L, d, h->d_sol, h->d_xs, h->d_us, h->d_status, on, (xbase || ubase) ? n_alpha : 0, h->cfg.batch, begin, count,
+                         lane.stream));
+  h->launches += 1;
+#define D2H(field, block, nn) \
+  if ((e = field_d2h(lane, v.field, block, nn, count, d.field.ptr)) != O2C_OK) return e;
+  D2H(K, m * n, N + 1) D2H(dbias, m, N + 1) D2H(bias, m, N + 1) D2H(Sm, n * n, N + 1) D2H(Sv, n, N + 1) D2H(s, 1, N + 1)
+#undef D2H
+  for (int a = 0; a < n_alpha; ++a) {
+    if (xbase) {
+      o2c_field fx = v.x;
+      fx.ptr += (long long)a * v.x_alpha_stride;
+      if ((e = field_d2h(lane, fx, n, on, count, xbase + (size_t)a * count * on * n)) != O2C_OK) return e;
+    }
+    if (ubase) {
+      o2c_field fu = v.u;
+      fu.ptr += (long long)a * v.u_alpha_stride;
+      if ((e = field_d2h(lane, fu, m, on, count, ubase + (size_t)a * count * on * m)) != O2C_OK) return e;
+    }
+  }
+  if (v.status) O2C_CUDA(cudaMemcpyAsync(v.status, status_stage, sizeof(int) * count, cudaMemcpyDeviceToHost, lane.stream));
+  return O2C_OK;
+}
+
+o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) {
+  if (count == 0) return O2C_OK;
+  const DeviceBuffers buf = h->buffers();
+  if (h->st.algorithm == O2C_ALG_ILQR) {
+    if (h->use_fast) {
+      int l = 0;
+      O2C_CUDA(launch_ilqr_fast(h->L, h->st, buf, false, 1.0, h->cfg.batch, begin, count, stream, &l));
+      h->launches += l;
+    } else {
+      O2C_CUDA(launch_ilqr_generic(h->L, h->st, buf, begin, count, stream));
+      h->launches += 1;
+    }
+  } else {
+    if (!h->time_set) return fail(O2C_ERR_NOT_READY, "SLQ needs the node times (o2c_set_time or lq_view.time) before o2c_backward");
+    O2C_CUDA(launch_slq_generic(h->L, h->st, buf, h->d_slq_steps, h->n_slq_steps, begin, count, stream));
+    h->launches += 1;
+  }
+  return O2C_OK;
+}
+
+o2c_error rollout_on(o2c_handle* h, cudaStream_t stream, const double* alphas_dev, int n_alpha, int begin, int count) {
+  if (count == 0 || n_alpha == 0) return O2C_OK;
+  const DeviceBuffers buf = h->buffers();
+  if (h->st.algorithm == O2C_ALG_ILQR) {
+    O2C_CUDA(launch_rollout_discrete(h->L, buf, alphas_dev, n_alpha, h->cfg.batch, begin, count, stream));
+  } else {
+    if (!h->time_set) return fail(O2C_ERR_NOT_READY, "continuous rollout needs the node times");
+    O2C_CUDA(launch_rollout_continuous(h->L, buf, h->d_ro_steps, h->n_ro_steps, h->ro_first_idx, h->ro_first_alpha, h->out_nodes, alphas_dev,
+                                       n_alpha, h->cfg.batch, begin, count, stream));
+  }
+  h->launches += 1;
+  return O2C_OK;
+}
+
+o2c_error solve_on(o2c_handle* h, cudaStream_t stream, double* alpha_slot_dev, double alpha, int begin, int count) {
+  if (count == 0) return O2C_OK;
+  if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast) {
+    int l = 0;
+    O2C_CUDA(launch_ilqr_fast(h->L, h->st, h->buffers(), true, alpha, h->cfg.batch, begin, count, stream, &l));
+    h->launches += l;
+    return O2C_OK;
+  }
+  o2c_error e = backward_on(h, stream, begin, count);
+  if (e != O2C_OK) return e;
+  O2C_CUDA(cudaMemcpyAsync(alpha_slot_dev, &alpha, sizeof(double), cudaMemcpyHostToDevice, stream));
+  return rollout_on(h, stream, alpha_slot_dev, 1, begin, count);
+}
+
+void release(o2c_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (auto& lane : h->lanes) {
+    if (lane.stream) cudaStreamSynchronize(lane.stream);
+  }
+  void* ptrs[] = {h->d_lq,  h->d_term, h->d_xnom, h->d_unom,   h->d_x0,        h->d_time,    h->d_sol,
+                  h->d_xs,  h->d_us,   h->d_alphas, h->d_nc,   h->d_status,    h->d_slq_steps, h->d_ro_steps};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (auto& lane : h->lanes) {
+    if (lane.stage_in) cudaFree(lane.stage_in);
+    if (lane.stage_out) cudaFree(lane.stage_out);
+    if (lane.stream) cudaStreamDestroy(lane.stream);
+  }
+  delete h;
+}
+
+}  // namespace
+
+extern "C" {
+
+int o2c_abi_version(void) { return O2C_ABI_VERSION; }
+const char* o2c_last_error(void) { return g_last_error.c_str(); }
+
+o2c_error o2c_create(const o2c_config* cfg, o2c_handle** out) {
+  if (!cfg || !out) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (cfg->nx < 1 || cfg->nu < 1 || cfg->nx > 64 || cfg->nu > 64) return fail(O2C_ERR_INVALID_ARGUMENT, "nx, nu must be in [1, 64]");
+  if (cfg->nc_max < 0 || cfg->nc_max > cfg->nu) return fail(O2C_ERR_INVALID_ARGUMENT, "nc_max must be in [0, nu]");
+  if (cfg->nc_max > 32) return fail(O2C_ERR_UNSUPPORTED, "nc_max > 32 is not supported");
+  if (cfg->num_stages < 1 || cfg->num_stages > 1022) return fail(O2C_ERR_INVALID_ARGUMENT, "num_stages must be in [1, 1022]");
+  if (cfg->batch < 1) return fail(O2C_ERR_INVALID_ARGUMENT, "batch must be positive");
+  if (cfg->algorithm != O2C_ALG_ILQR && cfg->algorithm != O2C_ALG_SLQ) return fail(O2C_ERR_INVALID_ARGUMENT, "unknown algorithm");
+  if (cfg->strategy != O2C_STRATEGY_LINE_SEARCH && cfg->strategy != O2C_STRATEGY_LEVENBERG_MARQUARDT)
+    return fail(O2C_ERR_INVALID_ARGUMENT, "unknown strategy");
+  if (cfg->riccati_form != O2C_FORM_FULL && cfg->riccati_form != O2C_FORM_REDUCED) return fail(O2C_ERR_INVALID_ARGUMENT, "unknown riccati_form");
+  if (cfg->strategy == O2C_STRATEGY_LINE_SEARCH && cfg->hessian_correction != O2C_HC_DIAGONAL_SHIFT &&
+      cfg->hessian_correction != O2C_HC_GERSHGORIN_MODIFICATION)
+    return fail(O2C_ERR_UNSUPPORTED, "hessian_correction must be DIAGONAL_SHIFT or GERSHGORIN_MODIFICATION");
+  if (cfg->riccati_form == O2C_FORM_REDUCED && cfg->strategy != O2C_STRATEGY_LINE_SEARCH)
+    return fail(O2C_ERR_INVALID_ARGUMENT, "the reduced Riccati form is only valid with LINE_SEARCH (ILQR.cpp:68, SLQ.cpp:65)");
+  if (cfg->max_alphas < 1) return fail(O2C_ERR_INVALID_ARGUMENT, "max_alphas must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(O2C_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(O2C_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+  O2C_CUDA(cudaSetDevice(cfg->device));
+  o2c_handle* h = new o2c_handle();
+  h->cfg = *cfg;
+  h->L = make_layout(cfg->nx, cfg->nu, cfg->nc_max, cfg->num_stages, cfg->algorithm);
+  h->st = SolverSettings{cfg->algorithm, cfg->riccati_form == O2C_FORM_REDUCED ? 1 : 0, cfg->strategy, cfg->hessian_correction,
+                         cfg->hessian_multiple, cfg->lm_riccati_multiple, cfg->time_step};
+  const Layout& L = h->L;
+  const size_t B = (size_t)cfg->batch;
+  auto cleanup_fail = [&](o2c_error code) {
+    release(h);
+    return code;
+  };
+#define ALLOC(ptr, count)                                                                                      \
+  do {                                                                                                         \
+    cudaError_t _e = cudaMalloc(&(ptr), (count));                                                              \
+    if (_e != cudaSuccess) {                                                                                   \
+      cudaGetLastError();                                                                                      \
+      fail(O2C_ERR_OUT_OF_MEMORY, std::string("cudaMalloc(" #ptr "): ") + cudaGetErrorString(_e));            \
+      return cleanup_fail(O2C_ERR_OUT_OF_MEMORY);                                                              \
+    }                                                                                                          \
+  } while (0)
+  for (auto& lane : h->lanes) {
+    if (cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      fail(O2C_ERR_CUDA, "cudaStreamCreate failed");
+      return cleanup_fail(O2C_ERR_CUDA);
+    }
+  }
+  h->out_nodes = L.N + 1;
+  ALLOC(h->d_lq, sizeof(double) * B * L.nodes * L.rec);
+  ALLOC(h->d_term, sizeof(double) * B * L.trec);
+  ALLOC(h->d_x0, sizeof(double) * B * L.n);
+  ALLOC(h->d_time, sizeof(double) * (L.N + 1));
+  ALLOC(h->d_sol, sizeof(double) * B * (L.N + 1) * L.orec);
+  ALLOC(h->d_xs, sizeof(double) * (size_t)cfg->max_alphas * B * h->out_nodes * L.n);
+  ALLOC(h->d_us, sizeof(double) * (size_t)cfg->max_alphas * B * h->out_nodes * L.m);
+  ALLOC(h->d_alphas, sizeof(double) * (cfg->max_alphas + kLanes));
+  ALLOC(h->d_status, sizeof(int) * B);
+  if (cfg->has_nominal) {
+    ALLOC(h->d_xnom, sizeof(double) * B * (L.N + 1) * L.n);
+    ALLOC(h->d_unom, sizeof(double) * B * (L.N + 1) * L.m);
+    cudaMemsetAsync(h->d_xnom, 0, sizeof(double) * B * (L.N + 1) * L.n, h->lanes[0].stream);
+    cudaMemsetAsync(h->d_unom, 0, sizeof(double) * B * (L.N + 1) * L.m, h->lanes[0].stream);
+  }
+  if (cfg->nc_max > 0) {
+    ALLOC(h->d_nc, sizeof(int) * B * L.nodes);
+    const size_t cnt = B * L.nodes;
+    fill_int_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->lanes[0].stream>>>(h->d_nc, cfg->nc_max, cnt);
+  }
+#undef ALLOC
+  cudaMemsetAsync(h->d_status, 0, sizeof(int) * B, h->lanes[0].stream);
+  cudaMemsetAsync(h->d_x0, 0, sizeof(double) * B * L.n, h->lanes[0].stream);
+  h->use_fast = fast_ilqr_supported(h->L, h->st, h->buffers());
+  // default uniform time grid t_k = k * time_step (ILQR does not need it; SLQ callers normally override it)
+  std::vector<double> t(L.N + 1);
+  const double dt = cfg->time_step > 0.0 ? cfg->time_step : 1.0;
+  for (int k = 0; k <= L.N; ++k) t[k] = dt * (double)k;
+  o2c_error e = install_time(h, t.data());
+  if (e != O2C_OK) return cleanup_fail(e);
+  if (cudaStreamSynchronize(h->lanes[0].stream) != cudaSuccess) {
+    fail(O2C_ERR_CUDA, "initialisation failed");
+    return cleanup_fail(O2C_ERR_CUDA);
+  }
+  *out = h;
+  return O2C_OK;
+}
+
+o2c_error o2c_destroy(o2c_handle* h) {
+  release(h);
+  return O2C_OK;
+}
+
+o2c_error o2c_get_config(const o2c_handle* h, o2c_config* cfg) {
+  if (!h || !cfg) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  *cfg = h->cfg;
+  return O2C_OK;
+}
+
+o2c_error o2c_sync(o2c_handle* h) {
+  if (!h) return fail(O2C_ERR_INVALID_ARGUMENT, "null handle");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));
+  return O2C_OK;
+}
+
+o2c_error o2c_compute_stream(o2c_handle* h, void** stream) {
+  if (!h || !stream) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  *stream = (void*)h->lanes[0].stream;
+  return O2C_OK;
+}
+
+o2c_error o2c_device_lq_view(o2c_handle* h, o2c_lq_view* v) {
+  if (!h || !v) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  const Layout& L = h->L;
+  std::memset(v, 0, sizeof(*v));
+  const int64_t ps = (int64_t)L.nodes * L.rec, ns = L.rec;
+  auto rec = [&](int off) { return o2c_field{h->d_lq + off, ps, ns}; };
+  v->A = rec(L.oA);
+  v->B = rec(L.oB);
+  v->Hv = rec(L.oHv);
+  v->Q = rec(L.oQ);
+  v->P = rec(L.oP);
+  v->R = rec(L.oR);
+  v->q = rec(L.oq);
+  v->r = rec(L.or_);
+  v->c = rec(L.oc);
+  if (L.ncmax > 0) {
+    v->C = rec(L.oC);
+    v->D = rec(L.oD);
+    v->e = rec(L.oe);
+    v->nc = h->d_nc;
+    v->nc_problem_stride = L.nodes;
+    v->nc_node_stride = 1;
+  }
+  v->Qf = o2c_field{h->d_term + L.oQf, L.trec, 0};
+  v->qf = o2c_field{h->d_term + L.oqf, L.trec, 0};
+  v->cf = o2c_field{h->d_term + L.ocf, L.trec, 0};
+  if (h->d_xnom) v->x_nom = o2c_field{h->d_xnom, (int64_t)(L.N + 1) * L.n, L.n};
+  if (h->d_unom) v->u_nom = o2c_field{h->d_unom, (int64_t)(L.N + 1) * L.m, L.m};
+  v->x0 = o2c_field{h->d_x0, L.n, 0};
+  v->time = h->d_time;
+  return O2C_OK;
+}
+
+o2c_error o2c_device_solution_view(o2c_handle* h, o2c_solution_view* v) {
+  if (!h || !v) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  const Layout& L = h->L;
+  std::memset(v, 0, sizeof(*v));
+  const int64_t ps = (int64_t)(L.N + 1) * L.orec, ns = L.orec;
+  auto rec = [&](int off) { return o2c_field{h->d_sol + off, ps, ns}; };
+  v->K = rec(L.oK);
+  v->dbias = rec(L.odb);
+  v->bias = rec(L.obias);
+  v->Sm = rec(L.oSm);
+  v->Sv = rec(L.oSv);
+  v->s = rec(L.os);
+  v->x = o2c_field{h->d_xs, (int64_t)h->out_nodes * L.n, L.n};
+  v->u = o2c_field{h->d_us, (int64_t)h->out_nodes * L.m, L.m};
+  v->x_alpha_stride = (int64_t)h->cfg.batch * h->out_nodes * L.n;
+  v->u_alpha_stride = (int64_t)h->cfg.batch * h->out_nodes * L.m;
+  v->status = h->d_status;
+  return O2C_OK;
+}
+
+o2c_error o2c_rollout_num_nodes(o2c_handle* h, int32_t* out_nodes) {
+  if (!h || !out_nodes) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  *out_nodes = h->out_nodes;
+  return O2C_OK;
+}
+
+o2c_error o2c_rollout_times(o2c_handle* h, double* times) {
+  if (!h || !times) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  std::copy(h->ro_times.begin(), h->ro_times.end(), times);
+  return O2C_OK;
+}
+
+o2c_error o2c_set_time(o2c_handle* h, const double* host_time) {
+  if (!h || !host_time) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  return install_time(h, host_time);
+}
+
+o2c_error o2c_upload(o2c_handle* h, const o2c_lq_view* v, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  if (!v) return fail(O2C_ERR_INVALID_ARGUMENT, "null view");
+  if (!v->A.ptr || !v->B.ptr || !v->Q.ptr || !v->R.ptr || !v->Qf.ptr)
+    return fail(O2C_ERR_INVALID_ARGUMENT, "A, B, Q, R and Qf are required (absent Hv, P, q, r, c, qf, cf are taken as zero)");
+  if (h->L.ncmax > 0 && (!v->C.ptr || !v->D.ptr || !v->e.ptr)) return fail(O2C_ERR_INVALID_ARGUMENT, "C, D, e are required when nc_max > 0");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  if (v->time) {
+    e = install_time(h, v->time);
+    if (e != O2C_OK) return e;
+  }
+  Lane& lane = h->lanes[0];
+  const size_t per = stage_in_per_problem(h->L, h->cfg.has_nominal != 0) * sizeof(double);
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)count, ((size_t)1 << 30) / per));
+  for (int off = 0; off < count; off += chunk) {
+    const int c = std::min(chunk, count - off);
+    o2c_lq_view sub = *v;
+#define OFF(field) sub.field = offset_field(v->field, off);
+    OFF(A) OFF(B) OFF(Hv) OFF(Q) OFF(P) OFF(R) OFF(q) OFF(r) OFF(c) OFF(C) OFF(D) OFF(e) OFF(Qf) OFF(qf) OFF(cf) OFF(x_nom) OFF(u_nom) OFF(x0)
+#undef OFF
+    if (v->nc) sub.nc = v->nc + (long long)off * v->nc_problem_stride;
+    e = upload_chunk(h, lane, sub, begin + off, c);
+    if (e != O2C_OK) return e;
+  }
+  return O2C_OK;
+}
+
+o2c_error o2c_import_device(o2c_handle* h, const o2c_lq_view* v, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  if (!v) return fail(O2C_ERR_INVALID_ARGUMENT, "null view");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  if (v->time) {
+    std::vector<double> t(h->L.N + 1);
+    O2C_CUDA(cudaMemcpy(t.data(), v->time, sizeof(double) * t.size(), cudaMemcpyDeviceToHost));
+    e = install_time(h, t.data());
+    if (e != O2C_OK) return e;
+  }
+  LqViewDev d{};
+  auto cv = [](const o2c_field& f) { return FieldDev{f.ptr, (long long)f.problem_stride, (long long)f.node_stride}; };
+  d.A = cv(v->A);
+  d.B = cv(v->B);
+  d.Hv = cv(v->Hv);
+  d.Q = cv(v->Q);
+  d.P = cv(v->P);
+  d.R = cv(v->R);
+  d.q = cv(v->q);
+  d.r = cv(v->r);
+  d.c = cv(v->c);
+  d.C = cv(v->C);
+  d.D = cv(v->D);
+  d.e = cv(v->e);
+  d.Qf = cv(v->Qf);
+  d.qf = cv(v->qf);
+  d.cf = cv(v->cf);
+  d.x_nom = cv(v->x_nom);
+  d.u_nom = cv(v->u_nom);
+  d.x0 = cv(v->x0);
+  d.nc = v->nc;
+  d.nc_ps = v->nc_problem_stride;
+  d.nc_ns = v->nc_node_stride;
+  O2C_CUDA(launch_pack(h->L, d, h->d_lq, h->d_term, h->d_xnom, h->d_unom, h->d_nc, h->d_x0, begin, count, h->lanes[0].stream));
+  h->launches += 1;
+  return O2C_OK;
+}
+
+o2c_error o2c_download(o2c_handle* h, const o2c_solution_view* v, int32_t begin, int32_t count, int32_t n_alpha) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  if (!v) return fail(O2C_ERR_INVALID_ARGUMENT, "null view");
+  if (n_alpha < 0 || n_alpha > h->cfg.max_alphas) return fail(O2C_ERR_INVALID_ARGUMENT, "n_alpha outside [0, max_alphas]");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  Lane& lane = h->lanes[0];
+  const size_t per = stage_out_per_problem(h->L, h->out_nodes, std::max(n_alpha, 1)) * sizeof(double);
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)count, ((size_t)1 << 30) / per));
+  for (int off = 0; off < count; off += chunk) {
+    const int c = std::min(chunk, count - off);
+    o2c_solution_view sub = *v;
+#define OFF(field) sub.field = offset_field(v->field, off);
+    OFF(K) OFF(dbias) OFF(bias) OFF(Sm) OFF(Sv) OFF(s) OFF(x) OFF(u)
+#undef OFF
+    if (v->status) sub.status = v->status + off;
+    e = download_chunk(h, lane, sub, begin + off, c, n_alpha);
+    if (e != O2C_OK) return e;
+  }
+  O2C_CUDA(cudaStreamSynchronize(lane.stream));
+  return O2C_OK;
+}
+
+o2c_error o2c_backward(o2c_handle* h, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  return backward_on(h, h->lanes[0].stream, begin, count);
+}
+
+o2c_error o2c_rollout(o2c_handle* h, const double* alphas, int32_t n_alpha, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  if (!alphas || n_alpha < 1 || n_alpha > h->cfg.max_alphas) return fail(O2C_ERR_INVALID_ARGUMENT, "n_alpha outside [1, max_alphas]");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  O2C_CUDA(cudaMemcpyAsync(h->d_alphas, alphas, sizeof(double) * n_alpha, cudaMemcpyHostToDevice, h->lanes[0].stream));
+  return rollout_on(h, h->lanes[0].stream, h->d_alphas, n_alpha, begin, count);
+}
+
+o2c_error o2c_solve(o2c_handle* h, double alpha, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  return solve_on(h, h->lanes[0].stream, h->d_alphas, alpha, begin, count);
+}
+
+o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {
+  if (!h || !launches) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  *launches = h->launches;
+  return O2C_OK;
+}
+
+const char* o2c_kernel_variant(const o2c_handle* h) {
+  if (!h) return "";
+  if (h->st.algorithm == O2C_ALG_SLQ) return "slq_generic_kernel";
+  return h->use_fast ? "ilqr_dmma_kernel" : "ilqr_generic_kernel";
+}
+
+o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solution_view* sol, double alpha, int32_t count, int32_t chunk) {
+  o2c_error e = check_range(h, 0, count);
+  if (e != O2C_OK) return e;
+  if (!lq || !sol) return fail(O2C_ERR_INVALID_ARGUMENT, "null view");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  if (lq->time) {
+    e = install_time(h, lq->time);
+    if (e != O2C_OK) return e;
+  }
+  if (chunk <= 0) {
+    const size_t per = stage_in_per_problem(h->L, h->cfg.has_nominal != 0) * sizeof(double);
+    chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)(count + kLanes - 1) / kLanes, ((size_t)1 << 29) / per));
+  }
+  // lanes run [H2D -> pack -> sweep+rollout -> unpack -> D2H] for alternating chunks; copies of one lane overlap the kernels of another
+  for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));
+  int li = 0;
+  for (int off = 0; off < count; off += chunk, li = (li + 1) % kLanes) {
+    const int c = std::min(chunk, count - off);
+    Lane& lane = h->lanes[li];
+    o2c_lq_view sub = *lq;
+#define OFF(field) sub.field = offset_field(lq->field, off);
+    OFF(A) OFF(B) OFF(Hv) OFF(Q) OFF(P) OFF(R) OFF(q) OFF(r) OFF(c) OFF(C) OFF(D) OFF(e) OFF(Qf) OFF(qf) OFF(cf) OFF(x_nom) OFF(u_nom) OFF(x0)
+#undef OFF
+    if (lq->nc) sub.nc = lq->nc + (long long)off * lq->nc_problem_stride;
+    if ((e = upload_chunk(h, lane, sub, off, c)) != O2C_OK) return e;
+    if ((e = solve_on(h, lane.stream, h->d_alphas + h->cfg.max_alphas + li, alpha, off, c)) != O2C_OK) return e;
+    o2c_solution_view ss = *sol;
+#define OFF(field) ss.field = offset_field(sol->field, off);
+    OFF(K) OFF(dbias) OFF(bias) OFF(Sm) OFF(Sv) OFF(s) OFF(x) OFF(u)
+#undef OFF
+    if (sol->status) ss.status = sol->status + off;
+    if ((e = download_chunk(h, lane, ss, off, c, 1)) != O2C_OK) return e;
+  }
+  for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));
+  return O2C_OK;
+}
+
+o2c_error o2c_generate_synthetic(o2c_handle* h, uint64_t seed, int64_t first_problem_index, double dt) {
+  if (!h) return fail(O2C_ERR_INVALID_ARGUMENT, "null handle");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->lanes[0].stream;
+  O2C_CUDA(launch_generate(h->L, h->st.algorithm, h->d_lq, h->d_term, h->d_x0, seed, first_problem_index, dt, h->cfg.batch, s));
+  h->launches += 1;
+  if (h->d_nc) {
+    const size_t cnt = (size_t)h->cfg.batch * h->L.nodes;
+    fill_int_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(h->d_nc, h->L.ncmax, cnt);
+    O2C_CUDA(cudaGetLastError());
+  }
+  if (h->d_xnom) {
+    O2C_CUDA(cudaMemsetAsync(h->d_xnom, 0, sizeof(double) * (size_t)h->cfg.batch * (h->L.N + 1) * h->L.n, s));
+    O2C_CUDA(cudaMemsetAsync(h->d_unom, 0, sizeof(double) * (size_t)h->cfg.batch * (h->L.N + 1) * h->L.m, s));
+  }
+  std::vector<double> t(h->L.N + 1);
+  for (int k = 0; k <= h->L.N; ++k) t[k] = dt * (double)k;
+  return install_time(h, t.data());
+}
+
+o2c_error o2c_host_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  O2C_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return O2C_OK;
+}
+
+o2c_error o2c_host_free(void* ptr) {
+  if (ptr) O2C_CUDA(cudaFreeHost(ptr));
+  return O2C_OK;
+}
+
+}  // extern "C"

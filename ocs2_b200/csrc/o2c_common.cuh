@@ -1,0 +1,193 @@
+// o2c_common.cuh — shared declarations of libocs2_ddp_cuda (device layout, kernel parameter blocks, warp helpers).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ocs2_ddp_cuda.h"
+
+namespace o2c {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Device-resident layout (library-owned). One interleaved record per (problem, node):
+//   lq   [batch][nodes][rec]   rec = { A | B | Q | P | R | Hv | q | r | c | C | D | e } padded to an even number of doubles
+//   term [batch][trec]         trec = { Qf | qf | cf } padded
+//   sol  [batch][N+1][orec]    orec = { K | dbias | bias | Sm | Sv | s } padded
+//   xs   [alpha][batch][out_nodes][n],  us [alpha][batch][out_nodes][m]
+// Every record starts 16-byte aligned so a whole record is one cp.async.bulk (TMA) transfer.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Layout {
+  int n, m, ncmax, N, nodes;
+  int rec, oA, oB, oQ, oP, oR, oHv, oq, or_, oc, oC, oD, oe;
+  int trec, oQf, oqf, ocf;
+  int orec, oK, odb, obias, oSm, oSv, os;
+};
+
+inline int pad2(int v) { return (v + 1) & ~1; }
+
+inline Layout make_layout(int n, int m, int ncmax, int N, int algorithm) {
+  Layout L{};
+  L.n = n;
+  L.m = m;
+  L.ncmax = ncmax;
+  L.N = N;
+  L.nodes = (algorithm == O2C_ALG_SLQ) ? N + 1 : N;
+  int o = 0;
+  // every matrix block starts on a 16-byte boundary (even double offset) so that vector loads / bulk copies stay aligned
+  auto take = [&](int count) {
+    int at = o;
+    o = pad2(o + count);
+    return at;
+  };
+  L.oA = take(n * n);
+  L.oB = take(n * m);
+  L.oQ = take(n * n);
+  L.oP = take(m * n);
+  L.oR = take(m * m);
+  L.oHv = take(n);
+  L.oq = take(n);
+  L.or_ = take(m);
+  L.oc = take(1);
+  L.oC = take(ncmax * n);
+  L.oD = take(ncmax * m);
+  L.oe = take(ncmax);
+  L.rec = pad2(o);
+  o = 0;
+  L.oQf = take(n * n);
+  L.oqf = take(n);
+  L.ocf = take(1);
+  L.trec = pad2(o);
+  o = 0;
+  L.oK = take(m * n);
+  L.odb = take(m);
+  L.obias = take(m);
+  L.oSm = take(n * n);
+  L.oSv = take(n);
+  L.os = take(1);
+  L.orec = pad2(o);
+  return L;
+}
+
+struct SolverSettings {
+  int algorithm, reduced, strategy, hc;
+  double eps, mu, time_step;
+};
+
+struct DeviceBuffers {
+  const double* lq;
+  const double* term;
+  const double* x_nom;  // [batch][N+1][n] or nullptr
+  const double* u_nom;  // [batch][N+1][m] or nullptr
+  const int* nc;        // [batch][nodes] or nullptr
+  const double* x0;     // [batch][n]
+  const double* time;   // [N+1]
+  double* sol;
+  double* xs;
+  double* us;
+  int* status;
+};
+
+// one RK4 step of the SLQ backward integration (host-precomputed, mirrors boost::odeint integrate_times)
+struct SlqStep {
+  int interval;      // data interval i: lerp between nodes i and i+1
+  int observe_node;  // >= 0: after this step the state is the value function of this node
+  double h;
+  double alpha[4];   // weight of node i at the four RK4 stage times (1 - alpha on node i+1)
+};
+// one RK4 step of the continuous rollout (mirrors integrate_const + truncated last step)
+struct RolloutStep {
+  double h;
+  int idx[4];       // timeSegment index at the four stage times
+  double alpha[4];
+  int obs_idx;      // timeSegment of the observation time after the step
+  double obs_alpha;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// launchers implemented in the .cu files
+// ---------------------------------------------------------------------------------------------------------------------
+cudaError_t launch_ilqr_generic(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count,
+                                cudaStream_t stream);
+cudaError_t launch_slq_generic(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps,
+                               int begin, int count, cudaStream_t stream);
+cudaError_t launch_rollout_discrete(const Layout& L, const DeviceBuffers& buf, const double* alphas_dev, int n_alpha, int batch,
+                                    int begin, int count, cudaStream_t stream);
+cudaError_t launch_rollout_continuous(const Layout& L, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps, int first_idx,
+                                      double first_alpha, int out_nodes, const double* alphas_dev, int n_alpha, int batch, int begin,
+                                      int count, cudaStream_t stream);
+cudaError_t launch_generate(const Layout& L, int algorithm, double* lq, double* term, double* x0, uint64_t seed, int64_t first_index,
+                            double dt, int batch, cudaStream_t stream);
+struct FieldDev {
+  double* ptr;
+  long long ps, ns;
+};
+struct LqViewDev {
+  FieldDev A, B, Hv, Q, P, R, q, r, c, C, D, e, Qf, qf, cf, x_nom, u_nom, x0;
+  const int* nc;
+  long long nc_ps, nc_ns;
+};
+struct SolViewDev {
+  FieldDev K, dbias, bias, Sm, Sv, s, x, u;
+  long long x_as, u_as;
+  int* status;
+};
+// strided SoA (device) -> records, for problems [begin, begin+count); view indexed from 0
+cudaError_t launch_pack(const Layout& L, const LqViewDev& v, double* lq, double* term, double* x_nom, double* u_nom, int* nc, double* x0,
+                        int begin, int count, cudaStream_t stream);
+// records -> strided SoA (device)
+cudaError_t launch_unpack(const Layout& L, const SolViewDev& v, const double* sol, const double* xs, const double* us, const int* status,
+                          int out_nodes, int n_alpha, int batch, int begin, int count, cudaStream_t stream);
+
+// fast path (riccati_dmma.cu): returns cudaErrorNotSupported when the configuration has no specialised kernel
+bool fast_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
+cudaError_t launch_ilqr_fast(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,
+                             int begin, int count, cudaStream_t stream, int* launches);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------------
+// warp-cooperative dense helpers: one warp owns one problem; matrices live in shared memory, column-major.
+// Every helper ends with __syncwarp() so results are visible to all lanes.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// C(MxN) = beta*C + alpha * op(A)*op(B); op(A) is MxK, op(B) is KxN. TA: A stored KxM; TB: B stored NxK.
+template <bool TA, bool TB>
+__device__ __forceinline__ void wgemm(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
+                                      const double* __restrict__ B, int ldb, double beta, double* C, int ldc) {
+  const int lane = lane_id();
+  const int total = M * N;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int i = idx % M, j = idx / M;
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double a = TA ? A[k + i * lda] : A[i + k * lda];
+      const double b = TB ? B[j + k * ldb] : B[k + j * ldb];
+      acc = fma(a, b, acc);
+    }
+    double* c = C + i + j * ldc;
+    *c = (beta == 0.0 ? 0.0 : beta * (*c)) + alpha * acc;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void wcopy(int count, const double* __restrict__ src, double* __restrict__ dst) {
+  for (int i = lane_id(); i < count; i += 32) dst[i] = src[i];
+  __syncwarp();
+}
+__device__ __forceinline__ void wfill(int count, double v, double* dst) {
+  for (int i = lane_id(); i < count; i += 32) dst[i] = v;
+  __syncwarp();
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double wdot(int count, const double* a, const double* b) {
+  double acc = 0.0;
+  for (int i = lane_id(); i < count; i += 32) acc = fma(a[i], b[i], acc);
+  return warp_sum(acc);
+}
+#endif
+
+}  // namespace o2c

@@ -1,0 +1,318 @@
+"""Python host side over the C ABI, mirroring the reference's interface for the batched LQ path.
+
+Names follow the reference: ``Settings`` carries the ``ddp::Settings`` fields that change the hot-path arithmetic
+(ocs2_ddp/include/ocs2_ddp/DDP_Settings.h:63-120, search_strategy/StrategySettings.h:66-132); ``BatchedLqSolver`` exposes
+``solveSequentialRiccatiEquations`` / ``calculateController`` (GaussNewtonDDP.h:167-176) and ``rolloutTrajectory``
+(DDP_HelperFunctions.cpp:125-138); ``LinearController`` holds ``timeStamp_/gainArray_/biasArray_/deltaBiasArray_``
+(ocs2_core/include/ocs2_core/control/LinearController.h:109-112). Errors raise (the reference throws std::runtime_error).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import lib as _l
+
+
+@dataclass
+class Settings:
+    """Subset of ddp::Settings that reaches the LQ arithmetic."""
+    algorithm: int = _l.ALG_ILQR                      # ddp.algorithm (ILQR | SLQ)
+    preComputeRiccatiTerms: bool = True               # reduced-form Riccati (only with LINE_SEARCH)
+    strategy: int = _l.STRATEGY_LINE_SEARCH           # ddp.strategy
+    hessianCorrectionStrategy: int = _l.HC_DIAGONAL_SHIFT   # lineSearch.hessianCorrectionStrategy
+    hessianCorrectionMultiple: float = 1e-6           # lineSearch.hessianCorrectionMultiple (numeric_traits::limitEpsilon)
+    riccatiMultiple: float = 0.0                      # levenbergMarquardt riccatiMultiple
+    timeStep: float = 1e-2                            # ddp.timeStep / rollout.timeStep
+    backwardPassIntegratorType: str = "RK4"           # only RK4 is provided on the device
+    nThreads: int = 1                                 # ignored: parallelism comes from the batch
+
+    @property
+    def reduced_form(self) -> bool:
+        return bool(self.preComputeRiccatiTerms) and self.strategy == _l.STRATEGY_LINE_SEARCH
+
+
+def _colmajor(a: np.ndarray) -> np.ndarray:
+    """(..., rows, cols) natural -> contiguous buffer whose trailing block is column-major."""
+    return np.ascontiguousarray(np.swapaxes(np.asarray(a, dtype=np.float64), -1, -2))
+
+
+def _field(arr: Optional[np.ndarray], block: int, nodes: int) -> _l.Field:
+    if arr is None:
+        return _l.Field(None, 0, 0)
+    assert arr.flags["C_CONTIGUOUS"] and arr.dtype == np.float64
+    return _l.Field(arr.ctypes.data, nodes * block, block)
+
+
+@dataclass
+class LqBatch:
+    """Host LQ data of a batch in natural numpy layout (ModelData fields, ModelData.h:43-60):
+    A (B,nodes,n,n) B (B,nodes,n,m) Hv (B,nodes,n) Q (B,nodes,n,n) P (B,nodes,m,n) R (B,nodes,m,m) q (B,nodes,n) r (B,nodes,m)
+    c (B,nodes) C (B,nodes,ncmax,n) D (B,nodes,ncmax,m) e (B,nodes,ncmax) nc (B,nodes) int32 Qf (B,n,n) qf (B,n) cf (B,)
+    x_nom (B,N+1,n) u_nom (B,N+1,m) x0 (B,n) time (N+1,). nodes = N for ILQR, N+1 for SLQ."""
+    A: np.ndarray
+    B: np.ndarray
+    Q: np.ndarray
+    R: np.ndarray
+    Qf: np.ndarray
+    Hv: Optional[np.ndarray] = None
+    P: Optional[np.ndarray] = None
+    q: Optional[np.ndarray] = None
+    r: Optional[np.ndarray] = None
+    c: Optional[np.ndarray] = None
+    C: Optional[np.ndarray] = None
+    D: Optional[np.ndarray] = None
+    e: Optional[np.ndarray] = None
+    nc: Optional[np.ndarray] = None
+    qf: Optional[np.ndarray] = None
+    cf: Optional[np.ndarray] = None
+    x_nom: Optional[np.ndarray] = None
+    u_nom: Optional[np.ndarray] = None
+    x0: Optional[np.ndarray] = None
+    time: Optional[np.ndarray] = None
+    _keep: dict = field(default_factory=dict, repr=False)
+
+    @property
+    def batch(self) -> int:
+        return self.A.shape[0]
+
+    def view(self, N: int) -> _l.LqView:
+        """Builds the o2c_lq_view over column-major copies of the arrays (kept alive in self._keep)."""
+        k = self._keep
+        nodes = self.A.shape[1]
+        n, m = self.B.shape[-2], self.B.shape[-1]
+        ncm = 0 if self.D is None else self.D.shape[-2]
+        for name in ("A", "B", "Q", "P", "R", "C", "D", "Qf"):
+            v = getattr(self, name)
+            k[name] = _colmajor(v) if v is not None else None
+        for name in ("Hv", "q", "r", "c", "e", "qf", "cf", "x_nom", "u_nom", "x0", "time"):
+            v = getattr(self, name)
+            k[name] = np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
+        k["nc"] = np.ascontiguousarray(self.nc, dtype=np.int32) if self.nc is not None else None
+        lv = _l.LqView()
+        lv.A = _field(k["A"], n * n, nodes)
+        lv.B = _field(k["B"], n * m, nodes)
+        lv.Hv = _field(k["Hv"], n, nodes)
+        lv.Q = _field(k["Q"], n * n, nodes)
+        lv.P = _field(k["P"], m * n, nodes)
+        lv.R = _field(k["R"], m * m, nodes)
+        lv.q = _field(k["q"], n, nodes)
+        lv.r = _field(k["r"], m, nodes)
+        lv.c = _field(k["c"], 1, nodes)
+        if ncm:
+            lv.C = _field(k["C"], ncm * n, nodes)
+            lv.D = _field(k["D"], ncm * m, nodes)
+            lv.e = _field(k["e"], ncm, nodes)
+            if k["nc"] is not None:
+                lv.nc = k["nc"].ctypes.data
+                lv.nc_problem_stride = nodes
+                lv.nc_node_stride = 1
+        lv.Qf = _field(k["Qf"], n * n, 1)
+        lv.qf = _field(k["qf"], n, 1)
+        lv.cf = _field(k["cf"], 1, 1)
+        lv.x_nom = _field(k["x_nom"], n, N + 1)
+        lv.u_nom = _field(k["u_nom"], m, N + 1)
+        lv.x0 = _field(k["x0"], n, 1)
+        lv.time = k["time"].ctypes.data if k["time"] is not None else None
+        return lv
+
+
+@dataclass
+class LinearController:
+    """LinearController arrays for the batch: timeStamp_ (N+1,), gainArray_ (B,N+1,m,n), biasArray_ (B,N+1,m), deltaBiasArray_ (B,N+1,m)."""
+    timeStamp_: np.ndarray
+    gainArray_: np.ndarray
+    biasArray_: np.ndarray
+    deltaBiasArray_: np.ndarray
+
+
+@dataclass
+class Solution:
+    controller: LinearController
+    Sm: np.ndarray       # valueFunctionTrajectory dfdxx (B,N+1,n,n)
+    Sv: np.ndarray       # dfdx (B,N+1,n)
+    s: np.ndarray        # f (B,N+1)
+    status: np.ndarray   # (B,) int32 O2C_STATUS_* bits
+    x: Optional[np.ndarray] = None   # (n_alpha,B,out_nodes,n)
+    u: Optional[np.ndarray] = None   # (n_alpha,B,out_nodes,m)
+    t: Optional[np.ndarray] = None   # (out_nodes,)
+
+    @property
+    def K(self):
+        return self.controller.gainArray_
+
+    @property
+    def dbias(self):
+        return self.controller.deltaBiasArray_
+
+    @property
+    def bias(self):
+        return self.controller.biasArray_
+
+
+class BatchedLqSolver:
+    """One handle of libocs2_ddp_cuda.so: `batch` independent LQ problems resident on one CUDA device."""
+
+    def __init__(self, settings: Settings, nx: int, nu: int, num_stages: int, batch: int, nc_max: int = 0, device: int = 0,
+                 has_nominal: bool = False, max_alphas: int = 1):
+        if settings.algorithm == _l.ALG_SLQ and settings.backwardPassIntegratorType != "RK4":
+            raise _l.O2cError(2, "only the fixed-step RK4 backward pass is provided (backwardPassIntegratorType must be RK4)")
+        self._lib = _l.load_library()
+        self.settings = settings
+        self.nx, self.nu, self.N, self.batch, self.nc_max = nx, nu, num_stages, batch, nc_max
+        self.nodes = num_stages + 1 if settings.algorithm == _l.ALG_SLQ else num_stages
+        cfg = _l.Config(nx=nx, nu=nu, nc_max=nc_max, num_stages=num_stages, batch=batch, algorithm=settings.algorithm,
+                        riccati_form=_l.FORM_REDUCED if settings.reduced_form else _l.FORM_FULL, strategy=settings.strategy,
+                        hessian_correction=settings.hessianCorrectionStrategy, device=device, max_alphas=max_alphas,
+                        has_nominal=int(has_nominal), hessian_multiple=settings.hessianCorrectionMultiple,
+                        lm_riccati_multiple=settings.riccatiMultiple, time_step=settings.timeStep)
+        self._h = C.c_void_p()
+        _l.check(self._lib.o2c_create(C.byref(cfg), C.byref(self._h)))
+        self.max_alphas = max_alphas
+        self._n_alpha = 0
+
+    # ---- life cycle -------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.o2c_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    @property
+    def kernel_variant(self) -> str:
+        return self._lib.o2c_kernel_variant(self._h).decode()
+
+    @property
+    def launch_count(self) -> int:
+        v = C.c_int64(0)
+        _l.check(self._lib.o2c_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def compute_stream(self) -> int:
+        s = C.c_void_p()
+        _l.check(self._lib.o2c_compute_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def sync(self):
+        _l.check(self._lib.o2c_sync(self._h))
+
+    # ---- data -------------------------------------------------------------------------------------------------------
+    def upload(self, lq: LqBatch, problem_begin: int = 0):
+        view = lq.view(self.N)
+        _l.check(self._lib.o2c_upload(self._h, C.byref(view), problem_begin, lq.batch))
+        self.sync()
+
+    def set_time(self, time: Sequence[float]):
+        t = np.ascontiguousarray(time, dtype=np.float64)
+        assert t.shape == (self.N + 1,)
+        _l.check(self._lib.o2c_set_time(self._h, t.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def generate_synthetic(self, seed: int, first_problem_index: int = 0, dt: float = 0.01):
+        _l.check(self._lib.o2c_generate_synthetic(self._h, seed, first_problem_index, dt))
+
+    def device_lq_view(self) -> _l.LqView:
+        v = _l.LqView()
+        _l.check(self._lib.o2c_device_lq_view(self._h, C.byref(v)))
+        return v
+
+    def device_solution_view(self) -> _l.SolutionView:
+        v = _l.SolutionView()
+        _l.check(self._lib.o2c_device_solution_view(self._h, C.byref(v)))
+        return v
+
+    @property
+    def rollout_num_nodes(self) -> int:
+        v = C.c_int32(0)
+        _l.check(self._lib.o2c_rollout_num_nodes(self._h, C.byref(v)))
+        return v.value
+
+    def rollout_times(self) -> np.ndarray:
+        t = np.zeros(self.rollout_num_nodes)
+        _l.check(self._lib.o2c_rollout_times(self._h, t.ctypes.data_as(C.POINTER(C.c_double))))
+        return t
+
+    # ---- compute (asynchronous on the compute stream) -----------------------------------------------------------------
+    def solveSequentialRiccatiEquations(self, problem_begin: int = 0, problem_count: Optional[int] = None):
+        """Backward pass of every problem: ILQR::/SLQ::solveSequentialRiccatiEquations + calculateController."""
+        cnt = self.batch - problem_begin if problem_count is None else problem_count
+        _l.check(self._lib.o2c_backward(self._h, problem_begin, cnt))
+
+    def calculateController(self):
+        """The controller (K, bias, deltaBias) is produced by the same kernel as the backward pass; kept for API parity."""
+        return None
+
+    def rolloutTrajectory(self, alphas: Sequence[float] = (1.0,), problem_begin: int = 0, problem_count: Optional[int] = None):
+        """incrementController(alpha) + LQ-model rollout for every step length in `alphas`."""
+        a = np.ascontiguousarray(alphas, dtype=np.float64)
+        cnt = self.batch - problem_begin if problem_count is None else problem_count
+        _l.check(self._lib.o2c_rollout(self._h, a.ctypes.data_as(C.POINTER(C.c_double)), len(a), problem_begin, cnt))
+        self._n_alpha = len(a)
+
+    def solve(self, alpha: float = 1.0, problem_begin: int = 0, problem_count: Optional[int] = None):
+        """backward pass + one rollout: one 'LQ solve' per problem (the benchmark metric)."""
+        cnt = self.batch - problem_begin if problem_count is None else problem_count
+        _l.check(self._lib.o2c_solve(self._h, alpha, problem_begin, cnt))
+        self._n_alpha = 1
+
+    # ---- results ----------------------------------------------------------------------------------------------------
+    def _solution_buffers(self, count: int, n_alpha: int, want_value: bool = True):
+        n, m, N = self.nx, self.nu, self.N
+        on = self.rollout_num_nodes
+        bufs = dict(K=np.zeros((count, N + 1, n, m)), dbias=np.zeros((count, N + 1, m)), bias=np.zeros((count, N + 1, m)),
+                    Sm=np.zeros((count, N + 1, n, n)) if want_value else None, Sv=np.zeros((count, N + 1, n)) if want_value else None,
+                    s=np.zeros((count, N + 1)) if want_value else None, status=np.zeros(count, dtype=np.int32),
+                    x=np.zeros((max(n_alpha, 1), count, on, n)) if n_alpha else None,
+                    u=np.zeros((max(n_alpha, 1), count, on, m)) if n_alpha else None)
+        sv = _l.SolutionView()
+        sv.K = _field(bufs["K"], m * n, N + 1)
+        sv.dbias = _field(bufs["dbias"], m, N + 1)
+        sv.bias = _field(bufs["bias"], m, N + 1)
+        sv.Sm = _field(bufs["Sm"], n * n, N + 1)
+        sv.Sv = _field(bufs["Sv"], n, N + 1)
+        sv.s = _field(bufs["s"], 1, N + 1)
+        if n_alpha:
+            sv.x = _field(bufs["x"], n, on)
+            sv.u = _field(bufs["u"], m, on)
+            sv.x_alpha_stride = count * on * n
+            sv.u_alpha_stride = count * on * m
+        sv.status = bufs["status"].ctypes.data
+        return bufs, sv
+
+    def _to_solution(self, bufs, n_alpha) -> Solution:
+        ctrl = LinearController(timeStamp_=self.rollout_times() if self.settings.algorithm == _l.ALG_ILQR else None,
+                                gainArray_=np.swapaxes(bufs["K"], -1, -2), biasArray_=bufs["bias"], deltaBiasArray_=bufs["dbias"])
+        return Solution(controller=ctrl, Sm=np.swapaxes(bufs["Sm"], -1, -2) if bufs["Sm"] is not None else None, Sv=bufs["Sv"], s=bufs["s"],
+                        status=bufs["status"], x=bufs["x"], u=bufs["u"], t=self.rollout_times() if n_alpha else None)
+
+    def download(self, problem_begin: int = 0, problem_count: Optional[int] = None, n_alpha: Optional[int] = None) -> Solution:
+        cnt = self.batch - problem_begin if problem_count is None else problem_count
+        na = self._n_alpha if n_alpha is None else n_alpha
+        bufs, sv = self._solution_buffers(cnt, na)
+        _l.check(self._lib.o2c_download(self._h, C.byref(sv), problem_begin, cnt, na))
+        return self._to_solution(bufs, na)
+
+    def solve_host(self, lq: LqBatch, alpha: float = 1.0, chunk: int = 0) -> Solution:
+        """End to end through host buffers: chunked H2D -> sweep + rollout -> D2H pipeline (o2c_solve_host)."""
+        view = lq.view(self.N)
+        bufs, sv = self._solution_buffers(lq.batch, 1)
+        _l.check(self._lib.o2c_solve_host(self._h, C.byref(view), C.byref(sv), alpha, lq.batch, chunk))
+        return self._to_solution(bufs, 1)

@@ -1,0 +1,276 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerance: the north star asks for <= 1e-9 relative error on K, k (deltaBias), S, Sv, s and the rollout trajectories; the
+tests measure max|gpu - oracle| / max(1, max|oracle|) per field and problem and require it <= REL_TOL.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import ocs2_b200 as o2
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-9
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if not (np.isfinite(a).all() and np.isfinite(b).all()):
+        return 0.0 if np.array_equal(np.isnan(a), np.isnan(b)) else np.inf
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def orc_settings(st: o2.Settings):
+    return orc.make_settings(algorithm=st.algorithm, reduced_form=st.reduced_form, strategy=st.strategy,
+                             hessian_correction=st.hessianCorrectionStrategy, hessian_multiple=st.hessianCorrectionMultiple,
+                             lm_riccati_multiple=st.riccatiMultiple, time_step=st.timeStep)
+
+
+def check_against_oracle(st, pb, x0, sol, i, alphas=(1.0,), what=""):
+    """sol: ocs2_b200.Solution of a batch; i: index inside it; pb/x0: the oracle problem."""
+    ost = orc_settings(st)
+    ref = orc.backward(ost, pb)
+    assert int(sol.status[i]) & 1 == ref.status & 1, f"{what}: CHOL_NOT_PD flag differs"
+    for name, got, want in (("K", sol.K[i], ref.K), ("dbias", sol.dbias[i], ref.dbias), ("bias", sol.bias[i], ref.bias),
+                            ("Sm", sol.Sm[i], ref.Sm), ("Sv", sol.Sv[i], ref.Sv), ("s", sol.s[i], ref.s)):
+        err = rel_err(got, want)
+        assert err <= REL_TOL, f"{what} problem {i} field {name}: rel err {err:.3e}"
+    if sol.x is not None:
+        for ia, alpha in enumerate(alphas):
+            x, u, t, _ = orc.rollout(ost, pb, ref, x0, alpha=alpha)
+            assert sol.x.shape[2] == len(x), f"{what}: rollout node count {sol.x.shape[2]} vs oracle {len(x)}"
+            ex, eu = rel_err(sol.x[ia, i], x), rel_err(sol.u[ia, i], u)
+            assert ex <= REL_TOL and eu <= REL_TOL, f"{what} problem {i} alpha {alpha}: rollout rel err x {ex:.3e} u {eu:.3e}"
+            assert rel_err(sol.t, t) <= 1e-15
+    return ref
+
+
+SHAPES = {
+    "cartpole": (4, 1, 0),
+    "ballbot": (10, 3, 0),
+    "quadrotor": (12, 4, 0),
+    "manipulator": (9, 9, 3),
+    "legged": (24, 24, 0),
+    "test32c": (3, 2, 2),
+}
+
+
+@pytest.mark.parametrize("shape", ["cartpole", "ballbot", "manipulator", "legged", "test32c"])
+@pytest.mark.parametrize("variant", ["ls_reduced_diag", "ls_full_diag", "ls_reduced_gershgorin", "lm_full"])
+def test_ilqr_generated_batch_matches_oracle(shape, variant):
+    n, m, nc = SHAPES[shape]
+    N, batch, dt, seed = 100, 24, 0.01, 0
+    st = o2.Settings(algorithm=o2.ALG_ILQR, hessianCorrectionMultiple=1e-3 if shape != "legged" else 1e-5, timeStep=dt)
+    if variant == "ls_full_diag":
+        st.preComputeRiccatiTerms = False
+    elif variant == "ls_reduced_gershgorin":
+        st.hessianCorrectionStrategy = o2.HC_GERSHGORIN_MODIFICATION
+    elif variant == "lm_full":
+        st.strategy = o2.STRATEGY_LEVENBERG_MARQUARDT
+        st.riccatiMultiple = 0.37
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, max_alphas=2) as solver:
+        solver.generate_synthetic(seed, first_problem_index=1000, dt=dt)
+        solver.solveSequentialRiccatiEquations()
+        alphas = (1.0, 0.35)
+        solver.rolloutTrajectory(alphas)
+        sol = solver.download()
+        assert (sol.status == 0).all()
+        for i in (0, 7, batch - 1):
+            pb, x0 = orc.generate_problem(seed, 1000 + i, orc.ALG_ILQR, n, m, nc, N, dt)
+            check_against_oracle(st, pb, x0, sol, i, alphas, what=f"{shape}/{variant}")
+
+
+@pytest.mark.parametrize("shape,substeps", [("quadrotor", 1.0), ("test32c", 2.5), ("cartpole", 1.0)])
+@pytest.mark.parametrize("variant", ["ls_reduced_diag", "ls_full_gershgorin", "lm_full"])
+def test_slq_rk4_generated_batch_matches_oracle(shape, substeps, variant):
+    n, m, nc = SHAPES[shape]
+    N, batch, dt, seed = 100, 12, 0.01, 3
+    st = o2.Settings(algorithm=o2.ALG_SLQ, hessianCorrectionMultiple=1e-3, timeStep=dt / substeps)
+    if variant == "ls_full_gershgorin":
+        st.preComputeRiccatiTerms = False
+        st.hessianCorrectionStrategy = o2.HC_GERSHGORIN_MODIFICATION
+    elif variant == "lm_full":
+        st.strategy = o2.STRATEGY_LEVENBERG_MARQUARDT
+        st.riccatiMultiple = 0.2
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
+        solver.generate_synthetic(seed, first_problem_index=50, dt=dt)
+        solver.solve(alpha=1.0)
+        sol = solver.download()
+        assert (sol.status == 0).all()
+        for i in (0, batch - 1):
+            pb, x0 = orc.generate_problem(seed, 50 + i, orc.ALG_SLQ, n, m, nc, N, dt)
+            check_against_oracle(st, pb, x0, sol, i, what=f"slq {shape}/{variant}")
+
+
+def test_generator_is_bit_identical_to_oracle():
+    """The device generator must reproduce the oracle generator bit for bit (so sampled full-size parity is meaningful):
+    checked through a problem whose solution is exactly linear in the data: K, S of a 1-stage problem, and via x0."""
+    n, m, nc, N, dt = 9, 9, 3, 4, 0.01
+    st = o2.Settings(hessianCorrectionMultiple=0.0)
+    with o2.BatchedLqSolver(st, n, m, N, 3, nc_max=nc) as solver:
+        solver.generate_synthetic(11, first_problem_index=5, dt=dt)
+        solver.solve()
+        sol = solver.download()
+        for i in range(3):
+            pb, x0 = orc.generate_problem(11, 5 + i, orc.ALG_ILQR, n, m, nc, N, dt)
+            assert np.array_equal(sol.x[0, i, 0], x0)          # x0 passes through the rollout untouched
+            assert np.array_equal(sol.Sm[i, N], pb.Qf)         # terminal value function is a straight copy
+            assert np.array_equal(sol.Sv[i, N], pb.qf)
+
+
+def test_cartpole_anchor_fixture_batch1():
+    """config[0]: cartpole ILQR (nx=4, nu=1, N=100) single problem with non-zero nominal trajectories, uploaded from host."""
+    g = np.load(os.path.join(GOLDEN, "cartpole_ilqr.npz"))
+    N = int(g["N"])
+    st = o2.Settings(hessianCorrectionMultiple=float(g["eps"]), timeStep=float(g["dt"]))
+    lq = o2.LqBatch(A=g["A"][None], B=g["B"][None], Q=g["Q"][None], R=g["R"][None], Qf=g["Qf"][None], P=g["P"][None], q=g["q"][None],
+                    r=g["r"][None], c=g["c"][None], qf=g["qf"][None], cf=np.array([float(g["cf"])]), x_nom=g["x_nom"][None],
+                    u_nom=g["u_nom"][None], x0=g["x0"][None])
+    with o2.BatchedLqSolver(st, 4, 1, N, 1, has_nominal=True) as solver:
+        solver.upload(lq)
+        solver.solve()
+        sol = solver.download()
+    assert sol.status[0] == 0
+    for name in ("K", "dbias", "bias", "Sm", "Sv", "s"):
+        assert rel_err(getattr(sol, name)[0], g[name]) <= REL_TOL, name
+    assert rel_err(sol.x[0, 0], g["x"]) <= REL_TOL and rel_err(sol.u[0, 0], g["u"]) <= REL_TOL
+
+
+def _random_batch(rng, batch, n, m, N, ncmax, algorithm, ragged_nc=True, dt=0.02):
+    nodes = N + 1 if algorithm == o2.ALG_SLQ else N
+    disc = algorithm == o2.ALG_ILQR
+    A = rng.uniform(-1, 1, (batch, nodes, n, n)) * (dt if disc else 1.0) + (np.eye(n) if disc else 0.0)
+    Bm = rng.uniform(-1, 1, (batch, nodes, n, m)) * (3 * dt if disc else 1.0)
+    M = rng.uniform(-1, 1, (batch, nodes, n + m, n + m))
+    W = np.einsum("bkij,bkil->bkjl", M, M) / (n + m) + 0.1 * np.eye(n + m)
+    sc = dt if disc else 1.0
+    Mf = rng.uniform(-1, 1, (batch, n, n))
+    kw = {}
+    if ncmax:
+        D = rng.uniform(-1, 1, (batch, nodes, ncmax, m))
+        D[..., :ncmax] += 2 * np.eye(ncmax)
+        nc = rng.integers(0, ncmax + 1, (batch, nodes)).astype(np.int32) if ragged_nc else np.full((batch, nodes), ncmax, np.int32)
+        kw = dict(C=rng.uniform(-1, 1, (batch, nodes, ncmax, n)), D=D, e=0.1 * rng.uniform(-1, 1, (batch, nodes, ncmax)), nc=nc)
+    return o2.LqBatch(A=A, B=Bm, Q=sc * W[..., :n, :n], R=sc * W[..., n:, n:], P=sc * W[..., n:, :n], Hv=0.01 * rng.uniform(-1, 1, (batch, nodes, n)),
+                      q=sc * rng.uniform(-1, 1, (batch, nodes, n)), r=sc * rng.uniform(-1, 1, (batch, nodes, m)),
+                      c=sc * rng.uniform(0, 1, (batch, nodes)), Qf=np.einsum("bij,bil->bjl", Mf, Mf) / n + 0.1 * np.eye(n),
+                      qf=rng.uniform(-1, 1, (batch, n)), cf=rng.uniform(0, 1, batch), x_nom=0.1 * rng.uniform(-1, 1, (batch, N + 1, n)),
+                      u_nom=0.1 * rng.uniform(-1, 1, (batch, N + 1, m)), x0=rng.uniform(-1, 1, (batch, n)), time=dt * np.arange(N + 1), **kw)
+
+
+def _oracle_problem(lq, i, N):
+    g = lambda a: None if a is None else a[i]  # noqa: E731
+    return orc.Problem(N=N, A=lq.A[i], B=lq.B[i], Hv=lq.Hv[i], Q=lq.Q[i], P=lq.P[i], R=lq.R[i], q=lq.q[i], r=lq.r[i], c=lq.c[i], Qf=lq.Qf[i],
+                       qf=lq.qf[i], cf=float(lq.cf[i]), C=g(lq.C), D=g(lq.D), e=g(lq.e), nc=g(lq.nc), x_nom=g(lq.x_nom), u_nom=g(lq.u_nom),
+                       time=lq.time)
+
+
+@pytest.mark.parametrize("algorithm", [o2.ALG_ILQR, o2.ALG_SLQ])
+def test_host_upload_with_ragged_constraints_and_nominal(algorithm):
+    """Uploaded host SoA data, per-stage varying number of active constraints (incl. nc = 0 and nc = nc_max), nominal trajectories."""
+    rng = np.random.default_rng(21)
+    batch, n, m, N, ncmax = 6, 5, 4, 30, 3
+    lq = _random_batch(rng, batch, n, m, N, ncmax, algorithm)
+    st = o2.Settings(algorithm=algorithm, hessianCorrectionMultiple=1e-4, timeStep=0.02, preComputeRiccatiTerms=(algorithm == o2.ALG_ILQR))
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=ncmax, has_nominal=True) as solver:
+        solver.upload(lq)
+        solver.solve(alpha=0.8)
+        sol = solver.download()
+        for i in range(batch):
+            check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, alphas=(0.8,), what="ragged")
+
+
+def test_solve_host_pipeline_equals_resident_path():
+    rng = np.random.default_rng(5)
+    batch, n, m, N = 37, 6, 3, 25
+    lq = _random_batch(rng, batch, n, m, N, 0, o2.ALG_ILQR)
+    lq.x_nom = lq.u_nom = None
+    st = o2.Settings(hessianCorrectionMultiple=1e-4)
+    with o2.BatchedLqSolver(st, n, m, N, batch) as solver:
+        solver.upload(lq)
+        solver.solve()
+        a = solver.download()
+    with o2.BatchedLqSolver(st, n, m, N, batch) as solver:
+        b = solver.solve_host(lq, alpha=1.0, chunk=5)   # 8 chunks over 3 lanes
+    for name in ("K", "dbias", "bias", "Sm", "Sv", "s", "x", "u"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    check_against_oracle(st, _oracle_problem(lq, 36, N), lq.x0[36], b, 36, what="solve_host")
+
+
+def test_indefinite_hamiltonian_sets_status_like_oracle():
+    rng = np.random.default_rng(8)
+    batch, n, m, N = 4, 4, 2, 10
+    lq = _random_batch(rng, batch, n, m, N, 0, o2.ALG_ILQR)
+    lq.x_nom = lq.u_nom = None
+    lq.R[2, 5] = -np.eye(m)  # Hm = R + B'SB indefinite at stage 5 of problem 2
+    st = o2.Settings(hessianCorrectionMultiple=1e-4)
+    with o2.BatchedLqSolver(st, n, m, N, batch) as solver:
+        solver.upload(lq)
+        solver.solve()
+        sol = solver.download()
+    assert sol.status[2] & o2.STATUS_CHOL_NOT_PD and sol.status[2] & o2.STATUS_NONFINITE
+    assert (sol.status[[0, 1, 3]] == 0).all()
+    ref = orc.backward(orc_settings(st), _oracle_problem(lq, 2, N))
+    assert ref.status & 1
+    assert np.array_equal(np.isnan(sol.K[2]), np.isnan(ref.K))
+    check_against_oracle(st, _oracle_problem(lq, 1, N), lq.x0[1], sol, 1, what="neighbour of the failing problem")
+
+
+def test_abi_rejects_bad_arguments():
+    with pytest.raises(o2.O2cError):
+        o2.BatchedLqSolver(o2.Settings(hessianCorrectionStrategy=o2.HC_EIGENVALUE_MODIFICATION), 4, 2, 10, 1)
+    with pytest.raises(o2.O2cError):
+        o2.BatchedLqSolver(o2.Settings(), 4, 2, 10, 1, nc_max=3)
+    with pytest.raises(o2.O2cError):
+        o2.BatchedLqSolver(o2.Settings(algorithm=o2.ALG_SLQ, backwardPassIntegratorType="ODE45"), 4, 2, 10, 1)
+    with o2.BatchedLqSolver(o2.Settings(), 4, 2, 10, 2) as s:
+        with pytest.raises(o2.O2cError):
+            s.solve(problem_begin=1, problem_count=5)
+
+
+# ---- BASELINE.json's full sizes: sampled parity (the generator is counter based, so the oracle can regenerate any sampled
+# ---- problem) plus an all-problems status check ----
+FULL = [
+    ("ballbot", o2.ALG_ILQR, 65536, 1e-3),
+    ("quadrotor", o2.ALG_SLQ, 32768, 1e-3),
+    ("manipulator", o2.ALG_ILQR, 16384, 1e-3),
+    ("legged", o2.ALG_ILQR, 16384, 1e-5),
+]
+
+
+@pytest.mark.parametrize("shape,algorithm,batch,eps", FULL)
+def test_full_size_configs_sampled_parity(shape, algorithm, batch, eps):
+    n, m, nc = SHAPES[shape]
+    N, dt, seed = 100, 0.01, 0
+    st = o2.Settings(algorithm=algorithm, hessianCorrectionMultiple=eps, timeStep=dt)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
+        solver.generate_synthetic(seed, 0, dt)
+        solver.solve()
+        status = solver.download(n_alpha=0).status if batch <= 4096 else None
+        sample = [0, 1, batch // 3, batch // 2 + 1, batch - 1]
+        for i in sample:
+            sol = solver.download(problem_begin=i, problem_count=1)
+            assert sol.status[0] == 0
+            pb, x0 = orc.generate_problem(seed, i, algorithm, n, m, nc, N, dt)
+            ref = check_against_oracle(st, pb, x0, sol, 0, what=f"full {shape} #{i}")
+            if algorithm == o2.ALG_ILQR:
+                # size-independent property: V(x0) equals the rolled-out cost of the LQ model (alpha = 1, exact LQ data)
+                V = 0.5 * x0 @ sol.Sm[0, 0] @ x0 + sol.Sv[0, 0] @ x0 + sol.s[0, 0]
+                J = orc.discrete_lq_cost(pb, sol.x[0, 0], sol.u[0, 0])
+                # the eps*I shift makes V an upper bound that is tight to O(eps)
+                assert abs(V - J) <= 10 * eps * max(1.0, abs(J)) * N
+                del ref
+        # every problem finished without a status flag (download statuses only, in slabs)
+        import ctypes as C
+
+        from ocs2_b200 import lib as _l
+        stat = np.zeros(batch, dtype=np.int32)
+        sv = _l.SolutionView()
+        sv.status = stat.ctypes.data
+        _l.check(solver._lib.o2c_download(solver.handle, C.byref(sv), 0, batch, 0))
+        assert (stat == 0).all()
+        del status
