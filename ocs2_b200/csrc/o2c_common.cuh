@@ -10,7 +10,7 @@ namespace o2c {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Device-resident layout (library-owned). One interleaved record per (problem, node):
-//   lq   [batch][nodes][rec]   rec = { A | B | Q | P | R | Hv | q | r | c | C | D | e } padded to an even number of doubles
+//   lq   [batch][nodes][rec]   rec = { A | B | Hv | q | r | c | Q | P | R | C | D | e }, every block padded to an even number of doubles
 //   term [batch][trec]         trec = { Qf | qf | cf } padded
 //   sol  [batch][N+1][orec]    orec = { K | dbias | bias | Sm | Sv | s } padded
 //   xs   [alpha][batch][out_nodes][n],  us [alpha][batch][out_nodes][m]
@@ -39,15 +39,16 @@ inline Layout make_layout(int n, int m, int ncmax, int N, int algorithm) {
     o = pad2(o + count);
     return at;
   };
+  // operand part first (what the specialised sweep kernel stages into shared memory with one bulk copy), then the cost Hessians
   L.oA = take(n * n);
   L.oB = take(n * m);
-  L.oQ = take(n * n);
-  L.oP = take(m * n);
-  L.oR = take(m * m);
   L.oHv = take(n);
   L.oq = take(n);
   L.or_ = take(m);
   L.oc = take(1);
+  L.oQ = take(n * n);
+  L.oP = take(m * n);
+  L.oR = take(m * m);
   L.oC = take(ncmax * n);
   L.oD = take(ncmax * m);
   L.oe = take(ncmax);

@@ -274,3 +274,52 @@ def test_full_size_configs_sampled_parity(shape, algorithm, batch, eps):
         _l.check(solver._lib.o2c_download(solver.handle, C.byref(sv), 0, batch, 0))
         assert (stat == 0).all()
         del status
+
+
+# ---- the shape-specialised DMMA/TMA kernel (nx = nu = 24, unconstrained, LINE_SEARCH, reduced, DIAGONAL_SHIFT) ----
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 100])
+def test_legged_dmma_kernel_fused_solve_matches_oracle(N):
+    """o2c_solve on the legged shape runs ONE fused kernel (sweep + rollout); odd/even/minimal horizons exercise the TMA ring parities."""
+    n = m = 24
+    batch, dt, seed, alpha = 40, 0.01, 2, 0.6
+    st = o2.Settings(hessianCorrectionMultiple=1e-5, timeStep=dt)
+    with o2.BatchedLqSolver(st, n, m, N, batch) as solver:
+        assert solver.kernel_variant == "ilqr_dmma_kernel"
+        solver.generate_synthetic(seed, first_problem_index=300, dt=dt)
+        l0 = solver.launch_count
+        solver.solve(alpha=alpha)
+        assert solver.launch_count - l0 == 1
+        sol = solver.download()
+        assert (sol.status == 0).all()
+        for i in (0, 1, 17, batch - 1):
+            pb, x0 = orc.generate_problem(seed, 300 + i, orc.ALG_ILQR, n, m, 0, N, dt)
+            check_against_oracle(st, pb, x0, sol, i, (alpha,), what=f"dmma N={N}")
+        # backward alone + generic multi-alpha rollout give the same controller / trajectories
+        solver.solveSequentialRiccatiEquations()
+        solver.rolloutTrajectory((alpha,))
+        sol2 = solver.download()
+        for name in ("K", "dbias", "bias", "Sm", "Sv", "s"):
+            assert np.array_equal(getattr(sol, name), getattr(sol2, name)), name
+        assert rel_err(sol2.x, sol.x) <= 1e-12 and rel_err(sol2.u, sol.u) <= 1e-12
+
+
+def test_legged_dmma_kernel_uploaded_data_subrange_and_status():
+    """Host-uploaded random 24x24 data through the DMMA kernel: sub-range solve, an indefinite Hm in one problem, neighbours unaffected."""
+    rng = np.random.default_rng(77)
+    batch, n, m, N = 9, 24, 24, 12
+    lq = _random_batch(rng, batch, n, m, N, 0, o2.ALG_ILQR)
+    lq.x_nom = lq.u_nom = None
+    lq.R[4, 6] = -np.eye(m)
+    st = o2.Settings(hessianCorrectionMultiple=1e-4)
+    with o2.BatchedLqSolver(st, n, m, N, batch) as solver:
+        assert solver.kernel_variant == "ilqr_dmma_kernel"
+        solver.upload(lq)
+        solver.solve(alpha=1.0, problem_begin=2, problem_count=6)
+        sol = solver.download(problem_begin=2, problem_count=6)
+    assert sol.status[2] & o2.STATUS_CHOL_NOT_PD and sol.status[2] & o2.STATUS_NONFINITE
+    assert (np.delete(sol.status, 2) == 0).all()
+    ref = orc.backward(orc_settings(st), _oracle_problem(lq, 4, N))
+    assert ref.status & 1
+    assert np.array_equal(np.isnan(sol.K[2]), np.isnan(ref.K))
+    for i in (0, 1, 3, 5):
+        check_against_oracle(st, _oracle_problem(lq, 2 + i, N), lq.x0[2 + i], sol, i, what="dmma uploaded")
