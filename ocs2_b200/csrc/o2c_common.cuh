@@ -144,6 +144,11 @@ bool fast_ilqr_supported(const Layout& L, const SolverSettings& st, const Device
 cudaError_t launch_ilqr_fast(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,
                              int begin, int count, cudaStream_t stream, int* launches);
 
+// warp-per-problem variant of the same fast path (riccati_wpp.cu)
+bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
+cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,
+                            int begin, int count, cudaStream_t stream, int* launches);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------------
 // warp-cooperative dense helpers: one warp owns one problem; matrices live in shared memory, column-major.

@@ -1,0 +1,685 @@
+// riccati_wpp.cu — warp-per-problem ILQR sweep + fused LQ rollout for nx = nu = 24 (the legged-robot shape), FP64, sm_100a.
+//
+// One WARP owns one problem's whole time-sequential sweep and its rollout; a CTA is just four independent warps, there is no CTA
+// barrier after the prologue. Twelve problems are resident per SM (3 CTAs x 4 warps), so while one warp sits in the latency chain
+// of its Cholesky the other warps of the same scheduler keep the FP64 pipe busy with their contractions.
+//
+//   * The per-node operand block {A | B | Hv | q | r | c} (9.8 KB) is staged into the warp's shared-memory slot by ONE TMA bulk copy
+//     (cp.async.bulk + a per-warp mbarrier), issued half a stage ahead (the second half of a stage does not touch A, B); the block
+//     was pulled into L2 one stage earlier by cp.async.bulk.prefetch.L2, as were the cost Hessians Q, P, R, which are only ever
+//     added to accumulators and are therefore read straight from L2 into registers.
+//   * Every 24x24x24 contraction runs on the FP64 tensor pipe (mma.sync m8n8k4 f64 = DMMA; tcgen05 has no FP64 kind) in the form
+//     Z = X'Y, for which both operand fragments have the same register layout ("op": lane (r,c) holds M[8kb+2c..2c+1][8jb+r]) and the
+//     accumulator fragment of Z ("acc": lane holds Z[8ib+r][8jb+2c..2c+1]) IS the operand fragment of Z'. The sweep is arranged so
+//     that every product is consumed in exactly that transposed role, so the chain SA -> {G, Hm, T} -> Y -> {S, K} never leaves the
+//     register file:  ZA = A'S (= (SA)'), ZB = B'S, G' = P' + SA'B, Hm = R + SB'B, T = Q + eps I + SA'A, Y' = G' L^-T,
+//     S = T - Y'Y, K' = -Y' L^-1.
+//   * Only Hm takes a detour through a 5 KB shared scratch (leading dimension 26: conflict-free 8-byte transposed access): it is
+//     factorised there one row per lane (Cholesky + triangular inverse by the same right-looking recurrence), and the value function S
+//     is parked in the same scratch between stages so that it can be re-read in operand layout.
+//
+// Math (unconstrained, LINE_SEARCH, reduced Riccati form, DIAGONAL_SHIFT; same quantities as the reference, re-associated):
+//   Hm = R + B'(S B)                         ILQR::computeHamiltonianHessian              ocs2_ddp/src/ILQR.cpp:217-222
+//   Hm = L L',  Pu = U^-1 = L^-T             LinearAlgebra::computeInverseMatrixUUT       ocs2_core/src/misc/LinearAlgebra.cpp:119-124
+//   projected G~m = Pu'(P + B'SA) = L^-1 G =: Y,  G~v = L^-1 (r + B'w) =: Yv,  w = Sv + S Hv
+//                                            DiscreteTimeRiccatiEquations::computeMapILQR  .../DiscreteTimeRiccatiEquations.cpp:65-154
+//   S  = Q + eps I + A'(SA) - Y'Y ;  Sv = q + A'w - Y'Yv ;  s = s+ + c + Hv.w - 1/2 Hv.(S Hv) - 1/2 Yv.Yv
+//   K  = Pu K~ = -L^-T Y ;  dbias = -L^-T Yv ;  bias = 0 (deviation coordinates)        ILQR::calculateControllerWorker ILQR.cpp:162-181
+//   dQ = eps I: the reference forms (M + eps I) - M with M = Q~ - P~'P~ (LineSearchStrategy.cpp:294-312), which equals eps I up
+//   to one rounding of M_ii + eps (<= 1e-16 |M_ii|).
+// Rollout (fused, same warp): du_k = K_k dx_k + alpha dbias_k ; dx_{k+1} = A_k dx_k + B_k du_k + Hv_k
+//                                            DDP_HelperFunctions.cpp:125-138, 296-304; LinearController.cpp:79-87
+#include "o2c_common.cuh"
+
+namespace o2c {
+namespace {
+
+constexpr int kN = 24;            // nx == nu
+constexpr int kMat = kN * kN;     // 576
+constexpr int kLd = 26;           // leading dimension of the scratch matrix
+constexpr int kWarps = 4;         // problems per CTA
+constexpr int kThreads = 32 * kWarps;
+constexpr int kCtasPerSm = 3;
+constexpr int kOperand = 2 * kMat + 3 * kN + 2;  // {A|B|Hv|q|r|c,pad} doubles staged by TMA (= Layout::oQ for n = m = 24)
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, TMA bulk copy, L2 prefetch, DMMA
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WPP_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WPP_DONE;\n"
+      "bra WPP_WAIT;\n"
+      "WPP_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, non-tensor form); completion is signalled on the mbarrier as transferred bytes
+__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor pipe. Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4], d = D[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma(double2& d, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d.x), "+d"(d.y) : "d"(a), "d"(b));
+}
+// acc(Z tile) += X(kblock, i)' Y(kblock, j) for one 8-deep k block; x, y are "op" fragments (rows {2c, 2c+1} of the k block, column r),
+// so the two DMMAs contract k = {0,2,4,6} and {1,3,5,7} (the same permutation on both operands).
+__device__ __forceinline__ void dmma2(double2& d, const double2& x, const double2& y) {
+  dmma(d, x.x, y.x);
+  dmma(d, x.y, y.y);
+}
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, const double2& v) { *reinterpret_cast<double2*>(p) = v; }
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void stg2(double* p, const double2& v) { __stcg(reinterpret_cast<double2*>(p), v); }
+__device__ __forceinline__ double2 zero2() { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ bool finite2(const double2& v) { return isfinite(v.x) && isfinite(v.y); }
+// sign flip on the integer pipe (keeps the FP64 pipe for the contractions)
+__device__ __forceinline__ double neg(double v) { return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v)); }
+__device__ __forceinline__ double2 neg2(const double2& v) { return make_double2(neg(v.x), neg(v.y)); }
+
+// tile offsets: rows 8*rb.., columns 8*cb.. of a column-major matrix with leading dimension 24 (staged / global) or 26 (scratch)
+__device__ __forceinline__ constexpr int t24(int rb, int cb) { return 8 * rb + 8 * kN * cb; }
+__device__ __forceinline__ constexpr int t26(int rb, int cb) { return 8 * rb + 8 * kLd * cb; }
+// index of lower tile (ib >= jb) in a packed array of six
+__device__ __forceinline__ constexpr int lt(int ib, int jb) { return ib * (ib + 1) / 2 + jb; }
+
+struct __align__(16) WarpSmem {
+  double in[kOperand];   // TMA destination: {A | B | Hv | q | r | c,pad}
+  double W[kN * kLd];    // S of node k+1 (both triangles) -> Hm (lower) -> L -> L^-T
+  double Sv[kN], w[kN], Gv[kN], tv[kN], Yv[kN], xb[kN], ub[kN];
+  unsigned long long full;
+  unsigned long long pad_;
+};
+static_assert(sizeof(WarpSmem) % 16 == 0, "warp slots must keep 16-byte alignment");
+
+struct Args {
+  const double* lq;
+  const double* term;
+  const double* x0;
+  double* sol;
+  double* xs;
+  double* us;
+  int* status;
+  int rec, orec, N;
+  int oQ, oP, oR;
+  int oK, odb, obias, oSm, oSv, os;
+  int oQf, oqf, ocf, trec;
+  int begin, count, with_rollout;
+  double eps, alpha;
+};
+
+__device__ __forceinline__ double quad_sum(double v) {
+  v += __shfl_xor_sync(kFull, v, 1);
+  v += __shfl_xor_sync(kFull, v, 2);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double pick3(const double (&z)[3], int c) { return c == 0 ? z[0] : (c == 1 ? z[1] : z[2]); }
+
+// z[8 jb + r] = sum_k M[k + LD j] v[k] (transposed product) with the operand-fragment access pattern; every lane of quad r gets z[jb]
+template <int LD>
+__device__ __forceinline__ void matvec_cols(const double* M, const double* v, int r, int c, double (&z)[3]) {
+  double2 vf[3];
+#pragma unroll
+  for (int kb = 0; kb < 3; ++kb) vf[kb] = ld2(v + 8 * kb + 2 * c);
+#pragma unroll
+  for (int jb = 0; jb < 3; ++jb) {
+    double p = 0.0;
+#pragma unroll
+    for (int kb = 0; kb < 3; ++kb) {
+      const double2 mv = ld2(M + 2 * c + LD * r + 8 * kb + 8 * LD * jb);
+      p = fma(mv.x, vf[kb].x, p);
+      p = fma(mv.y, vf[kb].y, p);
+    }
+    z[jb] = quad_sum(p);
+  }
+}
+// z[i] = sum_k M[i + 24 k] v[k] for lane i < 24 (M column-major in shared memory, v in shared memory, broadcast reads)
+__device__ __forceinline__ double matvec_rows(const double* M, const double* v, int li) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int k = 0; k < kN; k += 4) {
+    const double2 v01 = ld2(v + k), v23 = ld2(v + k + 2);
+    a0 = fma(M[li + kN * k], v01.x, a0);
+    a1 = fma(M[li + kN * (k + 1)], v01.y, a1);
+    a2 = fma(M[li + kN * (k + 2)], v23.x, a2);
+    a3 = fma(M[li + kN * (k + 3)], v23.y, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+// Cholesky Hm = L L' in the scratch (one row per lane, the scaled column is broadcast through shared memory), then the rows of L^-T
+// by the same right-looking recurrence applied to the identity; lane 24 carries Gv through it and ends with Yv = L^-1 Gv.
+// On return h[] holds row `lane` of L^-T (lanes < 24) and the scratch holds L^-T column-major (exact zeros below the diagonal).
+__device__ __forceinline__ bool cholesky_inverse(WarpSmem& ws, int lane, double (&h)[kN]) {
+  const int li = lane < kN ? lane : kN - 1;
+  double* Hs = ws.W;
+#pragma unroll
+  for (int k = 0; k < kN; ++k) h[k] = Hs[li + kLd * k];
+  bool pd = true;
+#pragma unroll
+  for (int j = 0; j < kN; ++j) {
+    const double d = __shfl_sync(kFull, h[j], j);
+    const bool ok = d > 0.0;
+    pd = pd && ok;
+    const double rs = ok ? rsqrt(d) : __longlong_as_double(0x7ff8000000000000LL);  // NaNs propagate like the reference's LLT
+    const double l = h[j] * rs;
+    if (lane < kN) Hs[lane + kLd * j] = (lane == j) ? rs : l;
+    __syncwarp();
+#pragma unroll
+    for (int k = j + 1; k < kN; ++k) h[k] = fma(-l, Hs[k + kLd * j], h[k]);
+  }
+  // rows of L^-T: g <- e_lane' L^-T (lanes < 24); lane 24: g <- Gv' L^-T = Yv'
+#pragma unroll
+  for (int k = 0; k < kN; ++k) h[k] = (lane == kN) ? ws.Gv[k] : ((k == lane) ? 1.0 : 0.0);
+#pragma unroll
+  for (int j = 0; j < kN; ++j) {
+    const double a = h[j] * Hs[j + kLd * j];
+    h[j] = a;
+#pragma unroll
+    for (int k = j + 1; k < kN; ++k) h[k] = fma(-a, Hs[k + kLd * j], h[k]);
+  }
+  __syncwarp();  // every lane is done reading L
+  if (lane < kN) {
+#pragma unroll
+    for (int k = 0; k < kN; ++k) Hs[lane + kLd * k] = h[k];
+  } else if (lane == kN) {
+#pragma unroll
+    for (int k = 0; k < kN; ++k) ws.Yv[k] = h[k];
+  }
+  __syncwarp();
+  return pd;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+  const int r = lane >> 2, c = lane & 3;
+  const int lo24 = 2 * c + kN * r, lo26 = 2 * c + kLd * r;
+  const int li = lane < kN ? lane : kN - 1;
+  const int N = a.N;
+  const uint32_t opBytes = kOperand * sizeof(double);
+  const uint32_t hessBytes = (uint32_t)(a.rec - a.oQ) * sizeof(double);
+
+  if (lane == 0) {
+    mbar_init(&ws.full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phase = 0;
+
+  for (int pi = blockIdx.x * kWarps + warp; pi < a.count; pi += gridDim.x * kWarps) {
+    const int prob = a.begin + pi;
+    const double* lqp = a.lq + (size_t)prob * N * a.rec;
+    const double* term = a.term + (size_t)prob * a.trec;
+    double* solp = a.sol + (size_t)prob * (N + 1) * a.orec;
+
+    // operand block of node N-1 (TMA) and the L2 prefetch of what comes next
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&ws.full, opBytes);
+      tma_load(ws.in, lqp + (size_t)(N - 1) * a.rec, opBytes, &ws.full);
+      l2_prefetch(lqp + (size_t)(N - 1) * a.rec + a.oQ, hessBytes);
+      if (N >= 2) l2_prefetch(lqp + (size_t)(N - 2) * a.rec, opBytes);
+    }
+    // terminal condition: valueFunctionTrajectory.back() = finalValueFunction (GaussNewtonDDP.cpp:526)
+    {
+      double* outN = solp + (size_t)N * a.orec;
+      for (int i = lane; i < kMat; i += 32) {
+        const double v = term[a.oQf + i];
+        ws.W[(i % kN) + kLd * (i / kN)] = v;
+        outN[a.oSm + i] = v;
+      }
+      if (lane < kN) {
+        const double v = term[a.oqf + lane];
+        ws.Sv[lane] = v;
+        outN[a.oSv + lane] = v;
+      }
+      if (lane == 0) outN[a.os] = term[a.ocf];
+    }
+    double sval = term[a.ocf];  // s of node k+1
+    bool finite = true, pd = true;
+    __syncwarp();
+
+    for (int k = N - 1; k >= 0; --k) {
+      const double* A = ws.in;
+      const double* B = ws.in + kMat;
+      const double* Hv = ws.in + 2 * kMat;
+      const double* qv = Hv + kN;
+      const double* rv = qv + kN;
+      const double* rec = lqp + (size_t)k * a.rec;
+      double* out = solp + (size_t)k * a.orec;
+      double* out2 = (k == N - 1) ? solp + (size_t)N * a.orec : nullptr;  // node N := node N-1 (GaussNewtonDDP.cpp:609-618)
+      mbar_wait(&ws.full, phase);
+      phase ^= 1u;
+
+      // ---- vectors: w = Sv + S Hv, Gv = r + B'w, tv = q + A'w ----
+      double spart = 0.0;
+      {
+        double z[3];
+        matvec_cols<kLd>(ws.W, Hv, r, c, z);  // S symmetric: S Hv = S' Hv
+        if (c < 3) {
+          const int j = 8 * c + r;
+          const double shv = pick3(z, c);
+          const double wv = ws.Sv[j] + shv;
+          ws.w[j] = wv;
+          spart = Hv[j] * (wv - 0.5 * shv);
+        }
+        __syncwarp();
+        double zB[3], zA[3];
+        matvec_cols<kN>(B, ws.w, r, c, zB);
+        matvec_cols<kN>(A, ws.w, r, c, zA);
+        if (c < 3) {
+          const int j = 8 * c + r;
+          ws.Gv[j] = rv[j] + pick3(zB, c);
+          ws.tv[j] = qv[j] + pick3(zA, c);
+        }
+      }
+      const double cval = ws.in[2 * kMat + 3 * kN];
+
+      // ---- ZA = A'S (= op fragments of SA), ZB = B'S (= op fragments of SB) ----
+      double2 zA[3][3], zB[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) zA[i][j] = zB[i][j] = zero2();
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb) {
+        double2 s[3];
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) s[jb] = ld2(ws.W + lo26 + t26(kb, jb));
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) {
+          const double2 af = ld2(A + lo24 + t24(kb, ib)), bf = ld2(B + lo24 + t24(kb, ib));
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            dmma2(zA[ib][jb], af, s[jb]);
+            dmma2(zB[ib][jb], bf, s[jb]);
+          }
+        }
+      }
+      __syncwarp();  // S (scratch) is dead from here on
+
+      // ---- Hm = R + SB'B (lower tiles) -> scratch, lower triangle, transposed 8-byte stores ----
+      {
+        double2 h[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) h[i] = zero2();
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) {
+          double2 bf[3];
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) bf[jb] = ld2(B + lo24 + t24(kb, jb));
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+            for (int jb = 0; jb <= ib; ++jb) dmma2(h[lt(ib, jb)], zB[ib][kb], bf[jb]);
+        }
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) {
+            const double2 rr = ldg2(rec + a.oR + lo24 + t24(jb, ib));  // R[8ib+r][8jb+2c..] = R[8jb+2c..][8ib+r]
+            double* p = ws.W + (8 * ib + r) + kLd * (8 * jb + 2 * c);
+            p[0] = h[lt(ib, jb)].x + rr.x;
+            p[kLd] = h[lt(ib, jb)].y + rr.y;
+          }
+      }
+
+      // ---- G' = P' + SA'B (op fragments of G), T = Q + eps I + SA'A (lower tiles) ----
+      double2 g[3][3], t[6];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) g[i][j] = zero2();
+#pragma unroll
+      for (int i = 0; i < 6; ++i) t[i] = zero2();
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb) {
+        double2 bf[3], af[3];
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) {
+          bf[jb] = ld2(B + lo24 + t24(kb, jb));
+          af[jb] = ld2(A + lo24 + t24(kb, jb));
+        }
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) {
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], zA[ib][kb], bf[jb]);
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], zA[ib][kb], af[jb]);
+        }
+      }
+      __syncwarp();  // all lanes are done with the staged operand block: refill it for node k-1 while this stage finishes
+      if (lane == 0 && k >= 1) {
+        mbar_expect_tx(&ws.full, opBytes);
+        tma_load(ws.in, lqp + (size_t)(k - 1) * a.rec, opBytes, &ws.full);
+        l2_prefetch(lqp + (size_t)(k - 1) * a.rec + a.oQ, hessBytes);
+        if (k >= 2) l2_prefetch(lqp + (size_t)(k - 2) * a.rec, opBytes);
+      }
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib) {
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) {
+          const double2 pp = ldg2(rec + a.oP + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
+          g[ib][jb].x += pp.x;
+          g[ib][jb].y += pp.y;
+        }
+#pragma unroll
+        for (int jb = 0; jb <= ib; ++jb) {
+          const double2 qq = ldg2(rec + a.oQ + lo24 + t24(jb, ib));
+          t[lt(ib, jb)].x += qq.x;
+          t[lt(ib, jb)].y += qq.y;
+        }
+        t[lt(ib, ib)].x += (2 * c == r) ? a.eps : 0.0;
+        t[lt(ib, ib)].y += (2 * c + 1 == r) ? a.eps : 0.0;
+      }
+
+      // ---- Cholesky of Hm, L^-T, Yv; dbias = -L^-T Yv; s ----
+      {
+        double h[kN];
+        pd = cholesky_inverse(ws, lane, h) && pd;
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < kN; kk += 2) {
+          const double2 yv = ld2(ws.Yv + kk);
+          d0 = fma(h[kk], yv.x, d0);
+          d1 = fma(h[kk + 1], yv.y, d1);
+        }
+        const double db = -(d0 + d1);
+        if (lane < kN) {
+          __stcg(out + a.odb + lane, db);
+          __stcg(out + a.obias + lane, 0.0);
+          if (out2) {
+            __stcg(out2 + a.odb + lane, db);
+            __stcg(out2 + a.obias + lane, 0.0);
+          }
+          const double yv = ws.Yv[lane];
+          spart = fma(-0.5 * yv, yv, spart);
+        }
+        sval = sval + cval + warp_sum_all(spart);
+        if (lane == 0) __stcg(out + a.os, sval);
+        finite = finite && isfinite(sval);
+      }
+
+      // ---- Y' = G' L^-T (op fragments of Y); L^-T is block upper triangular ----
+      double2 y[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) y[i][j] = zero2();
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb)
+#pragma unroll
+        for (int kb = 0; kb <= jb; ++kb) {
+          const double2 lf = ld2(ws.W + lo26 + t26(kb, jb));
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) dmma2(y[ib][jb], g[ib][kb], lf);
+        }
+
+      // ---- K' = -Y' L^-1 (op fragments of K -> 16-byte global stores); L^-1 is block lower triangular ----
+      {
+        double2 kk[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) kk[i][j] = zero2();
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb)
+#pragma unroll
+          for (int kb = jb; kb < 3; ++kb) {
+            const double* p = ws.W + (8 * jb + r) + kLd * (8 * kb + 2 * c);  // L^-1[8kb+2c..][8jb+r] = L^-T[8jb+r][8kb+2c..]
+            const double2 lf = make_double2(p[0], p[kLd]);
+#pragma unroll
+            for (int ib = 0; ib < 3; ++ib) dmma2(kk[ib][jb], y[ib][kb], lf);
+          }
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            const double2 kv = neg2(kk[ib][jb]);
+            stg2(out + a.oK + lo24 + t24(jb, ib), kv);
+            if (out2) stg2(out2 + a.oK + lo24 + t24(jb, ib), kv);
+            finite = finite && finite2(kv);
+          }
+      }
+
+      // ---- Sv = tv - Y'Yv ----
+      {
+        double2 vf[3];
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) vf[kb] = ld2(ws.Yv + 8 * kb + 2 * c);
+        double z[3];
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          double p = 0.0;
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            p = fma(y[cb][kb].x, vf[kb].x, p);
+            p = fma(y[cb][kb].y, vf[kb].y, p);
+          }
+          z[cb] = quad_sum(p);
+        }
+        if (c < 3) {
+          const int j = 8 * c + r;
+          const double v = ws.tv[j] - pick3(z, c);
+          ws.Sv[j] = v;
+          __stcg(out + a.oSv + j, v);
+          finite = finite && isfinite(v);
+        }
+      }
+
+      // ---- S = T - Y'Y (lower tiles): accumulate Y'Y - T, flip the sign ----
+#pragma unroll
+      for (int i = 0; i < 6; ++i) t[i] = neg2(t[i]);
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], y[ib][kb], y[jb][kb]);
+      __syncwarp();  // every lane is done reading L^-T from the scratch
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+        for (int jb = 0; jb <= ib; ++jb) {
+          const double2 sv = neg2(t[lt(ib, jb)]);  // S[8ib+r][8jb+2c..] = S[8jb+2c..][8ib+r]
+          finite = finite && finite2(sv);
+          st2(ws.W + lo26 + t26(jb, ib), sv);
+          stg2(out + a.oSm + lo24 + t24(jb, ib), sv);
+          if (ib != jb) {
+            double* p = ws.W + (8 * ib + r) + kLd * (8 * jb + 2 * c);
+            p[0] = sv.x;
+            p[kLd] = sv.y;
+            double* gq = out + a.oSm + (8 * ib + r) + kN * (8 * jb + 2 * c);
+            __stcg(gq, sv.x);
+            __stcg(gq + kN, sv.y);
+          }
+        }
+      __syncwarp();
+    }
+
+    // ---- status ----
+    int bits = 0;
+    if (!__all_sync(kFull, pd)) bits |= O2C_STATUS_CHOL_NOT_PD;
+    if (!__all_sync(kFull, finite)) bits |= O2C_STATUS_NONFINITE;
+    if (!a.with_rollout) {
+      if (lane == 0) a.status[prob] = bits;
+      continue;
+    }
+
+    // ---- fused forward rollout of the LQ model. {A|B|Hv} of node k by TMA into the operand slot, K_k straight from L2 ----
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&ws.full, opBytes);
+      tma_load(ws.in, lqp, opBytes, &ws.full);
+      for (int k = 1; k < 4 && k < N; ++k) l2_prefetch(lqp + (size_t)k * a.rec, opBytes);
+      for (int k = 0; k < 4 && k < N; ++k) l2_prefetch(solp + (size_t)k * a.orec + a.oK, (kMat + kN) * sizeof(double));
+    }
+    double* xo = a.xs + (size_t)prob * (N + 1) * kN;
+    double* uo = a.us + (size_t)prob * (N + 1) * kN;
+    double x = a.x0[(size_t)prob * kN + li];
+    if (lane < kN) ws.xb[lane] = x;
+    __syncwarp();
+    bool xfinite = true;
+    double kreg[kN];
+    {
+      const double* Kg = solp + a.oK;
+#pragma unroll
+      for (int j = 0; j < kN; ++j) kreg[j] = __ldcg(Kg + li + kN * j);
+    }
+    double dbk = __ldcg(solp + a.odb + li);
+    for (int k = 0; k < N; ++k) {
+      // u = alpha dbias + K x
+      double u0 = a.alpha * dbk, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+      for (int j = 0; j < kN; j += 4) {
+        const double2 x01 = ld2(ws.xb + j), x23 = ld2(ws.xb + j + 2);
+        u0 = fma(kreg[j], x01.x, u0);
+        u1 = fma(kreg[j + 1], x01.y, u1);
+        u2 = fma(kreg[j + 2], x23.x, u2);
+        u3 = fma(kreg[j + 3], x23.y, u3);
+      }
+      const double u = (u0 + u1) + (u2 + u3);
+      if (lane < kN) {
+        ws.ub[lane] = u;
+        __stcg(xo + (size_t)k * kN + lane, x);
+        __stcg(uo + (size_t)k * kN + lane, u);
+      }
+      xfinite = xfinite && isfinite(x);
+      // gains of the next node (node N carries the copy of node N-1): in flight while this node's state update runs
+      {
+        const double* Kg = solp + (size_t)(k + 1) * a.orec + a.oK;
+#pragma unroll
+        for (int j = 0; j < kN; ++j) kreg[j] = __ldcg(Kg + li + kN * j);
+        dbk = __ldcg(solp + (size_t)(k + 1) * a.orec + a.odb + li);
+      }
+      mbar_wait(&ws.full, phase);
+      phase ^= 1u;
+      __syncwarp();
+      const double xn = ws.in[2 * kMat + li] + matvec_rows(ws.in, ws.xb, li) + matvec_rows(ws.in + kMat, ws.ub, li);
+      __syncwarp();
+      x = xn;
+      if (lane < kN) ws.xb[lane] = x;
+      if (lane == 0) {
+        if (k + 1 < N) {
+          mbar_expect_tx(&ws.full, opBytes);
+          tma_load(ws.in, lqp + (size_t)(k + 1) * a.rec, opBytes, &ws.full);
+        }
+        if (k + 4 < N) {
+          l2_prefetch(lqp + (size_t)(k + 4) * a.rec, opBytes);
+          l2_prefetch(solp + (size_t)(k + 4) * a.orec + a.oK, (kMat + kN) * sizeof(double));
+        }
+      }
+      __syncwarp();
+    }
+    // node N: state, and the input of the copied last policy re-evaluated at x_N (TimeTriggeredRollout.cpp:98-102)
+    {
+      double u0 = a.alpha * dbk, u1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < kN; j += 2) {
+        const double2 x01 = ld2(ws.xb + j);
+        u0 = fma(kreg[j], x01.x, u0);
+        u1 = fma(kreg[j + 1], x01.y, u1);
+      }
+      if (lane < kN) {
+        __stcg(xo + (size_t)N * kN + lane, x);
+        __stcg(uo + (size_t)N * kN + lane, u0 + u1);
+      }
+      xfinite = xfinite && isfinite(x);
+    }
+    if (!__all_sync(kFull, xfinite)) bits |= O2C_STATUS_NONFINITE;
+    if (lane == 0) a.status[prob] = bits;
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
+  return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
+         st.hc == O2C_HC_DIAGONAL_SHIFT && buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1 && L.oQ == kOperand;
+}
+
+cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,
+                            int begin, int count, cudaStream_t stream, int* launches) {
+  if (!wpp_ilqr_supported(L, st, buf)) return cudaErrorNotSupported;
+  static bool configured = false;
+  static int num_sms = 0;
+  const size_t smem = sizeof(WarpSmem) * kWarps;
+  cudaError_t e = cudaFuncSetAttribute(ilqr_wpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (!configured) {
+    cudaFuncSetAttribute(ilqr_wpp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  Args a{};
+  a.lq = buf.lq;
+  a.term = buf.term;
+  a.x0 = buf.x0;
+  a.sol = buf.sol;
+  a.xs = buf.xs;
+  a.us = buf.us;
+  a.status = buf.status;
+  a.rec = L.rec;
+  a.orec = L.orec;
+  a.N = L.N;
+  a.oQ = L.oQ;
+  a.oP = L.oP;
+  a.oR = L.oR;
+  a.oK = L.oK;
+  a.odb = L.odb;
+  a.obias = L.obias;
+  a.oSm = L.oSm;
+  a.oSv = L.oSv;
+  a.os = L.os;
+  a.oQf = L.oQf;
+  a.oqf = L.oqf;
+  a.ocf = L.ocf;
+  a.trec = L.trec;
+  a.begin = begin;
+  a.count = count;
+  a.with_rollout = with_rollout ? 1 : 0;
+  a.eps = st.eps;
+  a.alpha = alpha;
+  (void)batch;
+  const int ctas_needed = (count + kWarps - 1) / kWarps;
+  const int grid = ctas_needed < num_sms * kCtasPerSm ? ctas_needed : num_sms * kCtasPerSm;
+  ilqr_wpp_kernel<<<grid, kThreads, smem, stream>>>(a);
+  if (launches) *launches = 1;
+  return cudaGetLastError();
+}
+
+}  // namespace o2c

@@ -284,7 +284,7 @@ def test_legged_dmma_kernel_fused_solve_matches_oracle(N):
     batch, dt, seed, alpha = 40, 0.01, 2, 0.6
     st = o2.Settings(hessianCorrectionMultiple=1e-5, timeStep=dt)
     with o2.BatchedLqSolver(st, n, m, N, batch) as solver:
-        assert solver.kernel_variant == "ilqr_dmma_kernel"
+        assert solver.kernel_variant in ("ilqr_wpp_kernel", "ilqr_dmma_kernel")
         solver.generate_synthetic(seed, first_problem_index=300, dt=dt)
         l0 = solver.launch_count
         solver.solve(alpha=alpha)
@@ -312,7 +312,7 @@ def test_legged_dmma_kernel_uploaded_data_subrange_and_status():
     lq.R[4, 6] = -np.eye(m)
     st = o2.Settings(hessianCorrectionMultiple=1e-4)
     with o2.BatchedLqSolver(st, n, m, N, batch) as solver:
-        assert solver.kernel_variant == "ilqr_dmma_kernel"
+        assert solver.kernel_variant in ("ilqr_wpp_kernel", "ilqr_dmma_kernel")
         solver.upload(lq)
         solver.solve(alpha=1.0, problem_begin=2, problem_count=6)
         sol = solver.download(problem_begin=2, problem_count=6)
