@@ -59,7 +59,6 @@ struct o2c_handle {
   std::vector<double> time, ro_times;
   bool time_set = false;
   bool use_fast = false;
-  int fast_variant = 0;  // 1: CTA-per-problem DMMA kernel, 2: warp-per-problem DMMA kernel
   int64_t launches = 0;
   int stage_chunk = 0;
 
@@ -462,7 +461,7 @@ o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) 
   if (h->st.algorithm == O2C_ALG_ILQR) {
     if (h->use_fast) {
       int l = 0;
-      O2C_CUDA((h->fast_variant == 2 ? launch_ilqr_wpp : launch_ilqr_fast)(h->L, h->st, buf, false, 1.0, h->cfg.batch, begin, count, stream, &l));
+      O2C_CUDA(launch_ilqr_wpp(h->L, h->st, buf, false, 1.0, h->cfg.batch, begin, count, stream, &l));
       h->launches += l;
     } else {
       O2C_CUDA(launch_ilqr_generic(h->L, h->st, buf, begin, count, stream));
@@ -494,7 +493,7 @@ o2c_error solve_on(o2c_handle* h, cudaStream_t stream, double* alpha_slot_dev, d
   if (count == 0) return O2C_OK;
   if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast) {
     int l = 0;
-    O2C_CUDA((h->fast_variant == 2 ? launch_ilqr_wpp : launch_ilqr_fast)(h->L, h->st, h->buffers(), true, alpha, h->cfg.batch, begin, count, stream, &l));
+    O2C_CUDA(launch_ilqr_wpp(h->L, h->st, h->buffers(), true, alpha, h->cfg.batch, begin, count, stream, &l));
     h->launches += l;
     return O2C_OK;
   }
@@ -604,12 +603,7 @@ o2c_error o2c_create(const o2c_config* cfg, o2c_handle** out) {
 #undef ALLOC
   cudaMemsetAsync(h->d_status, 0, sizeof(int) * B, h->lanes[0].stream);
   cudaMemsetAsync(h->d_x0, 0, sizeof(double) * B * L.n, h->lanes[0].stream);
-  h->use_fast = fast_ilqr_supported(h->L, h->st, h->buffers());
-  if (h->use_fast) {
-    // O2C_LEGGED_KERNEL=cta selects the older CTA-per-problem kernel (kept for A/B profiling); default: warp-per-problem
-    const char* sel = getenv("O2C_LEGGED_KERNEL");
-    h->fast_variant = (sel && strcmp(sel, "cta") == 0) ? 1 : (wpp_ilqr_supported(h->L, h->st, h->buffers()) ? 2 : 1);
-  }
+  h->use_fast = wpp_ilqr_supported(h->L, h->st, h->buffers());
   // default uniform time grid t_k = k * time_step (ILQR does not need it; SLQ callers normally override it)
   std::vector<double> t(L.N + 1);
   const double dt = cfg->time_step > 0.0 ? cfg->time_step : 1.0;
@@ -841,8 +835,7 @@ o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {
 const char* o2c_kernel_variant(const o2c_handle* h) {
   if (!h) return "";
   if (h->st.algorithm == O2C_ALG_SLQ) return "slq_generic_kernel";
-  if (h->use_fast) return h->fast_variant == 2 ? "ilqr_wpp_kernel" : "ilqr_dmma_kernel";
-  return "ilqr_generic_kernel";
+  return h->use_fast ? "ilqr_wpp_kernel" : "ilqr_generic_kernel";
 }
 
 o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solution_view* sol, double alpha, int32_t count, int32_t chunk) {

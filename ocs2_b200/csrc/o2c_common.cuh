@@ -39,6 +39,11 @@ inline Layout make_layout(int n, int m, int ncmax, int N, int algorithm) {
     o = pad2(o + count);
     return at;
   };
+  // big shapes (a matrix block of >= 4 KB): the cost-Hessian part and every record start on a 128-byte boundary, so that the
+  // per-column L2 prefetches of the shape-specialised kernel touch whole 64-byte DRAM bursts. Small shapes stay densely packed
+  // (they are HBM-bound; padding would be pure extra traffic).
+  const int align = (n * n >= 512 || n * m >= 512) ? 16 : 2;
+  auto align_up = [&]() { o = (o + align - 1) / align * align; };
   // operand part first (what the specialised sweep kernel stages into shared memory with one bulk copy), then the cost Hessians
   L.oA = take(n * n);
   L.oB = take(n * m);
@@ -46,18 +51,21 @@ inline Layout make_layout(int n, int m, int ncmax, int N, int algorithm) {
   L.oq = take(n);
   L.or_ = take(m);
   L.oc = take(1);
+  align_up();
   L.oQ = take(n * n);
   L.oP = take(m * n);
   L.oR = take(m * m);
   L.oC = take(ncmax * n);
   L.oD = take(ncmax * m);
   L.oe = take(ncmax);
-  L.rec = pad2(o);
+  align_up();
+  L.rec = o;
   o = 0;
   L.oQf = take(n * n);
   L.oqf = take(n);
   L.ocf = take(1);
-  L.trec = pad2(o);
+  align_up();
+  L.trec = o;
   o = 0;
   L.oK = take(m * n);
   L.odb = take(m);
@@ -65,7 +73,8 @@ inline Layout make_layout(int n, int m, int ncmax, int N, int algorithm) {
   L.oSm = take(n * n);
   L.oSv = take(n);
   L.os = take(1);
-  L.orec = pad2(o);
+  align_up();
+  L.orec = o;
   return L;
 }
 
@@ -139,12 +148,7 @@ cudaError_t launch_pack(const Layout& L, const LqViewDev& v, double* lq, double*
 cudaError_t launch_unpack(const Layout& L, const SolViewDev& v, const double* sol, const double* xs, const double* us, const int* status,
                           int out_nodes, int n_alpha, int batch, int begin, int count, cudaStream_t stream);
 
-// fast path (riccati_dmma.cu): returns cudaErrorNotSupported when the configuration has no specialised kernel
-bool fast_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
-cudaError_t launch_ilqr_fast(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,
-                             int begin, int count, cudaStream_t stream, int* launches);
-
-// warp-per-problem variant of the same fast path (riccati_wpp.cu)
+// shape-specialised fast path (riccati_wpp.cu): warp-per-problem DMMA kernel for nx = nu = 24; cudaErrorNotSupported otherwise
 bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
 cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,
                             int begin, int count, cudaStream_t stream, int* launches);

@@ -36,11 +36,11 @@ namespace {
 
 constexpr int kN = 24;            // nx == nu
 constexpr int kMat = kN * kN;     // 576
-constexpr int kLd = 26;           // leading dimension of the scratch matrix
+constexpr int kLd = 26;           // leading dimension of the scratch matrix (conflict-free 8-byte transposed access)
 constexpr int kWarps = 4;         // problems per CTA
 constexpr int kThreads = 32 * kWarps;
 constexpr int kCtasPerSm = 3;
-constexpr int kOperand = 2 * kMat + 3 * kN + 2;  // {A|B|Hv|q|r|c,pad} doubles staged by TMA (= Layout::oQ for n = m = 24)
+constexpr int kOperand = 2 * kMat + 3 * kN + 2 + 6;  // {A|B|Hv|q|r|c,pad} doubles staged by TMA (= Layout::oQ for n = m = 24, 128-byte aligned)
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -80,7 +80,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor pipe. Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4], d = D[lane/4][2*(lane%4) + {0,1}].
 __device__ __forceinline__ void dmma(double2& d, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d.x), "+d"(d.y) : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d.x), "+d"(d.y) : "d"(a), "d"(b));
 }
 // acc(Z tile) += X(kblock, i)' Y(kblock, j) for one 8-deep k block; x, y are "op" fragments (rows {2c, 2c+1} of the k block, column r),
 // so the two DMMAs contract k = {0,2,4,6} and {1,3,5,7} (the same permutation on both operands).
@@ -93,10 +93,24 @@ __device__ __forceinline__ void st2(double* p, const double2& v) { *reinterpret_
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void stg2(double* p, const double2& v) { __stcg(reinterpret_cast<double2*>(p), v); }
 __device__ __forceinline__ double2 zero2() { return make_double2(0.0, 0.0); }
-__device__ __forceinline__ bool finite2(const double2& v) { return isfinite(v.x) && isfinite(v.y); }
 // sign flip on the integer pipe (keeps the FP64 pipe for the contractions)
 __device__ __forceinline__ double neg(double v) { return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v)); }
 __device__ __forceinline__ double2 neg2(const double2& v) { return make_double2(neg(v.x), neg(v.y)); }
+// exponent field all ones <=> Inf or NaN, tested on the integer pipe
+__device__ __forceinline__ bool finite_bits(double v) { return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000; }
+__device__ __forceinline__ bool finite2(const double2& v) { return finite_bits(v.x) && finite_bits(v.y); }
+
+// 1/sqrt(d) for a normal positive d: MUFU.RSQ64H seed (>= 20 good bits) and one third-order step, relative error below 1e-17
+// (the library rsqrt spends ~16 instructions on denormal / special-case handling the pivot test has already excluded)
+__device__ __forceinline__ double rsqrt_pivot(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  const double ye = y * e;
+  return fma(ye, p, y);
+}
 
 // tile offsets: rows 8*rb.., columns 8*cb.. of a column-major matrix with leading dimension 24 (staged / global) or 26 (scratch)
 __device__ __forceinline__ constexpr int t24(int rb, int cb) { return 8 * rb + 8 * kN * cb; }
@@ -106,7 +120,7 @@ __device__ __forceinline__ constexpr int lt(int ib, int jb) { return ib * (ib + 
 
 struct __align__(16) WarpSmem {
   double in[kOperand];   // TMA destination: {A | B | Hv | q | r | c,pad}
-  double W[kN * kLd];    // S of node k+1 (both triangles) -> Hm (lower) -> L -> L^-T
+  double W[kN * kLd];    // S of node k+1 (both triangles) -> Hm (lower) -> L -> L^-T (upper)
   double Sv[kN], w[kN], Gv[kN], tv[kN], Yv[kN], xb[kN], ub[kN];
   unsigned long long full;
   unsigned long long pad_;
@@ -141,8 +155,20 @@ __device__ __forceinline__ double warp_sum_all(double v) {
 }
 __device__ __forceinline__ double pick3(const double (&z)[3], int c) { return c == 0 ? z[0] : (c == 1 ? z[1] : z[2]); }
 
-// z[8 jb + r] = sum_k M[k + LD j] v[k] (transposed product) with the operand-fragment access pattern; every lane of quad r gets z[jb]
-template <int LD>
+// "transposed" fragment of the scratch: lane (r,c) gets M[8rb + r][8cb + 2c .. 2c+1] (two conflict-free 8-byte loads)
+__device__ __forceinline__ double2 tfrag(const double* W, int rb, int cb, int r, int c) {
+  const double* p = W + (8 * rb + r) + kLd * (8 * cb + 2 * c);
+  return make_double2(p[0], p[kLd]);
+}
+__device__ __forceinline__ void tput(double* W, int rb, int cb, int r, int c, const double2& v) {
+  double* p = W + (8 * rb + r) + kLd * (8 * cb + 2 * c);
+  p[0] = v.x;
+  p[kLd] = v.y;
+}
+
+// z[8 jb + r] = sum_k M[k + LD j] v[k] (transposed product) with the operand-fragment access pattern; every lane of quad r gets z[jb].
+// UPPER: M is block upper triangular (only tiles kb <= jb are read).
+template <int LD, bool UPPER>
 __device__ __forceinline__ void matvec_cols(const double* M, const double* v, int r, int c, double (&z)[3]) {
   double2 vf[3];
 #pragma unroll
@@ -151,7 +177,7 @@ __device__ __forceinline__ void matvec_cols(const double* M, const double* v, in
   for (int jb = 0; jb < 3; ++jb) {
     double p = 0.0;
 #pragma unroll
-    for (int kb = 0; kb < 3; ++kb) {
+    for (int kb = 0; kb < (UPPER ? jb + 1 : 3); ++kb) {
       const double2 mv = ld2(M + 2 * c + LD * r + 8 * kb + 8 * LD * jb);
       p = fma(mv.x, vf[kb].x, p);
       p = fma(mv.y, vf[kb].y, p);
@@ -173,46 +199,104 @@ __device__ __forceinline__ double matvec_rows(const double* M, const double* v, 
   return (a0 + a1) + (a2 + a3);
 }
 
-// Cholesky Hm = L L' in the scratch (one row per lane, the scaled column is broadcast through shared memory), then the rows of L^-T
-// by the same right-looking recurrence applied to the identity; lane 24 carries Gv through it and ends with Yv = L^-1 Gv.
-// On return h[] holds row `lane` of L^-T (lanes < 24) and the scratch holds L^-T column-major (exact zeros below the diagonal).
-__device__ __forceinline__ bool cholesky_inverse(WarpSmem& ws, int lane, double (&h)[kN]) {
-  const int li = lane < kN ? lane : kN - 1;
-  double* Hs = ws.W;
-#pragma unroll
-  for (int k = 0; k < kN; ++k) h[k] = Hs[li + kLd * k];
+// ---------------------------------------------------------------------------------------------------------------------
+// Blocked factorisation of Hm (24x24 in 8x8 blocks). In: the six lower tiles of Hm as accumulator fragments. Out: the scratch
+// holds L^-T column-major in its block upper triangle (exact zeros below the diagonal inside the diagonal tiles; the strictly
+// lower tiles hold left-over panels of L and are never read again).
+//   * each block column is factorised one row per lane (rows 8b..23: the unblocked right-looking recurrence restricted to the
+//     8 columns of the block, which also solves the panel below the diagonal block), 8 pivots per block;
+//   * the trailing tiles are updated on the tensor pipe (Hm_ij -= L_ib L_jb');
+//   * the three diagonal blocks are inverted together, one row of L_bb^-T per lane (8 steps), and the off-diagonal blocks of
+//     L^-1 follow from three small DMMA chains:  Li10 = -Li11 (L10 Li00),  Li21 = -Li22 (L21 Li11),
+//     Li20 = -Li22 (L20 Li00 + L21 Li10).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool factor_hm(double* W, double2 (&h)[6], int lane, int li, int r, int c) {
   bool pd = true;
-#pragma unroll
-  for (int j = 0; j < kN; ++j) {
-    const double d = __shfl_sync(kFull, h[j], j);
-    const bool ok = d > 0.0;
-    pd = pd && ok;
-    const double rs = ok ? rsqrt(d) : __longlong_as_double(0x7ff8000000000000LL);  // NaNs propagate like the reference's LLT
-    const double l = h[j] * rs;
-    if (lane < kN) Hs[lane + kLd * j] = (lane == j) ? rs : l;
+#pragma unroll 1
+  for (int b = 0; b < 3; ++b) {
+    if (b == 0) {
+      tput(W, 0, 0, r, c, h[lt(0, 0)]);
+      tput(W, 1, 0, r, c, h[lt(1, 0)]);
+      tput(W, 2, 0, r, c, h[lt(2, 0)]);
+    } else if (b == 1) {
+      tput(W, 1, 1, r, c, h[lt(1, 1)]);
+      tput(W, 2, 1, r, c, h[lt(2, 1)]);
+    } else {
+      tput(W, 2, 2, r, c, h[lt(2, 2)]);
+    }
     __syncwarp();
+    double* col = W + kLd * 8 * b;  // column 8b of the scratch
+    const bool owner = lane >= 8 * b && lane < kN;
+    double g[8];
 #pragma unroll
-    for (int k = j + 1; k < kN; ++k) h[k] = fma(-l, Hs[k + kLd * j], h[k]);
+    for (int k = 0; k < 8; ++k) g[k] = col[li + kLd * k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double d = __shfl_sync(kFull, g[j], 8 * b + j);
+      const bool ok = d > 0.0;
+      pd = pd && ok;
+      const double rs = ok ? rsqrt_pivot(d) : __longlong_as_double(0x7ff8000000000000LL);  // NaNs propagate like the reference's LLT
+      const double l = g[j] * rs;
+      if (owner) col[lane + kLd * j] = (lane == 8 * b + j) ? rs : l;  // 1/L_jj on the diagonal
+      __syncwarp();
+#pragma unroll
+      for (int k = j + 1; k < 8; ++k) g[k] = fma(-l, col[8 * b + k + kLd * j], g[k]);
+    }
+    if (b == 0) {
+      const double2 f1 = tfrag(W, 1, 0, r, c), f2 = tfrag(W, 2, 0, r, c);
+      const double2 n1 = neg2(f1), n2 = neg2(f2);
+      dmma2(h[lt(1, 1)], n1, f1);
+      dmma2(h[lt(2, 1)], n2, f1);
+      dmma2(h[lt(2, 2)], n2, f2);
+    } else if (b == 1) {
+      const double2 f2 = tfrag(W, 2, 1, r, c);
+      dmma2(h[lt(2, 2)], neg2(f2), f2);
+    }
   }
-  // rows of L^-T: g <- e_lane' L^-T (lanes < 24); lane 24: g <- Gv' L^-T = Yv'
+  // diagonal blocks: lane (8 bi + ii) computes row ii of L_bb^-T by the recurrence applied to e_ii
+  {
+    const int bi = li >> 3, ii = li & 7;
+    double* dg = W + 8 * bi + kLd * 8 * bi;
+    double g[8];
 #pragma unroll
-  for (int k = 0; k < kN; ++k) h[k] = (lane == kN) ? ws.Gv[k] : ((k == lane) ? 1.0 : 0.0);
+    for (int k = 0; k < 8; ++k) g[k] = (k == ii) ? 1.0 : 0.0;
 #pragma unroll
-  for (int j = 0; j < kN; ++j) {
-    const double a = h[j] * Hs[j + kLd * j];
-    h[j] = a;
+    for (int j = 0; j < 8; ++j) {
+      const double a = g[j] * dg[j + kLd * j];
+      g[j] = a;
 #pragma unroll
-    for (int k = j + 1; k < kN; ++k) h[k] = fma(-a, Hs[k + kLd * j], h[k]);
+      for (int k = j + 1; k < 8; ++k) g[k] = fma(-a, dg[k + kLd * j], g[k]);
+    }
+    __syncwarp();
+    if (lane < kN) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dg[ii + kLd * k] = g[k];
+    }
+    __syncwarp();
   }
-  __syncwarp();  // every lane is done reading L
-  if (lane < kN) {
-#pragma unroll
-    for (int k = 0; k < kN; ++k) Hs[lane + kLd * k] = h[k];
-  } else if (lane == kN) {
-#pragma unroll
-    for (int k = 0; k < kN; ++k) ws.Yv[k] = h[k];
+  // off-diagonal blocks of L^-1 (stored transposed into the upper tiles)
+  {
+    const double2 li00 = tfrag(W, 0, 0, r, c), li11 = tfrag(W, 1, 1, r, c);          // op fragments of Li00, Li11
+    const double2 l10 = tfrag(W, 1, 0, r, c), l20 = tfrag(W, 2, 0, r, c), l21 = tfrag(W, 2, 1, r, c);  // op fragments of L10', L20', L21'
+    const double2 lt11 = ld2(W + 2 * c + kLd * r + t26(1, 1)), lt22 = ld2(W + 2 * c + kLd * r + t26(2, 2));  // op fragments of Li11', Li22'
+    double2 x10 = zero2(), x21 = zero2(), x20 = zero2();
+    dmma2(x10, li00, l10);  // (L10 Li00)' as accumulator = op fragment of L10 Li00
+    dmma2(x21, li11, l21);
+    dmma2(x20, li00, l20);
+    double2 i10 = zero2(), i21 = zero2();
+    dmma2(i10, lt11, x10);
+    dmma2(i21, lt22, x21);
+    i10 = neg2(i10);
+    i21 = neg2(i21);
+    st2(W + 2 * c + kLd * r + t26(0, 1), i10);  // acc(Li10) = op fragment of (L^-T) tile (0,1)
+    st2(W + 2 * c + kLd * r + t26(1, 2), i21);
+    __syncwarp();
+    dmma2(x20, tfrag(W, 0, 1, r, c), l21);  // + (L21 Li10)': op fragment of Li10 = transposed read of tile (0,1)
+    double2 i20 = zero2();
+    dmma2(i20, lt22, x20);
+    st2(W + 2 * c + kLd * r + t26(0, 2), neg2(i20));
+    __syncwarp();
   }
-  __syncwarp();
   return pd;
 }
 
@@ -228,7 +312,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
   const int li = lane < kN ? lane : kN - 1;
   const int N = a.N;
   const uint32_t opBytes = kOperand * sizeof(double);
-  const uint32_t hessBytes = (uint32_t)(a.rec - a.oQ) * sizeof(double);
+  // per-lane share of the Hessian prefetch: lane j < 24 owns column j of Q and R (only the tiles on or above the block diagonal are
+  // read: rows 0 .. 8 (j/8 + 1)), lane 24 owns P
+  const int pfOff = lane < kN ? kN * lane : 0;
+  const uint32_t pfBytes = lane < kN ? 64u * (uint32_t)(lane / 8 + 1) : (uint32_t)(kMat * sizeof(double));
 
   if (lane == 0) {
     mbar_init(&ws.full, 1);
@@ -243,17 +330,25 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
     const double* term = a.term + (size_t)prob * a.trec;
     double* solp = a.sol + (size_t)prob * (N + 1) * a.orec;
 
-    // operand block of node N-1 (TMA) and the L2 prefetch of what comes next
+    // operand block of node N-1 (TMA) and the L2 prefetch of its cost Hessians
     if (lane == 0) {
       fence_proxy_async();
       mbar_expect_tx(&ws.full, opBytes);
       tma_load(ws.in, lqp + (size_t)(N - 1) * a.rec, opBytes, &ws.full);
-      l2_prefetch(lqp + (size_t)(N - 1) * a.rec + a.oQ, hessBytes);
-      if (N >= 2) l2_prefetch(lqp + (size_t)(N - 2) * a.rec, opBytes);
+    }
+    {
+      const double* rec = lqp + (size_t)(N - 1) * a.rec;
+      if (lane < kN) {
+        l2_prefetch(rec + a.oQ + pfOff, pfBytes);
+        l2_prefetch(rec + a.oR + pfOff, pfBytes);
+      } else if (lane == kN) {
+        l2_prefetch(rec + a.oP, pfBytes);
+      }
     }
     // terminal condition: valueFunctionTrajectory.back() = finalValueFunction (GaussNewtonDDP.cpp:526)
     {
       double* outN = solp + (size_t)N * a.orec;
+#pragma unroll 1
       for (int i = lane; i < kMat; i += 32) {
         const double v = term[a.oQf + i];
         ws.W[(i % kN) + kLd * (i / kN)] = v;
@@ -267,9 +362,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       if (lane == 0) outN[a.os] = term[a.ocf];
     }
     double sval = term[a.ocf];  // s of node k+1
-    bool finite = true, pd = true;
+    bool pd = true;
+    double2 t[6];               // T -> S (lower tiles); after the loop: S of node 0 for the finiteness test
+    double svn = 0.0;
     __syncwarp();
 
+#pragma unroll 1
     for (int k = N - 1; k >= 0; --k) {
       const double* A = ws.in;
       const double* B = ws.in + kMat;
@@ -278,15 +376,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       const double* rv = qv + kN;
       const double* rec = lqp + (size_t)k * a.rec;
       double* out = solp + (size_t)k * a.orec;
-      double* out2 = (k == N - 1) ? solp + (size_t)N * a.orec : nullptr;  // node N := node N-1 (GaussNewtonDDP.cpp:609-618)
       mbar_wait(&ws.full, phase);
       phase ^= 1u;
+      if (lane == 0 && k >= 1) l2_prefetch(lqp + (size_t)(k - 1) * a.rec, opBytes);  // next operand block: L2 now, shared memory at mid-stage
+
+      // Hm accumulators start from R (in flight during the ZA / ZB contractions)
+      double2 h[6];
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+        for (int jb = 0; jb <= ib; ++jb) h[lt(ib, jb)] = ldg2(rec + a.oR + lo24 + t24(jb, ib));  // R[8ib+r][8jb+2c..] = R[8jb+2c..][8ib+r]
 
       // ---- vectors: w = Sv + S Hv, Gv = r + B'w, tv = q + A'w ----
       double spart = 0.0;
       {
         double z[3];
-        matvec_cols<kLd>(ws.W, Hv, r, c, z);  // S symmetric: S Hv = S' Hv
+        matvec_cols<kLd, false>(ws.W, Hv, r, c, z);  // S symmetric: S Hv = S' Hv
         if (c < 3) {
           const int j = 8 * c + r;
           const double shv = pick3(z, c);
@@ -296,8 +401,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         }
         __syncwarp();
         double zB[3], zA[3];
-        matvec_cols<kN>(B, ws.w, r, c, zB);
-        matvec_cols<kN>(A, ws.w, r, c, zA);
+        matvec_cols<kN, false>(B, ws.w, r, c, zB);
+        matvec_cols<kN, false>(A, ws.w, r, c, zA);
         if (c < 3) {
           const int j = 8 * c + r;
           ws.Gv[j] = rv[j] + pick3(zB, c);
@@ -329,11 +434,29 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       }
       __syncwarp();  // S (scratch) is dead from here on
 
-      // ---- Hm = R + SB'B (lower tiles) -> scratch, lower triangle, transposed 8-byte stores ----
-      {
-        double2 h[6];
+      // ---- Hm = R + SB'B (lower tiles, stay in registers for the blocked factorisation) ----
 #pragma unroll
-        for (int i = 0; i < 6; ++i) h[i] = zero2();
+      for (int kb = 0; kb < 3; ++kb) {
+        double2 bf[3];
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) bf[jb] = ld2(B + lo24 + t24(kb, jb));
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) dmma2(h[lt(ib, jb)], zB[ib][kb], bf[jb]);
+      }
+
+      // ---- G' = P' + SA'B (op fragments of G) ----
+      double2 g[3][3];
+      {
+        double2 pp[3][3];
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            pp[ib][jb] = ldg2(rec + a.oP + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
+            g[ib][jb] = zero2();
+          }
 #pragma unroll
         for (int kb = 0; kb < 3; ++kb) {
           double2 bf[3];
@@ -342,93 +465,99 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 #pragma unroll
           for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-            for (int jb = 0; jb <= ib; ++jb) dmma2(h[lt(ib, jb)], zB[ib][kb], bf[jb]);
+            for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], zA[ib][kb], bf[jb]);
         }
 #pragma unroll
         for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb <= ib; ++jb) {
-            const double2 rr = ldg2(rec + a.oR + lo24 + t24(jb, ib));  // R[8ib+r][8jb+2c..] = R[8jb+2c..][8ib+r]
-            double* p = ws.W + (8 * ib + r) + kLd * (8 * jb + 2 * c);
-            p[0] = h[lt(ib, jb)].x + rr.x;
-            p[kLd] = h[lt(ib, jb)].y + rr.y;
+          for (int jb = 0; jb < 3; ++jb) {
+            g[ib][jb].x += pp[ib][jb].x;
+            g[ib][jb].y += pp[ib][jb].y;
           }
       }
-
-      // ---- G' = P' + SA'B (op fragments of G), T = Q + eps I + SA'A (lower tiles) ----
-      double2 g[3][3], t[6];
+      // ---- T = Q + eps I + SA'A (lower tiles) ----
+      {
+        double2 qq[6];
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
+        for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) g[i][j] = zero2();
+          for (int jb = 0; jb <= ib; ++jb) {
+            qq[lt(ib, jb)] = ldg2(rec + a.oQ + lo24 + t24(jb, ib));
+            t[lt(ib, jb)] = zero2();
+          }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) t[i] = zero2();
+        for (int kb = 0; kb < 3; ++kb) {
+          double2 af[3];
 #pragma unroll
-      for (int kb = 0; kb < 3; ++kb) {
-        double2 bf[3], af[3];
+          for (int jb = 0; jb < 3; ++jb) af[jb] = ld2(A + lo24 + t24(kb, jb));
 #pragma unroll
-        for (int jb = 0; jb < 3; ++jb) {
-          bf[jb] = ld2(B + lo24 + t24(kb, jb));
-          af[jb] = ld2(A + lo24 + t24(kb, jb));
+          for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+            for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], zA[ib][kb], af[jb]);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          t[i].x += qq[i].x;
+          t[i].y += qq[i].y;
         }
 #pragma unroll
         for (int ib = 0; ib < 3; ++ib) {
-#pragma unroll
-          for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], zA[ib][kb], bf[jb]);
-#pragma unroll
-          for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], zA[ib][kb], af[jb]);
+          t[lt(ib, ib)].x += (2 * c == r) ? a.eps : 0.0;
+          t[lt(ib, ib)].y += (2 * c + 1 == r) ? a.eps : 0.0;
         }
       }
       __syncwarp();  // all lanes are done with the staged operand block: refill it for node k-1 while this stage finishes
       if (lane == 0 && k >= 1) {
         mbar_expect_tx(&ws.full, opBytes);
         tma_load(ws.in, lqp + (size_t)(k - 1) * a.rec, opBytes, &ws.full);
-        l2_prefetch(lqp + (size_t)(k - 1) * a.rec + a.oQ, hessBytes);
-        if (k >= 2) l2_prefetch(lqp + (size_t)(k - 2) * a.rec, opBytes);
-      }
-#pragma unroll
-      for (int ib = 0; ib < 3; ++ib) {
-#pragma unroll
-        for (int jb = 0; jb < 3; ++jb) {
-          const double2 pp = ldg2(rec + a.oP + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
-          g[ib][jb].x += pp.x;
-          g[ib][jb].y += pp.y;
-        }
-#pragma unroll
-        for (int jb = 0; jb <= ib; ++jb) {
-          const double2 qq = ldg2(rec + a.oQ + lo24 + t24(jb, ib));
-          t[lt(ib, jb)].x += qq.x;
-          t[lt(ib, jb)].y += qq.y;
-        }
-        t[lt(ib, ib)].x += (2 * c == r) ? a.eps : 0.0;
-        t[lt(ib, ib)].y += (2 * c + 1 == r) ? a.eps : 0.0;
       }
 
-      // ---- Cholesky of Hm, L^-T, Yv; dbias = -L^-T Yv; s ----
-      {
-        double h[kN];
-        pd = cholesky_inverse(ws, lane, h) && pd;
-        double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < kN; kk += 2) {
-          const double2 yv = ld2(ws.Yv + kk);
-          d0 = fma(h[kk], yv.x, d0);
-          d1 = fma(h[kk + 1], yv.y, d1);
-        }
-        const double db = -(d0 + d1);
+      // ---- blocked Cholesky of Hm and L^-T into the scratch ----
+      pd = factor_hm(ws.W, h, lane, li, r, c) && pd;
+
+      // cost Hessians of node k-1 into L2 (needed from the first third of the next stage on)
+      if (k >= 1) {
+        const double* nrec = rec - a.rec;
         if (lane < kN) {
-          __stcg(out + a.odb + lane, db);
-          __stcg(out + a.obias + lane, 0.0);
-          if (out2) {
-            __stcg(out2 + a.odb + lane, db);
-            __stcg(out2 + a.obias + lane, 0.0);
-          }
-          const double yv = ws.Yv[lane];
+          l2_prefetch(nrec + a.oQ + pfOff, pfBytes);
+          l2_prefetch(nrec + a.oR + pfOff, pfBytes);
+        } else if (lane == kN) {
+          l2_prefetch(nrec + a.oP, pfBytes);
+        }
+      }
+
+      // ---- Yv = L^-1 Gv, dbias = -L^-T Yv, s ----
+      {
+        double z[3];
+        matvec_cols<kLd, true>(ws.W, ws.Gv, r, c, z);  // (L^-1 Gv)[j] = sum_k (L^-T)[k][j] Gv[k]
+        if (c < 3) {
+          const double yv = pick3(z, c);
+          ws.Yv[8 * c + r] = yv;
           spart = fma(-0.5 * yv, yv, spart);
+        }
+        __syncwarp();
+        // (L^-T Yv)[8jb + r] = sum_{kb >= jb} (L^-T)[8jb+r][8kb+2c..] Yv[8kb+2c..]
+        double2 vf[3];
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) vf[kb] = ld2(ws.Yv + 8 * kb + 2 * c);
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) {
+          double p = 0.0;
+#pragma unroll
+          for (int kb = jb; kb < 3; ++kb) {
+            const double2 mv = tfrag(ws.W, jb, kb, r, c);
+            p = fma(mv.x, vf[kb].x, p);
+            p = fma(mv.y, vf[kb].y, p);
+          }
+          z[jb] = quad_sum(p);
+        }
+        if (c < 3) {
+          const int j = 8 * c + r;
+          __stcg(out + a.odb + j, -pick3(z, c));
+          __stcg(out + a.obias + j, 0.0);
         }
         sval = sval + cval + warp_sum_all(spart);
         if (lane == 0) __stcg(out + a.os, sval);
-        finite = finite && isfinite(sval);
       }
 
       // ---- Y' = G' L^-T (op fragments of Y); L^-T is block upper triangular ----
@@ -457,20 +586,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         for (int jb = 0; jb < 3; ++jb)
 #pragma unroll
           for (int kb = jb; kb < 3; ++kb) {
-            const double* p = ws.W + (8 * jb + r) + kLd * (8 * kb + 2 * c);  // L^-1[8kb+2c..][8jb+r] = L^-T[8jb+r][8kb+2c..]
-            const double2 lf = make_double2(p[0], p[kLd]);
+            const double2 lf = tfrag(ws.W, jb, kb, r, c);  // L^-1[8kb+2c..][8jb+r] = L^-T[8jb+r][8kb+2c..]
 #pragma unroll
             for (int ib = 0; ib < 3; ++ib) dmma2(kk[ib][jb], y[ib][kb], lf);
           }
 #pragma unroll
         for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb < 3; ++jb) {
-            const double2 kv = neg2(kk[ib][jb]);
-            stg2(out + a.oK + lo24 + t24(jb, ib), kv);
-            if (out2) stg2(out2 + a.oK + lo24 + t24(jb, ib), kv);
-            finite = finite && finite2(kv);
-          }
+          for (int jb = 0; jb < 3; ++jb) stg2(out + a.oK + lo24 + t24(jb, ib), neg2(kk[ib][jb]));
       }
 
       // ---- Sv = tv - Y'Yv ----
@@ -491,10 +614,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         }
         if (c < 3) {
           const int j = 8 * c + r;
-          const double v = ws.tv[j] - pick3(z, c);
-          ws.Sv[j] = v;
-          __stcg(out + a.oSv + j, v);
-          finite = finite && isfinite(v);
+          svn = ws.tv[j] - pick3(z, c);
+          ws.Sv[j] = svn;
+          __stcg(out + a.oSv + j, svn);
         }
       }
 
@@ -513,13 +635,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 #pragma unroll
         for (int jb = 0; jb <= ib; ++jb) {
           const double2 sv = neg2(t[lt(ib, jb)]);  // S[8ib+r][8jb+2c..] = S[8jb+2c..][8ib+r]
-          finite = finite && finite2(sv);
+          t[lt(ib, jb)] = sv;
           st2(ws.W + lo26 + t26(jb, ib), sv);
           stg2(out + a.oSm + lo24 + t24(jb, ib), sv);
           if (ib != jb) {
-            double* p = ws.W + (8 * ib + r) + kLd * (8 * jb + 2 * c);
-            p[0] = sv.x;
-            p[kLd] = sv.y;
+            tput(ws.W, ib, jb, r, c, sv);
             double* gq = out + a.oSm + (8 * ib + r) + kN * (8 * jb + 2 * c);
             __stcg(gq, sv.x);
             __stcg(gq + kN, sv.y);
@@ -528,10 +648,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       __syncwarp();
     }
 
-    // ---- status ----
+    // node N of the controller := node N-1 (GaussNewtonDDP.cpp:609-618)
+    {
+      const double* src = solp + (size_t)(N - 1) * a.orec;
+      double* dst = solp + (size_t)N * a.orec;
+#pragma unroll 1
+      for (int i = lane; i < (kMat + 2 * kN) / 2; i += 32) stg2(dst + a.oK + 2 * i, ldg2(src + a.oK + 2 * i));  // K | dbias | bias are contiguous
+    }
+
+    // ---- status: a non-finite value anywhere in the sweep propagates into S, Sv, s of node 0 ----
     int bits = 0;
-    if (!__all_sync(kFull, pd)) bits |= O2C_STATUS_CHOL_NOT_PD;
-    if (!__all_sync(kFull, finite)) bits |= O2C_STATUS_NONFINITE;
+    {
+      bool finite = finite_bits(sval) && finite_bits(svn);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) finite = finite && finite2(t[i]);
+      if (!__all_sync(kFull, pd)) bits |= O2C_STATUS_CHOL_NOT_PD;
+      if (!__all_sync(kFull, finite)) bits |= O2C_STATUS_NONFINITE;
+    }
     if (!a.with_rollout) {
       if (lane == 0) a.status[prob] = bits;
       continue;
@@ -558,6 +691,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       for (int j = 0; j < kN; ++j) kreg[j] = __ldcg(Kg + li + kN * j);
     }
     double dbk = __ldcg(solp + a.odb + li);
+#pragma unroll 1
     for (int k = 0; k < N; ++k) {
       // u = alpha dbias + K x
       double u0 = a.alpha * dbk, u1 = 0.0, u2 = 0.0, u3 = 0.0;
@@ -575,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         __stcg(xo + (size_t)k * kN + lane, x);
         __stcg(uo + (size_t)k * kN + lane, u);
       }
-      xfinite = xfinite && isfinite(x);
+      xfinite = xfinite && finite_bits(x);
       // gains of the next node (node N carries the copy of node N-1): in flight while this node's state update runs
       {
         const double* Kg = solp + (size_t)(k + 1) * a.orec + a.oK;
@@ -615,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         __stcg(xo + (size_t)N * kN + lane, x);
         __stcg(uo + (size_t)N * kN + lane, u0 + u1);
       }
-      xfinite = xfinite && isfinite(x);
+      xfinite = xfinite && finite_bits(x);
     }
     if (!__all_sync(kFull, xfinite)) bits |= O2C_STATUS_NONFINITE;
     if (lane == 0) a.status[prob] = bits;
