@@ -76,6 +76,8 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+// per-thread L2 prefetch of the line holding p (CCTL.PF2): one instruction for the whole warp, every lane its own address
+__device__ __forceinline__ void l2_touch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor pipe. Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4], d = D[lane/4][2*(lane%4) + {0,1}].
@@ -122,7 +124,8 @@ struct __align__(16) WarpSmem {
   double in[kOperand];   // TMA destination: {A | B | Hv | q | r | c,pad}
   double W[kN * kLd];    // S of node k+1 (both triangles) -> Hm (lower) -> L -> L^-T (upper)
   double Sv[kN], w[kN], Gv[kN], tv[kN], Yv[kN], xb[kN], ub[kN];
-  unsigned long long full;
+  unsigned long long full;   // operand block landed (sweep)
+  unsigned long long bfull[2];  // rollout: B_k landed in slot k & 1
   unsigned long long pad_;
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp slots must keep 16-byte alignment");
@@ -300,6 +303,21 @@ __device__ __forceinline__ bool factor_hm(double* W, double2 (&h)[6], int lane, 
   return pd;
 }
 
+// L2 prefetch of exactly the cost-Hessian fragments a stage reads: all of P, and the tiles of Q and R on or above the block diagonal
+// (Q, R are symmetric; the sweep reads Q[8jb+2c..][8ib+r] for jb <= ib). Every lane touches the addresses of its own later loads.
+__device__ __forceinline__ void prefetch_hessians(const double* rec, const Args& a, int lo24) {
+#pragma unroll
+  for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+    for (int jb = 0; jb < 3; ++jb) {
+      l2_touch(rec + a.oP + lo24 + t24(jb, ib));
+      if (jb <= ib) {
+        l2_touch(rec + a.oQ + lo24 + t24(jb, ib));
+        l2_touch(rec + a.oR + lo24 + t24(jb, ib));
+      }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
@@ -312,17 +330,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
   const int li = lane < kN ? lane : kN - 1;
   const int N = a.N;
   const uint32_t opBytes = kOperand * sizeof(double);
-  // per-lane share of the Hessian prefetch: lane j < 24 owns column j of Q and R (only the tiles on or above the block diagonal are
-  // read: rows 0 .. 8 (j/8 + 1)), lane 24 owns P
-  const int pfOff = lane < kN ? kN * lane : 0;
-  const uint32_t pfBytes = lane < kN ? 64u * (uint32_t)(lane / 8 + 1) : (uint32_t)(kMat * sizeof(double));
 
   if (lane == 0) {
     mbar_init(&ws.full, 1);
+    mbar_init(&ws.bfull[0], 1);
+    mbar_init(&ws.bfull[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t phase = 0;
+  uint32_t phase = 0, bphase = 0;  // bphase: bit q = parity to wait for on bfull[q]
 
   for (int pi = blockIdx.x * kWarps + warp; pi < a.count; pi += gridDim.x * kWarps) {
     const int prob = a.begin + pi;
@@ -336,15 +352,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       mbar_expect_tx(&ws.full, opBytes);
       tma_load(ws.in, lqp + (size_t)(N - 1) * a.rec, opBytes, &ws.full);
     }
-    {
-      const double* rec = lqp + (size_t)(N - 1) * a.rec;
-      if (lane < kN) {
-        l2_prefetch(rec + a.oQ + pfOff, pfBytes);
-        l2_prefetch(rec + a.oR + pfOff, pfBytes);
-      } else if (lane == kN) {
-        l2_prefetch(rec + a.oP, pfBytes);
-      }
-    }
+    prefetch_hessians(lqp + (size_t)(N - 1) * a.rec, a, lo24);
     // terminal condition: valueFunctionTrajectory.back() = finalValueFunction (GaussNewtonDDP.cpp:526)
     {
       double* outN = solp + (size_t)N * a.orec;
@@ -516,15 +524,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       pd = factor_hm(ws.W, h, lane, li, r, c) && pd;
 
       // cost Hessians of node k-1 into L2 (needed from the first third of the next stage on)
-      if (k >= 1) {
-        const double* nrec = rec - a.rec;
-        if (lane < kN) {
-          l2_prefetch(nrec + a.oQ + pfOff, pfBytes);
-          l2_prefetch(nrec + a.oR + pfOff, pfBytes);
-        } else if (lane == kN) {
-          l2_prefetch(nrec + a.oP, pfBytes);
-        }
-      }
+      if (k >= 1) prefetch_hessians(rec - a.rec, a, lo24);
 
       // ---- Yv = L^-1 Gv, dbias = -L^-T Yv, s ----
       {
@@ -670,30 +670,37 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       continue;
     }
 
-    // ---- fused forward rollout of the LQ model. {A|B|Hv} of node k by TMA into the operand slot, K_k straight from L2 ----
+    // ---- fused forward rollout of the LQ model: du_k = K_k dx_k + alpha dbias_k, dx_{k+1} = A_k dx_k + B_k du_k + Hv_k. One row per lane.
+    // K_k and A_k live in registers and are re-loaded for node k+1 right after their last use (one stage of load latency hidden behind
+    // the other half of the stage); B_k comes through a two-slot TMA ring over the (now free) operand slot, two stages ahead. ----
+    const uint32_t matBytes = kMat * sizeof(double);
     if (lane == 0) {
       fence_proxy_async();
-      mbar_expect_tx(&ws.full, opBytes);
-      tma_load(ws.in, lqp, opBytes, &ws.full);
-      for (int k = 1; k < 4 && k < N; ++k) l2_prefetch(lqp + (size_t)k * a.rec, opBytes);
-      for (int k = 0; k < 4 && k < N; ++k) l2_prefetch(solp + (size_t)k * a.orec + a.oK, (kMat + kN) * sizeof(double));
+      for (int k = 0; k < 2 && k < N; ++k) {
+        mbar_expect_tx(&ws.bfull[k], matBytes);
+        tma_load(ws.in + kMat * k, lqp + (size_t)k * a.rec + kMat, matBytes, &ws.bfull[k]);
+      }
+      for (int k = 1; k < 6 && k < N; ++k) l2_prefetch(lqp + (size_t)k * a.rec, opBytes);
+      for (int k = 1; k < 6 && k < N; ++k) l2_prefetch(solp + (size_t)k * a.orec + a.oK, (kMat + kN) * sizeof(double));
     }
     double* xo = a.xs + (size_t)prob * (N + 1) * kN;
     double* uo = a.us + (size_t)prob * (N + 1) * kN;
     double x = a.x0[(size_t)prob * kN + li];
     if (lane < kN) ws.xb[lane] = x;
-    __syncwarp();
     bool xfinite = true;
-    double kreg[kN];
-    {
-      const double* Kg = solp + a.oK;
+    double kreg[kN], areg[kN];
 #pragma unroll
-      for (int j = 0; j < kN; ++j) kreg[j] = __ldcg(Kg + li + kN * j);
+    for (int j = 0; j < kN; ++j) {
+      kreg[j] = __ldcg(solp + a.oK + li + kN * j);
+      areg[j] = __ldcg(lqp + li + kN * j);
     }
-    double dbk = __ldcg(solp + a.odb + li);
+    double dbk = __ldcg(solp + a.odb + li), hvk = __ldcg(lqp + 2 * kMat + li);
+    __syncwarp();
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
-      // u = alpha dbias + K x
+      const double* nsol = solp + (size_t)(k + 1) * a.orec;             // node N carries the copy of node N-1
+      const double* nrec = lqp + (size_t)(k + 1 < N ? k + 1 : k) * a.rec;  // (the last reload is a harmless repeat)
+      // u = alpha dbias + K x ; the gains of node k+1 take the registers over as they are consumed
       double u0 = a.alpha * dbk, u1 = 0.0, u2 = 0.0, u3 = 0.0;
 #pragma unroll
       for (int j = 0; j < kN; j += 4) {
@@ -703,6 +710,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         u2 = fma(kreg[j + 2], x23.x, u2);
         u3 = fma(kreg[j + 3], x23.y, u3);
       }
+#pragma unroll
+      for (int j = 0; j < kN; ++j) kreg[j] = __ldcg(nsol + a.oK + li + kN * j);
+      dbk = __ldcg(nsol + a.odb + li);
       const double u = (u0 + u1) + (u2 + u3);
       if (lane < kN) {
         ws.ub[lane] = u;
@@ -710,28 +720,35 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         __stcg(uo + (size_t)k * kN + lane, u);
       }
       xfinite = xfinite && finite_bits(x);
-      // gains of the next node (node N carries the copy of node N-1): in flight while this node's state update runs
-      {
-        const double* Kg = solp + (size_t)(k + 1) * a.orec + a.oK;
+      // x+ = Hv + A x + B u
+      double a0 = hvk, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-        for (int j = 0; j < kN; ++j) kreg[j] = __ldcg(Kg + li + kN * j);
-        dbk = __ldcg(solp + (size_t)(k + 1) * a.orec + a.odb + li);
+      for (int j = 0; j < kN; j += 4) {
+        const double2 x01 = ld2(ws.xb + j), x23 = ld2(ws.xb + j + 2);
+        a0 = fma(areg[j], x01.x, a0);
+        a1 = fma(areg[j + 1], x01.y, a1);
+        a2 = fma(areg[j + 2], x23.x, a2);
+        a3 = fma(areg[j + 3], x23.y, a3);
       }
-      mbar_wait(&ws.full, phase);
-      phase ^= 1u;
-      __syncwarp();
-      const double xn = ws.in[2 * kMat + li] + matvec_rows(ws.in, ws.xb, li) + matvec_rows(ws.in + kMat, ws.ub, li);
-      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kN; ++j) areg[j] = __ldcg(nrec + li + kN * j);
+      hvk = __ldcg(nrec + 2 * kMat + li);
+      const int q = k & 1;
+      mbar_wait(&ws.bfull[q], (bphase >> q) & 1u);
+      bphase ^= 1u << q;
+      __syncwarp();  // u of every lane is in shared memory
+      const double xn = ((a0 + a1) + (a2 + a3)) + matvec_rows(ws.in + kMat * q, ws.ub, li);
+      __syncwarp();  // every lane is done with x, u and slot q
       x = xn;
       if (lane < kN) ws.xb[lane] = x;
       if (lane == 0) {
-        if (k + 1 < N) {
-          mbar_expect_tx(&ws.full, opBytes);
-          tma_load(ws.in, lqp + (size_t)(k + 1) * a.rec, opBytes, &ws.full);
+        if (k + 2 < N) {
+          mbar_expect_tx(&ws.bfull[q], matBytes);
+          tma_load(ws.in + kMat * q, lqp + (size_t)(k + 2) * a.rec + kMat, matBytes, &ws.bfull[q]);
         }
-        if (k + 4 < N) {
-          l2_prefetch(lqp + (size_t)(k + 4) * a.rec, opBytes);
-          l2_prefetch(solp + (size_t)(k + 4) * a.orec + a.oK, (kMat + kN) * sizeof(double));
+        if (k + 6 < N) {
+          l2_prefetch(lqp + (size_t)(k + 6) * a.rec, opBytes);
+          l2_prefetch(solp + (size_t)(k + 6) * a.orec + a.oK, (kMat + kN) * sizeof(double));
         }
       }
       __syncwarp();
