@@ -29,6 +29,8 @@
 //   to one rounding of M_ii + eps (<= 1e-16 |M_ii|).
 // Rollout (fused, same warp): du_k = K_k dx_k + alpha dbias_k ; dx_{k+1} = A_k dx_k + B_k du_k + Hv_k
 //                                            DDP_HelperFunctions.cpp:125-138, 296-304; LinearController.cpp:79-87
+#include <cstdlib>
+
 #include "o2c_common.cuh"
 
 namespace o2c {
@@ -123,7 +125,7 @@ __device__ __forceinline__ constexpr int lt(int ib, int jb) { return ib * (ib + 
 struct __align__(16) WarpSmem {
   double in[kOperand];   // TMA destination: {A | B | Hv | q | r | c,pad}
   double W[kN * kLd];    // S of node k+1 (both triangles) -> Hm (lower) -> L -> L^-T (upper)
-  double Sv[kN], w[kN], Gv[kN], tv[kN], Yv[kN], xb[kN], ub[kN];
+  double Sv[kN], Gv[kN], Yv[kN], xb[kN], ub[kN];
   unsigned long long full;   // operand block landed (sweep)
   unsigned long long bfull[2];  // rollout: B_k landed in slot k & 1
   unsigned long long pad_;
@@ -236,9 +238,8 @@ __device__ __forceinline__ bool factor_hm(double* W, double2 (&h)[6], int lane, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const double d = __shfl_sync(kFull, g[j], 8 * b + j);
-      const bool ok = d > 0.0;
-      pd = pd && ok;
-      const double rs = ok ? rsqrt_pivot(d) : __longlong_as_double(0x7ff8000000000000LL);  // NaNs propagate like the reference's LLT
+      pd = pd && (__double2hiint(d) > 0);  // integer pipe, off the dependency chain; a non-positive pivot makes rs NaN / Inf,
+      const double rs = rsqrt_pivot(d);    // which then propagates like the NaNs of the reference's LLT
       const double l = g[j] * rs;
       if (owner) col[lane + kLd * j] = (lane == 8 * b + j) ? rs : l;  // 1/L_jj on the diagonal
       __syncwarp();
@@ -395,32 +396,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 #pragma unroll
         for (int jb = 0; jb <= ib; ++jb) h[lt(ib, jb)] = ldg2(rec + a.oR + lo24 + t24(jb, ib));  // R[8ib+r][8jb+2c..] = R[8jb+2c..][8ib+r]
 
-      // ---- vectors: w = Sv + S Hv, Gv = r + B'w, tv = q + A'w ----
-      double spart = 0.0;
-      {
-        double z[3];
-        matvec_cols<kLd, false>(ws.W, Hv, r, c, z);  // S symmetric: S Hv = S' Hv
-        if (c < 3) {
-          const int j = 8 * c + r;
-          const double shv = pick3(z, c);
-          const double wv = ws.Sv[j] + shv;
-          ws.w[j] = wv;
-          spart = Hv[j] * (wv - 0.5 * shv);
-        }
-        __syncwarp();
-        double zB[3], zA[3];
-        matvec_cols<kN, false>(B, ws.w, r, c, zB);
-        matvec_cols<kN, false>(A, ws.w, r, c, zA);
-        if (c < 3) {
-          const int j = 8 * c + r;
-          ws.Gv[j] = rv[j] + pick3(zB, c);
-          ws.tv[j] = qv[j] + pick3(zA, c);
-        }
-      }
-      const double cval = ws.in[2 * kMat + 3 * kN];
-
-      // ---- ZA = A'S (= op fragments of SA), ZB = B'S (= op fragments of SB) ----
+      // ---- ZA = A'S (= op fragments of SA), ZB = B'S (= op fragments of SB); the matrix-vector terms ride on the same fragments:
+      //      S Hv, A'Sv, B'Sv here, and (SA)'Hv = ZA Hv, (SB)'Hv = ZB Hv from the accumulators, so that
+      //      Gv = r + B'(Sv + S Hv), tv = q + A'(Sv + S Hv) never need w = Sv + S Hv in shared memory ----
       double2 zA[3][3], zB[3][3];
+      double2 hvf[3];
+      double pSH[3] = {0.0, 0.0, 0.0}, pA[3] = {0.0, 0.0, 0.0}, pB[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -428,11 +409,21 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) {
         double2 s[3];
+        hvf[kb] = ld2(Hv + 8 * kb + 2 * c);
+        const double2 svf = ld2(ws.Sv + 8 * kb + 2 * c);
 #pragma unroll
-        for (int jb = 0; jb < 3; ++jb) s[jb] = ld2(ws.W + lo26 + t26(kb, jb));
+        for (int jb = 0; jb < 3; ++jb) {
+          s[jb] = ld2(ws.W + lo26 + t26(kb, jb));
+          pSH[jb] = fma(s[jb].x, hvf[kb].x, pSH[jb]);
+          pSH[jb] = fma(s[jb].y, hvf[kb].y, pSH[jb]);
+        }
 #pragma unroll
         for (int ib = 0; ib < 3; ++ib) {
           const double2 af = ld2(A + lo24 + t24(kb, ib)), bf = ld2(B + lo24 + t24(kb, ib));
+          pA[ib] = fma(af.x, svf.x, pA[ib]);
+          pA[ib] = fma(af.y, svf.y, pA[ib]);
+          pB[ib] = fma(bf.x, svf.x, pB[ib]);
+          pB[ib] = fma(bf.y, svf.y, pB[ib]);
 #pragma unroll
           for (int jb = 0; jb < 3; ++jb) {
             dmma2(zA[ib][jb], af, s[jb]);
@@ -440,6 +431,31 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
           }
         }
       }
+      double spart = 0.0, tvj = 0.0;
+      {
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            pA[ib] = fma(zA[ib][jb].x, hvf[jb].x, pA[ib]);
+            pA[ib] = fma(zA[ib][jb].y, hvf[jb].y, pA[ib]);
+            pB[ib] = fma(zB[ib][jb].x, hvf[jb].x, pB[ib]);
+            pB[ib] = fma(zB[ib][jb].y, hvf[jb].y, pB[ib]);
+          }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          pSH[i] = quad_sum(pSH[i]);
+          pA[i] = quad_sum(pA[i]);
+          pB[i] = quad_sum(pB[i]);
+        }
+        if (c < 3) {
+          const int j = 8 * c + r;
+          spart = Hv[j] * (ws.Sv[j] + 0.5 * pick3(pSH, c));  // Hv.w - 1/2 Hv.(S Hv)
+          ws.Gv[j] = rv[j] + pick3(pB, c);
+          tvj = qv[j] + pick3(pA, c);
+        }
+      }
+      const double cval = ws.in[2 * kMat + 3 * kN];
       __syncwarp();  // S (scratch) is dead from here on
 
       // ---- Hm = R + SB'B (lower tiles, stay in registers for the blocked factorisation) ----
@@ -614,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         }
         if (c < 3) {
           const int j = 8 * c + r;
-          svn = ws.tv[j] - pick3(z, c);
+          svn = tvj - pick3(z, c);
           ws.Sv[j] = svn;
           __stcg(out + a.oSv + j, svn);
         }
@@ -827,7 +843,12 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   a.alpha = alpha;
   (void)batch;
   const int ctas_needed = (count + kWarps - 1) / kWarps;
-  const int grid = ctas_needed < num_sms * kCtasPerSm ? ctas_needed : num_sms * kCtasPerSm;
+  int ctas_per_sm = kCtasPerSm;
+  if (const char* e = getenv("O2C_WPP_CTAS_PER_SM")) {  // profiling knob: fewer resident problems per SM
+    const int v = atoi(e);
+    if (v >= 1 && v < kCtasPerSm) ctas_per_sm = v;
+  }
+  const int grid = ctas_needed < num_sms * ctas_per_sm ? ctas_needed : num_sms * ctas_per_sm;
   ilqr_wpp_kernel<<<grid, kThreads, smem, stream>>>(a);
   if (launches) *launches = 1;
   return cudaGetLastError();
