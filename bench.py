@@ -188,8 +188,12 @@ def main():
     batch = args.batch or default_batch
     st = o2.Settings(algorithm=alg, hessianCorrectionMultiple=eps, timeStep=DT)
     solver = o2.BatchedLqSolver(st, n, m, N_STAGES, batch, nc_max=nc, device=local_rank)
-    # shard by problem index: rank r owns global problems [r*batch, (r+1)*batch)
-    solver.generate_synthetic(seed=1, first_problem_index=rank * batch, dt=DT)
+    # shard by problem index (weak scaling: the global batch is world * batch): rank r owns the contiguous block shard_bounds gives it
+    from ocs2_b200.sharding import shard_bounds
+
+    first, count = shard_bounds(world * batch, world, rank)
+    assert count == batch
+    solver.generate_synthetic(seed=1, first_problem_index=first, dt=DT)
     solver.sync()
     stream = torch.cuda.ExternalStream(solver.compute_stream, device=torch.device("cuda", local_rank))
 

@@ -10,8 +10,8 @@
 //   dQ, dGm, dGv                                  computeRiccatiModification                 LineSearchStrategy.cpp:294-312, LevenbergMarquardtStrategy.cpp:230-240
 //   one-step map / flow map                       DiscreteTimeRiccatiEquations.cpp:65-154, ContinuousTimeRiccatiEquations.cpp:170-292
 //   K, bias, dbias                                ILQR/SLQ::calculateControllerWorker         ILQR.cpp:162-181, SLQ.cpp:127-169
-// The shape-specialised DMMA/TMA kernel for the unconstrained LINE_SEARCH/reduced/DIAGONAL_SHIFT ILQR sweep lives in
-// riccati_dmma.cu; o2c_backward dispatches to it when the configuration matches.
+// The shape-specialised warp-per-problem DMMA/TMA kernel for the unconstrained LINE_SEARCH/reduced/DIAGONAL_SHIFT ILQR sweep of the
+// legged shape lives in riccati_wpp.cu; o2c_backward / o2c_solve dispatch to it when the configuration matches.
 #include <cfloat>
 
 #include "o2c_common.cuh"

@@ -15,8 +15,11 @@
 //     register file:  ZA = A'S (= (SA)'), ZB = B'S, G' = P' + SA'B, Hm = R + SB'B, T = Q + eps I + SA'A, Y' = G' L^-T,
 //     S = T - Y'Y, K' = -Y' L^-1.
 //   * Only Hm takes a detour through a 5 KB shared scratch (leading dimension 26: conflict-free 8-byte transposed access): it is
-//     factorised there one row per lane (Cholesky + triangular inverse by the same right-looking recurrence), and the value function S
-//     is parked in the same scratch between stages so that it can be re-read in operand layout.
+//     factorised in 8x8 blocks (block columns one row per lane, trailing updates and the off-diagonal blocks of L^-1 on the tensor
+//     pipe, see factor_hm), and the value function S is parked in the same scratch between stages so that it can be re-read in
+//     operand layout.
+//   * The matrix-vector terms ride on the fragments of the contractions (S Hv, A'Sv, B'Sv in the ZA/ZB loop; (SA)'Hv and (SB)'Hv
+//     from the accumulators), so w = Sv + S Hv never exists in memory.
 //
 // Math (unconstrained, LINE_SEARCH, reduced Riccati form, DIAGONAL_SHIFT; same quantities as the reference, re-associated):
 //   Hm = R + B'(S B)                         ILQR::computeHamiltonianHessian              ocs2_ddp/src/ILQR.cpp:217-222
