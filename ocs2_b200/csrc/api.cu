@@ -59,6 +59,7 @@ struct o2c_handle {
   std::vector<double> time, ro_times;
   bool time_set = false;
   bool use_fast = false;
+  bool nc_ragged = false;  // a caller supplied per-node constraint counts (otherwise every node has nc_max: the kernels skip the lookup)
   int64_t launches = 0;
   int stage_chunk = 0;
 
@@ -68,7 +69,7 @@ struct o2c_handle {
     b.term = d_term;
     b.x_nom = d_xnom;
     b.u_nom = d_unom;
-    b.nc = d_nc;
+    b.nc = nc_ragged ? d_nc : nullptr;
     b.x0 = d_x0;
     b.time = d_time;
     b.sol = d_sol;
@@ -385,6 +386,7 @@ o2c_error upload_chunk(o2c_handle* h, Lane& lane, const o2c_lq_view& v, int begi
     O2C_CUDA(cudaMemcpyAsync(nc_stage, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, lane.stream));
     O2C_CUDA(cudaStreamSynchronize(lane.stream));
     d.nc = nc_stage;
+    h->nc_ragged = true;
     d.nc_ps = nodes;
     d.nc_ns = 1;
   }
@@ -662,6 +664,7 @@ o2c_error o2c_device_lq_view(o2c_handle* h, o2c_lq_view* v) {
     v->D = rec(L.oD);
     v->e = rec(L.oe);
     v->nc = h->d_nc;
+    h->nc_ragged = true;  // a device-side producer may write per-node counts through this view
     v->nc_problem_stride = L.nodes;
     v->nc_node_stride = 1;
   }
@@ -773,6 +776,7 @@ o2c_error o2c_import_device(o2c_handle* h, const o2c_lq_view* v, int32_t begin, 
   d.u_nom = cv(v->u_nom);
   d.x0 = cv(v->x0);
   d.nc = v->nc;
+  if (v->nc && h->L.ncmax > 0) h->nc_ragged = true;
   d.nc_ps = v->nc_problem_stride;
   d.nc_ns = v->nc_node_stride;
   O2C_CUDA(launch_pack(h->L, d, h->d_lq, h->d_term, h->d_xnom, h->d_unom, h->d_nc, h->d_x0, begin, count, h->lanes[0].stream));
@@ -834,8 +838,8 @@ o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {
 
 const char* o2c_kernel_variant(const o2c_handle* h) {
   if (!h) return "";
-  if (h->st.algorithm == O2C_ALG_SLQ) return "slq_generic_kernel";
-  return h->use_fast ? "ilqr_wpp_kernel" : "ilqr_generic_kernel";
+  if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast) return "ilqr_wpp_kernel";
+  return generic_variant_name(h->L, h->st);
 }
 
 o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solution_view* sol, double alpha, int32_t count, int32_t chunk) {

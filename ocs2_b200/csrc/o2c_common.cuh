@@ -118,6 +118,7 @@ struct RolloutStep {
 // ---------------------------------------------------------------------------------------------------------------------
 cudaError_t launch_ilqr_generic(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count,
                                 cudaStream_t stream);
+const char* generic_variant_name(const Layout& L, const SolverSettings& st);
 cudaError_t launch_slq_generic(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps,
                                int begin, int count, cudaStream_t stream);
 cudaError_t launch_rollout_discrete(const Layout& L, const DeviceBuffers& buf, const double* alphas_dev, int n_alpha, int batch,

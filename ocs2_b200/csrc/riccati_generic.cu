@@ -57,7 +57,7 @@ __host__ __device__ inline int work_doubles(const Layout& L, bool full, bool lm,
   return (t + 1) & ~1;
 }
 
-__device__ inline void carve(Work& W, double* base, const Layout& L, bool full, bool lm, bool gersh) {
+__device__ __forceinline__ void carve(Work& W, double* base, const Layout& L, bool full, bool lm, bool gersh) {
   const int n = L.n, m = L.m, nc = L.ncmax;
   const int mx = n > m ? n : m;
   double* p = base;
@@ -117,7 +117,7 @@ __device__ inline void carve(Work& W, double* base, const Layout& L, bool full, 
 }
 
 // in-place Cholesky (lower) of the m x m matrix H (ld m). Returns false if a pivot is not positive (NaNs propagate like the reference).
-__device__ bool warp_cholesky(int m, double* H) {
+__device__ __forceinline__ bool warp_cholesky(int m, double* H) {
   const int lane = lane_id();
   bool ok = true;
   for (int j = 0; j < m; ++j) {
@@ -142,7 +142,7 @@ __device__ bool warp_cholesky(int m, double* H) {
 }
 
 // X = U^-1 for an upper-triangular U given by U(i,k) = Ub[i*si + k*sk]; X is dim x dim, ld dim, strictly lower part zeroed.
-__device__ void warp_upper_inverse(int dim, const double* Ub, int si, int sk, double* X) {
+__device__ __forceinline__ void warp_upper_inverse(int dim, const double* Ub, int si, int sk, double* X) {
   for (int j = lane_id(); j < dim; j += 32) {
     for (int i = j; i >= 0; --i) {
       double v = (i == j) ? 1.0 : 0.0;
@@ -155,7 +155,7 @@ __device__ void warp_upper_inverse(int dim, const double* Ub, int si, int sk, do
 }
 
 // Householder QR of Mx (rows x cols, ld rows) restating Eigen::HouseholderQR; Q (rows x rows) formed explicitly.
-__device__ void warp_householder_qr(int rows, int cols, double* Mx, double* tau, double* Qm) {
+__device__ __forceinline__ void warp_householder_qr(int rows, int cols, double* Mx, double* tau, double* Qm) {
   const int lane = lane_id();
   for (int j = 0; j < cols; ++j) {
     double part = 0.0;
@@ -208,7 +208,7 @@ __device__ void warp_householder_qr(int rows, int cols, double* Mx, double* tau,
 // On return: A~ = W.A, Hv~ = W.Hv, Q~ = W.Q, q~ = W.q, c~ = W.ct, B~ = W.Bt, P~ = W.Pt (ld p), R~ = W.Rt (ld p, full form only),
 // r~ = W.rt, Pu = W.Pu, Px = W.Px / u0 = W.u0 (nc > 0), dQ diag in W.dqd (DIAGONAL_SHIFT) or full in W.dQ (GERSHGORIN),
 // dGm/dGv (LM).
-__device__ int project_stage(Work& W, const Layout& L, const SolverSettings& st, int nc, const double* Snext) {
+__device__ __forceinline__ int project_stage(Work& W, const Layout& L, const SolverSettings& st, int nc, const double* Snext) {
   const int n = L.n, m = L.m, ldc = L.ncmax > 0 ? L.ncmax : 1;
   const int lane = lane_id();
   const int p = m - nc;
@@ -327,7 +327,7 @@ __device__ __forceinline__ double dq_at(const Work& W, const SolverSettings& st,
   return W.dQ[i + j * n];
 }
 
-__device__ void load_record(const Layout& L, const double* __restrict__ g, double* s) {
+__device__ __forceinline__ void load_record(const Layout& L, const double* __restrict__ g, double* s) {
   const double2* g2 = reinterpret_cast<const double2*>(g);
   double2* s2 = reinterpret_cast<double2*>(s);
   for (int i = lane_id(); i < L.rec / 2; i += 32) s2[i] = __ldg(g2 + i);
@@ -335,7 +335,7 @@ __device__ void load_record(const Layout& L, const double* __restrict__ g, doubl
 }
 
 // un-projection of the controller and write of one output node: K = Px + Pu K~ ; dbias = u0 + Pu L~ ; bias = u_nom - K x_nom
-__device__ bool emit_controller(const Work& W, const Layout& L, int nc, const double* Km, const double* Lv, const double* xnom,
+__device__ __forceinline__ bool emit_controller(const Work& W, const Layout& L, int nc, const double* Km, const double* Lv, const double* xnom,
                                 const double* unom, double* out) {
   const int n = L.n, m = L.m, p = W.p, lane = lane_id();
   bool finite = true;
@@ -362,15 +362,34 @@ __device__ bool emit_controller(const Work& W, const Layout& L, int nc, const do
   return __all_sync(0xffffffffu, finite);
 }
 
-__device__ void copy_last_controller(const Layout& L, double* solp) {
+__device__ __forceinline__ void copy_last_controller(const Layout& L, double* solp) {
   // GaussNewtonDDP::calculateController, GaussNewtonDDP.cpp:609-618
   const double* src = solp + (size_t)(L.N - 1) * L.orec;
   double* dst = solp + (size_t)L.N * L.orec;
   for (int i = lane_id(); i < L.oSm; i += 32) dst[i] = src[i];  // K, dbias, bias precede Sm in the record
 }
 
+// Shape specialisation: CN > 0 fixes (n, m, ncmax) at compile time (loops unroll, index arithmetic folds); STD fixes the settings to
+// the benchmark configuration (reduced form, LINE_SEARCH, DIAGONAL_SHIFT) so the other variants' branches disappear. <0,0,0,false>
+// is the fully run-time version that serves every other shape / setting.
+template <int CN, int CM, int CNC, bool STD>
+__device__ __forceinline__ void specialise(Layout& L, SolverSettings& st) {
+  if (CN > 0) {
+    L.n = CN;
+    L.m = CM;
+    L.ncmax = CNC;
+  }
+  if (STD) {
+    st.reduced = 1;
+    st.strategy = O2C_STRATEGY_LINE_SEARCH;
+    st.hc = O2C_HC_DIAGONAL_SHIFT;
+  }
+}
+
+template <int CN, int CM, int CNC, bool STD>
 __global__ void __launch_bounds__(128) ilqr_generic_kernel(Layout L, SolverSettings st, DeviceBuffers buf, int begin, int count,
                                                            int warp_doubles) {
+  specialise<CN, CM, CNC, STD>(L, st);
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int wpb = blockDim.x >> 5;
@@ -513,7 +532,7 @@ __host__ __device__ inline int projset_doubles(const Layout& L, bool full, bool 
   return (t + 1) & ~1;
 }
 
-__device__ inline void carve_proj(ProjSet& S, double* base, const Layout& L, bool full, bool lm, bool gersh, bool with_unproject) {
+__device__ __forceinline__ void carve_proj(ProjSet& S, double* base, const Layout& L, bool full, bool lm, bool gersh, bool with_unproject) {
   const int n = L.n, m = L.m;
   double* p = base;
   auto take = [&](int cnt) {
@@ -541,7 +560,7 @@ __device__ inline void carve_proj(ProjSet& S, double* base, const Layout& L, boo
   }
 }
 
-__device__ void store_proj(const Work& W, const Layout& L, const SolverSettings& st, int nc, ProjSet& S) {
+__device__ __forceinline__ void store_proj(const Work& W, const Layout& L, const SolverSettings& st, int nc, ProjSet& S) {
   const int n = L.n, m = L.m, p = W.p;
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
   const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
@@ -575,7 +594,7 @@ __device__ void store_proj(const Work& W, const Layout& L, const SolverSettings&
 
 // alpha * lhs + (1 - alpha) * rhs on every projected field (LinearInterpolation::interpolate). If the projected input dimension
 // differs between the two nodes the reference takes the nearer node for input-sized fields.
-__device__ void lerp_proj(const Layout& L, bool full, bool lm, bool gersh, double a, const ProjSet& Lh, const ProjSet& Rh, ProjSet& O) {
+__device__ __forceinline__ void lerp_proj(const Layout& L, bool full, bool lm, bool gersh, double a, const ProjSet& Lh, const ProjSet& Rh, ProjSet& O) {
   const int n = L.n, lane = lane_id();
   const double b = 1.0 - a;
   const bool same = (Lh.p == Rh.p);
@@ -628,7 +647,7 @@ struct FlowWork {
 };
 
 // ContinuousTimeRiccatiEquations::computeFlowMapSLQ
-__device__ void flow_map(const Layout& L, const SolverSettings& st, const ProjSet& P, const FlowWork& F, const double* y, double* dy) {
+__device__ __forceinline__ void flow_map(const Layout& L, const SolverSettings& st, const ProjSet& P, const FlowWork& F, const double* y, double* dy) {
   const int n = L.n, p = P.p, lane = lane_id();
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
   const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
@@ -689,8 +708,10 @@ __device__ void flow_map(const Layout& L, const SolverSettings& st, const ProjSe
   __syncwarp();
 }
 
+template <int CN, int CM, int CNC, bool STD>
 __global__ void __launch_bounds__(128) slq_generic_kernel(Layout L, SolverSettings st, DeviceBuffers buf, const SlqStep* __restrict__ steps,
                                                           int nsteps, int begin, int count, int warp_doubles) {
+  specialise<CN, CM, CNC, STD>(L, st);
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int wpb = blockDim.x >> 5;
@@ -862,19 +883,56 @@ cudaError_t configure(Kernel kernel, int warp_doubles, int& wpb, size_t& smem) {
 
 }  // namespace
 
+namespace {
+bool std_settings(const SolverSettings& st) {
+  return st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT;
+}
+template <int CN, int CM, int CNC, bool STD>
+cudaError_t run_ilqr(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count, int warp_doubles,
+                     cudaStream_t stream) {
+  int wpb;
+  size_t smem;
+  cudaError_t e = configure(ilqr_generic_kernel<CN, CM, CNC, STD>, warp_doubles, wpb, smem);
+  if (e != cudaSuccess) return e;
+  const int grid = (count + wpb - 1) / wpb;
+  ilqr_generic_kernel<CN, CM, CNC, STD><<<grid, wpb * 32, smem, stream>>>(L, st, buf, begin, count, warp_doubles);
+  return cudaGetLastError();
+}
+template <int CN, int CM, int CNC, bool STD>
+cudaError_t run_slq(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin,
+                    int count, int warp_doubles, cudaStream_t stream) {
+  int wpb;
+  size_t smem;
+  cudaError_t e = configure(slq_generic_kernel<CN, CM, CNC, STD>, warp_doubles, wpb, smem);
+  if (e != cudaSuccess) return e;
+  const int grid = (count + wpb - 1) / wpb;
+  slq_generic_kernel<CN, CM, CNC, STD><<<grid, wpb * 32, smem, stream>>>(L, st, buf, steps, nsteps, begin, count, warp_doubles);
+  return cudaGetLastError();
+}
+}  // namespace
+
+// which compiled variant serves this configuration (diagnostics: o2c_kernel_variant)
+const char* generic_variant_name(const Layout& L, const SolverSettings& st) {
+  const bool s = std_settings(st);
+  if (st.algorithm == O2C_ALG_SLQ) return (s && L.n == 12 && L.m == 4 && L.ncmax == 0) ? "slq_generic_kernel<12,4,0>" : "slq_generic_kernel";
+  if (s && L.n == 10 && L.m == 3 && L.ncmax == 0) return "ilqr_generic_kernel<10,3,0>";
+  if (s && L.n == 9 && L.m == 9 && L.ncmax == 3) return "ilqr_generic_kernel<9,9,3>";
+  if (s && L.n == 4 && L.m == 1 && L.ncmax == 0) return "ilqr_generic_kernel<4,1,0>";
+  return "ilqr_generic_kernel";
+}
+
 cudaError_t launch_ilqr_generic(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count,
                                 cudaStream_t stream) {
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
   const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
   const int wd = work_doubles(L, full, lm, gersh) + 2 * L.n * L.n + 2 * L.n;
   const int warp_doubles = (wd + 1) & ~1;
-  int wpb;
-  size_t smem;
-  cudaError_t e = configure(ilqr_generic_kernel, warp_doubles, wpb, smem);
-  if (e != cudaSuccess) return e;
-  const int grid = (count + wpb - 1) / wpb;
-  ilqr_generic_kernel<<<grid, wpb * 32, smem, stream>>>(L, st, buf, begin, count, warp_doubles);
-  return cudaGetLastError();
+  if (std_settings(st)) {  // the named BASELINE shapes get compile-time dimensions
+    if (L.n == 10 && L.m == 3 && L.ncmax == 0) return run_ilqr<10, 3, 0, true>(L, st, buf, begin, count, warp_doubles, stream);
+    if (L.n == 9 && L.m == 9 && L.ncmax == 3) return run_ilqr<9, 9, 3, true>(L, st, buf, begin, count, warp_doubles, stream);
+    if (L.n == 4 && L.m == 1 && L.ncmax == 0) return run_ilqr<4, 1, 0, true>(L, st, buf, begin, count, warp_doubles, stream);
+  }
+  return run_ilqr<0, 0, 0, false>(L, st, buf, begin, count, warp_doubles, stream);
 }
 
 cudaError_t launch_slq_generic(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps,
@@ -882,13 +940,9 @@ cudaError_t launch_slq_generic(const Layout& L, const SolverSettings& st, const 
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
   const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
   const int warp_doubles = slq_warp_doubles(L, full, lm, gersh);
-  int wpb;
-  size_t smem;
-  cudaError_t e = configure(slq_generic_kernel, warp_doubles, wpb, smem);
-  if (e != cudaSuccess) return e;
-  const int grid = (count + wpb - 1) / wpb;
-  slq_generic_kernel<<<grid, wpb * 32, smem, stream>>>(L, st, buf, steps, nsteps, begin, count, warp_doubles);
-  return cudaGetLastError();
+  if (std_settings(st) && L.n == 12 && L.m == 4 && L.ncmax == 0)
+    return run_slq<12, 4, 0, true>(L, st, buf, steps, nsteps, begin, count, warp_doubles, stream);
+  return run_slq<0, 0, 0, false>(L, st, buf, steps, nsteps, begin, count, warp_doubles, stream);
 }
 
 }  // namespace o2c
