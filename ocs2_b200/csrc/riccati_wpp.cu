@@ -218,47 +218,60 @@ __device__ __forceinline__ double matvec_rows(const double* M, const double* v, 
 //     L^-1 follow from three small DMMA chains:  Li10 = -Li11 (L10 Li00),  Li21 = -Li22 (L21 Li11),
 //     Li20 = -Li22 (L20 Li00 + L21 Li10).
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool factor_hm(double* W, double2 (&h)[6], int lane, int li, int r, int c) {
+__device__ __forceinline__ bool factor_hm(double* W, int lane, int li, int r, int c) {
   bool pd = true;
 #pragma unroll 1
   for (int b = 0; b < 3; ++b) {
-    if (b == 0) {
-      tput(W, 0, 0, r, c, h[lt(0, 0)]);
-      tput(W, 1, 0, r, c, h[lt(1, 0)]);
-      tput(W, 2, 0, r, c, h[lt(2, 0)]);
-    } else if (b == 1) {
-      tput(W, 1, 1, r, c, h[lt(1, 1)]);
-      tput(W, 2, 1, r, c, h[lt(2, 1)]);
-    } else {
-      tput(W, 2, 2, r, c, h[lt(2, 2)]);
-    }
-    __syncwarp();
     double* col = W + kLd * 8 * b;  // column 8b of the scratch
     const bool owner = lane >= 8 * b && lane < kN;
     double g[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) g[k] = col[li + kLd * k];
+    // pivots in pairs (j, j+1): the second pivot of a pair is d1 = c - b^2/d0 with [d0 b; b c] the leading 2x2 block, so
+    // 1/sqrt(d1) = rsqrt(d0 c - b^2) sqrt(d0) does not wait for rsqrt(d0): two independent MUFU chains per round trip through
+    // shared memory instead of one (same conditioning: both forms subtract b^2 (/d0) from (d0) c).
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double d = __shfl_sync(kFull, g[j], 8 * b + j);
-      pd = pd && (__double2hiint(d) > 0);  // integer pipe, off the dependency chain; a non-positive pivot makes rs NaN / Inf,
-      const double rs = rsqrt_pivot(d);    // which then propagates like the NaNs of the reference's LLT
-      const double l = g[j] * rs;
-      if (owner) col[lane + kLd * j] = (lane == 8 * b + j) ? rs : l;  // 1/L_jj on the diagonal
+    for (int j = 0; j < 8; j += 2) {
+      const double d0 = __shfl_sync(kFull, g[j], 8 * b + j);
+      const double bq = __shfl_sync(kFull, g[j], 8 * b + j + 1);
+      const double cq = __shfl_sync(kFull, g[j + 1], 8 * b + j + 1);
+      const double det = fma(d0, cq, -bq * bq);
+      pd = pd && (__double2hiint(d0) > 0) && (__double2hiint(det) > 0);  // integer pipe, off the dependency chain; a non-positive
+      const double rs0 = rsqrt_pivot(d0);                                // pivot makes rs NaN / Inf, which then propagates like the
+      const double rdet = rsqrt_pivot(det);                              // NaNs of the reference's LLT
+      const double rs1 = rdet * (d0 * rs0);
+      const double l0 = g[j] * rs0;
+      const double lb = bq * rs0;  // L[j+1][j]
+      const double l1 = fma(-l0, lb, g[j + 1]) * rs1;
+      if (owner) {
+        col[lane + kLd * j] = (lane == 8 * b + j) ? rs0 : l0;  // 1/L_jj on the diagonal
+        col[lane + kLd * (j + 1)] = (lane == 8 * b + j + 1) ? rs1 : l1;
+      }
       __syncwarp();
 #pragma unroll
-      for (int k = j + 1; k < 8; ++k) g[k] = fma(-l, col[8 * b + k + kLd * j], g[k]);
+      for (int k = j + 2; k < 8; ++k) {
+        g[k] = fma(-l0, col[8 * b + k + kLd * j], g[k]);
+        g[k] = fma(-l1, col[8 * b + k + kLd * (j + 1)], g[k]);
+      }
     }
+    // trailing tiles (in the scratch): Hm_ij -= L_ib L_jb'
     if (b == 0) {
       const double2 f1 = tfrag(W, 1, 0, r, c), f2 = tfrag(W, 2, 0, r, c);
       const double2 n1 = neg2(f1), n2 = neg2(f2);
-      dmma2(h[lt(1, 1)], n1, f1);
-      dmma2(h[lt(2, 1)], n2, f1);
-      dmma2(h[lt(2, 2)], n2, f2);
+      double2 h11 = tfrag(W, 1, 1, r, c), h21 = tfrag(W, 2, 1, r, c), h22 = tfrag(W, 2, 2, r, c);
+      dmma2(h11, n1, f1);
+      dmma2(h21, n2, f1);
+      dmma2(h22, n2, f2);
+      tput(W, 1, 1, r, c, h11);
+      tput(W, 2, 1, r, c, h21);
+      tput(W, 2, 2, r, c, h22);
     } else if (b == 1) {
       const double2 f2 = tfrag(W, 2, 1, r, c);
-      dmma2(h[lt(2, 2)], neg2(f2), f2);
+      double2 h22 = tfrag(W, 2, 2, r, c);
+      dmma2(h22, neg2(f2), f2);
+      tput(W, 2, 2, r, c, h22);
     }
+    __syncwarp();
   }
   // diagonal blocks: lane (8 bi + ii) computes row ii of L_bb^-T by the recurrence applied to e_ii
   {
@@ -461,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       const double cval = ws.in[2 * kMat + 3 * kN];
       __syncwarp();  // S (scratch) is dead from here on
 
-      // ---- Hm = R + SB'B (lower tiles, stay in registers for the blocked factorisation) ----
+      // ---- Hm = R + SB'B (lower tiles) -> scratch ----
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) {
         double2 bf[3];
@@ -472,6 +485,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 #pragma unroll
           for (int jb = 0; jb <= ib; ++jb) dmma2(h[lt(ib, jb)], zB[ib][kb], bf[jb]);
       }
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+        for (int jb = 0; jb <= ib; ++jb) tput(ws.W, ib, jb, r, c, h[lt(ib, jb)]);  // lower triangle of the scratch (S is dead)
 
       // ---- G' = P' + SA'B (op fragments of G) ----
       double2 g[3][3];
@@ -540,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       }
 
       // ---- blocked Cholesky of Hm and L^-T into the scratch ----
-      pd = factor_hm(ws.W, h, lane, li, r, c) && pd;
+      pd = factor_hm(ws.W, lane, li, r, c) && pd;
 
       // cost Hessians of node k-1 into L2 (needed from the first third of the next stage on)
       if (k >= 1) prefetch_hessians(rec - a.rec, a, lo24);
