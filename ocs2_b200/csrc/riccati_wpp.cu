@@ -131,7 +131,7 @@ struct __align__(16) WarpSmem {
   double Sv[kN], Gv[kN], Yv[kN], xb[kN], ub[kN];
   unsigned long long full;   // operand block landed (sweep)
   unsigned long long bfull[2];  // rollout: B_k landed in slot k & 1
-  unsigned long long pad_;
+  unsigned long long hfull, hfull2;  // sweep: Q landed in the scratch / P landed in A's slot
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp slots must keep 16-byte alignment");
 
@@ -320,18 +320,16 @@ __device__ __forceinline__ bool factor_hm(double* W, int lane, int li, int r, in
   return pd;
 }
 
-// L2 prefetch of exactly the cost-Hessian fragments a stage reads: all of P, and the tiles of Q and R on or above the block diagonal
-// (Q, R are symmetric; the sweep reads Q[8jb+2c..][8ib+r] for jb <= ib). Every lane touches the addresses of its own later loads.
+// L2 prefetch of the cost Hessians a stage reads: all of P and Q (they are copied to shared memory whole by TMA), and the tiles of R on
+// or above the block diagonal (R is symmetric; the sweep reads R[8jb+2c..][8ib+r] for jb <= ib). One 16-byte touch per lane and tile.
 __device__ __forceinline__ void prefetch_hessians(const double* rec, const Args& a, int lo24) {
 #pragma unroll
   for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
     for (int jb = 0; jb < 3; ++jb) {
       l2_touch(rec + a.oP + lo24 + t24(jb, ib));
-      if (jb <= ib) {
-        l2_touch(rec + a.oQ + lo24 + t24(jb, ib));
-        l2_touch(rec + a.oR + lo24 + t24(jb, ib));
-      }
+      l2_touch(rec + a.oQ + lo24 + t24(jb, ib));
+      if (jb <= ib) l2_touch(rec + a.oR + lo24 + t24(jb, ib));
     }
 }
 
@@ -347,15 +345,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
   const int li = lane < kN ? lane : kN - 1;
   const int N = a.N;
   const uint32_t opBytes = kOperand * sizeof(double);
+  const uint32_t matBytes = kMat * sizeof(double);
 
   if (lane == 0) {
     mbar_init(&ws.full, 1);
     mbar_init(&ws.bfull[0], 1);
     mbar_init(&ws.bfull[1], 1);
+    mbar_init(&ws.hfull, 1);
+    mbar_init(&ws.hfull2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t phase = 0, bphase = 0;  // bphase: bit q = parity to wait for on bfull[q]
+  uint32_t phase = 0, hphase = 0, bphase = 0;  // bphase: bit q = parity to wait for on bfull[q]
 
   for (int pi = blockIdx.x * kWarps + warp; pi < a.count; pi += gridDim.x * kWarps) {
     const int prob = a.begin + pi;
@@ -403,7 +404,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       double* out = solp + (size_t)k * a.orec;
       mbar_wait(&ws.full, phase);
       phase ^= 1u;
-      if (lane == 0 && k >= 1) l2_prefetch(lqp + (size_t)(k - 1) * a.rec, opBytes);  // next operand block: L2 now, shared memory at mid-stage
+      if (k < N - 1) prefetch_hessians(rec, a, lo24);  // this node's Q, P, R into L2 now: first needed a third of a stage from here
+                                                        // (node N-1's were touched in the prologue); prefetching any earlier only
+                                                        // loses lines to L2 capacity misses with 1776 problems in flight
 
       // Hm accumulators start from R (in flight during the ZA / ZB contractions)
       double2 h[6];
@@ -474,7 +477,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       const double cval = ws.in[2 * kMat + 3 * kN];
       __syncwarp();  // S (scratch) is dead from here on
 
-      // ---- Hm = R + SB'B (lower tiles) -> scratch ----
+      // The cost Hessians Q and P ride through shared memory too, each in a slot that is dead for exactly as long as the copy needs:
+      // Q (4.6 KB, one TMA copy) into the scratch while Hm and T are being contracted, P into A's slot while G' is.
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&ws.hfull, matBytes);
+        tma_load(ws.W, rec + a.oQ, matBytes, &ws.hfull);
+      }
+
+      // ---- Hm = R + SB'B (lower tiles) ----
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) {
         double2 bf[3];
@@ -485,71 +496,69 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 #pragma unroll
           for (int jb = 0; jb <= ib; ++jb) dmma2(h[lt(ib, jb)], zB[ib][kb], bf[jb]);
       }
+
+      // ---- T = Q + eps I + SA'A (lower tiles) ----
+#pragma unroll
+      for (int i = 0; i < 6; ++i) t[i] = zero2();
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb) {
+        double2 af[3];
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) af[jb] = ld2(A + lo24 + t24(kb, jb));
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], zA[ib][kb], af[jb]);
+      }
+      __syncwarp();  // A is dead: its slot takes P
+      if (lane == 0) {
+        mbar_expect_tx(&ws.hfull2, matBytes);
+        tma_load(ws.in, rec + a.oP, matBytes, &ws.hfull2);
+      }
+      mbar_wait(&ws.hfull, hphase);
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib) {
+#pragma unroll
+        for (int jb = 0; jb <= ib; ++jb) {
+          const double2 qq = ld2(ws.W + lo24 + t24(jb, ib));  // Q[8ib+r][8jb+2c..] = Q[8jb+2c..][8ib+r], dense ld 24 as copied
+          t[lt(ib, jb)].x += qq.x;
+          t[lt(ib, jb)].y += qq.y;
+        }
+        t[lt(ib, ib)].x += (2 * c == r) ? a.eps : 0.0;
+        t[lt(ib, ib)].y += (2 * c + 1 == r) ? a.eps : 0.0;
+      }
+      __syncwarp();  // Q is consumed: the scratch takes Hm (lower triangle)
 #pragma unroll
       for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-        for (int jb = 0; jb <= ib; ++jb) tput(ws.W, ib, jb, r, c, h[lt(ib, jb)]);  // lower triangle of the scratch (S is dead)
+        for (int jb = 0; jb <= ib; ++jb) tput(ws.W, ib, jb, r, c, h[lt(ib, jb)]);
 
       // ---- G' = P' + SA'B (op fragments of G) ----
       double2 g[3][3];
-      {
-        double2 pp[3][3];
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) g[ib][jb] = zero2();
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb) {
+        double2 bf[3];
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) bf[jb] = ld2(B + lo24 + t24(kb, jb));
 #pragma unroll
         for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb < 3; ++jb) {
-            pp[ib][jb] = ldg2(rec + a.oP + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
-            g[ib][jb] = zero2();
-          }
-#pragma unroll
-        for (int kb = 0; kb < 3; ++kb) {
-          double2 bf[3];
-#pragma unroll
-          for (int jb = 0; jb < 3; ++jb) bf[jb] = ld2(B + lo24 + t24(kb, jb));
-#pragma unroll
-          for (int ib = 0; ib < 3; ++ib)
-#pragma unroll
-            for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], zA[ib][kb], bf[jb]);
-        }
-#pragma unroll
-        for (int ib = 0; ib < 3; ++ib)
-#pragma unroll
-          for (int jb = 0; jb < 3; ++jb) {
-            g[ib][jb].x += pp[ib][jb].x;
-            g[ib][jb].y += pp[ib][jb].y;
-          }
+          for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], zA[ib][kb], bf[jb]);
       }
-      // ---- T = Q + eps I + SA'A (lower tiles) ----
-      {
-        double2 qq[6];
+      mbar_wait(&ws.hfull2, hphase);
+      hphase ^= 1u;
 #pragma unroll
-        for (int ib = 0; ib < 3; ++ib)
+      for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb <= ib; ++jb) {
-            qq[lt(ib, jb)] = ldg2(rec + a.oQ + lo24 + t24(jb, ib));
-            t[lt(ib, jb)] = zero2();
-          }
-#pragma unroll
-        for (int kb = 0; kb < 3; ++kb) {
-          double2 af[3];
-#pragma unroll
-          for (int jb = 0; jb < 3; ++jb) af[jb] = ld2(A + lo24 + t24(kb, jb));
-#pragma unroll
-          for (int ib = 0; ib < 3; ++ib)
-#pragma unroll
-            for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], zA[ib][kb], af[jb]);
+        for (int jb = 0; jb < 3; ++jb) {
+          const double2 pp = ld2(ws.in + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
+          g[ib][jb].x += pp.x;
+          g[ib][jb].y += pp.y;
         }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          t[i].x += qq[i].x;
-          t[i].y += qq[i].y;
-        }
-#pragma unroll
-        for (int ib = 0; ib < 3; ++ib) {
-          t[lt(ib, ib)].x += (2 * c == r) ? a.eps : 0.0;
-          t[lt(ib, ib)].y += (2 * c + 1 == r) ? a.eps : 0.0;
-        }
-      }
       __syncwarp();  // all lanes are done with the staged operand block: refill it for node k-1 while this stage finishes
       if (lane == 0 && k >= 1) {
         mbar_expect_tx(&ws.full, opBytes);
@@ -558,9 +567,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 
       // ---- blocked Cholesky of Hm and L^-T into the scratch ----
       pd = factor_hm(ws.W, lane, li, r, c) && pd;
-
-      // cost Hessians of node k-1 into L2 (needed from the first third of the next stage on)
-      if (k >= 1) prefetch_hessians(rec - a.rec, a, lo24);
 
       // ---- Yv = L^-1 Gv, dbias = -L^-T Yv, s ----
       {
@@ -709,15 +715,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
     // ---- fused forward rollout of the LQ model: du_k = K_k dx_k + alpha dbias_k, dx_{k+1} = A_k dx_k + B_k du_k + Hv_k. One row per lane.
     // K_k and A_k live in registers and are re-loaded for node k+1 right after their last use (one stage of load latency hidden behind
     // the other half of the stage); B_k comes through a two-slot TMA ring over the (now free) operand slot, two stages ahead. ----
-    const uint32_t matBytes = kMat * sizeof(double);
     if (lane == 0) {
       fence_proxy_async();
       for (int k = 0; k < 2 && k < N; ++k) {
         mbar_expect_tx(&ws.bfull[k], matBytes);
         tma_load(ws.in + kMat * k, lqp + (size_t)k * a.rec + kMat, matBytes, &ws.bfull[k]);
       }
-      for (int k = 1; k < 6 && k < N; ++k) l2_prefetch(lqp + (size_t)k * a.rec, opBytes);
-      for (int k = 1; k < 6 && k < N; ++k) l2_prefetch(solp + (size_t)k * a.orec + a.oK, (kMat + kN) * sizeof(double));
+      for (int k = 1; k < 3 && k < N; ++k) l2_prefetch(lqp + (size_t)k * a.rec, 2 * matBytes + kN * sizeof(double));
+      for (int k = 1; k < 3 && k < N; ++k) l2_prefetch(solp + (size_t)k * a.orec + a.oK, (kMat + kN) * sizeof(double));
     }
     double* xo = a.xs + (size_t)prob * (N + 1) * kN;
     double* uo = a.us + (size_t)prob * (N + 1) * kN;
@@ -782,9 +787,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
           mbar_expect_tx(&ws.bfull[q], matBytes);
           tma_load(ws.in + kMat * q, lqp + (size_t)(k + 2) * a.rec + kMat, matBytes, &ws.bfull[q]);
         }
-        if (k + 6 < N) {
-          l2_prefetch(lqp + (size_t)(k + 6) * a.rec, opBytes);
-          l2_prefetch(solp + (size_t)(k + 6) * a.orec + a.oK, (kMat + kN) * sizeof(double));
+        if (k + 3 < N) {
+          l2_prefetch(lqp + (size_t)(k + 3) * a.rec, 2 * matBytes + kN * sizeof(double));  // A | B | Hv
+          l2_prefetch(solp + (size_t)(k + 3) * a.orec + a.oK, (kMat + kN) * sizeof(double));
         }
       }
       __syncwarp();
