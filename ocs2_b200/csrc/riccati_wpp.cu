@@ -47,6 +47,12 @@ constexpr int kThreads = 32 * kWarps;
 constexpr int kCtasPerSm = 3;
 constexpr int kOperand = 2 * kMat + 3 * kN + 2 + 6;  // {A|B|Hv|q|r|c,pad} doubles staged by TMA (= Layout::oQ for n = m = 24, 128-byte aligned)
 constexpr unsigned kFull = 0xffffffffu;
+// record offsets of make_layout(24, 24, 0, N, ILQR) as compile-time constants (address arithmetic folds into the instructions'
+// immediate fields); wpp_ilqr_supported() checks that the handle's layout is exactly this one
+constexpr int kRec = kOperand + 3 * kMat;  // 2960: { A | B | Hv | q | r | c,pad | Q | P | R }
+constexpr int kOQ = kOperand, kOP = kOperand + kMat, kOR = kOperand + 2 * kMat;
+constexpr int kOK = 0, kOdb = kMat, kObias = kMat + kN, kOSm = kMat + 2 * kN, kOSv = 2 * kMat + 2 * kN, kOs = 2 * kMat + 3 * kN;
+constexpr int kORec = 2 * kMat + 3 * kN + 2 + 6;  // 1232: { K | dbias | bias | Sm | Sv | s,pad }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA bulk copy, L2 prefetch, DMMA
@@ -143,9 +149,7 @@ struct Args {
   double* xs;
   double* us;
   int* status;
-  int rec, orec, N;
-  int oQ, oP, oR;
-  int oK, odb, obias, oSm, oSv, os;
+  int N;
   int oQf, oqf, ocf, trec;
   int begin, count, with_rollout;
   double eps, alpha;
@@ -327,9 +331,9 @@ __device__ __forceinline__ void prefetch_hessians(const double* rec, const Args&
   for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
     for (int jb = 0; jb < 3; ++jb) {
-      l2_touch(rec + a.oP + lo24 + t24(jb, ib));
-      l2_touch(rec + a.oQ + lo24 + t24(jb, ib));
-      if (jb <= ib) l2_touch(rec + a.oR + lo24 + t24(jb, ib));
+      l2_touch(rec + kOP + lo24 + t24(jb, ib));
+      l2_touch(rec + kOQ + lo24 + t24(jb, ib));
+      if (jb <= ib) l2_touch(rec + kOR + lo24 + t24(jb, ib));
     }
 }
 
@@ -360,32 +364,32 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 
   for (int pi = blockIdx.x * kWarps + warp; pi < a.count; pi += gridDim.x * kWarps) {
     const int prob = a.begin + pi;
-    const double* lqp = a.lq + (size_t)prob * N * a.rec;
+    const double* lqp = a.lq + (size_t)prob * N * kRec;
     const double* term = a.term + (size_t)prob * a.trec;
-    double* solp = a.sol + (size_t)prob * (N + 1) * a.orec;
+    double* solp = a.sol + (size_t)prob * (N + 1) * kORec;
 
     // operand block of node N-1 (TMA) and the L2 prefetch of its cost Hessians
     if (lane == 0) {
       fence_proxy_async();
       mbar_expect_tx(&ws.full, opBytes);
-      tma_load(ws.in, lqp + (size_t)(N - 1) * a.rec, opBytes, &ws.full);
+      tma_load(ws.in, lqp + (size_t)(N - 1) * kRec, opBytes, &ws.full);
     }
-    prefetch_hessians(lqp + (size_t)(N - 1) * a.rec, a, lo24);
+    prefetch_hessians(lqp + (size_t)(N - 1) * kRec, a, lo24);
     // terminal condition: valueFunctionTrajectory.back() = finalValueFunction (GaussNewtonDDP.cpp:526)
     {
-      double* outN = solp + (size_t)N * a.orec;
+      double* outN = solp + (size_t)N * kORec;
 #pragma unroll 1
       for (int i = lane; i < kMat; i += 32) {
         const double v = term[a.oQf + i];
         ws.W[(i % kN) + kLd * (i / kN)] = v;
-        outN[a.oSm + i] = v;
+        outN[kOSm + i] = v;
       }
       if (lane < kN) {
         const double v = term[a.oqf + lane];
         ws.Sv[lane] = v;
-        outN[a.oSv + lane] = v;
+        outN[kOSv + lane] = v;
       }
-      if (lane == 0) outN[a.os] = term[a.ocf];
+      if (lane == 0) outN[kOs] = term[a.ocf];
     }
     double sval = term[a.ocf];  // s of node k+1
     bool pd = true;
@@ -400,8 +404,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       const double* Hv = ws.in + 2 * kMat;
       const double* qv = Hv + kN;
       const double* rv = qv + kN;
-      const double* rec = lqp + (size_t)k * a.rec;
-      double* out = solp + (size_t)k * a.orec;
+      const double* rec = lqp + (size_t)k * kRec;
+      double* out = solp + (size_t)k * kORec;
       mbar_wait(&ws.full, phase);
       phase ^= 1u;
       if (k < N - 1) prefetch_hessians(rec, a, lo24);  // this node's Q, P, R into L2 now: first needed a third of a stage from here
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 #pragma unroll
       for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-        for (int jb = 0; jb <= ib; ++jb) h[lt(ib, jb)] = ldg2(rec + a.oR + lo24 + t24(jb, ib));  // R[8ib+r][8jb+2c..] = R[8jb+2c..][8ib+r]
+        for (int jb = 0; jb <= ib; ++jb) h[lt(ib, jb)] = ldg2(rec + kOR + lo24 + t24(jb, ib));  // R[8ib+r][8jb+2c..] = R[8jb+2c..][8ib+r]
 
       // ---- ZA = A'S (= op fragments of SA), ZB = B'S (= op fragments of SB); the matrix-vector terms ride on the same fragments:
       //      S Hv, A'Sv, B'Sv here, and (SA)'Hv = ZA Hv, (SB)'Hv = ZB Hv from the accumulators, so that
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       if (lane == 0) {
         fence_proxy_async();
         mbar_expect_tx(&ws.hfull, matBytes);
-        tma_load(ws.W, rec + a.oQ, matBytes, &ws.hfull);
+        tma_load(ws.W, rec + kOQ, matBytes, &ws.hfull);
       }
 
       // ---- Hm = R + SB'B (lower tiles) ----
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       __syncwarp();  // A is dead: its slot takes P
       if (lane == 0) {
         mbar_expect_tx(&ws.hfull2, matBytes);
-        tma_load(ws.in, rec + a.oP, matBytes, &ws.hfull2);
+        tma_load(ws.in, rec + kOP, matBytes, &ws.hfull2);
       }
       mbar_wait(&ws.hfull, hphase);
 #pragma unroll
@@ -562,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       __syncwarp();  // all lanes are done with the staged operand block: refill it for node k-1 while this stage finishes
       if (lane == 0 && k >= 1) {
         mbar_expect_tx(&ws.full, opBytes);
-        tma_load(ws.in, lqp + (size_t)(k - 1) * a.rec, opBytes, &ws.full);
+        tma_load(ws.in, lqp + (size_t)(k - 1) * kRec, opBytes, &ws.full);
       }
 
       // ---- blocked Cholesky of Hm and L^-T into the scratch ----
@@ -595,11 +599,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         }
         if (c < 3) {
           const int j = 8 * c + r;
-          __stcg(out + a.odb + j, -pick3(z, c));
-          __stcg(out + a.obias + j, 0.0);
+          __stcg(out + kOdb + j, -pick3(z, c));
+          __stcg(out + kObias + j, 0.0);
         }
         sval = sval + cval + warp_sum_all(spart);
-        if (lane == 0) __stcg(out + a.os, sval);
+        if (lane == 0) __stcg(out + kOs, sval);
       }
 
       // ---- Y' = G' L^-T (op fragments of Y); L^-T is block upper triangular ----
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 #pragma unroll
         for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb < 3; ++jb) stg2(out + a.oK + lo24 + t24(jb, ib), neg2(kk[ib][jb]));
+          for (int jb = 0; jb < 3; ++jb) stg2(out + kOK + lo24 + t24(jb, ib), neg2(kk[ib][jb]));
       }
 
       // ---- Sv = tv - Y'Yv ----
@@ -658,7 +662,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
           const int j = 8 * c + r;
           svn = tvj - pick3(z, c);
           ws.Sv[j] = svn;
-          __stcg(out + a.oSv + j, svn);
+          __stcg(out + kOSv + j, svn);
         }
       }
 
@@ -679,10 +683,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
           const double2 sv = neg2(t[lt(ib, jb)]);  // S[8ib+r][8jb+2c..] = S[8jb+2c..][8ib+r]
           t[lt(ib, jb)] = sv;
           st2(ws.W + lo26 + t26(jb, ib), sv);
-          stg2(out + a.oSm + lo24 + t24(jb, ib), sv);
+          stg2(out + kOSm + lo24 + t24(jb, ib), sv);
           if (ib != jb) {
             tput(ws.W, ib, jb, r, c, sv);
-            double* gq = out + a.oSm + (8 * ib + r) + kN * (8 * jb + 2 * c);
+            double* gq = out + kOSm + (8 * ib + r) + kN * (8 * jb + 2 * c);
             __stcg(gq, sv.x);
             __stcg(gq + kN, sv.y);
           }
@@ -692,10 +696,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 
     // node N of the controller := node N-1 (GaussNewtonDDP.cpp:609-618)
     {
-      const double* src = solp + (size_t)(N - 1) * a.orec;
-      double* dst = solp + (size_t)N * a.orec;
+      const double* src = solp + (size_t)(N - 1) * kORec;
+      double* dst = solp + (size_t)N * kORec;
 #pragma unroll 1
-      for (int i = lane; i < (kMat + 2 * kN) / 2; i += 32) stg2(dst + a.oK + 2 * i, ldg2(src + a.oK + 2 * i));  // K | dbias | bias are contiguous
+      for (int i = lane; i < (kMat + 2 * kN) / 2; i += 32) stg2(dst + kOK + 2 * i, ldg2(src + kOK + 2 * i));  // K | dbias | bias are contiguous
     }
 
     // ---- status: a non-finite value anywhere in the sweep propagates into S, Sv, s of node 0 ----
@@ -719,10 +723,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       fence_proxy_async();
       for (int k = 0; k < 2 && k < N; ++k) {
         mbar_expect_tx(&ws.bfull[k], matBytes);
-        tma_load(ws.in + kMat * k, lqp + (size_t)k * a.rec + kMat, matBytes, &ws.bfull[k]);
+        tma_load(ws.in + kMat * k, lqp + (size_t)k * kRec + kMat, matBytes, &ws.bfull[k]);
       }
-      for (int k = 1; k < 3 && k < N; ++k) l2_prefetch(lqp + (size_t)k * a.rec, 2 * matBytes + kN * sizeof(double));
-      for (int k = 1; k < 3 && k < N; ++k) l2_prefetch(solp + (size_t)k * a.orec + a.oK, (kMat + kN) * sizeof(double));
+      for (int k = 1; k < 3 && k < N; ++k) l2_prefetch(lqp + (size_t)k * kRec, 2 * matBytes + kN * sizeof(double));
+      for (int k = 1; k < 3 && k < N; ++k) l2_prefetch(solp + (size_t)k * kORec + kOK, (kMat + kN) * sizeof(double));
     }
     double* xo = a.xs + (size_t)prob * (N + 1) * kN;
     double* uo = a.us + (size_t)prob * (N + 1) * kN;
@@ -732,15 +736,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
     double kreg[kN], areg[kN];
 #pragma unroll
     for (int j = 0; j < kN; ++j) {
-      kreg[j] = __ldcg(solp + a.oK + li + kN * j);
+      kreg[j] = __ldcg(solp + kOK + li + kN * j);
       areg[j] = __ldcg(lqp + li + kN * j);
     }
-    double dbk = __ldcg(solp + a.odb + li), hvk = __ldcg(lqp + 2 * kMat + li);
+    double dbk = __ldcg(solp + kOdb + li), hvk = __ldcg(lqp + 2 * kMat + li);
     __syncwarp();
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
-      const double* nsol = solp + (size_t)(k + 1) * a.orec;             // node N carries the copy of node N-1
-      const double* nrec = lqp + (size_t)(k + 1 < N ? k + 1 : k) * a.rec;  // (the last reload is a harmless repeat)
+      const double* nsol = solp + (size_t)(k + 1) * kORec;             // node N carries the copy of node N-1
+      const double* nrec = lqp + (size_t)(k + 1 < N ? k + 1 : k) * kRec;  // (the last reload is a harmless repeat)
       // u = alpha dbias + K x ; the gains of node k+1 take the registers over as they are consumed
       double u0 = a.alpha * dbk, u1 = 0.0, u2 = 0.0, u3 = 0.0;
 #pragma unroll
@@ -752,8 +756,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         u3 = fma(kreg[j + 3], x23.y, u3);
       }
 #pragma unroll
-      for (int j = 0; j < kN; ++j) kreg[j] = __ldcg(nsol + a.oK + li + kN * j);
-      dbk = __ldcg(nsol + a.odb + li);
+      for (int j = 0; j < kN; ++j) kreg[j] = __ldcg(nsol + kOK + li + kN * j);
+      dbk = __ldcg(nsol + kOdb + li);
       const double u = (u0 + u1) + (u2 + u3);
       if (lane < kN) {
         ws.ub[lane] = u;
@@ -785,11 +789,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       if (lane == 0) {
         if (k + 2 < N) {
           mbar_expect_tx(&ws.bfull[q], matBytes);
-          tma_load(ws.in + kMat * q, lqp + (size_t)(k + 2) * a.rec + kMat, matBytes, &ws.bfull[q]);
+          tma_load(ws.in + kMat * q, lqp + (size_t)(k + 2) * kRec + kMat, matBytes, &ws.bfull[q]);
         }
         if (k + 3 < N) {
-          l2_prefetch(lqp + (size_t)(k + 3) * a.rec, 2 * matBytes + kN * sizeof(double));  // A | B | Hv
-          l2_prefetch(solp + (size_t)(k + 3) * a.orec + a.oK, (kMat + kN) * sizeof(double));
+          l2_prefetch(lqp + (size_t)(k + 3) * kRec, 2 * matBytes + kN * sizeof(double));  // A | B | Hv
+          l2_prefetch(solp + (size_t)(k + 3) * kORec + kOK, (kMat + kN) * sizeof(double));
         }
       }
       __syncwarp();
@@ -819,7 +823,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 
 bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
-         st.hc == O2C_HC_DIAGONAL_SHIFT && buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1 && L.oQ == kOperand;
+         st.hc == O2C_HC_DIAGONAL_SHIFT && buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
+         L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb && L.obias == kObias && L.oSm == kOSm &&
+         L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat;
 }
 
 cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,
@@ -845,18 +851,7 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   a.xs = buf.xs;
   a.us = buf.us;
   a.status = buf.status;
-  a.rec = L.rec;
-  a.orec = L.orec;
   a.N = L.N;
-  a.oQ = L.oQ;
-  a.oP = L.oP;
-  a.oR = L.oR;
-  a.oK = L.oK;
-  a.odb = L.odb;
-  a.obias = L.obias;
-  a.oSm = L.oSm;
-  a.oSv = L.oSv;
-  a.os = L.os;
   a.oQf = L.oQf;
   a.oqf = L.oqf;
   a.ocf = L.ocf;
