@@ -29,7 +29,7 @@ struct Work {
   double *A, *B, *Q, *P, *R, *Hv, *q, *r, *C, *D, *e;
   double *Hm, *Ui, *Qm, *Mx, *Rci, *Ddag, *PuBuf, *Px, *T;
   double *Bt, *Pt, *Rt, *SA, *SB, *Gm, *Km, *dGm, *dQ, *Kout;
-  double *u0, *tv, *rt, *Gv, *Lv, *dGv, *w, *SHv, *kout, *bout, *tau, *dqd, *HmLv;
+  double *u0, *tv, *rt, *Gv, *Lv, *dGv, *w, *SHv, *kout, *bout, *tau, *dqd, *HmLv, *dinv;
   double ct;        // projected c
   const double* Pu; // m x p (aliases Ui when nc == 0)
   const double* Tm; // P + R Px (aliases P when nc == 0)
@@ -53,7 +53,7 @@ __host__ __device__ inline int work_doubles(const Layout& L, bool full, bool lm,
   if (lm) t += m * n;             // dGm
   if (gersh) t += n * n;          // dQ
   t += m * n;                     // Kout
-  t += 9 * m + 3 * n + nc;        // u0 tv rt Gv Lv dGv kout bout HmLv | w SHv dqd | tau
+  t += 10 * m + 3 * n + nc;       // u0 tv rt Gv Lv dGv kout bout HmLv dinv | w SHv dqd | tau
   return (t + 1) & ~1;
 }
 
@@ -114,6 +114,7 @@ __device__ __forceinline__ void carve(Work& W, double* base, const Layout& L, bo
   W.SHv = take(n);
   W.dqd = take(n);
   W.tau = take(nc);
+  W.dinv = take(m);
 }
 
 // in-place Cholesky (lower) of the m x m matrix H (ld m). Returns false if a pivot is not positive (NaNs propagate like the reference).
@@ -126,9 +127,10 @@ __device__ __forceinline__ bool warp_cholesky(int m, double* H) {
       ok = false;
       d = __longlong_as_double(0x7ff8000000000000LL);
     }
-    const double ljj = sqrt(d);
+    const double rs = rsqrt(d);  // one reciprocal square root per pivot instead of a square root and a division
+    const double ljj = d * rs;
     __syncwarp();
-    for (int i = j + 1 + lane; i < m; i += 32) H[i + j * m] /= ljj;
+    for (int i = j + 1 + lane; i < m; i += 32) H[i + j * m] *= rs;
     if (lane == 0) H[j + j * m] = ljj;
     __syncwarp();
     const int rem = m - 1 - j;
@@ -142,12 +144,14 @@ __device__ __forceinline__ bool warp_cholesky(int m, double* H) {
 }
 
 // X = U^-1 for an upper-triangular U given by U(i,k) = Ub[i*si + k*sk]; X is dim x dim, ld dim, strictly lower part zeroed.
-__device__ __forceinline__ void warp_upper_inverse(int dim, const double* Ub, int si, int sk, double* X) {
+__device__ __forceinline__ void warp_upper_inverse(int dim, const double* Ub, int si, int sk, double* X, double* dinv) {
+  for (int i = lane_id(); i < dim; i += 32) dinv[i] = 1.0 / Ub[i * si + i * sk];  // the divisions, once and in parallel
+  __syncwarp();
   for (int j = lane_id(); j < dim; j += 32) {
     for (int i = j; i >= 0; --i) {
       double v = (i == j) ? 1.0 : 0.0;
       for (int k = i + 1; k <= j; ++k) v = fma(-Ub[i * si + k * sk], X[k + j * dim], v);
-      X[i + j * dim] = v / Ub[i * si + i * sk];
+      X[i + j * dim] = v * dinv[i];
     }
     for (int i = j + 1; i < dim; ++i) X[i + j * dim] = 0.0;
   }
@@ -226,7 +230,7 @@ __device__ __forceinline__ int project_stage(Work& W, const Layout& L, const Sol
   if (lm) wgemm<true, false>(m, m, n, st.mu, W.B, n, W.B, n, 1.0, W.Hm, m);
   // ---- Ui ----
   if (!warp_cholesky(m, W.Hm)) status |= O2C_STATUS_CHOL_NOT_PD;
-  warp_upper_inverse(m, W.Hm, m, 1, W.Ui);  // U(i,k) = L(k,i) = Hm[k + i*m]
+  warp_upper_inverse(m, W.Hm, m, 1, W.Ui, W.dinv);  // U(i,k) = L(k,i) = Hm[k + i*m]
   // ---- projectors ----
   if (nc == 0) {
     W.Pu = W.Ui;
@@ -245,7 +249,7 @@ __device__ __forceinline__ int project_stage(Work& W, const Layout& L, const Sol
     }
     if (__any_sync(0xffffffffu, clamped)) status |= O2C_STATUS_CONSTRAINT_RANK;
     __syncwarp();
-    warp_upper_inverse(nc, W.Mx, 1, m, W.Rci);  // Rc(i,k) = Mx[i + k*m]
+    warp_upper_inverse(nc, W.Mx, 1, m, W.Rci, W.dinv);  // Rc(i,k) = Mx[i + k*m]
     // tmp (m x nc) = Qc * RcInv'  -> reuse SB as scratch (max(n,m)*m >= m*nc)
     wgemm<false, true>(m, nc, nc, 1.0, W.Qm, m, W.Rci, nc, 0.0, W.SB, m);
     wgemm<false, false>(m, nc, m, 1.0, W.Ui, m, W.SB, m, 0.0, W.Ddag, m);

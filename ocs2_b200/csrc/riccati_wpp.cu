@@ -55,42 +55,8 @@ constexpr int kOK = 0, kOdb = kMat, kObias = kMat + kN, kOSm = kMat + 2 * kN, kO
 constexpr int kORec = 2 * kMat + 3 * kN + 2 + 6;  // 1232: { K | dbias | bias | Sm | Sv | s,pad }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// PTX wrappers: mbarrier, TMA bulk copy, L2 prefetch, DMMA
+// DMMA and fragment helpers (the mbarrier / TMA / prefetch wrappers live in o2c_common.cuh)
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WPP_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra WPP_DONE;\n"
-      "bra WPP_WAIT;\n"
-      "WPP_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy (TMA, non-tensor form); completion is signalled on the mbarrier as transferred bytes
-__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-// per-thread L2 prefetch of the line holding p (CCTL.PF2): one instruction for the whole warp, every lane its own address
-__device__ __forceinline__ void l2_touch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor pipe. Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4], d = D[lane/4][2*(lane%4) + {0,1}].
 __device__ __forceinline__ void dmma(double2& d, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d.x), "+d"(d.y) : "d"(a), "d"(b));
