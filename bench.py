@@ -206,7 +206,7 @@ def main():
     for _ in range(args.warmup):
         solver.solve(1.0)
     solver.sync()
-    split = solver.kernel_variant not in ("ilqr_dmma_kernel", "ilqr_wpp_kernel")  # generic path: backward and rollout are separate launches
+    split = solver.kernel_variant not in ("ilqr_wpp_kernel", "ilqr_rpl_kernel")  # generic path: backward and rollout are separate launches
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)

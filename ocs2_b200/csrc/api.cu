@@ -58,7 +58,8 @@ struct o2c_handle {
   int out_nodes = 0;
   std::vector<double> time, ro_times;
   bool time_set = false;
-  bool use_fast = false;
+  bool use_fast = false;  // legged shape: warp-per-problem DMMA kernel
+  bool use_rpl = false;   // small shapes: row-per-lane kernel
   bool nc_ragged = false;  // a caller supplied per-node constraint counts (otherwise every node has nc_max: the kernels skip the lookup)
   int64_t launches = 0;
   int stage_chunk = 0;
@@ -465,6 +466,10 @@ o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) 
       int l = 0;
       O2C_CUDA(launch_ilqr_wpp(h->L, h->st, buf, false, 1.0, h->cfg.batch, begin, count, stream, &l));
       h->launches += l;
+    } else if (h->use_rpl) {
+      int l = 0;
+      O2C_CUDA(launch_ilqr_rpl(h->L, h->st, buf, false, 1.0, begin, count, stream, &l));
+      h->launches += l;
     } else {
       O2C_CUDA(launch_ilqr_generic(h->L, h->st, buf, begin, count, stream));
       h->launches += 1;
@@ -493,9 +498,12 @@ o2c_error rollout_on(o2c_handle* h, cudaStream_t stream, const double* alphas_de
 
 o2c_error solve_on(o2c_handle* h, cudaStream_t stream, double* alpha_slot_dev, double alpha, int begin, int count) {
   if (count == 0) return O2C_OK;
-  if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast) {
+  if (h->st.algorithm == O2C_ALG_ILQR && (h->use_fast || h->use_rpl)) {
     int l = 0;
-    O2C_CUDA(launch_ilqr_wpp(h->L, h->st, h->buffers(), true, alpha, h->cfg.batch, begin, count, stream, &l));
+    if (h->use_fast)
+      O2C_CUDA(launch_ilqr_wpp(h->L, h->st, h->buffers(), true, alpha, h->cfg.batch, begin, count, stream, &l));
+    else
+      O2C_CUDA(launch_ilqr_rpl(h->L, h->st, h->buffers(), true, alpha, begin, count, stream, &l));
     h->launches += l;
     return O2C_OK;
   }
@@ -606,6 +614,7 @@ o2c_error o2c_create(const o2c_config* cfg, o2c_handle** out) {
   cudaMemsetAsync(h->d_status, 0, sizeof(int) * B, h->lanes[0].stream);
   cudaMemsetAsync(h->d_x0, 0, sizeof(double) * B * L.n, h->lanes[0].stream);
   h->use_fast = wpp_ilqr_supported(h->L, h->st, h->buffers());
+  h->use_rpl = !h->use_fast && rpl_ilqr_supported(h->L, h->st, h->buffers());
   // default uniform time grid t_k = k * time_step (ILQR does not need it; SLQ callers normally override it)
   std::vector<double> t(L.N + 1);
   const double dt = cfg->time_step > 0.0 ? cfg->time_step : 1.0;
@@ -839,6 +848,7 @@ o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {
 const char* o2c_kernel_variant(const o2c_handle* h) {
   if (!h) return "";
   if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast) return "ilqr_wpp_kernel";
+  if (h->st.algorithm == O2C_ALG_ILQR && h->use_rpl) return "ilqr_rpl_kernel";
   return generic_variant_name(h->L, h->st);
 }
 

@@ -154,6 +154,11 @@ bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceB
 cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,
                             int begin, int count, cudaStream_t stream, int* launches);
 
+// shape-specialised fast path for small shapes (riccati_rpl.cu): row-per-lane kernel, several problems per warp
+bool rpl_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
+cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int begin,
+                            int count, cudaStream_t stream, int* launches);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA bulk copy (cp.async.bulk), L2 prefetch

@@ -1,0 +1,453 @@
+// riccati_rpl.cu — "row per lane" ILQR sweep + fused LQ rollout for SMALL shapes (nx <= 16), FP64, sm_100a.
+//
+// Small problems (ballbot nx = 10, nu = 3; cartpole nx = 4, nu = 1) are HBM-bound: 2.3 KB in / 1.3 KB out
+// and only 3.5 k FMA per stage. A warp per problem wastes most lanes on 10x10 matrices and a tensor-core tile (8x8x4) would be
+// three quarters padding, so here a warp carries P = 32 / nx problems at once and inside a problem LANE i OWNS ROW i of every
+// nx-row matrix (S, SA, T, G', Y', K'), kept in registers; the operand that every row needs in full (A, B, SA, SB, Y', L) is
+// broadcast from shared memory with 16-byte loads (two FMAs per load, no bank conflicts: all lanes of a problem read one address).
+// Every product is arranged to be nx-row oriented (the nu-row ones are computed transposed), so all nx lanes work all the time:
+//
+//   SA_i  = S_i A            SB_i = S_i B            w_i = Sv_i + S_i Hv                       (S_i: row i of S, registers)
+//   T_i   = Q_i + eps e_i + A(:,i)' SA            tv_i = q_i + A(:,i)' w
+//   G'_i  = P(:,i)' + SA(:,i)' B                  (row i of G' = column i of G = P + B'SA)
+//   Hm_l  = R_l + B(:,l)' SB   (lanes l < nu)     Cholesky Hm = L L' by shuffles inside the lane group, 1/L_jj kept on the diagonal
+//   Y'_i  = G'_i L^-T  (forward substitution)     K'_i = -Y'_i L^-1 (back substitution)       -> K(:,i), coalesced
+//   S_i   = T_i - Y'_i Y''   Sv_i = tv_i - Y'_i Yv   s = s+ + c + Hv.w - 1/2 Hv.(S Hv) - 1/2 Yv.Yv
+//
+// which are the quantities of ILQR::riccatiEquationsWorker (ocs2_ddp/src/ILQR.cpp:227-299), computeMapILQR
+// (riccati_equations/DiscreteTimeRiccatiEquations.cpp:65-154), computeInverseMatrixUUT (ocs2_core/src/misc/LinearAlgebra.cpp:119-124)
+// and calculateControllerWorker (ILQR.cpp:162-181) for nc = 0, LINE_SEARCH, reduced form, DIAGONAL_SHIFT (same re-association as
+// riccati_wpp.cu: Y = L^-1 G, S = T - Y'Y, K = -L^-T Y). The stage records of the P problems arrive by TMA bulk copies
+// (cp.async.bulk + one mbarrier per warp), double buffered, node k-1 in flight while node k is processed; outputs are written once.
+// The forward rollout of the LQ model (DDP_HelperFunctions.cpp:125-138, 296-304; LinearController.cpp:79-87) is fused behind the
+// sweep and streams the same records forwards through the same two buffers.
+#include "o2c_common.cuh"
+
+namespace o2c {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int cpad2(int v) { return (v + 1) & ~1; }
+
+template <int NX, int NU>
+struct Shape {
+  static constexpr int G = NX;        // lanes per problem
+  static constexpr int P = 32 / NX;   // problems per warp
+  // record offsets of make_layout(NX, NU, 0, N, ILQR) for shapes below the 128-byte alignment threshold
+  static constexpr int oA = 0, oB = cpad2(NX * NX), oHv = oB + cpad2(NX * NU), oq = oHv + cpad2(NX), or_ = oq + cpad2(NX),
+                       oc = or_ + cpad2(NU), oQ = oc + 2, oP = oQ + cpad2(NX * NX), oR = oP + cpad2(NU * NX), rec = oR + cpad2(NU * NU);
+  static constexpr int oK = 0, odb = cpad2(NU * NX), obias = odb + cpad2(NU), oSm = obias + cpad2(NU), oSv = oSm + cpad2(NX * NX),
+                       os = oSv + cpad2(NX), orec = os + 2;
+  static constexpr int oQf = 0, oqf = cpad2(NX * NX), ocf = oqf + cpad2(NX), trec = ocf + 2;
+  // shared memory of one problem slot (doubles)
+  static constexpr int sRec = 0, sSA = 2 * rec, sSB = sSA + cpad2(NX * NX), sYt = sSB + cpad2(NX * NU), sL = sYt + cpad2(NX * NU),
+                       sW = sL + cpad2(NU * NU), sGv = sW + cpad2(NX), sYv = sGv + cpad2(NU), sX = sYv + cpad2(NU), sU = sX + cpad2(NX),
+                       sK = sU + cpad2(NU), slot = sK + cpad2(NU * NX + NU);
+  static constexpr int warp_doubles = P * slot + 2;  // + the warp's mbarrier
+};
+
+struct Args {
+  const double* lq;
+  const double* term;
+  const double* x0;
+  double* sol;
+  double* xs;
+  double* us;
+  int* status;
+  int N, begin, count, with_rollout;
+  double eps, alpha;
+};
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ bool finite_bits(double v) { return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000; }
+__device__ __forceinline__ double rsqrt_pivot(double d) {  // MUFU.RSQ64H seed + one third-order step (see riccati_wpp.cu)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
+}
+// acc += sum_k a[k] * M[k] for a contiguous shared-memory column M (16-byte aligned when LEN is even), a in registers
+template <int LEN>
+__device__ __forceinline__ double dot_col(const double (&a)[LEN], const double* M, double acc) {
+  if (LEN % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < LEN; k += 2) {
+      const double2 v = ld2(M + k);
+      acc = fma(a[k], v.x, acc);
+      acc = fma(a[k + 1], v.y, acc);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < LEN; ++k) acc = fma(a[k], M[k], acc);
+  }
+  return acc;
+}
+
+template <int NX, int NU>
+__global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
+  using S = Shape<NX, NU>;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)warp * S::warp_doubles;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(wbase + S::P * S::slot);
+  const int graw = lane / NX;
+  const bool in_group = graw < S::P;
+  const int gi = in_group ? graw : S::P - 1;   // left-over lanes shadow the last slot and never store
+  const int i = in_group ? lane - graw * NX : NX - 1;
+  const int gbase = gi * NX;                   // first lane of the group
+  double* sm = wbase + gi * S::slot;
+  const int N = a.N;
+  const uint32_t recBytes = S::rec * sizeof(double);
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+
+  for (int base = (blockIdx.x * (blockDim.x >> 5) + warp) * S::P; base < a.count; base += warps_total * S::P) {
+    const int nprob = (a.count - base) < S::P ? (a.count - base) : S::P;  // problems this warp carries in this round
+    const bool valid = in_group && gi < nprob;
+    const int prob = a.begin + base + (gi < nprob ? gi : nprob - 1);      // inactive groups shadow a live problem (never store)
+    const double* lqp = a.lq + (size_t)prob * N * S::rec;
+    const double* term = a.term + (size_t)prob * S::trec;
+    double* solp = a.sol + (size_t)prob * (N + 1) * S::orec;
+
+    // records of node N-1 (one TMA copy per carried problem)
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(bar, recBytes * nprob);
+      for (int g = 0; g < nprob; ++g)
+        tma_load(wbase + g * S::slot + S::sRec + ((N - 1) & 1) * S::rec, a.lq + ((size_t)(a.begin + base + g) * N + (N - 1)) * S::rec, recBytes, bar);
+    }
+    // terminal condition: valueFunctionTrajectory.back() = finalValueFunction (GaussNewtonDDP.cpp:526)
+    double Srow[NX];
+    double* outN = solp + (size_t)N * S::orec;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      Srow[j] = term[S::oQf + i + NX * j];
+      if (valid) outN[S::oSm + i + NX * j] = Srow[j];
+    }
+    double Svi = term[S::oqf + i];
+    if (valid) outN[S::oSv + i] = Svi;
+    double sval = term[S::ocf];
+    if (valid && i == 0) outN[S::os] = sval;
+    bool pd = true;
+
+#pragma unroll 1
+    for (int k = N - 1; k >= 0; --k) {
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      const double* rec = sm + S::sRec + (k & 1) * S::rec;
+      if (lane == 0 && k >= 1) {  // the other buffer was released by the __syncwarp that ended node k+1
+        fence_proxy_async();
+        mbar_expect_tx(bar, recBytes * nprob);
+        for (int g = 0; g < nprob; ++g)
+          tma_load(wbase + g * S::slot + S::sRec + ((k - 1) & 1) * S::rec, a.lq + ((size_t)(a.begin + base + g) * N + (k - 1)) * S::rec, recBytes, bar);
+      }
+      const double* A = rec + S::oA;
+      const double* B = rec + S::oB;
+      const double* Hv = rec + S::oHv;
+      double* out = solp + (size_t)k * S::orec;
+
+      // ---- w_i = Sv_i + S_i Hv ; SA_i = S_i A ; SB_i = S_i B ----
+      const double shv = dot_col<NX>(Srow, Hv, 0.0);
+      const double wi = Svi + shv;
+      sm[S::sW + i] = wi;
+      double spart = Hv[i] * (wi - 0.5 * shv);  // this row's share of Hv.w - 1/2 Hv.(S Hv)
+#pragma unroll
+      for (int j = 0; j < NX; ++j) sm[S::sSA + i + NX * j] = dot_col<NX>(Srow, A + NX * j, 0.0);
+#pragma unroll
+      for (int l = 0; l < NU; ++l) sm[S::sSB + i + NX * l] = dot_col<NX>(Srow, B + NX * l, 0.0);
+      __syncwarp();
+
+      // ---- T_i = Q_i + eps e_i + A(:,i)' SA ; tv_i = q_i + A(:,i)' w ----
+      double acol[NX];
+#pragma unroll
+      for (int kk = 0; kk < NX; ++kk) acol[kk] = A[kk + NX * i];
+      double Trow[NX];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) Trow[j] = dot_col<NX>(acol, sm + S::sSA + NX * j, rec[S::oQ + i + NX * j] + ((j == i) ? a.eps : 0.0));
+      const double tvi = dot_col<NX>(acol, sm + S::sW, rec[S::oq + i]);
+
+      // ---- G'_i = P(:,i)' + SA(:,i)' B (row i of G') ----
+      double gt[NU];
+      {
+        double sacol[NX];
+#pragma unroll
+        for (int kk = 0; kk < NX; ++kk) sacol[kk] = sm[S::sSA + kk + NX * i];
+#pragma unroll
+        for (int l = 0; l < NU; ++l) gt[l] = dot_col<NX>(sacol, B + NX * l, rec[S::oP + l + NU * i]);
+      }
+
+      // ---- Hm_l = R_l + B(:,l)' SB and Gv_l = r_l + B(:,l)' w on lanes l < nu; Cholesky by shuffles inside the group ----
+      double h[NU];
+      {
+        const int l = i < NU ? i : NU - 1;
+        double bcol[NX];
+#pragma unroll
+        for (int kk = 0; kk < NX; ++kk) bcol[kk] = B[kk + NX * l];
+#pragma unroll
+        for (int l2 = 0; l2 < NU; ++l2) h[l2] = dot_col<NX>(bcol, sm + S::sSB + NX * l2, rec[S::oR + l + NU * l2]);
+        const double gv = dot_col<NX>(bcol, sm + S::sW, rec[S::or_ + l]);
+        if (i < NU) sm[S::sGv + i] = gv;
+      }
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        const double d = __shfl_sync(kFull, h[j], gbase + j);
+        pd = pd && (__double2hiint(d) > 0);
+        const double rs = rsqrt_pivot(d);  // a non-positive pivot gives NaN / Inf, which propagates like the reference's LLT
+        const double lj = h[j] * rs;       // L[i][j] on lane i (i >= j); lane j holds sqrt(d)
+        if (i < NU) sm[S::sL + i + NU * j] = (i == j) ? rs : lj;  // 1/L_jj on the diagonal
+#pragma unroll
+        for (int k2 = j + 1; k2 < NU; ++k2) {
+          const double lk = __shfl_sync(kFull, lj, gbase + k2);
+          h[k2] = fma(-lj, lk, h[k2]);
+        }
+      }
+      __syncwarp();
+
+      // ---- Y'_i = G'_i L^-T (forward substitution), K'_i = -Y'_i L^-1 (back substitution), Yv = L^-1 Gv, dbias = -L^-T Yv ----
+      const double* Lm = sm + S::sL;
+      double yt[NU], kt[NU], yv[NU], db[NU];
+#pragma unroll
+      for (int l = 0; l < NU; ++l) {
+        double v = gt[l], vv = sm[S::sGv + l];
+#pragma unroll
+        for (int l2 = 0; l2 < l; ++l2) {
+          v = fma(-Lm[l + NU * l2], yt[l2], v);
+          vv = fma(-Lm[l + NU * l2], yv[l2], vv);
+        }
+        yt[l] = v * Lm[l + NU * l];
+        yv[l] = vv * Lm[l + NU * l];
+      }
+#pragma unroll
+      for (int l = NU - 1; l >= 0; --l) {
+        double v = -yt[l], vv = -yv[l];
+#pragma unroll
+        for (int l2 = l + 1; l2 < NU; ++l2) {
+          v = fma(-Lm[l2 + NU * l], kt[l2], v);
+          vv = fma(-Lm[l2 + NU * l], db[l2], vv);
+        }
+        kt[l] = v * Lm[l + NU * l];
+        db[l] = vv * Lm[l + NU * l];
+      }
+#pragma unroll
+      for (int l = 0; l < NU; ++l) sm[S::sYt + i + NX * l] = yt[l];
+      if (valid) {
+#pragma unroll
+        for (int l = 0; l < NU; ++l) out[S::oK + l + NU * i] = kt[l];  // column i of K: the group writes nu*nx contiguous doubles
+        if (i < NU) {
+          double dbi = db[0];
+#pragma unroll
+          for (int l = 1; l < NU; ++l) dbi = (i == l) ? db[l] : dbi;
+          out[S::odb + i] = dbi;
+          out[S::obias + i] = 0.0;
+        }
+      }
+      __syncwarp();
+
+      // ---- S_i = T_i - Y'_i Y'' ; Sv_i = tv_i - Y'_i Yv ; s ----
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        double v = Trow[j];
+#pragma unroll
+        for (int l = 0; l < NU; ++l) v = fma(-yt[l], sm[S::sYt + j + NX * l], v);
+        Srow[j] = v;
+      }
+      Svi = tvi;
+#pragma unroll
+      for (int l = 0; l < NU; ++l) Svi = fma(-yt[l], yv[l], Svi);
+      // s: rows sum their shares inside the group (xor butterflies stay inside aligned power-of-two blocks only when nx is one,
+      // so the group sum goes through shared memory)
+      sm[S::sX + i] = spart;
+      __syncwarp();
+      {
+        double sh = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) sh += sm[S::sX + j];
+        double yy = 0.0;
+#pragma unroll
+        for (int l = 0; l < NU; ++l) yy = fma(yv[l], yv[l], yy);
+        sval = sval + rec[S::oc] + sh - 0.5 * yy;
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) out[S::oSm + i + NX * j] = Srow[j];
+        out[S::oSv + i] = Svi;
+        if (i == 0) out[S::os] = sval;
+      }
+      __syncwarp();  // every lane is done with this node's record and scratch
+    }
+
+    // node N of the controller := node N-1 (GaussNewtonDDP.cpp:609-618)
+    if (valid) {
+      const double* src = solp + (size_t)(N - 1) * S::orec;
+      double* dst = solp + (size_t)N * S::orec;
+      for (int e = i; e < S::oSm; e += NX) dst[e] = __ldcg(src + e);  // K | dbias | bias precede Sm in the record
+    }
+    // status: a non-finite value anywhere in the sweep propagates into S, Sv, s of node 0
+    bool finite = finite_bits(Svi) && finite_bits(sval);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) finite = finite && finite_bits(Srow[j]);
+    const unsigned gmask = (NX == 32) ? kFull : (((1u << NX) - 1u) << gbase);
+    const unsigned bad_pd = __ballot_sync(kFull, !pd), bad_fin = __ballot_sync(kFull, !finite);
+    int bits = ((bad_pd & gmask) ? O2C_STATUS_CHOL_NOT_PD : 0) | ((bad_fin & gmask) ? O2C_STATUS_NONFINITE : 0);
+    if (!a.with_rollout) {
+      if (valid && i == 0) a.status[prob] = bits;
+      __syncwarp();
+      continue;
+    }
+
+    // ---- fused forward rollout: du_k = K_k dx_k + alpha dbias_k ; dx_{k+1} = A_k dx_k + B_k du_k + Hv_k ----
+    __syncwarp();
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(bar, recBytes * nprob);
+      for (int g = 0; g < nprob; ++g) tma_load(wbase + g * S::slot + S::sRec, a.lq + (size_t)(a.begin + base + g) * N * S::rec, recBytes, bar);
+    }
+    double* xo = a.xs + (size_t)prob * (N + 1) * NX;
+    double* uo = a.us + (size_t)prob * (N + 1) * NU;
+    double x = a.x0[(size_t)prob * NX + i];
+    bool xfinite = true;
+    // column i of K_k and (lanes < nu) dbias_k: coalesced loads one node ahead
+    double kc[NU], dbk;
+#pragma unroll
+    for (int l = 0; l < NU; ++l) kc[l] = __ldcg(solp + S::oK + l + NU * i);
+    dbk = __ldcg(solp + S::odb + (i < NU ? i : 0));
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+      sm[S::sX + i] = x;
+#pragma unroll
+      for (int l = 0; l < NU; ++l) sm[S::sK + l + NU * i] = kc[l];
+      __syncwarp();
+      // u_l = alpha dbias_l + K(l,:) x on lanes l < nu
+      {
+        const int l = i < NU ? i : NU - 1;
+        double u = a.alpha * dbk;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) u = fma(sm[S::sK + l + NU * j], sm[S::sX + j], u);
+        if (i < NU) {
+          sm[S::sU + i] = u;
+          if (valid) __stcg(uo + (size_t)k * NU + i, u);
+        }
+      }
+      if (valid) __stcg(xo + (size_t)k * NX + i, x);
+      xfinite = xfinite && finite_bits(x);
+      // gains of node k+1 (node N carries the copy of node N-1)
+      {
+        const double* nsol = solp + (size_t)(k + 1) * S::orec;
+#pragma unroll
+        for (int l = 0; l < NU; ++l) kc[l] = __ldcg(nsol + S::oK + l + NU * i);
+        dbk = __ldcg(nsol + S::odb + (i < NU ? i : 0));
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      __syncwarp();
+      const double* rec = sm + S::sRec + (k & 1) * S::rec;
+      if (lane == 0 && k + 1 < N) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, recBytes * nprob);
+        for (int g = 0; g < nprob; ++g)
+          tma_load(wbase + g * S::slot + S::sRec + ((k + 1) & 1) * S::rec, a.lq + ((size_t)(a.begin + base + g) * N + (k + 1)) * S::rec, recBytes, bar);
+      }
+      double xn = rec[S::oHv + i];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) xn = fma(rec[S::oA + i + NX * j], sm[S::sX + j], xn);
+#pragma unroll
+      for (int l = 0; l < NU; ++l) xn = fma(rec[S::oB + i + NX * l], sm[S::sU + l], xn);
+      __syncwarp();
+      x = xn;
+    }
+    // node N: state, and the input of the copied last policy re-evaluated at x_N (TimeTriggeredRollout.cpp:98-102)
+    sm[S::sX + i] = x;
+#pragma unroll
+    for (int l = 0; l < NU; ++l) sm[S::sK + l + NU * i] = kc[l];
+    __syncwarp();
+    {
+      const int l = i < NU ? i : NU - 1;
+      double u = a.alpha * dbk;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) u = fma(sm[S::sK + l + NU * j], sm[S::sX + j], u);
+      if (valid && i < NU) __stcg(uo + (size_t)N * NU + i, u);
+    }
+    if (valid) __stcg(xo + (size_t)N * NX + i, x);
+    xfinite = xfinite && finite_bits(x);
+    if (__ballot_sync(kFull, !xfinite) & gmask) bits |= O2C_STATUS_NONFINITE;
+    if (valid && i == 0) a.status[prob] = bits;
+    __syncwarp();
+  }
+}
+
+template <int NX, int NU>
+bool layout_matches(const Layout& L) {
+  using S = Shape<NX, NU>;
+  return L.n == NX && L.m == NU && L.ncmax == 0 && L.rec == S::rec && L.oA == S::oA && L.oB == S::oB && L.oHv == S::oHv && L.oq == S::oq &&
+         L.or_ == S::or_ && L.oc == S::oc && L.oQ == S::oQ && L.oP == S::oP && L.oR == S::oR && L.orec == S::orec && L.oK == S::oK &&
+         L.odb == S::odb && L.obias == S::obias && L.oSm == S::oSm && L.oSv == S::oSv && L.os == S::os && L.trec == S::trec &&
+         L.oQf == S::oQf && L.oqf == S::oqf && L.ocf == S::ocf;
+}
+
+template <int NX, int NU>
+cudaError_t launch(const Args& a, cudaStream_t stream) {
+  using S = Shape<NX, NU>;
+  static int num_sms = 0;
+  constexpr int wpb = 4;
+  const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ilqr_rpl_kernel<NX, NU>, wpb * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int per_cta = wpb * S::P;
+  const int needed = (a.count + per_cta - 1) / per_cta;
+  const int cap = num_sms * ctas_per_sm;  // persistent warps: one resident wave, static stride over the problem index
+  ilqr_rpl_kernel<NX, NU><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const Layout& L) {
+  return st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
+         buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1;
+}
+
+}  // namespace
+
+bool rpl_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
+  if (!settings_match(st, buf, L)) return false;
+  return layout_matches<10, 3>(L) || layout_matches<4, 1>(L);
+}
+
+cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int begin,
+                            int count, cudaStream_t stream, int* launches) {
+  if (!rpl_ilqr_supported(L, st, buf)) return cudaErrorNotSupported;
+  Args a{};
+  a.lq = buf.lq;
+  a.term = buf.term;
+  a.x0 = buf.x0;
+  a.sol = buf.sol;
+  a.xs = buf.xs;
+  a.us = buf.us;
+  a.status = buf.status;
+  a.N = L.N;
+  a.begin = begin;
+  a.count = count;
+  a.with_rollout = with_rollout ? 1 : 0;
+  a.eps = st.eps;
+  a.alpha = alpha;
+  if (launches) *launches = 1;
+  if (layout_matches<10, 3>(L)) return launch<10, 3>(a, stream);
+  return launch<4, 1>(a, stream);
+}
+
+}  // namespace o2c
