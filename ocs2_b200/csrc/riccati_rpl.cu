@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
   double* sm = wbase + gi * S::slot;
   const int N = a.N;
   const uint32_t recBytes = S::rec * sizeof(double);
+  const uint32_t dynBytes = S::oq * sizeof(double);  // { A | B | Hv }: all the rollout reads of a record
 
   if (lane == 0) {
     mbar_init(bar, 1);
@@ -307,8 +308,8 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
     __syncwarp();
     if (lane == 0) {
       fence_proxy_async();
-      mbar_expect_tx(bar, recBytes * nprob);
-      for (int g = 0; g < nprob; ++g) tma_load(wbase + g * S::slot + S::sRec, a.lq + (size_t)(a.begin + base + g) * N * S::rec, recBytes, bar);
+      mbar_expect_tx(bar, dynBytes * nprob);
+      for (int g = 0; g < nprob; ++g) tma_load(wbase + g * S::slot + S::sRec, a.lq + (size_t)(a.begin + base + g) * N * S::rec, dynBytes, bar);
     }
     double* xo = a.xs + (size_t)prob * (N + 1) * NX;
     double* uo = a.us + (size_t)prob * (N + 1) * NU;
@@ -351,9 +352,9 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       const double* rec = sm + S::sRec + (k & 1) * S::rec;
       if (lane == 0 && k + 1 < N) {
         fence_proxy_async();
-        mbar_expect_tx(bar, recBytes * nprob);
+        mbar_expect_tx(bar, dynBytes * nprob);
         for (int g = 0; g < nprob; ++g)
-          tma_load(wbase + g * S::slot + S::sRec + ((k + 1) & 1) * S::rec, a.lq + ((size_t)(a.begin + base + g) * N + (k + 1)) * S::rec, recBytes, bar);
+          tma_load(wbase + g * S::slot + S::sRec + ((k + 1) & 1) * S::rec, a.lq + ((size_t)(a.begin + base + g) * N + (k + 1)) * S::rec, dynBytes, bar);
       }
       double xn = rec[S::oHv + i];
 #pragma unroll
@@ -396,7 +397,7 @@ template <int NX, int NU>
 cudaError_t launch(const Args& a, cudaStream_t stream) {
   using S = Shape<NX, NU>;
   static int num_sms = 0;
-  constexpr int wpb = 4;
+  constexpr int wpb = 2;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
