@@ -466,7 +466,7 @@ o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) 
       int l = 0;
       O2C_CUDA(launch_ilqr_wpp(h->L, h->st, buf, false, 1.0, h->cfg.batch, begin, count, stream, &l));
       h->launches += l;
-    } else if (h->use_rpl) {
+    } else if (h->use_rpl && rpl_ilqr_supported(h->L, h->st, buf)) {  // (ragged constraint counts fall through to the generic kernel)
       int l = 0;
       O2C_CUDA(launch_ilqr_rpl(h->L, h->st, buf, false, 1.0, begin, count, stream, &l));
       h->launches += l;
@@ -498,7 +498,7 @@ o2c_error rollout_on(o2c_handle* h, cudaStream_t stream, const double* alphas_de
 
 o2c_error solve_on(o2c_handle* h, cudaStream_t stream, double* alpha_slot_dev, double alpha, int begin, int count) {
   if (count == 0) return O2C_OK;
-  if (h->st.algorithm == O2C_ALG_ILQR && (h->use_fast || h->use_rpl)) {
+  if (h->st.algorithm == O2C_ALG_ILQR && (h->use_fast || (h->use_rpl && rpl_ilqr_supported(h->L, h->st, h->buffers())))) {
     int l = 0;
     if (h->use_fast)
       O2C_CUDA(launch_ilqr_wpp(h->L, h->st, h->buffers(), true, alpha, h->cfg.batch, begin, count, stream, &l));
@@ -848,7 +848,7 @@ o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {
 const char* o2c_kernel_variant(const o2c_handle* h) {
   if (!h) return "";
   if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast) return "ilqr_wpp_kernel";
-  if (h->st.algorithm == O2C_ALG_ILQR && h->use_rpl) return "ilqr_rpl_kernel";
+  if (h->st.algorithm == O2C_ALG_ILQR && h->use_rpl && rpl_ilqr_supported(h->L, h->st, h->buffers())) return "ilqr_rpl_kernel";
   return generic_variant_name(h->L, h->st);
 }
 

@@ -29,20 +29,21 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int cpad2(int v) { return (v + 1) & ~1; }
 
-template <int NX, int NU>
+template <int NX, int NU, int NC>
 struct Shape {
   static constexpr int G = NX;        // lanes per problem
   static constexpr int P = 32 / NX;   // problems per warp
-  // record offsets of make_layout(NX, NU, 0, N, ILQR) for shapes below the 128-byte alignment threshold
+  // record offsets of make_layout(NX, NU, NC, N, ILQR) for shapes below the 128-byte alignment threshold
   static constexpr int oA = 0, oB = cpad2(NX * NX), oHv = oB + cpad2(NX * NU), oq = oHv + cpad2(NX), or_ = oq + cpad2(NX),
-                       oc = or_ + cpad2(NU), oQ = oc + 2, oP = oQ + cpad2(NX * NX), oR = oP + cpad2(NU * NX), rec = oR + cpad2(NU * NU);
+                       oc = or_ + cpad2(NU), oQ = oc + 2, oP = oQ + cpad2(NX * NX), oR = oP + cpad2(NU * NX), oC = oR + cpad2(NU * NU),
+                       oD = oC + cpad2(NC * NX), oe = oD + cpad2(NC * NU), rec = oe + cpad2(NC);
   static constexpr int oK = 0, odb = cpad2(NU * NX), obias = odb + cpad2(NU), oSm = obias + cpad2(NU), oSv = oSm + cpad2(NX * NX),
                        os = oSv + cpad2(NX), orec = os + 2;
   static constexpr int oQf = 0, oqf = cpad2(NX * NX), ocf = oqf + cpad2(NX), trec = ocf + 2;
   // shared memory of one problem slot (doubles)
   static constexpr int sRec = 0, sSA = 2 * rec, sSB = sSA + cpad2(NX * NX), sYt = sSB + cpad2(NX * NU), sL = sYt + cpad2(NX * NU),
                        sW = sL + cpad2(NU * NU), sGv = sW + cpad2(NX), sYv = sGv + cpad2(NU), sX = sYv + cpad2(NU), sU = sX + cpad2(NX),
-                       sK = sU + cpad2(NU), slot = sK + cpad2(NU * NX + NU);
+                       sK = sU + cpad2(NU), sZ = sK + cpad2(NU * NX + NU), sVx = sZ + cpad2(NU * NC), slot = sVx + cpad2(NC * NX);
   static constexpr int warp_doubles = P * slot + 2;  // + the warp's mbarrier
 };
 
@@ -85,9 +86,9 @@ __device__ __forceinline__ double dot_col(const double (&a)[LEN], const double* 
   return acc;
 }
 
-template <int NX, int NU>
+template <int NX, int NU, int NC>
 __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
-  using S = Shape<NX, NU>;
+  using S = Shape<NX, NU, NC>;
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* wbase = smem + (size_t)warp * S::warp_doubles;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
     if (valid) outN[S::oSv + i] = Svi;
     double sval = term[S::ocf];
     if (valid && i == 0) outN[S::os] = sval;
-    bool pd = true;
+    bool pd = true, rank_ok = true;
 
 #pragma unroll 1
     for (int k = N - 1; k >= 0; --k) {
@@ -226,16 +227,112 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
         yt[l] = v * Lm[l + NU * l];
         yv[l] = vv * Lm[l + NU * l];
       }
+      // ---- state-input equality constraints C x + D u + e = 0 (range-space form of the reference's projection, see the file header):
+      //      Z = L^-1 D', M = Z'Z = L_M L_M' (L_M' is the R factor of the reference's QR of U^-T D'), Vx = L_M^-1 (Z'Y - C),
+      //      vv = L_M^-1 (Z'Yv - e);  the constrained minimiser is Y^ = Y - Z L_M^-T Vx, Yv^ = Yv - Z L_M^-T vv and the value function
+      //      gains + Vx'Vx, + Vx'vv, + 1/2 vv'vv ----
+      double yh[NU], yvh[NU], vx[NC > 0 ? NC : 1], vv[NC > 0 ? NC : 1];
+#pragma unroll
+      for (int l = 0; l < NU; ++l) {
+        yh[l] = yt[l];
+        yvh[l] = yv[l];
+      }
+      if (NC > 0) {
+        {  // lane c < nc: column c of Z by forward substitution
+          const int cc = i < NC ? i : NC - 1;
+          double z[NU];
+#pragma unroll
+          for (int l = 0; l < NU; ++l) {
+            double v = rec[S::oD + cc + NC * l];
+#pragma unroll
+            for (int l2 = 0; l2 < l; ++l2) v = fma(-Lm[l + NU * l2], z[l2], v);
+            z[l] = v * Lm[l + NU * l];
+          }
+          if (i < NC) {
+#pragma unroll
+            for (int l = 0; l < NU; ++l) sm[S::sZ + l + NU * i] = z[l];
+          }
+        }
+        __syncwarp();
+        const double* Z = sm + S::sZ;
+        // M = Z'Z and its Cholesky, redundantly in every lane (nc is tiny); 1/L_M,cc on the diagonal
+        double lm[NC > 0 ? NC : 1][NC > 0 ? NC : 1];
+#pragma unroll
+        for (int c1 = 0; c1 < NC; ++c1)
+#pragma unroll
+          for (int c2 = 0; c2 <= c1; ++c2) {
+            double v = 0.0;
+#pragma unroll
+            for (int l = 0; l < NU; ++l) v = fma(Z[l + NU * c1], Z[l + NU * c2], v);
+            lm[c1][c2] = v;
+          }
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          double d = lm[j][j];
+          // the reference clamps |Rc_jj| = L_M,jj to 1e-9 (LinearAlgebra.cpp:38-47) and we flag it
+          if (!(d >= 1e-18)) {
+            rank_ok = false;
+            d = 1e-18;
+          }
+          const double rs = rsqrt_pivot(d);
+          lm[j][j] = rs;
+#pragma unroll
+          for (int c1 = j + 1; c1 < NC; ++c1) lm[c1][j] *= rs;
+#pragma unroll
+          for (int c1 = j + 1; c1 < NC; ++c1)
+#pragma unroll
+            for (int c2 = j + 1; c2 <= c1; ++c2) lm[c1][c2] = fma(-lm[c1][j], lm[c2][j], lm[c1][c2]);
+        }
+        // Vx(:,i) = L_M^-1 (Z'Y(:,i) - C(:,i)),  vv = L_M^-1 (Z'Yv - e)
+#pragma unroll
+        for (int c1 = 0; c1 < NC; ++c1) {
+          double v = -rec[S::oC + c1 + NC * i], w2 = -rec[S::oe + c1];
+#pragma unroll
+          for (int l = 0; l < NU; ++l) {
+            v = fma(Z[l + NU * c1], yt[l], v);
+            w2 = fma(Z[l + NU * c1], yv[l], w2);
+          }
+#pragma unroll
+          for (int c2 = 0; c2 < c1; ++c2) {
+            v = fma(-lm[c1][c2], vx[c2], v);
+            w2 = fma(-lm[c1][c2], vv[c2], w2);
+          }
+          vx[c1] = v * lm[c1][c1];
+          vv[c1] = w2 * lm[c1][c1];
+        }
+#pragma unroll
+        for (int c1 = 0; c1 < NC; ++c1) sm[S::sVx + i + NX * c1] = vx[c1];
+        // t = L_M^-T Vx(:,i), tv = L_M^-T vv;  Y^ = Y - Z t, Yv^ = Yv - Z tv
+        double tx[NC > 0 ? NC : 1], tvv[NC > 0 ? NC : 1];
+#pragma unroll
+        for (int c1 = NC - 1; c1 >= 0; --c1) {
+          double v = vx[c1], w2 = vv[c1];
+#pragma unroll
+          for (int c2 = c1 + 1; c2 < NC; ++c2) {
+            v = fma(-lm[c2][c1], tx[c2], v);
+            w2 = fma(-lm[c2][c1], tvv[c2], w2);
+          }
+          tx[c1] = v * lm[c1][c1];
+          tvv[c1] = w2 * lm[c1][c1];
+        }
+#pragma unroll
+        for (int l = 0; l < NU; ++l)
+#pragma unroll
+          for (int c1 = 0; c1 < NC; ++c1) {
+            yh[l] = fma(-Z[l + NU * c1], tx[c1], yh[l]);
+            yvh[l] = fma(-Z[l + NU * c1], tvv[c1], yvh[l]);
+          }
+      }
 #pragma unroll
       for (int l = NU - 1; l >= 0; --l) {
-        double v = -yt[l], vv = -yv[l];
+        double v = -yh[l], vv2 = -yvh[l];
 #pragma unroll
         for (int l2 = l + 1; l2 < NU; ++l2) {
           v = fma(-Lm[l2 + NU * l], kt[l2], v);
-          vv = fma(-Lm[l2 + NU * l], db[l2], vv);
+          vv2 = fma(-Lm[l2 + NU * l], db[l2], vv2);
         }
         kt[l] = v * Lm[l + NU * l];
-        db[l] = vv * Lm[l + NU * l];
+        db[l] = vv2 * Lm[l + NU * l];
       }
 #pragma unroll
       for (int l = 0; l < NU; ++l) sm[S::sYt + i + NX * l] = yt[l];
@@ -258,11 +355,15 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
         double v = Trow[j];
 #pragma unroll
         for (int l = 0; l < NU; ++l) v = fma(-yt[l], sm[S::sYt + j + NX * l], v);
+#pragma unroll
+        for (int c1 = 0; c1 < NC; ++c1) v = fma(vx[c1], sm[S::sVx + j + NX * c1], v);
         Srow[j] = v;
       }
       Svi = tvi;
 #pragma unroll
       for (int l = 0; l < NU; ++l) Svi = fma(-yt[l], yv[l], Svi);
+#pragma unroll
+      for (int c1 = 0; c1 < NC; ++c1) Svi = fma(vx[c1], vv[c1], Svi);
       // s: rows sum their shares inside the group (xor butterflies stay inside aligned power-of-two blocks only when nx is one,
       // so the group sum goes through shared memory)
       sm[S::sX + i] = spart;
@@ -274,6 +375,8 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
         double yy = 0.0;
 #pragma unroll
         for (int l = 0; l < NU; ++l) yy = fma(yv[l], yv[l], yy);
+#pragma unroll
+        for (int c1 = 0; c1 < NC; ++c1) yy = fma(-vv[c1], vv[c1], yy);
         sval = sval + rec[S::oc] + sh - 0.5 * yy;
       }
       if (valid) {
@@ -296,8 +399,9 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
 #pragma unroll
     for (int j = 0; j < NX; ++j) finite = finite && finite_bits(Srow[j]);
     const unsigned gmask = (NX == 32) ? kFull : (((1u << NX) - 1u) << gbase);
-    const unsigned bad_pd = __ballot_sync(kFull, !pd), bad_fin = __ballot_sync(kFull, !finite);
-    int bits = ((bad_pd & gmask) ? O2C_STATUS_CHOL_NOT_PD : 0) | ((bad_fin & gmask) ? O2C_STATUS_NONFINITE : 0);
+    const unsigned bad_pd = __ballot_sync(kFull, !pd), bad_fin = __ballot_sync(kFull, !finite), bad_rank = __ballot_sync(kFull, !rank_ok);
+    int bits = ((bad_pd & gmask) ? O2C_STATUS_CHOL_NOT_PD : 0) | ((bad_fin & gmask) ? O2C_STATUS_NONFINITE : 0) |
+               ((bad_rank & gmask) ? O2C_STATUS_CONSTRAINT_RANK : 0);
     if (!a.with_rollout) {
       if (valid && i == 0) a.status[prob] = bits;
       __syncwarp();
@@ -384,22 +488,22 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
   }
 }
 
-template <int NX, int NU>
+template <int NX, int NU, int NC>
 bool layout_matches(const Layout& L) {
-  using S = Shape<NX, NU>;
-  return L.n == NX && L.m == NU && L.ncmax == 0 && L.rec == S::rec && L.oA == S::oA && L.oB == S::oB && L.oHv == S::oHv && L.oq == S::oq &&
+  using S = Shape<NX, NU, NC>;
+  return L.n == NX && L.m == NU && L.ncmax == NC && (NC == 0 || (L.oC == S::oC && L.oD == S::oD && L.oe == S::oe)) && L.rec == S::rec && L.oA == S::oA && L.oB == S::oB && L.oHv == S::oHv && L.oq == S::oq &&
          L.or_ == S::or_ && L.oc == S::oc && L.oQ == S::oQ && L.oP == S::oP && L.oR == S::oR && L.orec == S::orec && L.oK == S::oK &&
          L.odb == S::odb && L.obias == S::obias && L.oSm == S::oSm && L.oSv == S::oSv && L.os == S::os && L.trec == S::trec &&
          L.oQf == S::oQf && L.oqf == S::oqf && L.ocf == S::ocf;
 }
 
-template <int NX, int NU>
+template <int NX, int NU, int NC>
 cudaError_t launch(const Args& a, cudaStream_t stream) {
-  using S = Shape<NX, NU>;
+  using S = Shape<NX, NU, NC>;
   static int num_sms = 0;
   constexpr int wpb = 2;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (num_sms == 0) {
     int dev = 0;
@@ -407,13 +511,13 @@ cudaError_t launch(const Args& a, cudaStream_t stream) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ilqr_rpl_kernel<NX, NU>, wpb * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ilqr_rpl_kernel<NX, NU, NC>, wpb * 32, smem);
   if (e != cudaSuccess) return e;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int per_cta = wpb * S::P;
   const int needed = (a.count + per_cta - 1) / per_cta;
   const int cap = num_sms * ctas_per_sm;  // persistent warps: one resident wave, static stride over the problem index
-  ilqr_rpl_kernel<NX, NU><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
+  ilqr_rpl_kernel<NX, NU, NC><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -426,7 +530,8 @@ bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const La
 
 bool rpl_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   if (!settings_match(st, buf, L)) return false;
-  return layout_matches<10, 3>(L) || layout_matches<4, 1>(L);
+  if (L.ncmax > 0 && buf.nc != nullptr) return false;  // ragged per-node constraint counts: the generic kernel handles those
+  return layout_matches<10, 3, 0>(L) || layout_matches<4, 1, 0>(L) || layout_matches<9, 9, 3>(L);
 }
 
 cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int begin,
@@ -447,8 +552,9 @@ cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const Dev
   a.eps = st.eps;
   a.alpha = alpha;
   if (launches) *launches = 1;
-  if (layout_matches<10, 3>(L)) return launch<10, 3>(a, stream);
-  return launch<4, 1>(a, stream);
+  if (layout_matches<10, 3, 0>(L)) return launch<10, 3, 0>(a, stream);
+  if (layout_matches<9, 9, 3>(L)) return launch<9, 9, 3>(a, stream);
+  return launch<4, 1, 0>(a, stream);
 }
 
 }  // namespace o2c
