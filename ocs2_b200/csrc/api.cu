@@ -476,7 +476,10 @@ o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) 
     }
   } else {
     if (!h->time_set) return fail(O2C_ERR_NOT_READY, "SLQ needs the node times (o2c_set_time or lq_view.time) before o2c_backward");
-    O2C_CUDA(launch_slq_generic(h->L, h->st, buf, h->d_slq_steps, h->n_slq_steps, begin, count, stream));
+    if (rpl_slq_supported(h->L, h->st, buf))
+      O2C_CUDA(launch_slq_rpl(h->L, h->st, buf, h->d_slq_steps, h->n_slq_steps, begin, count, stream));
+    else
+      O2C_CUDA(launch_slq_generic(h->L, h->st, buf, h->d_slq_steps, h->n_slq_steps, begin, count, stream));
     h->launches += 1;
   }
   return O2C_OK;
@@ -847,6 +850,7 @@ o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {
 
 const char* o2c_kernel_variant(const o2c_handle* h) {
   if (!h) return "";
+  if (h->st.algorithm == O2C_ALG_SLQ && rpl_slq_supported(h->L, h->st, h->buffers())) return "slq_rpl_kernel";
   if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast) return "ilqr_wpp_kernel";
   if (h->st.algorithm == O2C_ALG_ILQR && h->use_rpl && rpl_ilqr_supported(h->L, h->st, h->buffers())) return "ilqr_rpl_kernel";
   return generic_variant_name(h->L, h->st);

@@ -159,6 +159,10 @@ bool rpl_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceB
 cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int begin,
                             int count, cudaStream_t stream, int* launches);
 
+bool rpl_slq_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
+cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin,
+                           int count, cudaStream_t stream);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA bulk copy (cp.async.bulk), L2 prefetch

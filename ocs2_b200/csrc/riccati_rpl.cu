@@ -488,6 +488,382 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// SLQ: the continuous-time Riccati flow map under fixed-step RK4, same row-per-lane mapping (nc = 0, LINE_SEARCH, reduced form,
+// DIAGONAL_SHIFT). Per node k the projection with Hm = R (SLQ.cpp:183-208): R = L L', Pu = L^-T, B~ = B Pu, P~ = Pu'P, r~ = Pu'r;
+// the flow map (ContinuousTimeRiccatiEquations.cpp:170-292) on the data lerped between the two nodes of the interval:
+//   G~m = P~ + B~'S, G~v = r~ + B~'Sv,  dS/dz = Q + eps I + S A + (S A)' - G~m'G~m,  dSv/dz = q + S Hv + A'Sv - G~m'G~v,
+//   ds/dz = c + Hv.Sv - 1/2 G~v.G~v;  the RK4 step schedule (boost::odeint integrate_times semantics) is precomputed on the host
+//   (SlqStep). Lane i integrates row i of S (and Sv_i; s redundantly); A, B~, S A, G~m' are broadcast from shared memory.
+//   Controller at an observed node (SLQ.cpp:127-169): K(:,i) = -L^-T (P~(:,i) + B~'S(:,i)), dbias = -L^-T (r~ + B~'Sv).
+// Stage records arrive by TMA into a ring of three slots (nodes k, k+1 in use, node k-1 in flight).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NX, int NU>
+struct SlqShape {
+  using R = Shape<NX, NU, 0>;
+  static constexpr int P = 32 / NX;
+  static constexpr int rec = R::rec;
+  static constexpr int sRec = 0, sBt = 3 * rec, sLm = sBt + 2 * cpad2(NX * NU), sAl = sLm + 2 * cpad2(NU * NU), sBl = sAl + cpad2(NX * NX),
+                       sMs = sBl + cpad2(NX * NU), sGs = sMs + cpad2(NX * NX), sSv = sGs + cpad2(NX * NU), sHv = sSv + cpad2(NX),
+                       sGv = sHv + cpad2(NX), slot = sGv + cpad2(NU);
+  static constexpr int warp_doubles = P * slot + 2;
+};
+
+struct SlqArgs {
+  const double* lq;
+  const double* term;
+  double* sol;
+  int* status;
+  const SlqStep* steps;
+  int nsteps, N, begin, count;
+  double eps;
+};
+
+template <int NX, int NU>
+__global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
+  using S = SlqShape<NX, NU>;
+  using R = typename S::R;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)warp * S::warp_doubles;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(wbase + S::P * S::slot);
+  const int graw = lane / NX;
+  const bool in_group = graw < S::P;
+  const int gi = in_group ? graw : S::P - 1;
+  const int i = in_group ? lane - graw * NX : NX - 1;
+  const int gbase = gi * NX;
+  double* sm = wbase + gi * S::slot;
+  const int N = a.N, nodes = N + 1;
+  const uint32_t recBytes = S::rec * sizeof(double);
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+
+  for (int base = (blockIdx.x * (blockDim.x >> 5) + warp) * S::P; base < a.count; base += warps_total * S::P) {
+    const int nprob = (a.count - base) < S::P ? (a.count - base) : S::P;
+    const bool valid = in_group && gi < nprob;
+    const int prob = a.begin + base + (gi < nprob ? gi : nprob - 1);
+    const double* term = a.term + (size_t)prob * R::trec;
+    double* solp = a.sol + (size_t)prob * (N + 1) * R::orec;
+
+    auto issue_node = [&](int k) {  // records of node k of every carried problem -> ring slot k % 3
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, recBytes * nprob);
+        for (int g = 0; g < nprob; ++g)
+          tma_load(wbase + g * S::slot + S::sRec + (k % 3) * S::rec, a.lq + ((size_t)(a.begin + base + g) * nodes + k) * S::rec, recBytes, bar);
+      }
+    };
+
+    // state of the integration: row i of S, Sv_i, s
+    double Srow[NX], Svi, sval;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) Srow[j] = term[R::oQf + ((i <= j) ? i + NX * j : j + NX * i)];  // convert2Vector keeps the upper triangle
+    Svi = term[R::oqf + i];
+    sval = term[R::ocf];
+    bool pd = true;
+
+    // node-resident lane-private data: set 0 = node i0 (left end of the interval), set 1 = node i0 + 1
+    double qr0[NX], qr1[NX], pt0[NU], pt1[NU], rt0[NU], rt1[NU], hv0 = 0.0, hv1 = 0.0, q0 = 0.0, q1 = 0.0, c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) qr0[j] = qr1[j] = 0.0;
+#pragma unroll
+    for (int l = 0; l < NU; ++l) pt0[l] = pt1[l] = rt0[l] = rt1[l] = 0.0;
+
+    auto write_value = [&](int k) {
+      if (valid) {
+        double* out = solp + (size_t)k * R::orec;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) out[R::oSm + i + NX * j] = Srow[j];
+        out[R::oSv + i] = Svi;
+        if (i == 0) out[R::os] = sval;
+      }
+    };
+    // projection of node k (record in its ring slot) into set 0; B~ and L go to shared memory slot k & 1
+    auto project_node = [&](int k) {
+      const double* rec = sm + S::sRec + (k % 3) * S::rec;
+      double Lr[NU][NU];
+#pragma unroll
+      for (int l = 0; l < NU; ++l)
+#pragma unroll
+        for (int l2 = 0; l2 <= l; ++l2) Lr[l][l2] = rec[R::oR + l + NU * l2];
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        const double d = Lr[j][j];
+        pd = pd && (__double2hiint(d) > 0);
+        const double rs = rsqrt_pivot(d);
+        Lr[j][j] = rs;
+#pragma unroll
+        for (int l = j + 1; l < NU; ++l) Lr[l][j] *= rs;
+#pragma unroll
+        for (int l = j + 1; l < NU; ++l)
+#pragma unroll
+          for (int l2 = j + 1; l2 <= l; ++l2) Lr[l][l2] = fma(-Lr[l][j], Lr[l2][j], Lr[l][l2]);
+      }
+      double* Lm = sm + S::sLm + (k & 1) * cpad2(NU * NU);
+      double* Bt = sm + S::sBt + (k & 1) * cpad2(NX * NU);
+      if (i == 0) {
+#pragma unroll
+        for (int l = 0; l < NU; ++l)
+#pragma unroll
+          for (int l2 = 0; l2 <= l; ++l2) Lm[l + NU * l2] = Lr[l][l2];
+      }
+      double bt[NU];
+#pragma unroll
+      for (int l = 0; l < NU; ++l) {  // B~_i = B_i L^-T, P~(:,i) = L^-1 P(:,i), r~ = L^-1 r: forward substitutions
+        double vb = rec[R::oB + i + NX * l], vp = rec[R::oP + l + NU * i], vr = rec[R::or_ + l];
+#pragma unroll
+        for (int l2 = 0; l2 < l; ++l2) {
+          vb = fma(-Lr[l][l2], bt[l2], vb);
+          vp = fma(-Lr[l][l2], pt0[l2], vp);
+          vr = fma(-Lr[l][l2], rt0[l2], vr);
+        }
+        bt[l] = vb * Lr[l][l];
+        pt0[l] = vp * Lr[l][l];
+        rt0[l] = vr * Lr[l][l];
+        Bt[i + NX * l] = bt[l];
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) qr0[j] = rec[R::oQ + ((i <= j) ? i + NX * j : j + NX * i)];
+      hv0 = rec[R::oHv + i];
+      q0 = rec[R::oq + i];
+      c0 = rec[R::oc];
+      __syncwarp();
+    };
+    // SLQ::calculateControllerWorker at node k (whose projection is set 0) from the current state
+    auto controller = [&](int k) {
+      const double* Lm = sm + S::sLm + (k & 1) * cpad2(NU * NU);
+      const double* Bt = sm + S::sBt + (k & 1) * cpad2(NX * NU);
+      sm[S::sSv + i] = Svi;
+      __syncwarp();
+      double kt[NU], db[NU], g[NU], gv[NU];
+#pragma unroll
+      for (int l = 0; l < NU; ++l) {
+        g[l] = dot_col<NX>(Srow, Bt + NX * l, pt0[l]);
+        double v = rt0[l];
+        if (NX % 2 == 0) {
+#pragma unroll
+          for (int kk = 0; kk < NX; kk += 2) {
+            const double2 bb = ld2(Bt + NX * l + kk), ss = ld2(sm + S::sSv + kk);
+            v = fma(bb.x, ss.x, v);
+            v = fma(bb.y, ss.y, v);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < NX; ++kk) v = fma(Bt[NX * l + kk], sm[S::sSv + kk], v);
+        }
+        gv[l] = v;
+      }
+#pragma unroll
+      for (int l = NU - 1; l >= 0; --l) {  // back substitution with L': x = L^-T (-g)
+        double v = -g[l], vv = -gv[l];
+#pragma unroll
+        for (int l2 = l + 1; l2 < NU; ++l2) {
+          v = fma(-Lm[l2 + NU * l], kt[l2], v);
+          vv = fma(-Lm[l2 + NU * l], db[l2], vv);
+        }
+        kt[l] = v * Lm[l + NU * l];
+        db[l] = vv * Lm[l + NU * l];
+      }
+      if (valid) {
+        double* out = solp + (size_t)k * R::orec;
+#pragma unroll
+        for (int l = 0; l < NU; ++l) out[R::oK + l + NU * i] = kt[l];
+        if (i < NU) {
+          double dbi = db[0];
+#pragma unroll
+          for (int l = 1; l < NU; ++l) dbi = (i == l) ? db[l] : dbi;
+          out[R::odb + i] = dbi;
+          out[R::obias + i] = 0.0;
+        }
+      }
+      __syncwarp();
+    };
+
+    write_value(N);
+    issue_node(N);
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    project_node(N);
+    controller(N);  // overwritten below by the copy of node N-1 (GaussNewtonDDP.cpp:609-618)
+    if (N >= 1) issue_node(N - 1);
+    int loaded_lo = N;
+
+#pragma unroll 1
+    for (int sidx = 0; sidx < a.nsteps; ++sidx) {
+      const SlqStep sp = a.steps[sidx];
+      const int i0 = sp.interval;
+      if (i0 < loaded_lo) {  // the interval moved one node down: set 1 <- set 0, set 0 <- node i0
+#pragma unroll
+        for (int j = 0; j < NX; ++j) qr1[j] = qr0[j];
+#pragma unroll
+        for (int l = 0; l < NU; ++l) {
+          pt1[l] = pt0[l];
+          rt1[l] = rt0[l];
+        }
+        hv1 = hv0;
+        q1 = q0;
+        c1 = c0;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        project_node(i0);
+        if (i0 >= 1) issue_node(i0 - 1);  // its ring slot held node i0 + 2, which is dead
+        loaded_lo = i0;
+      }
+      const double* A0 = sm + S::sRec + (i0 % 3) * S::rec + R::oA;
+      const double* A1 = sm + S::sRec + ((i0 + 1) % 3) * S::rec + R::oA;
+      const double* Bt0 = sm + S::sBt + (i0 & 1) * cpad2(NX * NU);
+      const double* Bt1 = sm + S::sBt + ((i0 + 1) & 1) * cpad2(NX * NU);
+      const double h = sp.h;
+      // classic RK4 (boost::odeint runge_kutta4): k_s = f(y + c_s h k_{s-1}), y += h (k1 + 2 k2 + 2 k3 + k4) / 6
+      double ys[NX], ysv = Svi, acc[NX], accv = Svi, accs = sval;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) ys[j] = acc[j] = Srow[j];
+#pragma unroll 1
+      for (int stg = 0; stg < 4; ++stg) {
+        const double al = sp.alpha[stg], be = 1.0 - al;
+        // lerped data: column i of A, row i of B~ -> shared (broadcast operands); lane-private pieces stay in registers
+        if (NX % 2 == 0) {
+#pragma unroll
+          for (int kk = 0; kk < NX; kk += 2) {
+            const double2 v0 = ld2(A0 + kk + NX * i), v1 = ld2(A1 + kk + NX * i);
+            *reinterpret_cast<double2*>(sm + S::sAl + kk + NX * i) = make_double2(fma(al, v0.x, be * v1.x), fma(al, v0.y, be * v1.y));
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < NX; ++kk) sm[S::sAl + kk + NX * i] = fma(al, A0[kk + NX * i], be * A1[kk + NX * i]);
+        }
+        double ptl[NU];
+#pragma unroll
+        for (int l = 0; l < NU; ++l) {
+          sm[S::sBl + i + NX * l] = fma(al, Bt0[i + NX * l], be * Bt1[i + NX * l]);
+          ptl[l] = fma(al, pt0[l], be * pt1[l]);
+        }
+        sm[S::sHv + i] = fma(al, hv0, be * hv1);
+        sm[S::sSv + i] = ysv;
+        __syncwarp();
+        // M_i = S_i A, G'_i = P~(:,i)' + S_i B~, G~v on lanes < nu
+        double Mrow[NX], gt[NU];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          Mrow[j] = dot_col<NX>(ys, sm + S::sAl + NX * j, 0.0);
+          sm[S::sMs + i + NX * j] = Mrow[j];
+        }
+#pragma unroll
+        for (int l = 0; l < NU; ++l) {
+          gt[l] = dot_col<NX>(ys, sm + S::sBl + NX * l, ptl[l]);
+          sm[S::sGs + i + NX * l] = gt[l];
+        }
+        {
+          const int l = i < NU ? i : NU - 1;
+          double rl = fma(al, rt0[0], be * rt1[0]);
+#pragma unroll
+          for (int l2 = 1; l2 < NU; ++l2) rl = (l == l2) ? fma(al, rt0[l2], be * rt1[l2]) : rl;
+          double v = rl;
+#pragma unroll
+          for (int kk = 0; kk < NX; ++kk) v = fma(sm[S::sBl + kk + NX * l], sm[S::sSv + kk], v);
+          if (i < NU) sm[S::sGv + i] = v;
+        }
+        __syncwarp();
+        // derivatives of this lane's row
+        double gv[NU];
+#pragma unroll
+        for (int l = 0; l < NU; ++l) gv[l] = sm[S::sGv + l];
+        double kS[NX], kv, ks;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          double v = fma(al, qr0[j], be * qr1[j]) + ((j == i) ? a.eps : 0.0) + Mrow[j] + sm[S::sMs + j + NX * i];
+#pragma unroll
+          for (int l = 0; l < NU; ++l) v = fma(-gt[l], sm[S::sGs + j + NX * l], v);
+          kS[j] = v;
+        }
+        {
+          double v = fma(al, q0, be * q1);
+          double hs = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < NX; ++kk) {
+            const double hvk = sm[S::sHv + kk], svk = sm[S::sSv + kk];
+            v = fma(ys[kk], hvk, v);                       // S_i Hv
+            v = fma(sm[S::sAl + kk + NX * i], svk, v);     // A(:,i)' Sv
+            hs = fma(hvk, svk, hs);                        // Hv . Sv
+          }
+          double gg = 0.0;
+#pragma unroll
+          for (int l = 0; l < NU; ++l) {
+            v = fma(-gt[l], gv[l], v);
+            gg = fma(gv[l], gv[l], gg);
+          }
+          kv = v;
+          ks = fma(al, c0, be * c1) + hs - 0.5 * gg;
+        }
+        __syncwarp();  // the shared operands of this stage are dead
+        // accumulate and form the next stage's argument
+        const double bw = h * ((stg == 0 || stg == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
+        const double cw = h * ((stg == 2) ? 1.0 : 0.5);
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          acc[j] = fma(bw, kS[j], acc[j]);
+          ys[j] = fma(cw, kS[j], Srow[j]);
+        }
+        accv = fma(bw, kv, accv);
+        accs = fma(bw, ks, accs);
+        ysv = fma(cw, kv, Svi);
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) Srow[j] = acc[j];
+      Svi = accv;
+      sval = accs;
+      if (sp.observe_node >= 0) {
+        write_value(sp.observe_node);
+        controller(sp.observe_node);
+      }
+    }
+    __syncwarp();
+    if (valid && N >= 1) {  // node N of the controller := node N-1 (GaussNewtonDDP.cpp:609-618)
+      const double* src = solp + (size_t)(N - 1) * R::orec;
+      double* dst = solp + (size_t)N * R::orec;
+      for (int e = i; e < R::oSm; e += NX) dst[e] = __ldcg(src + e);
+    }
+    bool finite = finite_bits(Svi) && finite_bits(sval);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) finite = finite && finite_bits(Srow[j]);
+    const unsigned gmask = (NX == 32) ? kFull : (((1u << NX) - 1u) << gbase);
+    const unsigned bad_pd = __ballot_sync(kFull, !pd), bad_fin = __ballot_sync(kFull, !finite);
+    const int bits = ((bad_pd & gmask) ? O2C_STATUS_CHOL_NOT_PD : 0) | ((bad_fin & gmask) ? O2C_STATUS_NONFINITE : 0);
+    if (valid && i == 0) a.status[prob] = bits;
+    __syncwarp();
+  }
+}
+
+template <int NX, int NU>
+cudaError_t launch_slq(const SlqArgs& a, cudaStream_t stream) {
+  using S = SlqShape<NX, NU>;
+  static int num_sms = 0;
+  constexpr int wpb = 2;
+  const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(slq_rpl_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, slq_rpl_kernel<NX, NU>, wpb * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int per_cta = wpb * S::P;
+  const int needed = (a.count + per_cta - 1) / per_cta;
+  const int cap = num_sms * ctas_per_sm;
+  slq_rpl_kernel<NX, NU><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
 template <int NX, int NU, int NC>
 bool layout_matches(const Layout& L) {
   using S = Shape<NX, NU, NC>;
@@ -527,6 +903,30 @@ bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const La
 }
 
 }  // namespace
+
+bool rpl_slq_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
+  if (!(st.algorithm == O2C_ALG_SLQ && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
+        buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1 && L.nodes == L.N + 1))
+    return false;
+  return layout_matches<12, 4, 0>(L);
+}
+
+cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin,
+                           int count, cudaStream_t stream) {
+  if (!rpl_slq_supported(L, st, buf)) return cudaErrorNotSupported;
+  SlqArgs a{};
+  a.lq = buf.lq;
+  a.term = buf.term;
+  a.sol = buf.sol;
+  a.status = buf.status;
+  a.steps = steps;
+  a.nsteps = nsteps;
+  a.N = L.N;
+  a.begin = begin;
+  a.count = count;
+  a.eps = st.eps;
+  return launch_slq<12, 4>(a, stream);
+}
 
 bool rpl_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   if (!settings_match(st, buf, L)) return false;
