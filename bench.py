@@ -38,10 +38,17 @@ DT = 0.01
 FP64_PEAK_TFLOPS_MEASURED = 37.1  # profiles/r01_fp64_peak_microbench.log (DMMA m8n8k4, this pool's B200)
 
 
-def algorithmic_per_solve(n, m, nc, N):
-    """compulsory bytes (each input read once, each output written once) and flops of one ILQR solve."""
+def algorithmic_per_solve(n, m, nc, N, alg=0):
+    """compulsory bytes (each input read once, each output written once) and flops of one solve
+    (ILQR sweep + discrete rollout, or SLQ-RK4 flow map with one step per interval + continuous rollout)."""
     bytes_in = 8 * (2 * n * n + 2 * n * m + m * m + 2 * n + m + 1 + nc * (n + m + 1))
     bytes_out = 8 * (n * m + m + n * n + n + 1 + n + m)
+    if alg == 1:
+        p = m - nc
+        flops = 4 * (2 * n**3 + 4 * n * n * p + 7 * n * n + 4 * n * p + 3 * (3 * n * n + 2 * n * p + 3 * n + 2 * p + 1)) + 10 * (n * (n + 1) / 2 + n + 1)
+        flops += (11.0 / 3.0) * m**3 + 3 * n * m * m + 4 * n * n * m  # per-node projection + controller
+        flops += 4 * (2 * n * n + 4 * n * m)                          # continuous rollout, 4 RK4 stages per interval
+        return N * (bytes_in + bytes_out), N * flops
     flops = 4 * n**3 + 6 * n * n * m + 4 * n * m * m + (2.0 / 3.0) * m**3 + 4 * n * n + 4 * n * m + 2 * m * m + 2 * n * n + 4 * n * m
     if nc:
         flops += 6 * m * m * nc + 2 * nc * nc * (m - nc / 3.0) + 2 * nc * n * m + 2 * nc * m
@@ -250,8 +257,8 @@ def main():
 
     # ---- roofline of the dominant kernel ----
     peaks, which = measured_peaks()
-    bytes_solve, flops_solve = algorithmic_per_solve(n, m, nc, N_STAGES)
-    kernel_s = sweep_ms * 1e-3
+    bytes_solve, flops_solve = algorithmic_per_solve(n, m, nc, N_STAGES, alg)
+    kernel_s = (ms_per_step if split else sweep_ms) * 1e-3  # split paths: sweep and rollout are two launches, both counted
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
