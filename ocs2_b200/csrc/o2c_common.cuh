@@ -163,6 +163,11 @@ bool rpl_slq_supported(const Layout& L, const SolverSettings& st, const DeviceBu
 cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin,
                            int count, cudaStream_t stream);
 
+bool rpl_rollout_cont_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
+cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,
+                                    int first_idx, double first_alpha, int out_nodes, const double* alphas_dev, int n_alpha, int batch,
+                                    int begin, int count, cudaStream_t stream);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA bulk copy (cp.async.bulk), L2 prefetch

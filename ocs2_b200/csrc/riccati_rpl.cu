@@ -864,6 +864,197 @@ cudaError_t launch_slq(const SlqArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Continuous rollout of the LQ model under the LinearController (SLQ): xdot = A(t) x + B(t) u(t,x) + Hv(t),
+// u = lerp(bias + alpha dbias)(t) + lerp(K)(t) x, classic RK4 on the host-precomputed step schedule (RolloutStep: the timeSegment
+// index / weight of every stage and observation time; TimeTriggeredRollout.cpp:46-115, LinearController.cpp:79-87,
+// DDP_HelperFunctions.cpp:296-304). Lane i owns x_i; x and u are broadcast through shared memory. The {A|B|Hv} part of the stage
+// records and the {K|dbias|bias} part of the solution records stream forwards through a three-slot TMA ring (the two nodes of the
+// current time segment in use, the next one in flight); the lerps are applied on the fly to this lane's row.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NX, int NU>
+struct RoShape {
+  using R = Shape<NX, NU, 0>;
+  static constexpr int P = 32 / NX;
+  static constexpr int dyn = R::oq;      // { A | B | Hv } doubles of a stage record
+  static constexpr int pol = R::oSm;     // { K | dbias | bias } doubles of a solution record
+  static constexpr int sDyn = 0, sPol = 3 * dyn, sX = sPol + 3 * pol, sU = sX + cpad2(NX), slot = sU + cpad2(NU);
+  static constexpr int warp_doubles = P * slot + 2;
+};
+
+struct RoArgs {
+  const double* lq;
+  const double* sol;
+  const double* x0;
+  double* xs;
+  double* us;
+  int* status;
+  const RolloutStep* steps;
+  const double* alphas;
+  int nsteps, first_idx, out_nodes, N, batch, begin, count;
+  double first_alpha;
+};
+
+template <int NX, int NU>
+__global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
+  using S = RoShape<NX, NU>;
+  using R = typename S::R;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)warp * S::warp_doubles;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(wbase + S::P * S::slot);
+  const int graw = lane / NX;
+  const bool in_group = graw < S::P;
+  const int gi = in_group ? graw : S::P - 1;
+  const int i = in_group ? lane - graw * NX : NX - 1;
+  const int gbase = gi * NX;
+  double* sm = wbase + gi * S::slot;
+  const int N = a.N, nodes = N + 1;
+  const uint32_t dynBytes = S::dyn * sizeof(double), polBytes = S::pol * sizeof(double);
+  const int ia = blockIdx.y;
+  const double alpha = a.alphas[ia];
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+
+  for (int base = (blockIdx.x * (blockDim.x >> 5) + warp) * S::P; base < a.count; base += warps_total * S::P) {
+    const int nprob = (a.count - base) < S::P ? (a.count - base) : S::P;
+    const bool valid = in_group && gi < nprob;
+    const int prob = a.begin + base + (gi < nprob ? gi : nprob - 1);
+    double* xo = a.xs + ((size_t)ia * a.batch + prob) * (size_t)a.out_nodes * NX;
+    double* uo = a.us + ((size_t)ia * a.batch + prob) * (size_t)a.out_nodes * NU;
+
+    auto issue_node = [&](int k) {  // {A|B|Hv} and {K|dbias|bias} of node k of every carried problem -> ring slot k % 3
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, (dynBytes + polBytes) * nprob);
+        for (int g = 0; g < nprob; ++g) {
+          const size_t pb = (size_t)(a.begin + base + g);
+          tma_load(wbase + g * S::slot + S::sDyn + (k % 3) * S::dyn, a.lq + (pb * nodes + k) * R::rec, dynBytes, bar);
+          tma_load(wbase + g * S::slot + S::sPol + (k % 3) * S::pol, a.sol + (pb * nodes + k) * R::orec, polBytes, bar);
+        }
+      }
+    };
+    int loaded_hi = -1, issued_hi = -1;
+    // make nodes <= q resident; called with q = idx + 1 of the time segment about to be used (idx is non-decreasing along the
+    // schedule, so when node q has landed node q - 2 is dead and its slot takes the prefetch of node q + 1)
+    auto ensure = [&](int q) {
+      q = q < N ? q : N;
+      while (loaded_hi < q) {
+        if (issued_hi == loaded_hi) {
+          issue_node(loaded_hi + 1);
+          issued_hi = loaded_hi + 1;
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        loaded_hi += 1;
+        if (loaded_hi >= q && loaded_hi + 1 <= N) {
+          __syncwarp();
+          issue_node(loaded_hi + 1);
+          issued_hi = loaded_hi + 1;
+        }
+      }
+    };
+    // u(t, x) on lanes < nu from the x in shared memory; result broadcast through shared memory
+    auto policy = [&](int idx, double w0) {
+      const double w1 = 1.0 - w0;
+      const double* p0 = sm + S::sPol + (idx % 3) * S::pol;
+      const double* p1 = sm + S::sPol + ((idx + 1) % 3) * S::pol;
+      const int l = i < NU ? i : NU - 1;
+      double u = w0 * (p0[R::obias + l] + alpha * p0[R::odb + l]) + w1 * (p1[R::obias + l] + alpha * p1[R::odb + l]);
+#pragma unroll
+      for (int j = 0; j < NX; ++j) u = fma(fma(w0, p0[R::oK + l + NU * j], w1 * p1[R::oK + l + NU * j]), sm[S::sX + j], u);
+      if (i < NU) sm[S::sU + i] = u;
+      __syncwarp();
+    };
+    // dx_i/dt at (idx, w0) for the x in shared memory
+    auto flow = [&](int idx, double w0) -> double {
+      policy(idx, w0);
+      const double w1 = 1.0 - w0;
+      const double* d0 = sm + S::sDyn + (idx % 3) * S::dyn;
+      const double* d1 = sm + S::sDyn + ((idx + 1) % 3) * S::dyn;
+      double acc = fma(w0, d0[R::oHv + i], w1 * d1[R::oHv + i]);
+#pragma unroll
+      for (int j = 0; j < NX; ++j) acc = fma(fma(w0, d0[R::oA + i + NX * j], w1 * d1[R::oA + i + NX * j]), sm[S::sX + j], acc);
+#pragma unroll
+      for (int l = 0; l < NU; ++l) acc = fma(fma(w0, d0[R::oB + i + NX * l], w1 * d1[R::oB + i + NX * l]), sm[S::sU + l], acc);
+      __syncwarp();  // x, u in shared memory are dead
+      return acc;
+    };
+
+    double x = a.x0[(size_t)prob * NX + i];
+    bool finite = true;
+    auto observe = [&](int o, int idx, double w0) {
+      ensure(idx + 1);
+      sm[S::sX + i] = x;
+      __syncwarp();
+      policy(idx, w0);
+      if (valid) {
+        __stcg(xo + (size_t)o * NX + i, x);
+        if (i < NU) __stcg(uo + (size_t)o * NU + i, sm[S::sU + i]);
+      }
+      finite = finite && finite_bits(x);
+      __syncwarp();
+    };
+    observe(0, a.first_idx, a.first_alpha);
+#pragma unroll 1
+    for (int sidx = 0; sidx < a.nsteps; ++sidx) {
+      const RolloutStep sp = a.steps[sidx];
+      const double h = sp.h;
+      double acc = x, xs = x;
+#pragma unroll 1
+      for (int stg = 0; stg < 4; ++stg) {
+        ensure(sp.idx[stg] + 1);
+        sm[S::sX + i] = xs;
+        __syncwarp();
+        const double kx = flow(sp.idx[stg], sp.alpha[stg]);
+        acc = fma(h * ((stg == 0 || stg == 3) ? (1.0 / 6.0) : (1.0 / 3.0)), kx, acc);
+        xs = fma(h * ((stg == 2) ? 1.0 : 0.5), kx, x);
+      }
+      x = acc;
+      observe(sidx + 1, sp.obs_idx, sp.obs_alpha);
+    }
+    // drain a prefetch that is still in flight before the ring is reused by the next round
+    if (issued_hi > loaded_hi) {
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+    }
+    const unsigned gmask = (NX == 32) ? kFull : (((1u << NX) - 1u) << gbase);
+    if ((__ballot_sync(kFull, !finite) & gmask) && valid && i == 0) atomicOr(a.status + prob, O2C_STATUS_NONFINITE);
+    __syncwarp();
+  }
+}
+
+template <int NX, int NU>
+cudaError_t launch_ro(const RoArgs& a, int n_alpha, cudaStream_t stream) {
+  using S = RoShape<NX, NU>;
+  static int num_sms = 0;
+  constexpr int wpb = 4;
+  const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(rollout_cont_rpl_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, rollout_cont_rpl_kernel<NX, NU>, wpb * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int per_cta = wpb * S::P;
+  const int needed = (a.count + per_cta - 1) / per_cta;
+  const int cap = num_sms * ctas_per_sm;
+  dim3 grid(needed < cap ? needed : cap, n_alpha);
+  rollout_cont_rpl_kernel<NX, NU><<<grid, wpb * 32, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
 template <int NX, int NU, int NC>
 bool layout_matches(const Layout& L) {
   using S = Shape<NX, NU, NC>;
@@ -926,6 +1117,34 @@ cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const Devi
   a.count = count;
   a.eps = st.eps;
   return launch_slq<12, 4>(a, stream);
+}
+
+bool rpl_rollout_cont_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
+  return st.algorithm == O2C_ALG_SLQ && buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1 && L.nodes == L.N + 1 && layout_matches<12, 4, 0>(L);
+}
+
+cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,
+                                    int first_idx, double first_alpha, int out_nodes, const double* alphas_dev, int n_alpha, int batch,
+                                    int begin, int count, cudaStream_t stream) {
+  if (!rpl_rollout_cont_supported(L, st, buf)) return cudaErrorNotSupported;
+  RoArgs a{};
+  a.lq = buf.lq;
+  a.sol = buf.sol;
+  a.x0 = buf.x0;
+  a.xs = buf.xs;
+  a.us = buf.us;
+  a.status = buf.status;
+  a.steps = steps;
+  a.alphas = alphas_dev;
+  a.nsteps = nsteps;
+  a.first_idx = first_idx;
+  a.first_alpha = first_alpha;
+  a.out_nodes = out_nodes;
+  a.N = L.N;
+  a.batch = batch;
+  a.begin = begin;
+  a.count = count;
+  return launch_ro<12, 4>(a, n_alpha, stream);
 }
 
 bool rpl_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
