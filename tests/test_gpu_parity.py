@@ -323,3 +323,64 @@ def test_legged_dmma_kernel_uploaded_data_subrange_and_status():
     assert np.array_equal(np.isnan(sol.K[2]), np.isnan(ref.K))
     for i in (0, 1, 3, 5):
         check_against_oracle(st, _oracle_problem(lq, 2 + i, N), lq.x0[2 + i], sol, i, what="dmma uploaded")
+
+
+# ---- the row-per-lane kernels (small shapes: several problems per warp) ----
+@pytest.mark.parametrize("shape,algorithm,variant", [("ballbot", o2.ALG_ILQR, "ilqr_rpl_kernel"), ("manipulator", o2.ALG_ILQR, "ilqr_rpl_kernel"),
+                                                     ("cartpole", o2.ALG_ILQR, "ilqr_rpl_kernel"), ("quadrotor", o2.ALG_SLQ, "slq_rpl_kernel")])
+@pytest.mark.parametrize("batch,begin,count", [(1, 0, 1), (2, 1, 1), (7, 0, 7), (11, 3, 5)])
+def test_rpl_kernels_partial_warps_and_subranges(shape, algorithm, variant, batch, begin, count):
+    """A warp carries 32 // nx problems: batches that do not fill the last warp, and sub-range solves, must not touch neighbours."""
+    n, m, nc = SHAPES[shape]
+    N, dt, seed = 9, 0.01, 5
+    st = o2.Settings(algorithm=algorithm, hessianCorrectionMultiple=1e-3, timeStep=dt)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, max_alphas=2) as solver:
+        assert solver.kernel_variant == variant
+        solver.generate_synthetic(seed, first_problem_index=20, dt=dt)
+        solver.solve(alpha=0.7, problem_begin=begin, problem_count=count)
+        sol = solver.download(problem_begin=begin, problem_count=count)
+        assert (sol.status == 0).all()
+        for i in sorted({0, count - 1}):
+            pb, x0 = orc.generate_problem(seed, 20 + begin + i, algorithm, n, m, nc, N, dt)
+            check_against_oracle(st, pb, x0, sol, i, (0.7,), what=f"rpl {shape} batch {batch}")
+        # several step lengths through o2c_rollout (the continuous rollout of SLQ has its own row-per-lane kernel)
+        solver.solveSequentialRiccatiEquations(begin, count)
+        solver.rolloutTrajectory((1.0, 0.25), begin, count)
+        sol2 = solver.download(problem_begin=begin, problem_count=count)
+        pb, x0 = orc.generate_problem(seed, 20 + begin, algorithm, n, m, nc, N, dt)
+        check_against_oracle(st, pb, x0, sol2, 0, (1.0, 0.25), what=f"rpl {shape} multi-alpha")
+
+
+def test_rpl_constraints_rank_deficient_flag_and_ragged_fallback():
+    """Manipulator shape through the range-space constraint path: a duplicated constraint row sets CONSTRAINT_RANK on that problem
+    only; per-node (ragged) constraint counts make the handle fall back to the generic kernel, with the same results."""
+    rng = np.random.default_rng(5)
+    batch, n, m, nc, N = 6, 9, 9, 3, 10
+    lq = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=False)
+    lq.x_nom = lq.u_nom = None
+    lq.nc = None
+    lq.D[2, 4, 1] = lq.D[2, 4, 0]  # rows 0 and 1 of D identical at node 4 of problem 2
+    lq.C[2, 4, 1] = lq.C[2, 4, 0]
+    lq.e[2, 4, 1] = lq.e[2, 4, 0]
+    st = o2.Settings(hessianCorrectionMultiple=1e-3)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
+        solver.upload(lq)
+        assert solver.kernel_variant == "ilqr_rpl_kernel"
+        solver.solve()
+        sol = solver.download()
+    assert sol.status[2] & o2.STATUS_CONSTRAINT_RANK
+    assert (np.delete(sol.status, 2) == 0).all()
+    lq.nc = np.full((batch, N), nc, np.int32)
+    for i in (0, 1, 3, 5):
+        check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, what="rpl constraints uploaded")
+    # ragged counts: generic kernel
+    lq2 = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=True)
+    lq2.x_nom = lq2.u_nom = None
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
+        solver.upload(lq2)
+        assert solver.kernel_variant.startswith("ilqr_generic_kernel")
+        solver.solve()
+        sol2 = solver.download()
+    assert (sol2.status == 0).all()
+    for i in (0, batch - 1):
+        check_against_oracle(st, _oracle_problem(lq2, i, N), lq2.x0[i], sol2, i, what="ragged fallback")
