@@ -162,6 +162,31 @@ o2c_error o2c_launch_count(const o2c_handle* handle, int64_t* launches);
 /* name of the sweep kernel variant that o2c_backward dispatches to for this config (diagnostics / profiles) */
 const char* o2c_kernel_variant(const o2c_handle* handle);
 
+/* ---- the step after: batched Armijo line search on the LQ model ----
+ * LineSearchStrategy::run / lineSearchTask (ocs2_ddp/src/search_strategy/LineSearchStrategy.cpp:125-258): the candidates
+ * alpha_e = max_step_length * contraction_rate^e, as long as alpha_e >= min_step_length (numerics::almost_ge), are rolled out on the
+ * LQ model (all candidates of all problems in one launch; at most max_alphas of them), the merit of a rollout is its LQ-model cost
+ * (computeRolloutPerformanceIndex with no constraint terms: the LQ rollout satisfies the linearised constraints), and per problem the
+ * largest alpha with  merit < baseline - armijo_coefficient * alpha * IS(deltaBias)  wins; 0 (index -1) if none does.
+ * IS = trapezoidal integral of |deltaBias|^2 over the controller time stamps (computeControllerUpdateIS,
+ * DDP_HelperFunctions.cpp:285-291). Discrete (ILQR) model only; O2C_ERR_UNSUPPORTED for SLQ. Requires o2c_backward. */
+typedef struct o2c_line_search_settings { /* search_strategy::line_search::Settings, StrategySettings.h:85-105 */
+  double min_step_length;    /* 0.05 */
+  double max_step_length;    /* 1.0  */
+  double contraction_rate;   /* 0.5  */
+  double armijo_coefficient; /* 1e-4 */
+} o2c_line_search_settings;
+/* baseline_merit: host array with one merit per problem of the range (the performance index of the nominal trajectory), or NULL =
+ * the LQ cost of the zero-deviation trajectory (sum of the constants c_k + cf). The rollouts of all candidates stay resident (x, u of
+ * candidate e are rollout e of o2c_download). */
+o2c_error o2c_line_search(o2c_handle* handle, const o2c_line_search_settings* settings, const double* baseline_merit, int32_t problem_begin,
+                          int32_t problem_count);
+/* results of the last o2c_line_search for problems [begin, begin+count) (host arrays, any may be NULL): chosen step length and
+ * candidate index per problem, merits [n_candidates][problem_count], baseline and IS per problem, the candidate step lengths
+ * (capacity max_alphas) and their number */
+o2c_error o2c_line_search_result(o2c_handle* handle, double* step_length, int32_t* candidate_index, double* merits, double* baseline,
+                                 double* update_is, double* candidates, int32_t* n_candidates, int32_t problem_begin, int32_t problem_count);
+
 /* ---- end-to-end convenience: host buffers in, host buffers out, chunked H2D / compute / D2H pipeline ---- */
 o2c_error o2c_solve_host(o2c_handle* handle, const o2c_lq_view* host_lq, const o2c_solution_view* host_solution, double alpha,
                          int32_t problem_count, int32_t chunk);

@@ -50,6 +50,10 @@ struct o2c_handle {
   double *d_lq = nullptr, *d_term = nullptr, *d_xnom = nullptr, *d_unom = nullptr, *d_x0 = nullptr, *d_time = nullptr;
   double *d_sol = nullptr, *d_xs = nullptr, *d_us = nullptr, *d_alphas = nullptr;
   int *d_nc = nullptr, *d_status = nullptr;
+  double *d_ls_merit = nullptr, *d_ls_base = nullptr, *d_ls_is = nullptr, *d_ls_step = nullptr, *d_ls_basein = nullptr;  // line search
+  int* d_ls_index = nullptr;
+  std::vector<double> ls_candidates;
+  bool backward_done = false;
   SlqStep* d_slq_steps = nullptr;
   int n_slq_steps = 0;
   RolloutStep* d_ro_steps = nullptr;
@@ -460,6 +464,7 @@ o2c_error download_chunk(o2c_handle* h, Lane& lane, const o2c_solution_view& v, 
 
 o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) {
   if (count == 0) return O2C_OK;
+  h->backward_done = true;
   const DeviceBuffers buf = h->buffers();
   if (h->st.algorithm == O2C_ALG_ILQR) {
     if (h->use_fast) {
@@ -507,6 +512,7 @@ o2c_error solve_on(o2c_handle* h, cudaStream_t stream, double* alpha_slot_dev, d
   if (count == 0) return O2C_OK;
   if (h->st.algorithm == O2C_ALG_ILQR && (h->use_fast || (h->use_rpl && rpl_ilqr_supported(h->L, h->st, h->buffers())))) {
     int l = 0;
+    h->backward_done = true;
     if (h->use_fast)
       O2C_CUDA(launch_ilqr_wpp(h->L, h->st, h->buffers(), true, alpha, h->cfg.batch, begin, count, stream, &l));
     else
@@ -527,7 +533,8 @@ void release(o2c_handle* h) {
     if (lane.stream) cudaStreamSynchronize(lane.stream);
   }
   void* ptrs[] = {h->d_lq,  h->d_term, h->d_xnom, h->d_unom,   h->d_x0,        h->d_time,    h->d_sol,
-                  h->d_xs,  h->d_us,   h->d_alphas, h->d_nc,   h->d_status,    h->d_slq_steps, h->d_ro_steps};
+                  h->d_xs,  h->d_us,   h->d_alphas, h->d_nc,   h->d_status,    h->d_slq_steps, h->d_ro_steps,
+                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& lane : h->lanes) {
@@ -844,6 +851,75 @@ o2c_error o2c_solve(o2c_handle* h, double alpha, int32_t begin, int32_t count) {
   if (e != O2C_OK) return e;
   O2C_CUDA(cudaSetDevice(h->cfg.device));
   return solve_on(h, h->lanes[0].stream, h->d_alphas, alpha, begin, count);
+}
+
+o2c_error o2c_line_search(o2c_handle* h, const o2c_line_search_settings* ls, const double* baseline, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  if (!ls) return fail(O2C_ERR_INVALID_ARGUMENT, "null settings");
+  if (h->st.algorithm != O2C_ALG_ILQR) return fail(O2C_ERR_UNSUPPORTED, "o2c_line_search evaluates the discrete (ILQR) LQ model only");
+  if (!h->backward_done) return fail(O2C_ERR_NOT_READY, "o2c_line_search needs the controller of o2c_backward");
+  if (!(ls->max_step_length > 0.0) || !(ls->min_step_length > 0.0) || !(ls->contraction_rate > 0.0 && ls->contraction_rate < 1.0) ||
+      !(ls->armijo_coefficient >= 0.0))
+    return fail(O2C_ERR_INVALID_ARGUMENT, "line search settings out of range");
+  // candidates alpha_e = max * rate^e while almost_ge(alpha_e, min) (LineSearchStrategy.cpp:189-199, Numerics.h almost_eq)
+  std::vector<double> cand;
+  for (int ex = 0; ex < 64; ++ex) {
+    const double a = ls->max_step_length * std::pow(ls->contraction_rate, (double)ex);
+    const double diff = std::fabs(a - ls->min_step_length), mag = std::min(std::fabs(a), std::fabs(ls->min_step_length));
+    const bool almost_eq = diff <= std::numeric_limits<double>::epsilon() * mag || diff < std::numeric_limits<double>::min();
+    if (!(a > ls->min_step_length || almost_eq)) break;
+    cand.push_back(a);
+  }
+  if (cand.empty()) return fail(O2C_ERR_INVALID_ARGUMENT, "max_step_length is below min_step_length: no candidate step length");
+  if ((int)cand.size() > h->cfg.max_alphas)
+    return fail(O2C_ERR_INVALID_ARGUMENT, "the settings give " + std::to_string(cand.size()) + " candidate step lengths but the handle was created with max_alphas = " +
+                                              std::to_string(h->cfg.max_alphas));
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t stream = h->lanes[0].stream;
+  const size_t B = (size_t)h->cfg.batch;
+  if (!h->d_ls_merit) {
+    O2C_CUDA(cudaMalloc(&h->d_ls_merit, sizeof(double) * B * h->cfg.max_alphas));
+    O2C_CUDA(cudaMalloc(&h->d_ls_base, sizeof(double) * B));
+    O2C_CUDA(cudaMalloc(&h->d_ls_is, sizeof(double) * B));
+    O2C_CUDA(cudaMalloc(&h->d_ls_step, sizeof(double) * B));
+    O2C_CUDA(cudaMalloc(&h->d_ls_basein, sizeof(double) * B));
+    O2C_CUDA(cudaMalloc(&h->d_ls_index, sizeof(int) * B));
+  }
+  h->ls_candidates = cand;
+  const int na = (int)cand.size();
+  O2C_CUDA(cudaMemcpyAsync(h->d_alphas, cand.data(), sizeof(double) * na, cudaMemcpyHostToDevice, stream));
+  if (baseline) O2C_CUDA(cudaMemcpyAsync(h->d_ls_basein, baseline, sizeof(double) * count, cudaMemcpyHostToDevice, stream));
+  if ((e = rollout_on(h, stream, h->d_alphas, na, begin, count)) != O2C_OK) return e;
+  const DeviceBuffers buf = h->buffers();
+  O2C_CUDA(launch_merit(h->L, buf, h->out_nodes, na, h->cfg.batch, begin, count, h->d_ls_merit, stream));
+  O2C_CUDA(launch_select(h->L, buf, h->d_ls_merit, h->d_alphas, na, h->cfg.batch, begin, count, ls->armijo_coefficient,
+                         baseline ? h->d_ls_basein : nullptr, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_index, stream));
+  h->launches += 2;
+  if (baseline) O2C_CUDA(cudaStreamSynchronize(stream));  // the caller's baseline array may be pageable memory
+  return O2C_OK;
+}
+
+o2c_error o2c_line_search_result(o2c_handle* h, double* step, int32_t* index, double* merits, double* baseline, double* update_is,
+                                 double* candidates, int32_t* n_candidates, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  if (!h->d_ls_merit || h->ls_candidates.empty()) return fail(O2C_ERR_NOT_READY, "o2c_line_search has not run on this handle");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t stream = h->lanes[0].stream;
+  const int na = (int)h->ls_candidates.size();
+  if (step) O2C_CUDA(cudaMemcpyAsync(step, h->d_ls_step + begin, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+  if (index) O2C_CUDA(cudaMemcpyAsync(index, h->d_ls_index + begin, sizeof(int) * count, cudaMemcpyDeviceToHost, stream));
+  if (baseline) O2C_CUDA(cudaMemcpyAsync(baseline, h->d_ls_base + begin, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+  if (update_is) O2C_CUDA(cudaMemcpyAsync(update_is, h->d_ls_is + begin, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+  if (merits)
+    for (int ex = 0; ex < na; ++ex)
+      O2C_CUDA(cudaMemcpyAsync(merits + (size_t)ex * count, h->d_ls_merit + (size_t)ex * h->cfg.batch + begin, sizeof(double) * count,
+                               cudaMemcpyDeviceToHost, stream));
+  O2C_CUDA(cudaStreamSynchronize(stream));
+  if (candidates) std::copy(h->ls_candidates.begin(), h->ls_candidates.end(), candidates);
+  if (n_candidates) *n_candidates = na;
+  return O2C_OK;
 }
 
 o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {

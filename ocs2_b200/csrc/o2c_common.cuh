@@ -168,6 +168,13 @@ cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, c
                                     int first_idx, double first_alpha, int out_nodes, const double* alphas_dev, int n_alpha, int batch,
                                     int begin, int count, cudaStream_t stream);
 
+// batched Armijo line search on the LQ model (line_search.cu)
+cudaError_t launch_merit(const Layout& L, const DeviceBuffers& buf, int out_nodes, int n_alpha, int batch, int begin, int count, double* merit,
+                         cudaStream_t stream);
+cudaError_t launch_select(const Layout& L, const DeviceBuffers& buf, const double* merit, const double* alphas_dev, int n_alpha, int batch,
+                          int begin, int count, double armijo, const double* baseline_in_dev, double* baseline_out, double* update_is,
+                          double* step, int* index, cudaStream_t stream);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA bulk copy (cp.async.bulk), L2 prefetch

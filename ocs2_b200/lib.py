@@ -36,6 +36,11 @@ class Config(C.Structure):
     ]
 
 
+class LineSearchSettings(C.Structure):
+    _fields_ = [("min_step_length", C.c_double), ("max_step_length", C.c_double), ("contraction_rate", C.c_double),
+                ("armijo_coefficient", C.c_double)]
+
+
 class Field(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("problem_stride", C.c_int64), ("node_stride", C.c_int64)]
 
@@ -55,7 +60,7 @@ EXPORTED_SYMBOLS = [
     "o2c_abi_version", "o2c_last_error", "o2c_create", "o2c_destroy", "o2c_get_config", "o2c_sync", "o2c_compute_stream",
     "o2c_device_lq_view", "o2c_device_solution_view", "o2c_rollout_num_nodes", "o2c_rollout_times", "o2c_upload", "o2c_import_device",
     "o2c_download", "o2c_set_time", "o2c_backward", "o2c_rollout", "o2c_solve", "o2c_launch_count", "o2c_kernel_variant",
-    "o2c_solve_host", "o2c_generate_synthetic", "o2c_host_alloc", "o2c_host_free",
+    "o2c_solve_host", "o2c_generate_synthetic", "o2c_host_alloc", "o2c_host_free", "o2c_line_search", "o2c_line_search_result",
 ]
 
 
@@ -102,6 +107,8 @@ def load_library():
         "o2c_generate_synthetic": [hp, C.c_uint64, C.c_int64, C.c_double],
         "o2c_host_alloc": [C.POINTER(C.c_void_p), C.c_uint64],
         "o2c_host_free": [C.c_void_p],
+        "o2c_line_search": [hp, C.POINTER(LineSearchSettings), _dp, C.c_int32, C.c_int32],
+        "o2c_line_search_result": [hp, _dp, _ip, _dp, _dp, _dp, _dp, _ip, C.c_int32, C.c_int32],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

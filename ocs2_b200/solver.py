@@ -121,6 +121,25 @@ class LqBatch:
 
 
 @dataclass
+class LineSearchSettings:
+    """search_strategy::line_search::Settings (ocs2_ddp/include/ocs2_ddp/search_strategy/StrategySettings.h:85-105)."""
+    minStepLength: float = 0.05
+    maxStepLength: float = 1.0
+    contractionRate: float = 0.5
+    armijoCoefficient: float = 1e-4
+
+
+@dataclass
+class LineSearchResult:
+    stepLength: np.ndarray      # (count,) chosen step length per problem, 0 when no candidate satisfies the Armijo condition
+    candidateIndex: np.ndarray  # (count,) index into `candidates`, -1 when none
+    merits: np.ndarray          # (n_candidates, count) LQ-model cost of every candidate rollout
+    baselineMerit: np.ndarray   # (count,)
+    controllerUpdateIS: np.ndarray  # (count,) trapezoidal integral of |deltaBias|^2 (computeControllerUpdateIS)
+    candidates: np.ndarray      # (n_candidates,) step lengths, largest first
+
+
+@dataclass
 class LinearController:
     """LinearController arrays for the batch: timeStamp_ (N+1,), gainArray_ (B,N+1,m,n), biasArray_ (B,N+1,m), deltaBiasArray_ (B,N+1,m)."""
     timeStamp_: np.ndarray
@@ -272,6 +291,26 @@ class BatchedLqSolver:
         cnt = self.batch - problem_begin if problem_count is None else problem_count
         _l.check(self._lib.o2c_solve(self._h, alpha, problem_begin, cnt))
         self._n_alpha = 1
+
+    def lineSearch(self, settings: Optional[LineSearchSettings] = None, baselineMerit: Optional[np.ndarray] = None, problem_begin: int = 0,
+                   problem_count: Optional[int] = None) -> LineSearchResult:
+        """LineSearchStrategy::run on the LQ model: every candidate step length of every problem is rolled out in one launch and the
+        largest one satisfying the Armijo condition is chosen per problem (o2c_line_search)."""
+        ls = settings or LineSearchSettings()
+        cnt = self.batch - problem_begin if problem_count is None else problem_count
+        cs = _l.LineSearchSettings(ls.minStepLength, ls.maxStepLength, ls.contractionRate, ls.armijoCoefficient)
+        base = None if baselineMerit is None else np.ascontiguousarray(baselineMerit, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        _l.check(self._lib.o2c_line_search(self._h, C.byref(cs), base.ctypes.data_as(dp) if base is not None else None, problem_begin, cnt))
+        step, idx = np.zeros(cnt), np.zeros(cnt, dtype=np.int32)
+        merits, bl, upd, cand = np.zeros((self.max_alphas, cnt)), np.zeros(cnt), np.zeros(cnt), np.zeros(self.max_alphas)
+        nc = C.c_int32(0)
+        _l.check(self._lib.o2c_line_search_result(self._h, step.ctypes.data_as(dp), idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                  merits.ctypes.data_as(dp), bl.ctypes.data_as(dp), upd.ctypes.data_as(dp),
+                                                  cand.ctypes.data_as(dp), C.byref(nc), problem_begin, cnt))
+        self._n_alpha = nc.value
+        # o2c_line_search_result packs the merits as [n_candidates][count]
+        return LineSearchResult(step, idx, merits.reshape(-1)[:nc.value * cnt].reshape(nc.value, cnt), bl, upd, cand[:nc.value])
 
     # ---- results ----------------------------------------------------------------------------------------------------
     def _solution_buffers(self, count: int, n_alpha: int, want_value: bool = True):

@@ -350,6 +350,39 @@ def discrete_lq_cost(pb: Problem, x, u) -> float:
     return val
 
 
+def line_search(st: Settings, pb: Problem, sol: Solution, x0, min_step=0.05, max_step=1.0, rate=0.5, armijo=1e-4, baseline=None):
+    """LineSearchStrategy::run / lineSearchTask (ocs2_ddp/src/search_strategy/LineSearchStrategy.cpp:125-258) restated for the
+    single-thread case ("equivalent to a single core line search") on the discrete LQ model: candidates max*rate^e >= min
+    (numerics::almost_ge), merit = LQ-model cost of the rollout, Armijo condition against
+    baseline - armijo * alpha * computeControllerUpdateIS (DDP_HelperFunctions.cpp:285-291, trapezoidal rule over the time stamps).
+    Returns (step length, candidate index or -1, merits, baseline, IS, candidates)."""
+    eps, tiny = np.finfo(np.float64).eps, np.finfo(np.float64).tiny
+    cands, e = [], 0
+    while True:
+        a = max_step * rate ** e
+        diff, mag = abs(a - min_step), min(abs(a), abs(min_step))
+        if not (a > min_step or diff <= eps * mag or diff < tiny):
+            break
+        cands.append(a)
+        e += 1
+    t = np.asarray(pb.time, dtype=np.float64)
+    sq = (np.asarray(sol.dbias) ** 2).sum(axis=1)
+    IS = 0.0
+    for k in range(1, len(t)):
+        IS += (sq[k - 1] + sq[k]) * (0.5 * (t[k] - t[k - 1]))
+    base = float(baseline) if baseline is not None else float(np.sum(pb.c[:pb.N]) + pb.cf)
+    merits = []
+    for a in cands:
+        x, u, _, _ = rollout(st, pb, sol, x0, alpha=a)
+        merits.append(discrete_lq_cost(pb, x, u))
+    best, idx = 0.0, -1
+    for e, a in enumerate(cands):
+        if merits[e] < base - armijo * a * IS:
+            best, idx = a, e
+            break
+    return best, idx, np.array(merits), base, IS, np.array(cands)
+
+
 def generate_problem(seed, problem, algorithm, n, m, nc, N, dt):
     """One problem of the seeded synthetic family (bit-identical to the CUDA generator). Returns (Problem, x0)."""
     nodes = N if algorithm == ALG_ILQR else N + 1

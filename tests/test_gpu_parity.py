@@ -384,3 +384,70 @@ def test_rpl_constraints_rank_deficient_flag_and_ragged_fallback():
     assert (sol2.status == 0).all()
     for i in (0, batch - 1):
         check_against_oracle(st, _oracle_problem(lq2, i, N), lq2.x0[i], sol2, i, what="ragged fallback")
+
+
+# ---- the step after the backward pass: batched Armijo line search on the LQ model (o2c_line_search) ----
+@pytest.mark.parametrize("shape", ["ballbot", "manipulator", "legged", "test32c"])
+def test_line_search_matches_oracle(shape):
+    n, m, nc = SHAPES[shape]
+    N, batch, dt, seed = 20, 9, 0.01, 4
+    st = o2.Settings(hessianCorrectionMultiple=1e-3 if shape != "legged" else 1e-5, timeStep=dt)
+    ls = o2.LineSearchSettings(minStepLength=0.05, maxStepLength=1.0, contractionRate=0.5, armijoCoefficient=1e-4)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, max_alphas=6) as solver:
+        solver.generate_synthetic(seed, first_problem_index=0, dt=dt)
+        solver.solveSequentialRiccatiEquations()
+        sol = solver.download(n_alpha=0)
+        res0 = solver.lineSearch(ls)
+        assert len(res0.candidates) == 5 and np.allclose(res0.candidates, [1.0, 0.5, 0.25, 0.125, 0.0625])
+        refs = []
+        for i in range(batch):
+            pb, x0 = orc.generate_problem(seed, i, orc.ALG_ILQR, n, m, nc, N, dt)
+            refs.append((pb, x0, orc.backward(orc_settings(st), pb)))
+        # On the exact LQ model alpha = 1 minimises the merit, so with the default coefficient candidate 0 always wins; larger Armijo
+        # coefficients (the penalty scales with alpha) move the choice down the candidate list: thresholds from problem 0's merits
+        base_all = res0.merits.max(axis=0) + 0.05 * (res0.merits.max(axis=0) - res0.merits.min(axis=0)) + 1e-12
+        ce = (base_all[0] - res0.merits[:, 0]) / (res0.candidates * res0.controllerUpdateIS[0])
+        coefficients = [1e-4, 0.5 * (ce[0] + ce[1]), 0.5 * (ce[2] + ce[3]), 10.0 * ce.max()]
+        picked = set()
+        for coef in coefficients:
+            ls.armijoCoefficient = float(coef)
+            base_in = None if coef == coefficients[0] else base_all
+            res = solver.lineSearch(ls, baselineMerit=base_in)
+            rolled = solver.download()
+            for i, (pb, x0, ref) in enumerate(refs):
+                step, idx, merits, b, IS, cands = orc.line_search(orc_settings(st), pb, ref, x0, ls.minStepLength, ls.maxStepLength,
+                                                                  ls.contractionRate, ls.armijoCoefficient,
+                                                                  None if base_in is None else base_in[i])
+                assert rel_err(res.merits[:, i], merits) <= REL_TOL, f"{shape} #{i}: merits"
+                assert abs(res.controllerUpdateIS[i] - IS) <= REL_TOL * max(1.0, abs(IS))
+                assert abs(res.baselineMerit[i] - b) <= REL_TOL * max(1.0, abs(b))
+                # the Armijo comparison is only decidable when it is not a tie to rounding
+                margins = np.abs(merits - (b - ls.armijoCoefficient * cands * IS)) / max(1.0, abs(b))
+                if margins.min() > 1e-9:
+                    assert res.candidateIndex[i] == idx and res.stepLength[i] == step, f"{shape} #{i}: picked {res.candidateIndex[i]} vs {idx}"
+                picked.add(int(res.candidateIndex[i]))
+                # the rollouts of all candidates stay resident: candidate e is rollout e
+                e = max(int(res.candidateIndex[i]), 0)
+                x, u, _, _ = orc.rollout(orc_settings(st), pb, ref, x0, alpha=float(res.candidates[e]))
+                assert rel_err(rolled.x[e, i], x) <= REL_TOL and rel_err(rolled.u[e, i], u) <= REL_TOL
+        assert len(picked) >= 3, f"the coefficients should exercise several outcomes of the Armijo rule, got {picked}"
+        del sol
+
+
+def test_line_search_argument_checks():
+    with o2.BatchedLqSolver(o2.Settings(), 4, 2, 10, 3, max_alphas=2) as s:
+        s.generate_synthetic(0, 0, 0.01)
+        with pytest.raises(o2.O2cError) as e:
+            s.lineSearch()  # before the backward pass
+        assert e.value.code == 5
+        s.solveSequentialRiccatiEquations()
+        with pytest.raises(o2.O2cError):
+            s.lineSearch(o2.LineSearchSettings())  # 5 candidates > max_alphas = 2
+        r = s.lineSearch(o2.LineSearchSettings(minStepLength=0.5))
+        assert list(r.candidates) == [1.0, 0.5]
+    with o2.BatchedLqSolver(o2.Settings(algorithm=o2.ALG_SLQ), 4, 2, 10, 3, max_alphas=6) as s:
+        s.generate_synthetic(0, 0, 0.01)
+        s.solveSequentialRiccatiEquations()
+        with pytest.raises(o2.O2cError) as e:
+            s.lineSearch()
+        assert e.value.code == 2  # discrete model only
