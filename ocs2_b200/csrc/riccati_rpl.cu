@@ -51,6 +51,8 @@ struct Args {
   const double* lq;
   const double* term;
   const double* x0;
+  const double* x_nom;  // [batch][N+1][nx] nominal trajectories, or nullptr (deviation coordinates): kernel instantiation NOM
+  const double* u_nom;
   double* sol;
   double* xs;
   double* us;
@@ -86,7 +88,7 @@ __device__ __forceinline__ double dot_col(const double (&a)[LEN], const double* 
   return acc;
 }
 
-template <int NX, int NU, int NC>
+template <int NX, int NU, int NC, bool NOM>
 __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
   using S = Shape<NX, NU, NC>;
   extern __shared__ __align__(16) double smem[];
@@ -344,8 +346,19 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
 #pragma unroll
           for (int l = 1; l < NU; ++l) dbi = (i == l) ? db[l] : dbi;
           out[S::odb + i] = dbi;
-          out[S::obias + i] = 0.0;
+          if (!NOM) out[S::obias + i] = 0.0;
         }
+      }
+      if (NOM) {  // bias = u_nom - K x_nom (GaussNewtonDDP.cpp:604-606): this lane's column of K times x_nom_i, summed over the group
+        const double xni = __ldg(a.x_nom + ((size_t)prob * (N + 1) + k) * NX + i);
+#pragma unroll
+        for (int l = 0; l < NU; ++l) sm[S::sK + l + NU * i] = kt[l] * xni;
+        __syncwarp();
+        const int l = i < NU ? i : NU - 1;
+        double kx = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) kx += sm[S::sK + l + NU * j];
+        if (valid && i < NU) out[S::obias + i] = __ldg(a.u_nom + ((size_t)prob * (N + 1) + k) * NU + i) - kx;
       }
       __syncwarp();
 
@@ -417,7 +430,10 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
     }
     double* xo = a.xs + (size_t)prob * (N + 1) * NX;
     double* uo = a.us + (size_t)prob * (N + 1) * NU;
-    double x = a.x0[(size_t)prob * NX + i];
+    // with nominal trajectories the rollout runs in deviation coordinates (dx = x - x_nom, du = u - u_nom) and shifts the outputs back
+    const double* xnp = NOM ? a.x_nom + (size_t)prob * (N + 1) * NX : nullptr;
+    const double* unp = NOM ? a.u_nom + (size_t)prob * (N + 1) * NU : nullptr;
+    double x = a.x0[(size_t)prob * NX + i] - (NOM ? __ldg(xnp + i) : 0.0);
     bool xfinite = true;
     // column i of K_k and (lanes < nu) dbias_k: coalesced loads one node ahead
     double kc[NU], dbk;
@@ -438,10 +454,10 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
         for (int j = 0; j < NX; ++j) u = fma(sm[S::sK + l + NU * j], sm[S::sX + j], u);
         if (i < NU) {
           sm[S::sU + i] = u;
-          if (valid) __stcg(uo + (size_t)k * NU + i, u);
+          if (valid) __stcg(uo + (size_t)k * NU + i, u + (NOM ? __ldg(unp + (size_t)k * NU + i) : 0.0));
         }
       }
-      if (valid) __stcg(xo + (size_t)k * NX + i, x);
+      if (valid) __stcg(xo + (size_t)k * NX + i, x + (NOM ? __ldg(xnp + (size_t)k * NX + i) : 0.0));
       xfinite = xfinite && finite_bits(x);
       // gains of node k+1 (node N carries the copy of node N-1)
       {
@@ -468,19 +484,21 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       __syncwarp();
       x = xn;
     }
-    // node N: state, and the input of the copied last policy re-evaluated at x_N (TimeTriggeredRollout.cpp:98-102)
-    sm[S::sX + i] = x;
+    // node N: state, and the input of the copied last policy re-evaluated at x_N (TimeTriggeredRollout.cpp:98-102); with nominal
+    // trajectories the copied policy acts on the absolute state: u = bias + alpha dbias + K x
+    const double xabs = x + (NOM ? __ldg(xnp + (size_t)N * NX + i) : 0.0);
+    sm[S::sX + i] = xabs;
 #pragma unroll
     for (int l = 0; l < NU; ++l) sm[S::sK + l + NU * i] = kc[l];
     __syncwarp();
     {
       const int l = i < NU ? i : NU - 1;
-      double u = a.alpha * dbk;
+      double u = a.alpha * dbk + (NOM ? __ldcg(solp + (size_t)N * S::orec + S::obias + l) : 0.0);
 #pragma unroll
       for (int j = 0; j < NX; ++j) u = fma(sm[S::sK + l + NU * j], sm[S::sX + j], u);
       if (valid && i < NU) __stcg(uo + (size_t)N * NU + i, u);
     }
-    if (valid) __stcg(xo + (size_t)N * NX + i, x);
+    if (valid) __stcg(xo + (size_t)N * NX + i, xabs);
     xfinite = xfinite && finite_bits(x);
     if (__ballot_sync(kFull, !xfinite) & gmask) bits |= O2C_STATUS_NONFINITE;
     if (valid && i == 0) a.status[prob] = bits;
@@ -1064,13 +1082,13 @@ bool layout_matches(const Layout& L) {
          L.oQf == S::oQf && L.oqf == S::oqf && L.ocf == S::ocf;
 }
 
-template <int NX, int NU, int NC>
+template <int NX, int NU, int NC, bool NOM>
 cudaError_t launch(const Args& a, cudaStream_t stream) {
   using S = Shape<NX, NU, NC>;
   static int num_sms = 0;
   constexpr int wpb = 2;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU, NC, NOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (num_sms == 0) {
     int dev = 0;
@@ -1078,19 +1096,19 @@ cudaError_t launch(const Args& a, cudaStream_t stream) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ilqr_rpl_kernel<NX, NU, NC>, wpb * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ilqr_rpl_kernel<NX, NU, NC, NOM>, wpb * 32, smem);
   if (e != cudaSuccess) return e;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int per_cta = wpb * S::P;
   const int needed = (a.count + per_cta - 1) / per_cta;
   const int cap = num_sms * ctas_per_sm;  // persistent warps: one resident wave, static stride over the problem index
-  ilqr_rpl_kernel<NX, NU, NC><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
+  ilqr_rpl_kernel<NX, NU, NC, NOM><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
 bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const Layout& L) {
   return st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
-         buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1;
+         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1;
 }
 
 }  // namespace
@@ -1160,6 +1178,8 @@ cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const Dev
   a.lq = buf.lq;
   a.term = buf.term;
   a.x0 = buf.x0;
+  a.x_nom = buf.x_nom;
+  a.u_nom = buf.u_nom;
   a.sol = buf.sol;
   a.xs = buf.xs;
   a.us = buf.us;
@@ -1171,9 +1191,10 @@ cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const Dev
   a.eps = st.eps;
   a.alpha = alpha;
   if (launches) *launches = 1;
-  if (layout_matches<10, 3, 0>(L)) return launch<10, 3, 0>(a, stream);
-  if (layout_matches<9, 9, 3>(L)) return launch<9, 9, 3>(a, stream);
-  return launch<4, 1, 0>(a, stream);
+  const bool nom = buf.x_nom != nullptr;
+  if (layout_matches<10, 3, 0>(L)) return nom ? launch<10, 3, 0, true>(a, stream) : launch<10, 3, 0, false>(a, stream);
+  if (layout_matches<9, 9, 3>(L)) return nom ? launch<9, 9, 3, true>(a, stream) : launch<9, 9, 3, false>(a, stream);
+  return nom ? launch<4, 1, 0, true>(a, stream) : launch<4, 1, 0, false>(a, stream);
 }
 
 }  // namespace o2c

@@ -111,6 +111,8 @@ struct Args {
   const double* lq;
   const double* term;
   const double* x0;
+  const double* x_nom;  // [batch][N+1][24] nominal trajectories, or nullptr (deviation coordinates): kernel instantiation NOM
+  const double* u_nom;
   double* sol;
   double* xs;
   double* us;
@@ -306,6 +308,7 @@ __device__ __forceinline__ void prefetch_hessians(const double* rec, const Args&
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
+template <bool NOM>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -566,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         if (c < 3) {
           const int j = 8 * c + r;
           __stcg(out + kOdb + j, -pick3(z, c));
-          __stcg(out + kObias + j, 0.0);
+          if (!NOM) __stcg(out + kObias + j, 0.0);
         }
         sval = sval + cval + warp_sum_all(spart);
         if (lane == 0) __stcg(out + kOs, sval);
@@ -606,6 +609,33 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
           for (int jb = 0; jb < 3; ++jb) stg2(out + kOK + lo24 + t24(jb, ib), neg2(kk[ib][jb]));
+        if (NOM) {
+          // bias = u_nom - K x_nom (GaussNewtonDDP.cpp:604-606). The accumulators hold -K' = Y'L^-1: lane (r,c) owns the terms of
+          // state 8ib + r for inputs 8jb + 2c, 2c+1; the sum over the states is a butterfly over r
+          const double* xn = a.x_nom + ((size_t)prob * (N + 1) + k) * kN;
+          const double* un = a.u_nom + ((size_t)prob * (N + 1) + k) * kN;
+          double xr[3];
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) xr[ib] = __ldg(xn + 8 * ib + r);
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            double px = 0.0, py = 0.0;
+#pragma unroll
+            for (int ib = 0; ib < 3; ++ib) {
+              px = fma(kk[ib][jb].x, xr[ib], px);
+              py = fma(kk[ib][jb].y, xr[ib], py);
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              px += __shfl_xor_sync(kFull, px, o);
+              py += __shfl_xor_sync(kFull, py, o);
+            }
+            if (r == 0) {
+              const double2 u2 = *reinterpret_cast<const double2*>(un + 8 * jb + 2 * c);
+              stg2(out + kObias + 8 * jb + 2 * c, make_double2(u2.x + px, u2.y + py));
+            }
+          }
+        }
       }
 
       // ---- Sv = tv - Y'Yv ----
@@ -696,7 +726,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
     }
     double* xo = a.xs + (size_t)prob * (N + 1) * kN;
     double* uo = a.us + (size_t)prob * (N + 1) * kN;
-    double x = a.x0[(size_t)prob * kN + li];
+    // with nominal trajectories the rollout runs in deviation coordinates dx = x - x_nom, du = u - u_nom (the LQ model is
+    // x_{k+1} = x_nom_{k+1} + A dx + B du + Hv, u = u_nom + K dx + alpha dbias) and the outputs are shifted back
+    const double* xnp = NOM ? a.x_nom + (size_t)prob * (N + 1) * kN : nullptr;
+    const double* unp = NOM ? a.u_nom + (size_t)prob * (N + 1) * kN : nullptr;
+    double x = a.x0[(size_t)prob * kN + li] - (NOM ? __ldg(xnp + li) : 0.0);
     if (lane < kN) ws.xb[lane] = x;
     bool xfinite = true;
     double kreg[kN], areg[kN];
@@ -727,8 +761,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       const double u = (u0 + u1) + (u2 + u3);
       if (lane < kN) {
         ws.ub[lane] = u;
-        __stcg(xo + (size_t)k * kN + lane, x);
-        __stcg(uo + (size_t)k * kN + lane, u);
+        __stcg(xo + (size_t)k * kN + lane, x + (NOM ? __ldg(xnp + (size_t)k * kN + lane) : 0.0));
+        __stcg(uo + (size_t)k * kN + lane, u + (NOM ? __ldg(unp + (size_t)k * kN + lane) : 0.0));
       }
       xfinite = xfinite && finite_bits(x);
       // x+ = Hv + A x + B u
@@ -766,7 +800,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
     }
     // node N: state, and the input of the copied last policy re-evaluated at x_N (TimeTriggeredRollout.cpp:98-102)
     {
+      const double xabs = x + (NOM ? __ldg(xnp + (size_t)N * kN + li) : 0.0);
       double u0 = a.alpha * dbk, u1 = 0.0;
+      if (NOM) {  // the copied policy of node N-1 is evaluated at the absolute state: u = bias + alpha dbias + K x
+        __syncwarp();
+        if (lane < kN) ws.xb[lane] = xabs;
+        __syncwarp();
+        u0 += __ldcg(solp + (size_t)N * kORec + kObias + li);
+      }
 #pragma unroll
       for (int j = 0; j < kN; j += 2) {
         const double2 x01 = ld2(ws.xb + j);
@@ -774,7 +815,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         u1 = fma(kreg[j + 1], x01.y, u1);
       }
       if (lane < kN) {
-        __stcg(xo + (size_t)N * kN + lane, x);
+        __stcg(xo + (size_t)N * kN + lane, xabs);
         __stcg(uo + (size_t)N * kN + lane, u0 + u1);
       }
       xfinite = xfinite && finite_bits(x);
@@ -789,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 
 bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
-         st.hc == O2C_HC_DIAGONAL_SHIFT && buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
+         st.hc == O2C_HC_DIAGONAL_SHIFT && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
          L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb && L.obias == kObias && L.oSm == kOSm &&
          L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat;
 }
@@ -800,10 +841,12 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   static bool configured = false;
   static int num_sms = 0;
   const size_t smem = sizeof(WarpSmem) * kWarps;
-  cudaError_t e = cudaFuncSetAttribute(ilqr_wpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool nom = buf.x_nom != nullptr;
+  cudaError_t e = cudaFuncSetAttribute(nom ? ilqr_wpp_kernel<true> : ilqr_wpp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (!configured) {
-    cudaFuncSetAttribute(ilqr_wpp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ilqr_wpp_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ilqr_wpp_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -813,6 +856,8 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   a.lq = buf.lq;
   a.term = buf.term;
   a.x0 = buf.x0;
+  a.x_nom = buf.x_nom;
+  a.u_nom = buf.u_nom;
   a.sol = buf.sol;
   a.xs = buf.xs;
   a.us = buf.us;
@@ -835,7 +880,10 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
     if (v >= 1 && v < kCtasPerSm) ctas_per_sm = v;
   }
   const int grid = ctas_needed < num_sms * ctas_per_sm ? ctas_needed : num_sms * ctas_per_sm;
-  ilqr_wpp_kernel<<<grid, kThreads, smem, stream>>>(a);
+  if (nom)
+    ilqr_wpp_kernel<true><<<grid, kThreads, smem, stream>>>(a);
+  else
+    ilqr_wpp_kernel<false><<<grid, kThreads, smem, stream>>>(a);
   if (launches) *launches = 1;
   return cudaGetLastError();
 }

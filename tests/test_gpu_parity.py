@@ -451,3 +451,32 @@ def test_line_search_argument_checks():
         with pytest.raises(o2.O2cError) as e:
             s.lineSearch()
         assert e.value.code == 2  # discrete model only
+
+
+@pytest.mark.parametrize("shape,variant", [("legged", "ilqr_wpp_kernel"), ("ballbot", "ilqr_rpl_kernel"), ("manipulator", "ilqr_rpl_kernel"),
+                                           ("cartpole", "ilqr_rpl_kernel")])
+def test_fast_kernels_with_nominal_trajectories(shape, variant):
+    """The real DDP iteration linearises about a nominal trajectory: bias = u_nom - K x_nom and the rollout is
+    x_{k+1} = x_nom_{k+1} + A dx + B du + Hv. The specialised kernels keep serving that case (has_nominal = 1)."""
+    n, m, nc = SHAPES[shape]
+    rng = np.random.default_rng(21)
+    batch, N = 7, 11
+    lq = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=False)
+    lq.nc = None
+    st = o2.Settings(hessianCorrectionMultiple=1e-4)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=True, max_alphas=2) as solver:
+        solver.upload(lq)
+        assert solver.kernel_variant == variant
+        solver.solve(alpha=0.6)
+        sol = solver.download()
+        assert (sol.status == 0).all()
+        if nc:
+            lq.nc = np.full((batch, N), nc, np.int32)
+        for i in (0, 3, batch - 1):
+            check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, (0.6,), what=f"{shape} with nominal")
+        # the generic multi-alpha rollout on the same controller agrees with the fused one
+        solver.solveSequentialRiccatiEquations()
+        solver.rolloutTrajectory((0.6,))
+        sol2 = solver.download()
+        assert np.array_equal(sol.bias, sol2.bias)
+        assert rel_err(sol2.x, sol.x) <= 1e-12 and rel_err(sol2.u, sol.u) <= 1e-12
