@@ -38,7 +38,7 @@ extern "C" {
 typedef enum o2c_error {
   O2C_OK = 0,
   O2C_ERR_INVALID_ARGUMENT = 1,
-  O2C_ERR_UNSUPPORTED = 2, /* e.g. CHOLESKY_MODIFICATION / EIGENVALUE_MODIFICATION hessian correction */
+  O2C_ERR_UNSUPPORTED = 2, /* e.g. the CHOLESKY_MODIFICATION hessian correction */
   O2C_ERR_CUDA = 3,
   O2C_ERR_OUT_OF_MEMORY = 4,
   O2C_ERR_NOT_READY = 5 /* rollout before backward, download before compute, ... */
@@ -51,7 +51,7 @@ enum { O2C_STRATEGY_LINE_SEARCH = 0, O2C_STRATEGY_LEVENBERG_MARQUARDT = 1 }; /* 
 enum {                                                      /* hessian_correction::Strategy (HessianCorrection.h:44-49) */
   O2C_HC_DIAGONAL_SHIFT = 0,
   O2C_HC_CHOLESKY_MODIFICATION = 1,   /* unsupported */
-  O2C_HC_EIGENVALUE_MODIFICATION = 2, /* unsupported */
+  O2C_HC_EIGENVALUE_MODIFICATION = 2, /* LinearAlgebra::makePsdEigenvalue, LinearAlgebra.cpp:52-72 (generic kernels) */
   O2C_HC_GERSHGORIN_MODIFICATION = 3
 };
 

@@ -565,8 +565,9 @@ o2c_error o2c_create(const o2c_config* cfg, o2c_handle** out) {
     return fail(O2C_ERR_INVALID_ARGUMENT, "unknown strategy");
   if (cfg->riccati_form != O2C_FORM_FULL && cfg->riccati_form != O2C_FORM_REDUCED) return fail(O2C_ERR_INVALID_ARGUMENT, "unknown riccati_form");
   if (cfg->strategy == O2C_STRATEGY_LINE_SEARCH && cfg->hessian_correction != O2C_HC_DIAGONAL_SHIFT &&
-      cfg->hessian_correction != O2C_HC_GERSHGORIN_MODIFICATION)
-    return fail(O2C_ERR_UNSUPPORTED, "hessian_correction must be DIAGONAL_SHIFT or GERSHGORIN_MODIFICATION");
+      cfg->hessian_correction != O2C_HC_GERSHGORIN_MODIFICATION && cfg->hessian_correction != O2C_HC_EIGENVALUE_MODIFICATION)
+    return fail(O2C_ERR_UNSUPPORTED, "hessian_correction must be DIAGONAL_SHIFT, GERSHGORIN_MODIFICATION or EIGENVALUE_MODIFICATION "
+                                     "(CHOLESKY_MODIFICATION is Eigen::IncompleteCholesky in the reference and is not provided)");
   if (cfg->riccati_form == O2C_FORM_REDUCED && cfg->strategy != O2C_STRATEGY_LINE_SEARCH)
     return fail(O2C_ERR_INVALID_ARGUMENT, "the reduced Riccati form is only valid with LINE_SEARCH (ILQR.cpp:68, SLQ.cpp:65)");
   if (cfg->max_alphas < 1) return fail(O2C_ERR_INVALID_ARGUMENT, "max_alphas must be >= 1");

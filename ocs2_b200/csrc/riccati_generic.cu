@@ -28,7 +28,7 @@ struct Work {
   double* rec;  // stage record, transformed in place (A -> A~, Q -> Q~, Hv -> Hv~, q -> q~)
   double *A, *B, *Q, *P, *R, *Hv, *q, *r, *C, *D, *e;
   double *Hm, *Ui, *Qm, *Mx, *Rci, *Ddag, *PuBuf, *Px, *T;
-  double *Bt, *Pt, *Rt, *SA, *SB, *Gm, *Km, *dGm, *dQ, *Kout;
+  double *Bt, *Pt, *Rt, *SA, *SB, *Gm, *Km, *dGm, *dQ, *Kout, *Ev, *ew;
   double *u0, *tv, *rt, *Gv, *Lv, *dGv, *w, *SHv, *kout, *bout, *tau, *dqd, *HmLv, *dinv;
   double ct;        // projected c
   const double* Pu; // m x p (aliases Ui when nc == 0)
@@ -51,7 +51,7 @@ __host__ __device__ inline int work_doubles(const Layout& L, bool full, bool lm,
   if (full) t += m * m;           // Rt
   t += n * n + mx * m + 2 * m * n;  // SA, SB, Gm, Km
   if (lm) t += m * n;             // dGm
-  if (gersh) t += n * n;          // dQ
+  if (gersh) t += 2 * n * n + n;  // dQ, and the eigenvector / eigenvalue scratch of EIGENVALUE_MODIFICATION
   t += m * n;                     // Kout
   t += 10 * m + 3 * n + nc;       // u0 tv rt Gv Lv dGv kout bout HmLv dinv | w SHv dqd | tau
   return (t + 1) & ~1;
@@ -100,6 +100,8 @@ __device__ __forceinline__ void carve(Work& W, double* base, const Layout& L, bo
   W.Km = take(m * n);
   W.dGm = lm ? take(m * n) : nullptr;
   W.dQ = gersh ? take(n * n) : nullptr;
+  W.Ev = gersh ? take(n * n) : nullptr;
+  W.ew = gersh ? take(n) : nullptr;
   W.Kout = take(m * n);
   W.u0 = take(m);
   W.tv = take(m);
@@ -208,6 +210,77 @@ __device__ __forceinline__ void warp_householder_qr(int rows, int cols, double* 
   }
 }
 
+// LinearAlgebra::makePsdEigenvalue (ocs2_core/src/misc/LinearAlgebra.cpp:52-72) on the symmetric matrix whose lower triangle is in M:
+// R = V max(lambda, eps) V' if an eigenvalue is below eps, sym(M) otherwise. A, V: n x n scratch, w: n scratch; the result lands in A.
+// The common case (spectrum above eps) is detected by a Cholesky of M - eps I, the rare one runs cyclic Jacobi rotations
+// (Eigen's tridiagonal QR is not restated: V max(lambda, eps) V' does not depend on the algorithm beyond rounding).
+__device__ __forceinline__ void warp_make_psd_eigenvalue(int n, const double* M, double eps, double* A, double* V, double* w) {
+  const int lane = lane_id();
+  for (int idx = lane; idx < n * n; idx += 32) {
+    const int i = idx % n, j = idx / n;
+    const double v = (i >= j) ? M[i + j * n] : M[j + i * n];
+    A[idx] = v;
+    V[idx] = v - ((i == j) ? eps : 0.0);
+  }
+  __syncwarp();
+  if (warp_cholesky(n, V)) {  // every eigenvalue is above eps: only the symmetrisation remains
+    for (int idx = lane; idx < n * n; idx += 32) {
+      const int i = idx % n, j = idx / n;
+      A[idx] = 0.5 * (M[i + j * n] + M[j + i * n]);
+    }
+    __syncwarp();
+    return;
+  }
+  for (int idx = lane; idx < n * n; idx += 32) V[idx] = (idx % n == idx / n) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int idx = lane; idx < n * n; idx += 32) {
+      const double v = A[idx] * A[idx];
+      if (idx % n == idx / n)
+        dg += v;
+      else
+        off += v;
+    }
+    off = warp_sum(off);
+    dg = warp_sum(dg);
+    if (off <= 1e-30 * dg || off == 0.0) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p + q * n];
+        if (apq == 0.0) continue;  // uniform over the warp: every lane reads the same element
+        const double theta = (A[q + q * n] - A[p + p * n]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) {  // A <- A J, V <- V J (columns p, q)
+          const double akp = A[k + p * n], akq = A[k + q * n];
+          A[k + p * n] = c * akp - sn * akq;
+          A[k + q * n] = sn * akp + c * akq;
+          const double vkp = V[k + p * n], vkq = V[k + q * n];
+          V[k + p * n] = c * vkp - sn * vkq;
+          V[k + q * n] = sn * vkp + c * vkq;
+        }
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) {  // A <- J' A (rows p, q)
+          const double apk = A[p + k * n], aqk = A[q + k * n];
+          A[p + k * n] = c * apk - sn * aqk;
+          A[q + k * n] = sn * apk + c * aqk;
+        }
+        __syncwarp();
+      }
+  }
+  for (int i = lane; i < n; i += 32) w[i] = fmax(A[i + i * n], eps);
+  __syncwarp();
+  for (int idx = lane; idx < n * n; idx += 32) {
+    const int i = idx % n, j = idx / n;
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc += V[i + k * n] * w[k] * V[j + k * n];
+    A[idx] = acc;
+  }
+  __syncwarp();
+}
+
 // GaussNewtonDDP::computeProjectionAndRiccatiModification on the record loaded in W.rec. Snext == nullptr: Hm = R (SLQ).
 // On return: A~ = W.A, Hv~ = W.Hv, Q~ = W.Q, q~ = W.q, c~ = W.ct, B~ = W.Bt, P~ = W.Pt (ld p), R~ = W.Rt (ld p, full form only),
 // r~ = W.rt, Pu = W.Pu, Px = W.Px / u0 = W.u0 (nc > 0), dQ diag in W.dqd (DIAGONAL_SHIFT) or full in W.dQ (GERSHGORIN),
@@ -296,6 +369,13 @@ __device__ __forceinline__ int project_stage(Work& W, const Layout& L, const Sol
         mii -= pp;
         W.dqd[i] = (mii + st.eps) - mii;
       }
+      __syncwarp();
+    } else if (st.hc == O2C_HC_EIGENVALUE_MODIFICATION) {
+      // EIGENVALUE: dQ = makePsdEigenvalue(M) - M with M = Q~ - P~'P~ (LineSearchStrategy.cpp:294-312). SA is free here: holds M.
+      wcopy(n * n, W.Q, W.SA);
+      wgemm<true, false>(n, n, p, -1.0, W.Pt, p, W.Pt, p, 1.0, W.SA, n);
+      warp_make_psd_eigenvalue(n, W.SA, st.eps, W.dQ, W.Ev, W.ew);
+      for (int idx = lane; idx < n * n; idx += 32) W.dQ[idx] -= W.SA[idx];
       __syncwarp();
     } else {
       // GERSHGORIN: M -> sym(M), M_ii = max(M_ii, R_i + eps); dQ = that - M (LinearAlgebra.cpp:77-85). SA is free here: holds M.
@@ -402,7 +482,7 @@ __global__ void __launch_bounds__(128) ilqr_generic_kernel(Layout L, SolverSetti
   const int prob = begin + local;
   const int n = L.n, m = L.m;
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
-  const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
+  const bool gersh = !lm && (st.hc == O2C_HC_GERSHGORIN_MODIFICATION || st.hc == O2C_HC_EIGENVALUE_MODIFICATION);  // full dQ matrix
   double* base = smem + (size_t)warp * warp_doubles;
   Work W;
   carve(W, base + 2 * n * n + 2 * n, L, full, lm, gersh);
@@ -567,7 +647,7 @@ __device__ __forceinline__ void carve_proj(ProjSet& S, double* base, const Layou
 __device__ __forceinline__ void store_proj(const Work& W, const Layout& L, const SolverSettings& st, int nc, ProjSet& S) {
   const int n = L.n, m = L.m, p = W.p;
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
-  const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
+  const bool gersh = !lm && (st.hc == O2C_HC_GERSHGORIN_MODIFICATION || st.hc == O2C_HC_EIGENVALUE_MODIFICATION);  // full dQ matrix
   S.p = p;
   S.nc = nc;
   S.ct = W.ct;
@@ -654,7 +734,7 @@ struct FlowWork {
 __device__ __forceinline__ void flow_map(const Layout& L, const SolverSettings& st, const ProjSet& P, const FlowWork& F, const double* y, double* dy) {
   const int n = L.n, p = P.p, lane = lane_id();
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
-  const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
+  const bool gersh = !lm && (st.hc == O2C_HC_GERSHGORIN_MODIFICATION || st.hc == O2C_HC_EIGENVALUE_MODIFICATION);  // full dQ matrix
   const int ntri = n * (n + 1) / 2;
   const double* Sv = y + ntri;
   for (int idx = lane; idx < n * n; idx += 32) {
@@ -724,7 +804,7 @@ __global__ void __launch_bounds__(128) slq_generic_kernel(Layout L, SolverSettin
   const int prob = begin + local;
   const int n = L.n, m = L.m, N = L.N;
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
-  const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
+  const bool gersh = !lm && (st.hc == O2C_HC_GERSHGORIN_MODIFICATION || st.hc == O2C_HC_EIGENVALUE_MODIFICATION);  // full dQ matrix
   const int ntri = n * (n + 1) / 2, dim = ntri + n + 1;
   const int dimp = (dim + 1) & ~1;
 
@@ -928,7 +1008,7 @@ const char* generic_variant_name(const Layout& L, const SolverSettings& st) {
 cudaError_t launch_ilqr_generic(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count,
                                 cudaStream_t stream) {
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
-  const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
+  const bool gersh = !lm && (st.hc == O2C_HC_GERSHGORIN_MODIFICATION || st.hc == O2C_HC_EIGENVALUE_MODIFICATION);  // full dQ matrix
   const int wd = work_doubles(L, full, lm, gersh) + 2 * L.n * L.n + 2 * L.n;
   const int warp_doubles = (wd + 1) & ~1;
   if (std_settings(st)) {  // the named BASELINE shapes get compile-time dimensions
@@ -942,7 +1022,7 @@ cudaError_t launch_ilqr_generic(const Layout& L, const SolverSettings& st, const
 cudaError_t launch_slq_generic(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps,
                                int begin, int count, cudaStream_t stream) {
   const bool full = !st.reduced, lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT;
-  const bool gersh = !lm && st.hc == O2C_HC_GERSHGORIN_MODIFICATION;
+  const bool gersh = !lm && (st.hc == O2C_HC_GERSHGORIN_MODIFICATION || st.hc == O2C_HC_EIGENVALUE_MODIFICATION);  // full dQ matrix
   const int warp_doubles = slq_warp_doubles(L, full, lm, gersh);
   if (std_settings(st) && L.n == 12 && L.m == 4 && L.ncmax == 0)
     return run_slq<12, 4, 0, true>(L, st, buf, steps, nsteps, begin, count, warp_doubles, stream);

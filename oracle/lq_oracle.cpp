@@ -171,6 +171,71 @@ void make_psd_gershgorin(int n, double* M, double minEigenvalue) {
   }
 }
 
+// Symmetric eigen-decomposition by cyclic Jacobi rotations: A (lower triangle read, like Eigen::SelfAdjointEigenSolver) = V diag(w) V'.
+// Eigen's tridiagonal-QR algorithm is not restated; V max(w, eps) V' does not depend on the algorithm beyond rounding.
+void jacobi_eigh(int n, const double* Ain, double* w, double* V) {
+  vec A((size_t)n * n);
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) A[i + (size_t)j * n] = (i >= j) ? Ain[i + (size_t)j * n] : Ain[j + (size_t)i * n];
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) V[i + (size_t)j * n] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) (i == j ? diag : off) += A[i + (size_t)j * n] * A[i + (size_t)j * n];
+    if (off <= 1e-30 * diag || off == 0.0) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p + (size_t)q * n];
+        if (apq == 0.0) continue;
+        const double theta = (A[q + (size_t)q * n] - A[p + (size_t)p * n]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) {  // A <- A J (columns p, q)
+          const double akp = A[k + (size_t)p * n], akq = A[k + (size_t)q * n];
+          A[k + (size_t)p * n] = c * akp - sn * akq;
+          A[k + (size_t)q * n] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {  // A <- J' A (rows p, q)
+          const double apk = A[p + (size_t)k * n], aqk = A[q + (size_t)k * n];
+          A[p + (size_t)k * n] = c * apk - sn * aqk;
+          A[q + (size_t)k * n] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {  // V <- V J
+          const double vkp = V[k + (size_t)p * n], vkq = V[k + (size_t)q * n];
+          V[k + (size_t)p * n] = c * vkp - sn * vkq;
+          V[k + (size_t)q * n] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < n; ++i) w[i] = A[i + (size_t)i * n];
+}
+
+// LinearAlgebra::makePsdEigenvalue, ocs2_core/src/misc/LinearAlgebra.cpp:52-72
+void make_psd_eigenvalue(int n, double* M, double minEigenvalue) {
+  vec w(n), V((size_t)n * n);
+  jacobi_eigh(n, M, w.data(), V.data());
+  bool hasNegativeEigenValue = false;
+  for (int j = 0; j < n; ++j)
+    if (w[j] < minEigenvalue) {
+      hasNegativeEigenValue = true;
+      w[j] = minEigenvalue;
+    }
+  if (hasNegativeEigenValue) {  // V diag(lambda) V^-1 with V orthogonal
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc += V[i + (size_t)k * n] * w[k] * V[j + (size_t)k * n];
+        M[i + (size_t)j * n] = acc;
+      }
+  } else {
+    vec T((size_t)n * n);
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) T[i + (size_t)j * n] = 0.5 * (M[i + (size_t)j * n] + M[j + (size_t)i * n]);
+    std::copy(T.begin(), T.end(), M);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // projected stage storage
 // ---------------------------------------------------------------------------------------------------------------------
@@ -690,8 +755,11 @@ int orc_shift_hessian(int strategy, int n, double* M, double eps) {
     case ORC_HC_GERSHGORIN_MODIFICATION:
       make_psd_gershgorin(n, M, eps);
       return 0;
+    case ORC_HC_EIGENVALUE_MODIFICATION:
+      make_psd_eigenvalue(n, M, eps);
+      return 0;
     default:
-      return 1;  // CHOLESKY_MODIFICATION / EIGENVALUE_MODIFICATION: out of scope
+      return 1;  // CHOLESKY_MODIFICATION (Eigen::IncompleteCholesky): out of scope
   }
 }
 

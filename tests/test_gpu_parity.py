@@ -222,7 +222,7 @@ def test_indefinite_hamiltonian_sets_status_like_oracle():
 
 def test_abi_rejects_bad_arguments():
     with pytest.raises(o2.O2cError):
-        o2.BatchedLqSolver(o2.Settings(hessianCorrectionStrategy=o2.HC_EIGENVALUE_MODIFICATION), 4, 2, 10, 1)
+        o2.BatchedLqSolver(o2.Settings(hessianCorrectionStrategy=o2.HC_CHOLESKY_MODIFICATION), 4, 2, 10, 1)
     with pytest.raises(o2.O2cError):
         o2.BatchedLqSolver(o2.Settings(), 4, 2, 10, 1, nc_max=3)
     with pytest.raises(o2.O2cError):
@@ -480,3 +480,35 @@ def test_fast_kernels_with_nominal_trajectories(shape, variant):
         sol2 = solver.download()
         assert np.array_equal(sol.bias, sol2.bias)
         assert rel_err(sol2.x, sol.x) <= 1e-12 and rel_err(sol2.u, sol.u) <= 1e-12
+
+
+@pytest.mark.parametrize("algorithm", [o2.ALG_ILQR, o2.ALG_SLQ])
+@pytest.mark.parametrize("n,m,nc", [(5, 3, 0), (6, 4, 2), (24, 24, 0)])
+def test_eigenvalue_modification_matches_oracle(algorithm, n, m, nc):
+    """hessian_correction::EIGENVALUE_MODIFICATION (LinearAlgebra::makePsdEigenvalue): state costs made indefinite at some nodes so
+    that the eigenvalue clamp really acts (other nodes take the symmetrise-only branch)."""
+    rng = np.random.default_rng(3)
+    batch, N = 4, 6
+    lq = _random_batch(rng, batch, n, m, N, nc, algorithm, ragged_nc=False)
+    lq.x_nom = lq.u_nom = None
+    lq.nc = None
+    nodes = lq.Q.shape[1]
+    scale = np.abs(lq.Q).max()
+    for b in range(batch):
+        for k in range(0, nodes, 2):  # every other node: push part of the spectrum of Q below zero
+            v = rng.uniform(-1, 1, (n, 2))
+            lq.Q[b, k] -= 3.0 * scale * (v @ v.T) / n
+    st = o2.Settings(algorithm=algorithm, hessianCorrectionStrategy=o2.HC_EIGENVALUE_MODIFICATION, hessianCorrectionMultiple=1e-3, timeStep=0.02)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
+        assert "generic" in solver.kernel_variant
+        solver.upload(lq)
+        solver.solve(alpha=1.0)
+        sol = solver.download()
+    if nc:
+        lq.nc = np.full((batch, nodes), nc, np.int32)
+    clamped = 0
+    for i in range(batch):
+        pb = _oracle_problem(lq, i, N)
+        check_against_oracle(st, pb, lq.x0[i], sol, i, what=f"eigenvalue modification n={n}")
+        clamped += int(np.linalg.eigvalsh(lq.Q[i, 0]).min() < 0)
+    assert clamped > 0, "the test data should contain indefinite state costs"

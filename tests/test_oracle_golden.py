@@ -98,8 +98,27 @@ def test_diagonal_shift_and_unsupported():
     M = spd(5)
     out, rc = orc.shift_hessian(orc.HC_DIAGONAL_SHIFT, M, 1e-3)
     assert rc == 0 and np.array_equal(out, M + 1e-3 * np.eye(5))
-    _, rc = orc.shift_hessian(orc.HC_EIGENVALUE_MODIFICATION, M, 1e-3)
+    _, rc = orc.shift_hessian(orc.HC_CHOLESKY_MODIFICATION, M, 1e-3)
     assert rc == 1
+
+
+@pytest.mark.parametrize("n", [1, 3, 10, 24])
+def test_make_psd_eigenvalue_against_numpy_eigh(n):
+    """LinearAlgebra::makePsdEigenvalue (LinearAlgebra.cpp:52-72): eigenvalues below eps are raised to eps (V max(L, eps) V'); a matrix
+    whose spectrum is already above eps is only symmetrised. The oracle's Jacobi solver is pinned against numpy's LAPACK eigh."""
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-1, 1, (n, n))
+    M = 0.5 * (X + X.T)  # indefinite
+    eps = 1e-3
+    out, rc = orc.shift_hessian(orc.HC_EIGENVALUE_MODIFICATION, M, eps)
+    w, V = np.linalg.eigh(M)
+    want = (V * np.maximum(w, eps)) @ V.T if w.min() < eps else 0.5 * (M + M.T)
+    assert rc == 0 and np.abs(out - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    assert np.linalg.eigvalsh(0.5 * (out + out.T)).min() >= eps * (1 - 1e-9)
+    # benign case: untouched up to symmetrisation, even for a slightly asymmetric input
+    P = spd(n) + 1e-13 * rng.uniform(-1, 1, (n, n))
+    out, _ = orc.shift_hessian(orc.HC_EIGENVALUE_MODIFICATION, P, eps)
+    assert np.array_equal(out, 0.5 * (P + P.T))
 
 
 @pytest.mark.parametrize("nc", [0, 2])
