@@ -54,6 +54,13 @@ struct o2c_handle {
   int* d_ls_index = nullptr;
   std::vector<double> ls_candidates;
   bool backward_done = false;
+  int* h_status = nullptr;  // pinned bounce buffer [batch]: a caller's status array may be pageable, and an asynchronous copy into
+                            // pageable memory blocks the host thread (it serialised the H2D / compute / D2H pipeline of o2c_solve_host)
+  struct PendingStatus {
+    int32_t* dst;
+    int begin, count;
+  };
+  std::vector<PendingStatus> pending_status;
   SlqStep* d_slq_steps = nullptr;
   int n_slq_steps = 0;
   RolloutStep* d_ro_steps = nullptr;
@@ -458,8 +465,17 @@ o2c_error download_chunk(o2c_handle* h, Lane& lane, const o2c_solution_view& v, 
       if ((e = field_d2h(lane, fu, m, on, count, ubase + (size_t)a * count * on * m)) != O2C_OK) return e;
     }
   }
-  if (v.status) O2C_CUDA(cudaMemcpyAsync(v.status, status_stage, sizeof(int) * count, cudaMemcpyDeviceToHost, lane.stream));
+  if (v.status) {
+    if (!h->h_status) O2C_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_status), sizeof(int) * (size_t)h->cfg.batch, cudaHostAllocDefault));
+    O2C_CUDA(cudaMemcpyAsync(h->h_status + begin, status_stage, sizeof(int) * count, cudaMemcpyDeviceToHost, lane.stream));
+    h->pending_status.push_back({v.status, begin, count});  // handed to the caller by flush_status once the lanes are synchronised
+  }
   return O2C_OK;
+}
+
+void flush_status(o2c_handle* h) {
+  for (const auto& p : h->pending_status) std::memcpy(p.dst, h->h_status + p.begin, sizeof(int) * (size_t)p.count);
+  h->pending_status.clear();
 }
 
 o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) {
@@ -537,6 +553,7 @@ void release(o2c_handle* h) {
                   h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (h->h_status) cudaFreeHost(h->h_status);
   for (auto& lane : h->lanes) {
     if (lane.stage_in) cudaFree(lane.stage_in);
     if (lane.stage_out) cudaFree(lane.stage_out);
@@ -828,6 +845,7 @@ o2c_error o2c_download(o2c_handle* h, const o2c_solution_view* v, int32_t begin,
     if (e != O2C_OK) return e;
   }
   O2C_CUDA(cudaStreamSynchronize(lane.stream));
+  flush_status(h);
   return O2C_OK;
 }
 
@@ -971,6 +989,7 @@ o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solutio
     if ((e = download_chunk(h, lane, ss, off, c, 1)) != O2C_OK) return e;
   }
   for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));
+  flush_status(h);
   return O2C_OK;
 }
 
