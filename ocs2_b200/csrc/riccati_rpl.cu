@@ -530,6 +530,8 @@ struct SlqShape {
 struct SlqArgs {
   const double* lq;
   const double* term;
+  const double* x_nom;  // [batch][N+1][nx] or nullptr
+  const double* u_nom;
   double* sol;
   int* status;
   const SlqStep* steps;
@@ -697,8 +699,19 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
 #pragma unroll
           for (int l = 1; l < NU; ++l) dbi = (i == l) ? db[l] : dbi;
           out[R::odb + i] = dbi;
-          out[R::obias + i] = 0.0;
+          if (!a.x_nom) out[R::obias + i] = 0.0;
         }
+      }
+      if (a.x_nom) {  // bias = u_nom - K x_nom (GaussNewtonDDP.cpp:604-606); sAl is free between flow-map evaluations
+        const double xni = __ldg(a.x_nom + ((size_t)prob * (N + 1) + k) * NX + i);
+#pragma unroll
+        for (int l = 0; l < NU; ++l) sm[S::sAl + l + NU * i] = kt[l] * xni;
+        __syncwarp();
+        const int l = i < NU ? i : NU - 1;
+        double kx = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) kx += sm[S::sAl + l + NU * j];
+        if (valid && i < NU) solp[(size_t)k * R::orec + R::obias + i] = __ldg(a.u_nom + ((size_t)prob * (N + 1) + k) * NU + i) - kx;
       }
       __syncwarp();
     };
@@ -896,7 +909,7 @@ struct RoShape {
   static constexpr int P = 32 / NX;
   static constexpr int dyn = R::oq;      // { A | B | Hv } doubles of a stage record
   static constexpr int pol = R::oSm;     // { K | dbias | bias } doubles of a solution record
-  static constexpr int sDyn = 0, sPol = 3 * dyn, sX = sPol + 3 * pol, sU = sX + cpad2(NX), slot = sU + cpad2(NU);
+  static constexpr int sDyn = 0, sPol = 3 * dyn, sX = sPol + 3 * pol, sU = sX + cpad2(NX), sDx = sU + cpad2(NU), slot = sDx + cpad2(NX);
   static constexpr int warp_doubles = P * slot + 2;
 };
 
@@ -904,6 +917,8 @@ struct RoArgs {
   const double* lq;
   const double* sol;
   const double* x0;
+  const double* x_nom;  // [batch][N+1][nx] or nullptr: xdot = A (x - x_nom(t)) + B (u - u_nom(t)) + Hv with lerped nominal trajectories
+  const double* u_nom;
   double* xs;
   double* us;
   int* status;
@@ -996,9 +1011,19 @@ __global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
       const double w1 = 1.0 - w0;
       const double* d0 = sm + S::sDyn + (idx % 3) * S::dyn;
       const double* d1 = sm + S::sDyn + ((idx + 1) % 3) * S::dyn;
+      const double* xv = sm + S::sX;
+      if (a.x_nom) {  // deviations from the lerped nominal trajectories (TimeTriggeredRollout on the LQ model of an SLQ iteration)
+        const double* xn = a.x_nom + ((size_t)prob * (N + 1) + idx) * NX;
+        const double* un = a.u_nom + ((size_t)prob * (N + 1) + idx) * NU;
+        sm[S::sDx + i] = sm[S::sX + i] - fma(w0, __ldg(xn + i), w1 * __ldg(xn + NX + i));
+        __syncwarp();
+        if (i < NU) sm[S::sU + i] -= fma(w0, __ldg(un + i), w1 * __ldg(un + NU + i));
+        __syncwarp();
+        xv = sm + S::sDx;
+      }
       double acc = fma(w0, d0[R::oHv + i], w1 * d1[R::oHv + i]);
 #pragma unroll
-      for (int j = 0; j < NX; ++j) acc = fma(fma(w0, d0[R::oA + i + NX * j], w1 * d1[R::oA + i + NX * j]), sm[S::sX + j], acc);
+      for (int j = 0; j < NX; ++j) acc = fma(fma(w0, d0[R::oA + i + NX * j], w1 * d1[R::oA + i + NX * j]), xv[j], acc);
 #pragma unroll
       for (int l = 0; l < NU; ++l) acc = fma(fma(w0, d0[R::oB + i + NX * l], w1 * d1[R::oB + i + NX * l]), sm[S::sU + l], acc);
       __syncwarp();  // x, u in shared memory are dead
@@ -1115,7 +1140,7 @@ bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const La
 
 bool rpl_slq_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   if (!(st.algorithm == O2C_ALG_SLQ && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
-        buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1 && L.nodes == L.N + 1))
+        (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.nodes == L.N + 1))
     return false;
   return layout_matches<12, 4, 0>(L);
 }
@@ -1126,6 +1151,8 @@ cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const Devi
   SlqArgs a{};
   a.lq = buf.lq;
   a.term = buf.term;
+  a.x_nom = buf.x_nom;
+  a.u_nom = buf.u_nom;
   a.sol = buf.sol;
   a.status = buf.status;
   a.steps = steps;
@@ -1138,7 +1165,8 @@ cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const Devi
 }
 
 bool rpl_rollout_cont_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
-  return st.algorithm == O2C_ALG_SLQ && buf.x_nom == nullptr && buf.u_nom == nullptr && L.N >= 1 && L.nodes == L.N + 1 && layout_matches<12, 4, 0>(L);
+  return st.algorithm == O2C_ALG_SLQ && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.nodes == L.N + 1 &&
+         layout_matches<12, 4, 0>(L);
 }
 
 cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,
@@ -1149,6 +1177,8 @@ cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, c
   a.lq = buf.lq;
   a.sol = buf.sol;
   a.x0 = buf.x0;
+  a.x_nom = buf.x_nom;
+  a.u_nom = buf.u_nom;
   a.xs = buf.xs;
   a.us = buf.us;
   a.status = buf.status;

@@ -453,17 +453,19 @@ def test_line_search_argument_checks():
         assert e.value.code == 2  # discrete model only
 
 
-@pytest.mark.parametrize("shape,variant", [("legged", "ilqr_wpp_kernel"), ("ballbot", "ilqr_rpl_kernel"), ("manipulator", "ilqr_rpl_kernel"),
-                                           ("cartpole", "ilqr_rpl_kernel")])
-def test_fast_kernels_with_nominal_trajectories(shape, variant):
+@pytest.mark.parametrize("shape,algorithm,variant", [("legged", o2.ALG_ILQR, "ilqr_wpp_kernel"), ("ballbot", o2.ALG_ILQR, "ilqr_rpl_kernel"),
+                                                     ("manipulator", o2.ALG_ILQR, "ilqr_rpl_kernel"), ("cartpole", o2.ALG_ILQR, "ilqr_rpl_kernel"),
+                                                     ("quadrotor", o2.ALG_SLQ, "slq_rpl_kernel")])
+def test_fast_kernels_with_nominal_trajectories(shape, algorithm, variant):
     """The real DDP iteration linearises about a nominal trajectory: bias = u_nom - K x_nom and the rollout is
-    x_{k+1} = x_nom_{k+1} + A dx + B du + Hv. The specialised kernels keep serving that case (has_nominal = 1)."""
+    x_{k+1} = x_nom_{k+1} + A dx + B du + Hv (xdot = A (x - x_nom(t)) + B (u - u_nom(t)) + Hv for SLQ). The specialised kernels keep
+    serving that case (has_nominal = 1)."""
     n, m, nc = SHAPES[shape]
     rng = np.random.default_rng(21)
     batch, N = 7, 11
-    lq = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=False)
+    lq = _random_batch(rng, batch, n, m, N, nc, algorithm, ragged_nc=False)
     lq.nc = None
-    st = o2.Settings(hessianCorrectionMultiple=1e-4)
+    st = o2.Settings(algorithm=algorithm, hessianCorrectionMultiple=1e-4, timeStep=0.02)
     with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=True, max_alphas=2) as solver:
         solver.upload(lq)
         assert solver.kernel_variant == variant
