@@ -32,6 +32,7 @@ constexpr int cpad2(int v) { return (v + 1) & ~1; }
 template <int NX, int NU, int NC>
 struct Shape {
   static constexpr int G = NX;        // lanes per problem
+  static constexpr int XP = NX + (NX & 1);  // leading dimension of the kernel's own shared matrices: columns stay 16-byte aligned
   static constexpr int P = 32 / NX;   // problems per warp
   // record offsets of make_layout(NX, NU, NC, N, ILQR) for shapes below the 128-byte alignment threshold
   static constexpr int oA = 0, oB = cpad2(NX * NX), oHv = oB + cpad2(NX * NU), oq = oHv + cpad2(NX), or_ = oq + cpad2(NX),
@@ -41,9 +42,9 @@ struct Shape {
                        os = oSv + cpad2(NX), orec = os + 2;
   static constexpr int oQf = 0, oqf = cpad2(NX * NX), ocf = oqf + cpad2(NX), trec = ocf + 2;
   // shared memory of one problem slot (doubles)
-  static constexpr int sRec = 0, sSA = 2 * rec, sSB = sSA + cpad2(NX * NX), sYt = sSB + cpad2(NX * NU), sL = sYt + cpad2(NX * NU),
+  static constexpr int sRec = 0, sSA = 2 * rec, sSB = sSA + XP * NX, sYt = sSB + XP * NU, sL = sYt + XP * NU,
                        sW = sL + cpad2(NU * NU), sGv = sW + cpad2(NX), sYv = sGv + cpad2(NU), sX = sYv + cpad2(NU), sU = sX + cpad2(NX),
-                       sK = sU + cpad2(NU), sZ = sK + cpad2(NU * NX + NU), sVx = sZ + cpad2(NU * NC), slot = sVx + cpad2(NC * NX);
+                       sK = sU + cpad2(NU), sZ = sK + cpad2(NU * NX + NU), sVx = sZ + cpad2(NU * NC), slot = sVx + NC * XP;
   static constexpr int warp_doubles = P * slot + 2;  // + the warp's mbarrier
 };
 
@@ -71,19 +72,28 @@ __device__ __forceinline__ double rsqrt_pivot(double d) {  // MUFU.RSQ64H seed +
   const double p = fma(0.375, e, 0.5);
   return fma(y * e, p, y);
 }
-// acc += sum_k a[k] * M[k] for a contiguous shared-memory column M (16-byte aligned when LEN is even), a in registers
+// acc += sum_k a[k] * M[k] for a contiguous shared-memory column M, a in registers. Two FMAs per 16-byte load; par = 1 says that M sits
+// an odd number of doubles after a 16-byte boundary (odd leading dimensions: the pairs then start at element 1). par is a
+// compile-time constant at every call site once the loops are unrolled.
 template <int LEN>
-__device__ __forceinline__ double dot_col(const double (&a)[LEN], const double* M, double acc) {
-  if (LEN % 2 == 0) {
+__device__ __forceinline__ double dot_col(const double (&a)[LEN], const double* M, double acc, int par = 0) {
+  if (par) {
+    acc = fma(a[0], M[0], acc);
 #pragma unroll
-    for (int k = 0; k < LEN; k += 2) {
+    for (int k = 1; k + 1 < LEN; k += 2) {
       const double2 v = ld2(M + k);
       acc = fma(a[k], v.x, acc);
       acc = fma(a[k + 1], v.y, acc);
     }
+    if (LEN % 2 == 0) acc = fma(a[LEN - 1], M[LEN - 1], acc);
   } else {
 #pragma unroll
-    for (int k = 0; k < LEN; ++k) acc = fma(a[k], M[k], acc);
+    for (int k = 0; k + 1 < LEN; k += 2) {
+      const double2 v = ld2(M + k);
+      acc = fma(a[k], v.x, acc);
+      acc = fma(a[k + 1], v.y, acc);
+    }
+    if (LEN % 2 == 1) acc = fma(a[LEN - 1], M[LEN - 1], acc);
   }
   return acc;
 }
@@ -164,9 +174,9 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       sm[S::sW + i] = wi;
       double spart = Hv[i] * (wi - 0.5 * shv);  // this row's share of Hv.w - 1/2 Hv.(S Hv)
 #pragma unroll
-      for (int j = 0; j < NX; ++j) sm[S::sSA + i + NX * j] = dot_col<NX>(Srow, A + NX * j, 0.0);
+      for (int j = 0; j < NX; ++j) sm[S::sSA + i + S::XP * j] = dot_col<NX>(Srow, A + NX * j, 0.0, (NX * j) & 1);
 #pragma unroll
-      for (int l = 0; l < NU; ++l) sm[S::sSB + i + NX * l] = dot_col<NX>(Srow, B + NX * l, 0.0);
+      for (int l = 0; l < NU; ++l) sm[S::sSB + i + S::XP * l] = dot_col<NX>(Srow, B + NX * l, 0.0, (NX * l) & 1);
       __syncwarp();
 
       // ---- T_i = Q_i + eps e_i + A(:,i)' SA ; tv_i = q_i + A(:,i)' w ----
@@ -175,7 +185,7 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       for (int kk = 0; kk < NX; ++kk) acol[kk] = A[kk + NX * i];
       double Trow[NX];
 #pragma unroll
-      for (int j = 0; j < NX; ++j) Trow[j] = dot_col<NX>(acol, sm + S::sSA + NX * j, rec[S::oQ + i + NX * j] + ((j == i) ? a.eps : 0.0));
+      for (int j = 0; j < NX; ++j) Trow[j] = dot_col<NX>(acol, sm + S::sSA + S::XP * j, rec[S::oQ + i + NX * j] + ((j == i) ? a.eps : 0.0));
       const double tvi = dot_col<NX>(acol, sm + S::sW, rec[S::oq + i]);
 
       // ---- G'_i = P(:,i)' + SA(:,i)' B (row i of G') ----
@@ -183,9 +193,9 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       {
         double sacol[NX];
 #pragma unroll
-        for (int kk = 0; kk < NX; ++kk) sacol[kk] = sm[S::sSA + kk + NX * i];
+        for (int kk = 0; kk < NX; ++kk) sacol[kk] = sm[S::sSA + kk + S::XP * i];
 #pragma unroll
-        for (int l = 0; l < NU; ++l) gt[l] = dot_col<NX>(sacol, B + NX * l, rec[S::oP + l + NU * i]);
+        for (int l = 0; l < NU; ++l) gt[l] = dot_col<NX>(sacol, B + NX * l, rec[S::oP + l + NU * i], (NX * l) & 1);
       }
 
       // ---- Hm_l = R_l + B(:,l)' SB and Gv_l = r_l + B(:,l)' w on lanes l < nu; Cholesky by shuffles inside the group ----
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
 #pragma unroll
         for (int kk = 0; kk < NX; ++kk) bcol[kk] = B[kk + NX * l];
 #pragma unroll
-        for (int l2 = 0; l2 < NU; ++l2) h[l2] = dot_col<NX>(bcol, sm + S::sSB + NX * l2, rec[S::oR + l + NU * l2]);
+        for (int l2 = 0; l2 < NU; ++l2) h[l2] = dot_col<NX>(bcol, sm + S::sSB + S::XP * l2, rec[S::oR + l + NU * l2]);
         const double gv = dot_col<NX>(bcol, sm + S::sW, rec[S::or_ + l]);
         if (i < NU) sm[S::sGv + i] = gv;
       }
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
           vv[c1] = w2 * lm[c1][c1];
         }
 #pragma unroll
-        for (int c1 = 0; c1 < NC; ++c1) sm[S::sVx + i + NX * c1] = vx[c1];
+        for (int c1 = 0; c1 < NC; ++c1) sm[S::sVx + i + S::XP * c1] = vx[c1];
         // t = L_M^-T Vx(:,i), tv = L_M^-T vv;  Y^ = Y - Z t, Yv^ = Yv - Z tv
         double tx[NC > 0 ? NC : 1], tvv[NC > 0 ? NC : 1];
 #pragma unroll
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
         db[l] = vv2 * Lm[l + NU * l];
       }
 #pragma unroll
-      for (int l = 0; l < NU; ++l) sm[S::sYt + i + NX * l] = yt[l];
+      for (int l = 0; l < NU; ++l) sm[S::sYt + i + S::XP * l] = yt[l];
       if (valid) {
 #pragma unroll
         for (int l = 0; l < NU; ++l) out[S::oK + l + NU * i] = kt[l];  // column i of K: the group writes nu*nx contiguous doubles
@@ -364,13 +374,28 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
 
       // ---- S_i = T_i - Y'_i Y'' ; Sv_i = tv_i - Y'_i Yv ; s ----
 #pragma unroll
-      for (int j = 0; j < NX; ++j) {
-        double v = Trow[j];
+      for (int j = 0; j < NX; ++j) Srow[j] = Trow[j];
 #pragma unroll
-        for (int l = 0; l < NU; ++l) v = fma(-yt[l], sm[S::sYt + j + NX * l], v);
+      for (int l = 0; l < NU; ++l) {  // column l of Y' (contiguous, 16-byte aligned: leading dimension XP) updates the whole row
+        const double* col = sm + S::sYt + S::XP * l;
 #pragma unroll
-        for (int c1 = 0; c1 < NC; ++c1) v = fma(vx[c1], sm[S::sVx + j + NX * c1], v);
-        Srow[j] = v;
+        for (int j = 0; j + 1 < NX; j += 2) {
+          const double2 v = ld2(col + j);
+          Srow[j] = fma(-yt[l], v.x, Srow[j]);
+          Srow[j + 1] = fma(-yt[l], v.y, Srow[j + 1]);
+        }
+        if (NX % 2 == 1) Srow[NX - 1] = fma(-yt[l], col[NX - 1], Srow[NX - 1]);
+      }
+#pragma unroll
+      for (int c1 = 0; c1 < NC; ++c1) {
+        const double* col = sm + S::sVx + S::XP * c1;
+#pragma unroll
+        for (int j = 0; j + 1 < NX; j += 2) {
+          const double2 v = ld2(col + j);
+          Srow[j] = fma(vx[c1], v.x, Srow[j]);
+          Srow[j + 1] = fma(vx[c1], v.y, Srow[j + 1]);
+        }
+        if (NX % 2 == 1) Srow[NX - 1] = fma(vx[c1], col[NX - 1], Srow[NX - 1]);
       }
       Svi = tvi;
 #pragma unroll
