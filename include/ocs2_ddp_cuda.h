@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define O2C_ABI_VERSION 1
+#define O2C_ABI_VERSION 2
 
 typedef enum o2c_error {
   O2C_OK = 0,
@@ -101,6 +101,13 @@ typedef struct o2c_lq_view {
   o2c_field x_nom, u_nom;      /* nominal trajectories, N+1 nodes of n / m (only read when has_nominal) */
   o2c_field x0;                /* initial state for the rollout, n per problem; node_stride ignored */
   const double* time;          /* N+1 node times shared by the batch (required for SLQ; ILQR: optional) */
+  /* ILQR events (ILQR.cpp:263-295, RiccatiTransversalityConditions.h:40-56): event[problem][node] != 0 marks a PRE-EVENT node
+   * (time[node] == time[node+1], node+1 in postEventIndices_). Its A, Hv, Q, q, c blocks hold the jump ModelData
+   * (modelDataEventTimes: jump map linearisation x+ = A_e dx + Hv_e and pre-jump cost), its B, P, R, r, C, D, e the regular model
+   * data of the node, which only shape the controller entry. NULL = no events. Host memory in o2c_upload / o2c_solve_host, device
+   * memory in o2c_import_device. Handles with events use the generic kernels. */
+  const int32_t* event;
+  int64_t event_problem_stride, event_node_stride;
 } o2c_lq_view;
 
 /* Struct-of-arrays view of the solution. Controller and value function have N+1 nodes (node N of the controller is the copy of

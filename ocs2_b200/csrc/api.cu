@@ -52,6 +52,8 @@ struct o2c_handle {
   int *d_nc = nullptr, *d_status = nullptr;
   double *d_ls_merit = nullptr, *d_ls_base = nullptr, *d_ls_is = nullptr, *d_ls_step = nullptr, *d_ls_basein = nullptr;  // line search
   int* d_ls_index = nullptr;
+  int* d_event = nullptr;       // [batch][nodes] pre-event flags, allocated by the first upload that carries events
+  bool events_present = false;
   std::vector<double> ls_candidates;
   bool backward_done = false;
   int* h_status = nullptr;  // pinned bounce buffer [batch]: a caller's status array may be pageable, and an asynchronous copy into
@@ -82,6 +84,7 @@ struct o2c_handle {
     b.x_nom = d_xnom;
     b.u_nom = d_unom;
     b.nc = nc_ragged ? d_nc : nullptr;
+    b.event = events_present ? d_event : nullptr;
     b.x0 = d_x0;
     b.time = d_time;
     b.sol = d_sol;
@@ -367,6 +370,35 @@ o2c_error check_range(const o2c_handle* h, int begin, int count) {
   return O2C_OK;
 }
 
+// pre-event flags of problems [begin, begin+count): host (or device) array -> d_event; a view without events clears the range
+o2c_error install_events(o2c_handle* h, cudaStream_t stream, const int32_t* ev, long long ps, long long ns, bool device_memory, int begin,
+                         int count) {
+  const int nodes = h->L.nodes;
+  if (ev == nullptr) {
+    if (h->events_present) O2C_CUDA(cudaMemsetAsync(h->d_event + (size_t)begin * nodes, 0, sizeof(int) * (size_t)count * nodes, stream));
+    if (begin == 0 && count == h->cfg.batch) h->events_present = false;  // whole batch replaced: the specialised kernels serve it again
+    return O2C_OK;
+  }
+  if (h->st.algorithm != O2C_ALG_ILQR) return fail(O2C_ERR_UNSUPPORTED, "events are provided for the discrete (ILQR) backward pass only");
+  if (!h->d_event) {
+    O2C_CUDA(cudaMalloc(&h->d_event, sizeof(int) * (size_t)h->cfg.batch * nodes));
+    O2C_CUDA(cudaMemsetAsync(h->d_event, 0, sizeof(int) * (size_t)h->cfg.batch * nodes, stream));
+  }
+  h->events_present = true;
+  int* dst = h->d_event + (size_t)begin * nodes;
+  if (device_memory) {
+    if (ns != 1) return fail(O2C_ERR_UNSUPPORTED, "device event flags must be contiguous over the nodes (event_node_stride == 1)");
+    O2C_CUDA(cudaMemcpy2DAsync(dst, sizeof(int) * nodes, ev, sizeof(int) * (size_t)ps, sizeof(int) * nodes, count, cudaMemcpyDeviceToDevice, stream));
+    return O2C_OK;
+  }
+  std::vector<int> tmp((size_t)count * nodes);
+  for (int p = 0; p < count; ++p)
+    for (int k = 0; k < nodes; ++k) tmp[(size_t)p * nodes + k] = ev[p * ps + k * ns] != 0;
+  O2C_CUDA(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+  O2C_CUDA(cudaStreamSynchronize(stream));  // tmp is pageable and about to go out of scope
+  return O2C_OK;
+}
+
 // host view (already offset so that index 0 is the first problem of the chunk) -> records of problems [begin, begin+count)
 o2c_error upload_chunk(o2c_handle* h, Lane& lane, const o2c_lq_view& v, int begin, int count) {
   const Layout& L = h->L;
@@ -402,6 +434,7 @@ o2c_error upload_chunk(o2c_handle* h, Lane& lane, const o2c_lq_view& v, int begi
     d.nc_ps = nodes;
     d.nc_ns = 1;
   }
+  if ((e = install_events(h, lane.stream, v.event, v.event_problem_stride, v.event_node_stride, false, begin, count)) != O2C_OK) return e;
   O2C_CUDA(launch_pack(L, d, h->d_lq, h->d_term, h->d_xnom, h->d_unom, h->d_nc, h->d_x0, begin, count, lane.stream));
   h->launches += 1;
   return O2C_OK;
@@ -483,7 +516,7 @@ o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) 
   h->backward_done = true;
   const DeviceBuffers buf = h->buffers();
   if (h->st.algorithm == O2C_ALG_ILQR) {
-    if (h->use_fast) {
+    if (h->use_fast && wpp_ilqr_supported(h->L, h->st, buf)) {  // (handles with events fall through to the generic kernel)
       int l = 0;
       O2C_CUDA(launch_ilqr_wpp(h->L, h->st, buf, false, 1.0, h->cfg.batch, begin, count, stream, &l));
       h->launches += l;
@@ -526,7 +559,8 @@ o2c_error rollout_on(o2c_handle* h, cudaStream_t stream, const double* alphas_de
 
 o2c_error solve_on(o2c_handle* h, cudaStream_t stream, double* alpha_slot_dev, double alpha, int begin, int count) {
   if (count == 0) return O2C_OK;
-  if (h->st.algorithm == O2C_ALG_ILQR && (h->use_fast || (h->use_rpl && rpl_ilqr_supported(h->L, h->st, h->buffers())))) {
+  if (h->st.algorithm == O2C_ALG_ILQR && ((h->use_fast && wpp_ilqr_supported(h->L, h->st, h->buffers())) ||
+                                          (h->use_rpl && rpl_ilqr_supported(h->L, h->st, h->buffers())))) {
     int l = 0;
     h->backward_done = true;
     if (h->use_fast)
@@ -550,7 +584,7 @@ void release(o2c_handle* h) {
   }
   void* ptrs[] = {h->d_lq,  h->d_term, h->d_xnom, h->d_unom,   h->d_x0,        h->d_time,    h->d_sol,
                   h->d_xs,  h->d_us,   h->d_alphas, h->d_nc,   h->d_status,    h->d_slq_steps, h->d_ro_steps,
-                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index};
+                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
@@ -779,6 +813,7 @@ o2c_error o2c_upload(o2c_handle* h, const o2c_lq_view* v, int32_t begin, int32_t
     OFF(A) OFF(B) OFF(Hv) OFF(Q) OFF(P) OFF(R) OFF(q) OFF(r) OFF(c) OFF(C) OFF(D) OFF(e) OFF(Qf) OFF(qf) OFF(cf) OFF(x_nom) OFF(u_nom) OFF(x0)
 #undef OFF
     if (v->nc) sub.nc = v->nc + (long long)off * v->nc_problem_stride;
+    if (v->event) sub.event = v->event + (long long)off * v->event_problem_stride;
     e = upload_chunk(h, lane, sub, begin + off, c);
     if (e != O2C_OK) return e;
   }
@@ -820,6 +855,7 @@ o2c_error o2c_import_device(o2c_handle* h, const o2c_lq_view* v, int32_t begin, 
   if (v->nc && h->L.ncmax > 0) h->nc_ragged = true;
   d.nc_ps = v->nc_problem_stride;
   d.nc_ns = v->nc_node_stride;
+  if ((e = install_events(h, h->lanes[0].stream, v->event, v->event_problem_stride, v->event_node_stride, true, begin, count)) != O2C_OK) return e;
   O2C_CUDA(launch_pack(h->L, d, h->d_lq, h->d_term, h->d_xnom, h->d_unom, h->d_nc, h->d_x0, begin, count, h->lanes[0].stream));
   h->launches += 1;
   return O2C_OK;
@@ -950,7 +986,7 @@ o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {
 const char* o2c_kernel_variant(const o2c_handle* h) {
   if (!h) return "";
   if (h->st.algorithm == O2C_ALG_SLQ && rpl_slq_supported(h->L, h->st, h->buffers())) return "slq_rpl_kernel";
-  if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast) return "ilqr_wpp_kernel";
+  if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast && wpp_ilqr_supported(h->L, h->st, h->buffers())) return "ilqr_wpp_kernel";
   if (h->st.algorithm == O2C_ALG_ILQR && h->use_rpl && rpl_ilqr_supported(h->L, h->st, h->buffers())) return "ilqr_rpl_kernel";
   return generic_variant_name(h->L, h->st);
 }
@@ -970,6 +1006,8 @@ o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solutio
   }
   // lanes run [H2D -> pack -> sweep+rollout -> unpack -> D2H] for alternating chunks; copies of one lane overlap the kernels of another
   for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));
+  if (!lq->event && count == h->cfg.batch)  // whole batch replaced by problems without events (chunk uploads alone cannot tell)
+    if ((e = install_events(h, h->lanes[0].stream, nullptr, 0, 0, false, 0, count)) != O2C_OK) return e;
   int li = 0;
   for (int off = 0; off < count; off += chunk, li = (li + 1) % kLanes) {
     const int c = std::min(chunk, count - off);
@@ -979,6 +1017,7 @@ o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solutio
     OFF(A) OFF(B) OFF(Hv) OFF(Q) OFF(P) OFF(R) OFF(q) OFF(r) OFF(c) OFF(C) OFF(D) OFF(e) OFF(Qf) OFF(qf) OFF(cf) OFF(x_nom) OFF(u_nom) OFF(x0)
 #undef OFF
     if (lq->nc) sub.nc = lq->nc + (long long)off * lq->nc_problem_stride;
+    if (lq->event) sub.event = lq->event + (long long)off * lq->event_problem_stride;
     if ((e = upload_chunk(h, lane, sub, off, c)) != O2C_OK) return e;
     if ((e = solve_on(h, lane.stream, h->d_alphas + h->cfg.max_alphas + li, alpha, off, c)) != O2C_OK) return e;
     o2c_solution_view ss = *sol;
@@ -997,6 +1036,7 @@ o2c_error o2c_generate_synthetic(o2c_handle* h, uint64_t seed, int64_t first_pro
   if (!h) return fail(O2C_ERR_INVALID_ARGUMENT, "null handle");
   O2C_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t s = h->lanes[0].stream;
+  h->events_present = false;
   O2C_CUDA(launch_generate(h->L, h->st.algorithm, h->d_lq, h->d_term, h->d_x0, seed, first_problem_index, dt, h->cfg.batch, s));
   h->launches += 1;
   if (h->d_nc) {

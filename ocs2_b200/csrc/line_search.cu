@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) merit_kernel(Layout L, De
       for (int j = 0; j < n; ++j) qx = fma(rec[L.oQ + i + j * n], x[j] - (xn ? xn[j] : 0.0), qx);
       part += dxi * (rec[L.oq + i] + 0.5 * qx);
     }
-    for (int i = lane; i < m; i += 32) {
+    const bool jump = buf.event != nullptr && buf.event[(size_t)prob * L.nodes + k] != 0;  // pre-jump cost: state terms only
+    for (int i = lane; i < m && !jump; i += 32) {
       const double dui = u[i] - (un ? un[i] : 0.0);
       double px = 0.0, ru = 0.0;
       for (int j = 0; j < n; ++j) px = fma(rec[L.oP + i + j * m], x[j] - (xn ? xn[j] : 0.0), px);

@@ -89,6 +89,7 @@ struct DeviceBuffers {
   const double* x_nom;  // [batch][N+1][n] or nullptr
   const double* u_nom;  // [batch][N+1][m] or nullptr
   const int* nc;        // [batch][nodes] or nullptr
+  const int* event;     // [batch][nodes] pre-event node flags (ILQR) or nullptr: no events anywhere
   const double* x0;     // [batch][n]
   const double* time;   // [N+1]
   double* sol;

@@ -512,6 +512,29 @@ __global__ void __launch_bounds__(128) ilqr_generic_kernel(Layout L, SolverSetti
     load_record(L, buf.lq + ((size_t)prob * L.nodes + k) * L.rec, W.rec);
     W.ct = W.rec[L.oc];
     const int nc = (L.ncmax > 0) ? (buf.nc ? buf.nc[(size_t)prob * L.nodes + k] : L.ncmax) : 0;
+    const bool is_event = buf.event != nullptr && buf.event[(size_t)prob * L.nodes + k] != 0;
+    double sv;
+    if (is_event) {
+      // ---- pre-event node (ILQR.cpp:263-295): riccatiTransversalityConditions (RiccatiTransversalityConditions.h:40-56) on the jump
+      // model data held in A, Hv, Q, q, c; then the controller entry from the regular data projected with Sm = 0 (Hm = R) ----
+      wgemm<false, false>(n, 1, n, 1.0, Sa, n, W.Hv, n, 0.0, W.SHv, n);
+      wgemm<true, false>(n, n, n, 1.0, Sa, n, W.A, n, 0.0, W.SA, n);  // Sm' A_e
+      for (int i = lane; i < n; i += 32) W.w[i] = Sva[i] + W.SHv[i];
+      __syncwarp();
+      wcopy(n * n, W.Q, Sb);
+      wgemm<true, false>(n, n, n, 1.0, W.SA, n, W.A, n, 1.0, Sb, n);  // Q_e + (Sm' A_e)' A_e
+      wcopy(n, W.q, Svb);
+      wgemm<true, false>(n, 1, n, 1.0, W.A, n, W.w, n, 1.0, Svb, n);  // q_e + A_e' (Sv + Sm Hv_e)
+      sv = snext + W.ct + wdot(n, W.Hv, W.w) - 0.5 * wdot(n, W.Hv, W.SHv);
+      __syncwarp();
+      status |= project_stage(W, L, st, nc, nullptr);
+      const int pe = W.p;
+      for (int i = lane; i < pe * n; i += 32) W.Km[i] = -W.Pt[i] - (lm ? W.dGm[i] : 0.0);
+      for (int i = lane; i < pe; i += 32) W.Lv[i] = -W.rt[i] - (lm ? W.dGv[i] : 0.0);
+      __syncwarp();
+      wgemm<true, false>(pe, n, n, -1.0, W.Bt, n, Sb, n, 1.0, W.Km, pe);
+      wgemm<true, false>(pe, 1, n, -1.0, W.Bt, n, Svb, n, 1.0, W.Lv, pe);
+    } else {
     status |= project_stage(W, L, st, nc, Sa);
     const int p = W.p;
     // ---- DiscreteTimeRiccatiEquations::computeMapILQR ----
@@ -562,11 +585,12 @@ __global__ void __launch_bounds__(128) ilqr_generic_kernel(Layout L, SolverSetti
       Svb[i] = acc;
     }
     // s
-    double sv = snext + W.ct + wdot(n, W.Hv, W.w) - 0.5 * wdot(n, W.Hv, W.SHv);
+    sv = snext + W.ct + wdot(n, W.Hv, W.w) - 0.5 * wdot(n, W.Hv, W.SHv);
     if (st.reduced)
       sv += 0.5 * wdot(p, W.Lv, W.Gv);
     else
       sv += wdot(p, W.Lv, W.Gv) + 0.5 * wdot(p, W.Lv, W.HmLv);
+    }
     __syncwarp();
     // ---- outputs of node k ----
     double* out = solp + (size_t)k * L.orec;

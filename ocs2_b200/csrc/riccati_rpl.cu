@@ -1158,7 +1158,7 @@ cudaError_t launch(const Args& a, cudaStream_t stream) {
 
 bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const Layout& L) {
   return st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
-         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1;
+         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1;
 }
 
 }  // namespace

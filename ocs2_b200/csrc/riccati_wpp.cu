@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 
 bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
-         st.hc == O2C_HC_DIAGONAL_SHIFT && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
+         st.hc == O2C_HC_DIAGONAL_SHIFT && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
          L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb && L.obias == kObias && L.oSm == kOSm &&
          L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat;
 }

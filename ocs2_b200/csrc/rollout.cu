@@ -57,12 +57,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rollout_discrete_kernel(L
     const double* st = lqp + (size_t)k * L.rec;
     const double* A = st + L.oA;
     const double* B = st + L.oB;
+    const bool jump = buf.event != nullptr && buf.event[(size_t)prob * L.nodes + k] != 0;  // pre-event node: x+ = x_nom+ + A_e dx + Hv_e
     double xn_[2];
     int cnt = 0;
     for (int i = lane; i < n; i += 32) {
       double acc = st[L.oHv + i] + (xnom ? xnom[(size_t)(k + 1) * n + i] : 0.0);
       for (int j = 0; j < n; ++j) acc = fma(A[i + j * n], dx[j], acc);
-      for (int j = 0; j < m; ++j) acc = fma(B[i + j * n], du[j], acc);
+      if (!jump)
+        for (int j = 0; j < m; ++j) acc = fma(B[i + j * n], du[j], acc);
       xn_[cnt++] = acc;  // n <= 64
     }
     __syncwarp();

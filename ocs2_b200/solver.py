@@ -52,7 +52,7 @@ class LqBatch:
     """Host LQ data of a batch in natural numpy layout (ModelData fields, ModelData.h:43-60):
     A (B,nodes,n,n) B (B,nodes,n,m) Hv (B,nodes,n) Q (B,nodes,n,n) P (B,nodes,m,n) R (B,nodes,m,m) q (B,nodes,n) r (B,nodes,m)
     c (B,nodes) C (B,nodes,ncmax,n) D (B,nodes,ncmax,m) e (B,nodes,ncmax) nc (B,nodes) int32 Qf (B,n,n) qf (B,n) cf (B,)
-    x_nom (B,N+1,n) u_nom (B,N+1,m) x0 (B,n) time (N+1,). nodes = N for ILQR, N+1 for SLQ."""
+    x_nom (B,N+1,n) u_nom (B,N+1,m) x0 (B,n) time (N+1,) event (B,nodes) int. nodes = N for ILQR, N+1 for SLQ."""
     A: np.ndarray
     B: np.ndarray
     Q: np.ndarray
@@ -73,6 +73,7 @@ class LqBatch:
     u_nom: Optional[np.ndarray] = None
     x0: Optional[np.ndarray] = None
     time: Optional[np.ndarray] = None
+    event: Optional[np.ndarray] = None   # (B, nodes) int: 1 marks a pre-event node of ILQR (jump data in A, Hv, Q, q, c)
     _keep: dict = field(default_factory=dict, repr=False)
 
     @property
@@ -117,6 +118,11 @@ class LqBatch:
         lv.u_nom = _field(k["u_nom"], m, N + 1)
         lv.x0 = _field(k["x0"], n, 1)
         lv.time = k["time"].ctypes.data if k["time"] is not None else None
+        k["event"] = np.ascontiguousarray(self.event, dtype=np.int32) if self.event is not None else None
+        if k["event"] is not None:
+            lv.event = k["event"].ctypes.data
+            lv.event_problem_stride = nodes
+            lv.event_node_stride = 1
         return lv
 
 

@@ -549,6 +549,32 @@ int backward_ilqr(const orc_settings& st, const orc_problem& pb, orc_solution* s
   for (int k = N - 1; k >= 0; --k) {
     const StageIn in = stage_of(pb, k);
     const double* SmNext = sol->Sm + (size_t)(k + 1) * n * n;
+    if (pb.event && pb.event[k]) {
+      // pre-event node (ILQR.cpp:263-295): value function by riccatiTransversalityConditions (RiccatiTransversalityConditions.h:40-56)
+      // from the jump model data, controller from the regular model data projected with Sm = 0 and the pre-event value function
+      const double* SvNext = sol->Sv + (size_t)(k + 1) * n;
+      double* Sm = sol->Sm + (size_t)k * n * n;
+      double* Sv = sol->Sv + (size_t)k * n;
+      vec SmTransAm((size_t)n * n), SmHv(n), tmp(n);
+      gemm_tn(n, n, n, 1.0, SmNext, n, in.A, n, 0.0, SmTransAm.data(), n);  // Sm^T * dfdx
+      std::copy(in.Q, in.Q + (size_t)n * n, Sm);
+      gemm_tn(n, n, n, 1.0, SmTransAm.data(), n, in.A, n, 1.0, Sm, n);      // += SmTransAm^T * dfdx
+      gemm_nn(n, 1, n, 1.0, SmNext, n, in.Hv, n, 0.0, SmHv.data(), n);
+      for (int i = 0; i < n; ++i) tmp[i] = SvNext[i] + SmHv[i];
+      std::copy(in.q, in.q + n, Sv);
+      gemm_tn(n, 1, n, 1.0, in.A, n, tmp.data(), n, 1.0, Sv, n);
+      double acc = 0.0;
+      for (int i = 0; i < n; ++i) acc += in.Hv[i] * (SvNext[i] + 0.5 * SmHv[i]);
+      sol->s[k] = sol->s[k + 1] + in.c + acc;
+      status |= project_stage(st, in, nullptr, pr);  // SmDummy = 0 (ILQR.cpp:281-282): Hm = R
+      const int p = pr.p;
+      for (size_t i = 0; i < (size_t)p * n; ++i) Km[i] = -pr.Pt[i] - pr.dGm[i];
+      gemm_tn(p, n, n, -1.0, pr.Bt.data(), n, Sm, n, 1.0, Km.data(), p);
+      for (int i = 0; i < p; ++i) Lv[i] = -pr.rt[i] - pr.dGv[i];
+      gemm_tn(p, 1, n, -1.0, pr.Bt.data(), n, Sv, n, 1.0, Lv.data(), p);
+      unproject_controller(pb, k, pr, Km.data(), Lv.data(), sol);
+      continue;
+    }
     status |= project_stage(st, in, SmNext, pr);
     compute_map(st.reduced_form != 0, n, pr.p, ptrs_of(pr), SmNext, sol->Sv + (size_t)(k + 1) * n, sol->s[k + 1], Km.data(), Lv.data(),
                 sol->Sm + (size_t)k * n * n, sol->Sv + (size_t)k * n, &sol->s[k]);
@@ -884,7 +910,8 @@ int orc_rollout(const orc_settings* st, const orc_problem* pb, const orc_solutio
       double* xn = x + (size_t)(k + 1) * n;
       for (int i = 0; i < n; ++i) xn[i] = pb->Hv[(size_t)k * n + i] + (pb->x_nom ? pb->x_nom[(size_t)(k + 1) * n + i] : 0.0);
       gemm_nn(n, 1, n, 1.0, pb->A + (size_t)k * n * n, n, dx.data(), n, 1.0, xn, n);
-      gemm_nn(n, 1, m, 1.0, pb->B + (size_t)k * n * m, n, du.data(), m, 1.0, xn, n);
+      if (!(pb->event && pb->event[k]))  // a pre-event node jumps: x+ = x_nom+ + A_e dx + Hv_e, the input does not act
+        gemm_nn(n, 1, m, 1.0, pb->B + (size_t)k * n * m, n, du.data(), m, 1.0, xn, n);
       if (t_out) t_out[k] = pb->time ? pb->time[k] : (double)k;
     }
     if (t_out) t_out[N] = pb->time ? pb->time[N] : (double)N;
@@ -980,6 +1007,10 @@ double orc_discrete_lq_cost(const orc_problem* pb, const double* x, const double
     J += pb->c[k] + dot(n, pb->q + (size_t)k * n, dx.data()) + dot(m, pb->r + (size_t)k * m, du.data());
     gemm_nn(n, 1, n, 1.0, pb->Q + (size_t)k * n * n, n, dx.data(), n, 0.0, t1.data(), n);
     J += 0.5 * dot(n, dx.data(), t1.data());
+    if (pb->event && pb->event[k]) {  // pre-jump cost: state terms only (undo the r.du added above)
+      J -= dot(m, pb->r + (size_t)k * m, du.data());
+      continue;
+    }
     gemm_nn(m, 1, n, 1.0, pb->P + (size_t)k * m * n, m, dx.data(), n, 0.0, t1.data(), m);
     J += dot(m, du.data(), t1.data());
     gemm_nn(m, 1, m, 1.0, pb->R + (size_t)k * m * m, m, du.data(), m, 0.0, t1.data(), m);

@@ -59,6 +59,10 @@ typedef struct orc_problem {
   const double *Qf, *qf, *cf;       /* terminal value function (already Hessian-shifted, GaussNewtonDDP.cpp:724-727) */
   const double *x_nom, *u_nom;      /* [N+1][n], [N+1][m] nominal trajectories (NULL => 0) */
   const double* time;               /* [N+1] node times (SLQ / continuous rollout) */
+  const int32_t* event;             /* ILQR only, [N] or NULL: event[k] != 0 marks node k as a PRE-EVENT node (time[k] == time[k+1],
+                                       k+1 in postEventIndices_). Its A, Hv, Q, q, c are the jump ModelData (modelDataEventTimes:
+                                       jump map linearisation and pre-jump cost), its B, P, R, r, C, D, e the regular model data of the
+                                       node, used only for the controller (ILQR.cpp:263-295). */
 } orc_problem;
 
 typedef struct orc_solution {

@@ -38,7 +38,7 @@ class Settings(C.Structure):
 class _Problem(C.Structure):
     _fields_ = [("nx", C.c_int32), ("nu", C.c_int32), ("nc_max", C.c_int32), ("N", C.c_int32)] + [
         (name, _dp) for name in ("A", "B", "Hv", "Q", "P", "R", "q", "r", "c", "C", "D", "e")
-    ] + [("nc", _ip)] + [(name, _dp) for name in ("Qf", "qf", "cf", "x_nom", "u_nom", "time")]
+    ] + [("nc", _ip)] + [(name, _dp) for name in ("Qf", "qf", "cf", "x_nom", "u_nom", "time")] + [("event", _ip)]
 
 
 class _Solution(C.Structure):
@@ -260,6 +260,7 @@ class Problem:
     x_nom: np.ndarray | None = None
     u_nom: np.ndarray | None = None
     time: np.ndarray | None = None
+    event: np.ndarray | None = None  # (N,) int: 1 marks a pre-event node (ILQR): jump data in A, Hv, Q, q, c
 
     @property
     def nx(self):
@@ -284,12 +285,15 @@ class Problem:
         keep["Qf"] = np.ascontiguousarray(np.asarray(self.Qf, dtype=np.float64).T)
         keep["cf"] = np.array([self.cf], dtype=np.float64)
         keep["nc"] = np.ascontiguousarray(self.nc, dtype=np.int32) if self.nc is not None else None
+        ev = getattr(self, "event", None)
+        keep["event"] = np.ascontiguousarray(ev, dtype=np.int32) if ev is not None else None
         if keep["time"] is None:
             keep["time"] = np.arange(self.N + 1, dtype=np.float64)
         pb = _Problem(self.nx, self.nu, self.nc_max, self.N, _p(keep["A"]), _p(keep["B"]), _p(keep["Hv"]), _p(keep["Q"]), _p(keep["P"]),
                       _p(keep["R"]), _p(keep["q"]), _p(keep["r"]), _p(keep["c"]), _p(keep["C"]), _p(keep["D"]), _p(keep["e"]),
                       keep["nc"].ctypes.data_as(_ip) if keep["nc"] is not None else _ip(), _p(keep["Qf"]), _p(keep["qf"]), _p(keep["cf"]),
-                      _p(keep["x_nom"]), _p(keep["u_nom"]), _p(keep["time"]))
+                      _p(keep["x_nom"]), _p(keep["u_nom"]), _p(keep["time"]),
+                      keep["event"].ctypes.data_as(_ip) if keep["event"] is not None else _ip())
         return pb, keep
 
 

@@ -166,7 +166,7 @@ def _oracle_problem(lq, i, N):
     g = lambda a: None if a is None else a[i]  # noqa: E731
     return orc.Problem(N=N, A=lq.A[i], B=lq.B[i], Hv=lq.Hv[i], Q=lq.Q[i], P=lq.P[i], R=lq.R[i], q=lq.q[i], r=lq.r[i], c=lq.c[i], Qf=lq.Qf[i],
                        qf=lq.qf[i], cf=float(lq.cf[i]), C=g(lq.C), D=g(lq.D), e=g(lq.e), nc=g(lq.nc), x_nom=g(lq.x_nom), u_nom=g(lq.u_nom),
-                       time=lq.time)
+                       time=lq.time, event=g(lq.event))
 
 
 @pytest.mark.parametrize("algorithm", [o2.ALG_ILQR, o2.ALG_SLQ])
@@ -514,3 +514,55 @@ def test_eigenvalue_modification_matches_oracle(algorithm, n, m, nc):
         check_against_oracle(st, pb, lq.x0[i], sol, i, what=f"eigenvalue modification n={n}")
         clamped += int(np.linalg.eigvalsh(lq.Q[i, 0]).min() < 0)
     assert clamped > 0, "the test data should contain indefinite state costs"
+
+
+@pytest.mark.parametrize("n,m,nc,nominal", [(5, 3, 0, False), (6, 4, 2, True), (24, 24, 0, False), (10, 3, 0, True)])
+def test_ilqr_events_match_oracle(n, m, nc, nominal):
+    """Pre-event nodes (ILQR.cpp:263-295): value function through riccatiTransversalityConditions on the jump model data, controller
+    entry from the regular data with Sm = 0, rollout through the jump map. Handles with events use the generic kernels."""
+    rng = np.random.default_rng(17 + n)
+    batch, N = 5, 12
+    lq = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=False)
+    if not nominal:
+        lq.x_nom = lq.u_nom = None
+    event = np.zeros((batch, N), dtype=np.int32)
+    for b in range(batch):
+        for k in rng.choice(N, size=b % 3, replace=False):  # 0, 1 or 2 events per problem, different places (problem 0: none)
+            event[b, k] = 1
+            lq.A[b, k] = np.eye(n) + 0.3 * rng.uniform(-1, 1, (n, n))
+            lq.Hv[b, k] = 0.1 * rng.uniform(-1, 1, n)
+    event[1, N - 1] = 1  # an event at the last stage
+    lq.event = event
+    st = o2.Settings(hessianCorrectionMultiple=1e-4)
+    ls = o2.LineSearchSettings()
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=nominal, max_alphas=6) as solver:
+        solver.upload(lq)
+        assert "generic" in solver.kernel_variant
+        solver.solve(alpha=0.7)
+        sol = solver.download()
+        assert (sol.status == 0).all()
+        res = solver.lineSearch(ls)
+        for i in range(batch):
+            pb = _oracle_problem(lq, i, N)
+            ref = check_against_oracle(st, pb, lq.x0[i], sol, i, (0.7,), what=f"events n={n} #{i}")
+            _, _, merits, _, _, _ = orc.line_search(orc_settings(st), pb, ref, lq.x0[i], ls.minStepLength, ls.maxStepLength, ls.contractionRate,
+                                                    ls.armijoCoefficient)
+            assert rel_err(res.merits[:, i], merits) <= REL_TOL
+        # the host pipeline uploads in chunks: event flags travel with their chunk
+        sol_h = solver.solve_host(lq, alpha=0.7, chunk=2)
+        for name in ("K", "dbias", "Sm", "Sv", "s", "x", "u"):
+            assert np.array_equal(getattr(sol_h, name), getattr(sol, name)), f"solve_host with events: {name}"
+        # a later upload without events clears them: the specialised kernels come back where they exist
+        lq.event = None
+        solver.upload(lq)
+        assert ("generic" in solver.kernel_variant) == (n not in (24, 10))
+        solver.solve(alpha=0.7)
+        sol = solver.download()
+        check_against_oracle(st, _oracle_problem(lq, 2, N), lq.x0[2], sol, 2, (0.7,), what=f"events cleared n={n}")
+        lq.event = event
+        solver.upload(lq)
+        lq.event = None
+        sol_h = solver.solve_host(lq, alpha=0.7, chunk=2)
+        assert ("generic" in solver.kernel_variant) == (n not in (24, 10))
+        for name in ("K", "dbias", "Sm", "Sv", "s", "x", "u"):
+            assert rel_err(getattr(sol_h, name), getattr(sol, name)) <= 1e-12, f"solve_host after events were cleared: {name}"

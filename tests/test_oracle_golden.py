@@ -343,3 +343,43 @@ def test_generator_is_deterministic_and_well_posed():
     # constraints hold along the rollout: C x + D u + e = 0
     for k in range(pb.N):
         assert np.abs(pb.C[k] @ x[k] + pb.D[k] @ u[k] + pb.e[k]).max() < 1e-10
+
+
+@pytest.mark.parametrize("n,m,nc", [(4, 2, 0), (6, 3, 2)])
+def test_ilqr_events_match_dense_kkt(n, m, nc):
+    """Event (pre-jump) nodes, ILQR.cpp:263-295 + riccatiTransversalityConditions (RiccatiTransversalityConditions.h:40-56): the value
+    function passes through the jump map x+ = A_e x + Hv_e with the pre-jump cost (Q_e, q_e, c_e), no input acts. Equivalent dense KKT
+    problem: the same stages with B = 0, P = 0, r = 0 (and no constraint) at the event nodes."""
+    rng = np.random.default_rng(9 + n)
+    N = 14
+    pb = random_lq(rng, n, m, N, nc)
+    event = np.zeros(N, dtype=np.int32)
+    event[[3, 9, N - 1]] = 1  # includes an event at the last stage
+    for k in np.nonzero(event)[0]:
+        pb.A[k] = np.eye(n) + 0.3 * rng.uniform(-1, 1, (n, n))  # jump map
+        pb.Hv[k] = 0.1 * rng.uniform(-1, 1, n)
+    pb.event = event
+    st = orc.make_settings(algorithm=orc.ALG_ILQR, reduced_form=True, hessian_multiple=0.0)
+    sol = orc.backward(st, pb)
+    assert sol.status == 0
+    x0 = rng.uniform(-1, 1, n)
+    x, u, _, status = orc.rollout(st, pb, sol, x0, alpha=1.0)
+    assert status == 0
+    import copy
+    kk = copy.deepcopy(pb)
+    kk.event = None
+    for k in np.nonzero(event)[0]:
+        kk.B[k] = 0.0
+        kk.P[k] = 0.0
+        kk.r[k] = 0.0
+        kk.R[k] = np.eye(m)
+        if nc:
+            kk.nc = (np.full(N, nc, np.int32) if kk.nc is None else kk.nc.copy())
+            kk.nc[k] = 0
+    xk, uk, cost = kkt_oracle.solve_discrete_lq(kk, x0)
+    assert np.abs(x - xk).max() < 1e-9 * max(1.0, np.abs(xk).max())
+    reg = event == 0
+    assert np.abs(u[:N][reg] - uk[reg]).max() < 1e-9 * max(1.0, np.abs(uk).max())
+    V = 0.5 * x0 @ sol.Sm[0] @ x0 + sol.Sv[0] @ x0 + sol.s[0]
+    assert V == pytest.approx(cost, rel=1e-9, abs=1e-10)
+    assert orc.discrete_lq_cost(pb, x, u) == pytest.approx(cost, rel=1e-9, abs=1e-10)
