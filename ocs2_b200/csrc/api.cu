@@ -424,15 +424,24 @@ o2c_error upload_chunk(o2c_handle* h, Lane& lane, const o2c_lq_view& v, int begi
   if (ncm > 0 && v.nc != nullptr) {
     // int32 per (problem, node): gathered densely on the host, staged after the doubles
     std::vector<int> tmp((size_t)count * nodes);
+    bool ragged = false;
     for (int p = 0; p < count; ++p)
-      for (int k = 0; k < nodes; ++k) tmp[(size_t)p * nodes + k] = v.nc[p * v.nc_problem_stride + k * v.nc_node_stride];
+      for (int k = 0; k < nodes; ++k) {
+        const int c = v.nc[p * v.nc_problem_stride + k * v.nc_node_stride];
+        if (c < 0 || c > ncm) return fail(O2C_ERR_INVALID_ARGUMENT, "nc[problem][node] must lie in [0, nc_max]");
+        ragged = ragged || c != ncm;
+        tmp[(size_t)p * nodes + k] = c;
+      }
     nc_stage = reinterpret_cast<int*>(cur);
     O2C_CUDA(cudaMemcpyAsync(nc_stage, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, lane.stream));
     O2C_CUDA(cudaStreamSynchronize(lane.stream));
     d.nc = nc_stage;
-    h->nc_ragged = true;
+    // counts that all equal nc_max keep the kernels that skip the lookup; a whole-batch upload resets the flag
+    h->nc_ragged = (begin == 0 && count == h->cfg.batch) ? ragged : (h->nc_ragged || ragged);
     d.nc_ps = nodes;
     d.nc_ns = 1;
+  } else if (ncm > 0 && begin == 0 && count == h->cfg.batch) {
+    h->nc_ragged = false;  // pack_kernel rewrites every count to nc_max
   }
   if ((e = install_events(h, lane.stream, v.event, v.event_problem_stride, v.event_node_stride, false, begin, count)) != O2C_OK) return e;
   O2C_CUDA(launch_pack(L, d, h->d_lq, h->d_term, h->d_xnom, h->d_unom, h->d_nc, h->d_x0, begin, count, lane.stream));
