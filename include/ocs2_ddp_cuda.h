@@ -194,6 +194,15 @@ o2c_error o2c_line_search(o2c_handle* handle, const o2c_line_search_settings* se
 o2c_error o2c_line_search_result(o2c_handle* handle, double* step_length, int32_t* candidate_index, double* merits, double* baseline,
                                  double* update_is, double* candidates, int32_t* n_candidates, int32_t problem_begin, int32_t problem_count);
 
+/* ---- the data format after the path: the flattened policy of ocs2_msgs/mpc_flattened_controller ----
+ * LinearController::flatten at the controller's own time stamps (ocs2_core/src/control/LinearController.cpp:87-140, called from
+ * MPC_ROS_Interface::createMpcPolicyMsg, ocs2_ros_interfaces/src/mpc/MPC_ROS_Interface.cpp:175): per node one float32 record of
+ * m*(n+1) values, row i = [uff_i, K_i,:] (row-major), with uff = bias + step_length * deltaBias, i.e. the controller after
+ * incrementController(step_length). host_out: [problem_count][N+1][m*(n+1)] floats; the conversion runs on the device, so a consumer
+ * that only publishes the policy moves 4*m*(n+1) bytes per node instead of the FP64 controller arrays. Blocking. */
+o2c_error o2c_download_flattened_controller(o2c_handle* handle, float* host_out, double step_length, int32_t problem_begin,
+                                            int32_t problem_count);
+
 /* ---- end-to-end convenience: host buffers in, host buffers out, chunked H2D / compute / D2H pipeline ---- */
 o2c_error o2c_solve_host(o2c_handle* handle, const o2c_lq_view* host_lq, const o2c_solution_view* host_solution, double alpha,
                          int32_t problem_count, int32_t chunk);

@@ -18,6 +18,7 @@
  *                                                         the same std::runtime_error on non-finite gains / feedforward
  *   rolloutTrajectory / getRollout                     == incrementController + the LQ-model rollout (DDP_HelperFunctions.cpp:296-304)
  *   lineSearch                                         == LineSearchStrategy::run on the LQ model (LineSearchStrategy.cpp:125-258)
+ *   flatten                                            == LinearController::flatten at its own time stamps (LinearController.cpp:87-140)
  *
  * The header is dependency-free and duck-typed: every template works with the reference's Eigen-backed types
  * (ocs2::ModelData, ocs2::ScalarFunctionQuadraticApproximation, ocs2::LinearController, vector_t / matrix_t, all
@@ -226,6 +227,21 @@ class BatchedRiccatiSolver {
         throw std::runtime_error(errorMessage.str());
       }
     }
+  }
+
+  /**
+   * LinearController::flatten of instance b at the controller's own time stamps (LinearController.cpp:87-140), after
+   * incrementController(stepLength): flatArray2[k] = float rows [uff_i, K_i,:] of node k — the `data` entries of
+   * ocs2_msgs/mpc_flattened_controller (MPC_ROS_Interface.cpp:175). The FP64 -> float conversion runs on the device.
+   */
+  template <class FloatArray2>
+  void flatten(int b, double stepLength, FloatArray2& flatArray2) const {
+    requireSolved(b);
+    const std::size_t count = static_cast<std::size_t>(cfg_.num_stages) + 1, len = static_cast<std::size_t>(cfg_.nu) * (cfg_.nx + 1);
+    std::vector<float> flat(count * len);
+    check(o2c_download_flattened_controller(h_, flat.data(), stepLength, b, 1), "o2c_download_flattened_controller");
+    flatArray2.resize(count);
+    for (std::size_t k = 0; k < count; ++k) flatArray2[k].assign(flat.begin() + k * len, flat.begin() + (k + 1) * len);
   }
 
   /**

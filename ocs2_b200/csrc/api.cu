@@ -52,6 +52,7 @@ struct o2c_handle {
   int *d_nc = nullptr, *d_status = nullptr;
   double *d_ls_merit = nullptr, *d_ls_base = nullptr, *d_ls_is = nullptr, *d_ls_step = nullptr, *d_ls_basein = nullptr;  // line search
   int* d_ls_index = nullptr;
+  float* d_flat = nullptr;  // flattened controllers of the whole batch (o2c_download_flattened_controller), allocated on first use
   int* d_event = nullptr;       // [batch][nodes] pre-event flags, allocated by the first upload that carries events
   bool events_present = false;
   std::vector<double> ls_candidates;
@@ -593,7 +594,7 @@ void release(o2c_handle* h) {
   }
   void* ptrs[] = {h->d_lq,  h->d_term, h->d_xnom, h->d_unom,   h->d_x0,        h->d_time,    h->d_sol,
                   h->d_xs,  h->d_us,   h->d_alphas, h->d_nc,   h->d_status,    h->d_slq_steps, h->d_ro_steps,
-                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event};
+                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event, h->d_flat};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
@@ -983,6 +984,24 @@ o2c_error o2c_line_search_result(o2c_handle* h, double* step, int32_t* index, do
   O2C_CUDA(cudaStreamSynchronize(stream));
   if (candidates) std::copy(h->ls_candidates.begin(), h->ls_candidates.end(), candidates);
   if (n_candidates) *n_candidates = na;
+  return O2C_OK;
+}
+
+o2c_error o2c_download_flattened_controller(o2c_handle* h, float* host_out, double step_length, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  if (!host_out) return fail(O2C_ERR_INVALID_ARGUMENT, "null output");
+  if (!h->backward_done) return fail(O2C_ERR_NOT_READY, "o2c_backward has not run on this handle");
+  if (!std::isfinite(step_length)) return fail(O2C_ERR_INVALID_ARGUMENT, "step_length must be finite");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  const size_t per = (size_t)(h->L.N + 1) * h->L.m * (h->L.n + 1);
+  if (!h->d_flat) O2C_CUDA(cudaMalloc(&h->d_flat, sizeof(float) * per * h->cfg.batch));
+  cudaStream_t stream = h->lanes[0].stream;
+  float* dev = h->d_flat + per * begin;
+  O2C_CUDA(launch_flatten(h->L, h->d_sol, dev, step_length, begin, count, stream));
+  h->launches += 1;
+  O2C_CUDA(cudaMemcpyAsync(host_out, dev, sizeof(float) * per * count, cudaMemcpyDeviceToHost, stream));
+  O2C_CUDA(cudaStreamSynchronize(stream));
   return O2C_OK;
 }
 

@@ -150,6 +150,9 @@ cudaError_t launch_pack(const Layout& L, const LqViewDev& v, double* lq, double*
 cudaError_t launch_unpack(const Layout& L, const SolViewDev& v, const double* sol, const double* xs, const double* us, const int* status,
                           int out_nodes, int n_alpha, int batch, int begin, int count, cudaStream_t stream);
 
+// controller records -> float wire format of LinearController::flatten, out[count][N+1][m*(n+1)] (device)
+cudaError_t launch_flatten(const Layout& L, const double* sol, float* out, double alpha, int begin, int count, cudaStream_t stream);
+
 // shape-specialised fast path (riccati_wpp.cu): warp-per-problem DMMA kernel for nx = nu = 24; cudaErrorNotSupported otherwise
 bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
 cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,

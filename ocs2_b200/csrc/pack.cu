@@ -89,7 +89,31 @@ __global__ void __launch_bounds__(128) unpack_kernel(Layout L, SolViewDev v, con
   if (node == 0 && tid == 0 && v.status) v.status[lp] = status[prob];
 }
 
+// LinearController::flattenSingle at the controller's own time stamps (ocs2_core/src/control/LinearController.cpp:107-140): one float
+// record of m*(n+1) values per node, row i = [uff_i, K_i,:] (row-major), uff = bias + alpha * deltaBias (incrementController applied)
+__global__ void __launch_bounds__(128) flatten_kernel(Layout L, const double* __restrict__ sol, float* __restrict__ out, double alpha, int begin,
+                                                      int count) {
+  const int lp = blockIdx.x / (L.N + 1), node = blockIdx.x % (L.N + 1);
+  if (lp >= count) return;
+  const int n = L.n, m = L.m, len = m * (n + 1);
+  const double* rec = sol + ((size_t)(begin + lp) * (L.N + 1) + node) * L.orec;
+  float* dst = out + ((size_t)lp * (L.N + 1) + node) * len;
+  for (int idx = threadIdx.x; idx < len; idx += blockDim.x) {
+    const int i = idx / (n + 1), j = idx % (n + 1);
+    const double v = j == 0 ? rec[L.obias + i] + alpha * rec[L.odb + i] : rec[L.oK + i + m * (j - 1)];
+    dst[idx] = static_cast<float>(v);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_flatten(const Layout& L, const double* sol, float* out, double alpha, int begin, int count, cudaStream_t stream) {
+  const long long blocks = (long long)count * (L.N + 1);
+  if (blocks > 2147483647LL) return cudaErrorInvalidValue;
+  if (blocks == 0) return cudaSuccess;
+  flatten_kernel<<<(unsigned)blocks, 128, 0, stream>>>(L, sol, out, alpha, begin, count);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_pack(const Layout& L, const LqViewDev& v, double* lq, double* term, double* x_nom, double* u_nom, int* nc, double* x0,
                         int begin, int count, cudaStream_t stream) {

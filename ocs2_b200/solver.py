@@ -318,6 +318,14 @@ class BatchedLqSolver:
         # o2c_line_search_result packs the merits as [n_candidates][count]
         return LineSearchResult(step, idx, merits.reshape(-1)[:nc.value * cnt].reshape(nc.value, cnt), bl, upd, cand[:nc.value])
 
+    def flatten(self, stepLength: float = 1.0, problem_begin: int = 0, problem_count: Optional[int] = None) -> np.ndarray:
+        """LinearController::flatten at the controller's own time stamps, after incrementController(stepLength): float32
+        (count, N+1, m*(n+1)), rows [uff_i, K_i,:] — the payload of ocs2_msgs/mpc_flattened_controller. Converted on the device."""
+        cnt = self.batch - problem_begin if problem_count is None else problem_count
+        out = np.zeros((cnt, self.N + 1, self.nu * (self.nx + 1)), dtype=np.float32)
+        _l.check(self._lib.o2c_download_flattened_controller(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), float(stepLength), problem_begin, cnt))
+        return out
+
     # ---- results ----------------------------------------------------------------------------------------------------
     def _solution_buffers(self, count: int, n_alpha: int, want_value: bool = True):
         n, m, N = self.nx, self.nu, self.N

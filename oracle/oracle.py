@@ -387,6 +387,40 @@ def line_search(st: Settings, pb: Problem, sol: Solution, x0, min_step=0.05, max
     return best, idx, np.array(merits), base, IS, np.array(cands)
 
 
+def flatten_controller(time, K, bias, dbias=None, alpha=0.0, query_times=None):
+    """LinearController::flatten / flattenSingle (ocs2_core/src/control/LinearController.cpp:87-140): per query time the bias and gain
+    are linearly interpolated over the time stamps (LinearInterpolation::timeSegment) and serialised as float32 rows
+    [uff_i, K_i,:]. K (N+1,m,n), bias (N+1,m); with dbias the bias is first incremented by alpha*dbias (incrementController,
+    DDP_HelperFunctions.cpp:296-304). Returns (len(query_times), m*(n+1)) float32; query_times defaults to the time stamps."""
+    K, bias = np.asarray(K, dtype=np.float64), np.asarray(bias, dtype=np.float64)
+    if dbias is not None:
+        bias = bias + alpha * np.asarray(dbias, dtype=np.float64)
+    time = np.asarray(time, dtype=np.float64)
+    query = time if query_times is None else np.asarray(query_times, dtype=np.float64)
+    m, n = K.shape[1], K.shape[2]
+    out = np.zeros((len(query), m * (n + 1)), dtype=np.float32)
+    for t_i, t in enumerate(query):
+        idx, a = time_segment(float(t), time)
+        if len(time) > 1 and idx + 1 < len(time):
+            uff, k = a * bias[idx] + (1.0 - a) * bias[idx + 1], a * K[idx] + (1.0 - a) * K[idx + 1]
+        else:
+            uff, k = bias[idx], K[idx]
+        for i in range(m):
+            out[t_i, i * (n + 1)] = np.float32(uff[i])
+            for j in range(n):
+                out[t_i, i * (n + 1) + j + 1] = np.float32(k[i, j])
+    return out
+
+
+def unflatten_controller(flat, n, m):
+    """LinearController::unFlatten (LinearController.cpp:145-171): float rows [uff_i, K_i,:] -> (bias (T,m), gain (T,m,n)) in double."""
+    flat = np.asarray(flat, dtype=np.float32)
+    if flat.shape[1] != m + m * n:
+        raise RuntimeError("LinearController::unFlatten received array of wrong length.")
+    rows = flat.reshape(flat.shape[0], m, n + 1).astype(np.float64)
+    return rows[:, :, 0].copy(), rows[:, :, 1:].copy()
+
+
 def generate_problem(seed, problem, algorithm, n, m, nc, N, dt):
     """One problem of the seeded synthetic family (bit-identical to the CUDA generator). Returns (Problem, x0)."""
     nodes = N if algorithm == ALG_ILQR else N + 1

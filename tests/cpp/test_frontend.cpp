@@ -210,6 +210,23 @@ int runCase(const Case& cs) {
       worst = std::max(worst, relErr(ctrl.deltaBiasArray_[k].data(), &db[(size_t)k * m], m));
       worst = std::max(worst, relErr(ctrl.biasArray_[k].data(), &bias[(size_t)k * m], m));
     }
+    // the float wire format of the incremented controller: row i = [uff_i, K_i,:] (LinearController.cpp:107-140)
+    std::vector<std::vector<float>> flat;
+    solver.flatten(b, 0.5, flat);
+    if ((int)flat.size() != N + 1) {
+      std::printf("FAIL %s: flattened controller has %zu nodes\n", cs.name, flat.size());
+      return 1;
+    }
+    for (int k = 0; k <= N; ++k)
+      for (int i = 0; i < m; ++i) {
+        const float uff = static_cast<float>(ctrl.biasArray_[k].v[i] + 0.5 * ctrl.deltaBiasArray_[k].v[i]);
+        bool same = flat[k].size() == (size_t)m * (n + 1) && flat[k][(size_t)i * (n + 1)] == uff;
+        for (int j = 0; same && j < n; ++j) same = flat[k][(size_t)i * (n + 1) + j + 1] == static_cast<float>(ctrl.gainArray_[k].v[i + (size_t)m * j]);
+        if (!same) {
+          std::printf("FAIL %s: flattened controller of instance %d, node %d, row %d\n", cs.name, b, k, i);
+          return 1;
+        }
+      }
     for (size_t a = 0; a < alphas.size(); ++a) {
       const int cap = (int)rolloutTimes.size();
       std::vector<double> x((size_t)cap * n), u((size_t)cap * m), t(cap);

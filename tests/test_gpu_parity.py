@@ -566,3 +566,33 @@ def test_ilqr_events_match_oracle(n, m, nc, nominal):
         assert ("generic" in solver.kernel_variant) == (n not in (24, 10))
         for name in ("K", "dbias", "Sm", "Sv", "s", "x", "u"):
             assert rel_err(getattr(sol_h, name), getattr(sol, name)) <= 1e-12, f"solve_host after events were cleared: {name}"
+
+
+@pytest.mark.parametrize("n,m,nominal", [(24, 24, False), (10, 3, True), (5, 2, True)])
+def test_flattened_controller_matches_oracle(n, m, nominal):
+    """o2c_download_flattened_controller = LinearController::flatten (LinearController.cpp:87-140) of the incremented controller at
+    its own time stamps, converted to float32 on the device: bit-identical to the restated serialisation of the downloaded FP64
+    arrays, and within float precision of the oracle's controller (the reference's own round-trip tolerance is 1e-6)."""
+    rng = np.random.default_rng(23 + n)
+    batch, N = 6, 15
+    lq = _random_batch(rng, batch, n, m, N, 0, o2.ALG_ILQR, ragged_nc=False)
+    if not nominal:
+        lq.x_nom = lq.u_nom = None
+    st = o2.Settings(hessianCorrectionMultiple=1e-4)
+    with o2.BatchedLqSolver(st, n, m, N, batch, has_nominal=nominal) as solver:
+        solver.upload(lq)
+        with pytest.raises(o2.O2cError):
+            solver.flatten(1.0)  # NOT_READY before the backward pass
+        solver.solveSequentialRiccatiEquations()
+        sol = solver.download()
+        flat = solver.flatten(0.5)
+        assert flat.shape == (batch, N + 1, m * (n + 1)) and flat.dtype == np.float32
+        time = st.timeStep * np.arange(N + 1)
+        for i in range(batch):
+            want = orc.flatten_controller(time, sol.K[i], sol.bias[i], dbias=sol.dbias[i], alpha=0.5)
+            assert np.array_equal(flat[i], want), f"problem {i}: serialisation differs"
+            ref = orc.backward(orc_settings(st), _oracle_problem(lq, i, N))
+            want_ref = orc.flatten_controller(time, ref.K, ref.bias, dbias=ref.dbias, alpha=0.5)
+            assert rel_err(flat[i], want_ref) <= 1e-6
+        part = solver.flatten(0.5, problem_begin=2, problem_count=3)
+        assert np.array_equal(part, flat[2:5])

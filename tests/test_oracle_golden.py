@@ -383,3 +383,30 @@ def test_ilqr_events_match_dense_kkt(n, m, nc):
     V = 0.5 * x0 @ sol.Sm[0] @ x0 + sol.Sv[0] @ x0 + sol.s[0]
     assert V == pytest.approx(cost, rel=1e-9, abs=1e-10)
     assert orc.discrete_lq_cost(pb, x, u) == pytest.approx(cost, rel=1e-9, abs=1e-10)
+
+
+def test_flatten_controller_layout_and_round_trip():
+    """ocs2_core/test/control/testLinearController.cpp:7-26: flatten at the controller's time stamps, unFlatten, compare to 1e-6;
+    plus the serialisation order of LinearController.cpp:107-140 (row i = [uff_i, K_i,:], float32) and an interpolated query."""
+    rng = np.random.default_rng(5)
+    time = np.array([0.0, 1.0])
+    bias = rng.uniform(-1, 1, (2, 2))
+    gain = rng.uniform(-1, 1, (2, 2, 3))
+    flat = orc.flatten_controller(time, gain, bias)
+    assert flat.dtype == np.float32 and flat.shape == (2, 2 + 2 * 3)
+    for k in range(2):
+        for i in range(2):
+            assert flat[k, i * 4] == np.float32(bias[k, i])
+            assert (flat[k, i * 4 + 1:i * 4 + 4] == gain[k, i].astype(np.float32)).all()
+    bias_out, gain_out = orc.unflatten_controller(flat, 3, 2)
+    assert np.allclose(bias_out, bias, rtol=1e-6, atol=1e-6) and np.allclose(gain_out, gain, rtol=1e-6, atol=1e-6)
+    # a query between the stamps interpolates bias and gain linearly (LinearInterpolation::interpolate)
+    mid = orc.flatten_controller(time, gain, bias, query_times=[0.25])
+    b_mid, k_mid = orc.unflatten_controller(mid, 3, 2)
+    assert np.allclose(b_mid[0], 0.75 * bias[0] + 0.25 * bias[1], atol=1e-6) and np.allclose(k_mid[0], 0.75 * gain[0] + 0.25 * gain[1], atol=1e-6)
+    # incrementController: uff = bias + alpha * deltaBias
+    dbias = rng.uniform(-1, 1, (2, 2))
+    inc = orc.flatten_controller(time, gain, bias, dbias=dbias, alpha=0.5)
+    assert np.allclose(orc.unflatten_controller(inc, 3, 2)[0], bias + 0.5 * dbias, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        orc.unflatten_controller(flat[:, :-1], 3, 2)
