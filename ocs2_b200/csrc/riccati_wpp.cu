@@ -117,6 +117,7 @@ struct Args {
   double* xs;
   double* us;
   int* status;
+  const int* event;  // [batch][N] pre-event flags (ILQR.cpp:263-295), or nullptr: kernel instantiation EV
   int N;
   int oQf, oqf, ocf, trec;
   int begin, count, with_rollout;
@@ -308,7 +309,7 @@ __device__ __forceinline__ void prefetch_hessians(const double* rec, const Args&
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool NOM>
+template <bool NOM, bool EV>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
     const double* lqp = a.lq + (size_t)prob * N * kRec;
     const double* term = a.term + (size_t)prob * a.trec;
     double* solp = a.sol + (size_t)prob * (N + 1) * kORec;
+    const int* evp = EV ? a.event + (size_t)prob * N : nullptr;
 
     // operand block of node N-1 (TMA) and the L2 prefetch of its cost Hessians
     if (lane == 0) {
@@ -375,6 +377,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       const double* rv = qv + kN;
       const double* rec = lqp + (size_t)k * kRec;
       double* out = solp + (size_t)k * kORec;
+      // pre-event node (ILQR.cpp:263-295): the staged A, Hv, q, c and Q are the jump map and the pre-jump cost. The value function goes
+      // through riccatiTransversalityConditions (S- = Q_e + A_e'S A_e, Sv- = q_e + A_e'(Sv + S Hv), s- = s + c_e + Hv.(Sv + S Hv / 2));
+      // the controller entry comes from the node's B, P, R, r against a zero next value function (Hm = R) and S-, Sv-:
+      // G = P + B'S-, Gv = r + B'Sv-. Warp-uniform.
+      const bool ev = EV && __ldg(evp + k) != 0;
       mbar_wait(&ws.full, phase);
       phase ^= 1u;
       if (k < N - 1) prefetch_hessians(rec, a, lo24);  // this node's Q, P, R into L2 now: first needed a third of a stage from here
@@ -448,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         }
       }
       const double cval = ws.in[2 * kMat + 3 * kN];
+      const double epsk = ev ? 0.0 : a.eps;  // the transversality condition carries no Hessian correction
       __syncwarp();  // S (scratch) is dead from here on
 
       // The cost Hessians Q and P ride through shared memory too, each in a slot that is dead for exactly as long as the copy needs:
@@ -459,15 +467,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       }
 
       // ---- Hm = R + SB'B (lower tiles) ----
+      if (!ev) {
 #pragma unroll
-      for (int kb = 0; kb < 3; ++kb) {
-        double2 bf[3];
+        for (int kb = 0; kb < 3; ++kb) {
+          double2 bf[3];
 #pragma unroll
-        for (int jb = 0; jb < 3; ++jb) bf[jb] = ld2(B + lo24 + t24(kb, jb));
+          for (int jb = 0; jb < 3; ++jb) bf[jb] = ld2(B + lo24 + t24(kb, jb));
 #pragma unroll
-        for (int ib = 0; ib < 3; ++ib)
+          for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb <= ib; ++jb) dmma2(h[lt(ib, jb)], zB[ib][kb], bf[jb]);
+            for (int jb = 0; jb <= ib; ++jb) dmma2(h[lt(ib, jb)], zB[ib][kb], bf[jb]);
+        }
       }
 
       // ---- T = Q + eps I + SA'A (lower tiles) ----
@@ -497,30 +507,65 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
           t[lt(ib, jb)].x += qq.x;
           t[lt(ib, jb)].y += qq.y;
         }
-        t[lt(ib, ib)].x += (2 * c == r) ? a.eps : 0.0;
-        t[lt(ib, ib)].y += (2 * c + 1 == r) ? a.eps : 0.0;
+        t[lt(ib, ib)].x += (2 * c == r) ? epsk : 0.0;
+        t[lt(ib, ib)].y += (2 * c + 1 == r) ? epsk : 0.0;
       }
       __syncwarp();  // Q is consumed: the scratch takes Hm (lower triangle)
+      double2 g[3][3];
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) g[ib][jb] = zero2();
+      if (ev) {
+        // S- = T and Sv- = tv are final: through the scratch once more for G' = P' + S-B and Gv = r + B'Sv-
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) {
+            st2(ws.W + lo26 + t26(jb, ib), t[lt(ib, jb)]);
+            if (ib != jb) tput(ws.W, ib, jb, r, c, t[lt(ib, jb)]);
+          }
+        if (c < 3) ws.Sv[8 * c + r] = tvj;
+        __syncwarp();
+        double pG[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) {
+          double2 sf[3], bf[3];
+          const double2 svf = ld2(ws.Sv + 8 * kb + 2 * c);
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            sf[jb] = ld2(ws.W + lo26 + t26(kb, jb));
+            bf[jb] = ld2(B + lo24 + t24(kb, jb));
+            pG[jb] = fma(bf[jb].x, svf.x, pG[jb]);
+            pG[jb] = fma(bf[jb].y, svf.y, pG[jb]);
+          }
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+            for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], sf[ib], bf[jb]);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pG[i] = quad_sum(pG[i]);
+        if (c < 3) ws.Gv[8 * c + r] = rv[8 * c + r] + pick3(pG, c);
+        __syncwarp();  // every lane is done reading S- from the scratch
+      }
 #pragma unroll
       for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
         for (int jb = 0; jb <= ib; ++jb) tput(ws.W, ib, jb, r, c, h[lt(ib, jb)]);
 
       // ---- G' = P' + SA'B (op fragments of G) ----
-      double2 g[3][3];
+      if (!ev) {
 #pragma unroll
-      for (int ib = 0; ib < 3; ++ib)
+        for (int kb = 0; kb < 3; ++kb) {
+          double2 bf[3];
 #pragma unroll
-        for (int jb = 0; jb < 3; ++jb) g[ib][jb] = zero2();
+          for (int jb = 0; jb < 3; ++jb) bf[jb] = ld2(B + lo24 + t24(kb, jb));
 #pragma unroll
-      for (int kb = 0; kb < 3; ++kb) {
-        double2 bf[3];
+          for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-        for (int jb = 0; jb < 3; ++jb) bf[jb] = ld2(B + lo24 + t24(kb, jb));
-#pragma unroll
-        for (int ib = 0; ib < 3; ++ib)
-#pragma unroll
-          for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], zA[ib][kb], bf[jb]);
+            for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], zA[ib][kb], bf[jb]);
+        }
       }
       mbar_wait(&ws.hfull2, hphase);
       hphase ^= 1u;
@@ -548,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         if (c < 3) {
           const double yv = pick3(z, c);
           ws.Yv[8 * c + r] = yv;
-          spart = fma(-0.5 * yv, yv, spart);
+          if (!ev) spart = fma(-0.5 * yv, yv, spart);
         }
         __syncwarp();
         // (L^-T Yv)[8jb + r] = sum_{kb >= jb} (L^-T)[8jb+r][8kb+2c..] Yv[8kb+2c..]
@@ -656,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
         }
         if (c < 3) {
           const int j = 8 * c + r;
-          svn = tvj - pick3(z, c);
+          svn = ev ? tvj : tvj - pick3(z, c);
           ws.Sv[j] = svn;
           __stcg(out + kOSv + j, svn);
         }
@@ -665,12 +710,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       // ---- S = T - Y'Y (lower tiles): accumulate Y'Y - T, flip the sign ----
 #pragma unroll
       for (int i = 0; i < 6; ++i) t[i] = neg2(t[i]);
+      if (!ev) {
 #pragma unroll
-      for (int kb = 0; kb < 3; ++kb)
+        for (int kb = 0; kb < 3; ++kb)
 #pragma unroll
-        for (int ib = 0; ib < 3; ++ib)
+          for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], y[ib][kb], y[jb][kb]);
+            for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], y[ib][kb], y[jb][kb]);
+      }
       __syncwarp();  // every lane is done reading L^-T from the scratch
 #pragma unroll
       for (int ib = 0; ib < 3; ++ib)
@@ -740,6 +787,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       areg[j] = __ldcg(lqp + li + kN * j);
     }
     double dbk = __ldcg(solp + kOdb + li), hvk = __ldcg(lqp + 2 * kMat + li);
+    bool jump = EV && __ldg(evp) != 0;  // pre-event node: x+ = A_e x + Hv_e, the input does not enter the jump map
     __syncwarp();
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
@@ -782,7 +830,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       mbar_wait(&ws.bfull[q], (bphase >> q) & 1u);
       bphase ^= 1u << q;
       __syncwarp();  // u of every lane is in shared memory
-      const double xn = ((a0 + a1) + (a2 + a3)) + matvec_rows(ws.in + kMat * q, ws.ub, li);
+      const double xn = ((a0 + a1) + (a2 + a3)) + (jump ? 0.0 : matvec_rows(ws.in + kMat * q, ws.ub, li));
+      if (EV) jump = k + 1 < N && __ldg(evp + k + 1) != 0;
       __syncwarp();  // every lane is done with x, u and slot q
       x = xn;
       if (lane < kN) ws.xb[lane] = x;
@@ -830,7 +879,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 
 bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
-         st.hc == O2C_HC_DIAGONAL_SHIFT && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
+         st.hc == O2C_HC_DIAGONAL_SHIFT && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
          L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb && L.obias == kObias && L.oSm == kOSm &&
          L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat;
 }
@@ -841,12 +890,14 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   static bool configured = false;
   static int num_sms = 0;
   const size_t smem = sizeof(WarpSmem) * kWarps;
-  const bool nom = buf.x_nom != nullptr;
-  cudaError_t e = cudaFuncSetAttribute(nom ? ilqr_wpp_kernel<true> : ilqr_wpp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool nom = buf.x_nom != nullptr, ev = buf.event != nullptr;
+  void (*const kernels[4])(const Args) = {ilqr_wpp_kernel<false, false>, ilqr_wpp_kernel<true, false>, ilqr_wpp_kernel<false, true>,
+                                          ilqr_wpp_kernel<true, true>};
+  void (*const kernel)(const Args) = kernels[(nom ? 1 : 0) + (ev ? 2 : 0)];
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (!configured) {
-    cudaFuncSetAttribute(ilqr_wpp_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(ilqr_wpp_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    for (auto fn : kernels) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -862,6 +913,7 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   a.xs = buf.xs;
   a.us = buf.us;
   a.status = buf.status;
+  a.event = buf.event;
   a.N = L.N;
   a.oQf = L.oQf;
   a.oqf = L.oqf;
@@ -880,10 +932,7 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
     if (v >= 1 && v < kCtasPerSm) ctas_per_sm = v;
   }
   const int grid = ctas_needed < num_sms * ctas_per_sm ? ctas_needed : num_sms * ctas_per_sm;
-  if (nom)
-    ilqr_wpp_kernel<true><<<grid, kThreads, smem, stream>>>(a);
-  else
-    ilqr_wpp_kernel<false><<<grid, kThreads, smem, stream>>>(a);
+  kernel<<<grid, kThreads, smem, stream>>>(a);
   if (launches) *launches = 1;
   return cudaGetLastError();
 }

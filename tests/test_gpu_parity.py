@@ -516,10 +516,10 @@ def test_eigenvalue_modification_matches_oracle(algorithm, n, m, nc):
     assert clamped > 0, "the test data should contain indefinite state costs"
 
 
-@pytest.mark.parametrize("n,m,nc,nominal", [(5, 3, 0, False), (6, 4, 2, True), (24, 24, 0, False), (10, 3, 0, True)])
+@pytest.mark.parametrize("n,m,nc,nominal", [(5, 3, 0, False), (6, 4, 2, True), (24, 24, 0, False), (24, 24, 0, True), (10, 3, 0, True)])
 def test_ilqr_events_match_oracle(n, m, nc, nominal):
     """Pre-event nodes (ILQR.cpp:263-295): value function through riccatiTransversalityConditions on the jump model data, controller
-    entry from the regular data with Sm = 0, rollout through the jump map. Handles with events use the generic kernels."""
+    entry from the regular data with Sm = 0, rollout through the jump map."""
     rng = np.random.default_rng(17 + n)
     batch, N = 5, 12
     lq = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=False)
@@ -537,7 +537,8 @@ def test_ilqr_events_match_oracle(n, m, nc, nominal):
     ls = o2.LineSearchSettings()
     with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=nominal, max_alphas=6) as solver:
         solver.upload(lq)
-        assert "generic" in solver.kernel_variant
+        # the legged-shape kernel carries the event branch itself; the other shapes go through the generic kernels
+        assert ("ilqr_wpp" if n == 24 else "generic") in solver.kernel_variant
         solver.solve(alpha=0.7)
         sol = solver.download()
         assert (sol.status == 0).all()
