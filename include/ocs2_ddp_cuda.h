@@ -105,7 +105,7 @@ typedef struct o2c_lq_view {
    * (time[node] == time[node+1], node+1 in postEventIndices_). Its A, Hv, Q, q, c blocks hold the jump ModelData
    * (modelDataEventTimes: jump map linearisation x+ = A_e dx + Hv_e and pre-jump cost), its B, P, R, r, C, D, e the regular model
    * data of the node, which only shape the controller entry. NULL = no events. Host memory in o2c_upload / o2c_solve_host, device
-   * memory in o2c_import_device. Handles with events use the generic kernels. */
+   * memory in o2c_import_device. SLQ handles reject events (O2C_ERR_UNSUPPORTED). */
   const int32_t* event;
   int64_t event_problem_stride, event_node_stride;
 } o2c_lq_view;

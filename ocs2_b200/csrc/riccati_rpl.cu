@@ -58,6 +58,7 @@ struct Args {
   double* xs;
   double* us;
   int* status;
+  const int* event;  // [batch][N] pre-event flags (ILQR.cpp:263-295), or nullptr: kernel instantiation EV
   int N, begin, count, with_rollout;
   double eps, alpha;
 };
@@ -98,7 +99,7 @@ __device__ __forceinline__ double dot_col(const double (&a)[LEN], const double* 
   return acc;
 }
 
-template <int NX, int NU, int NC, bool NOM>
+template <int NX, int NU, int NC, bool NOM, bool EV>
 __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
   using S = Shape<NX, NU, NC>;
   extern __shared__ __align__(16) double smem[];
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
     const double* lqp = a.lq + (size_t)prob * N * S::rec;
     const double* term = a.term + (size_t)prob * S::trec;
     double* solp = a.sol + (size_t)prob * (N + 1) * S::orec;
+    const int* evp = EV ? a.event + (size_t)prob * N : nullptr;
 
     // records of node N-1 (one TMA copy per carried problem)
     if (lane == 0) {
@@ -167,6 +169,11 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       const double* B = rec + S::oB;
       const double* Hv = rec + S::oHv;
       double* out = solp + (size_t)k * S::orec;
+      // pre-event node (ILQR.cpp:263-295): A, Hv, Q, q, c of the record are the jump map and the pre-jump cost. The value function goes
+      // through riccatiTransversalityConditions (S- = Q_e + A_e'S A_e, Sv- = q_e + A_e'w, s- = s + c_e + Hv.(w - S Hv / 2)), the controller
+      // entry comes from B, P, R, r (and C, D, e) against a zero next value function and S-, Sv-: Hm = R, G = P + B'S-, Gv = r + B'Sv-.
+      // The flag differs between the problems of a warp: selects, no branches, around the warp-wide shuffles and barriers.
+      const bool ev = EV && __ldg(evp + k) != 0;
 
       // ---- w_i = Sv_i + S_i Hv ; SA_i = S_i A ; SB_i = S_i B ----
       const double shv = dot_col<NX>(Srow, Hv, 0.0);
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       for (int kk = 0; kk < NX; ++kk) acol[kk] = A[kk + NX * i];
       double Trow[NX];
 #pragma unroll
-      for (int j = 0; j < NX; ++j) Trow[j] = dot_col<NX>(acol, sm + S::sSA + S::XP * j, rec[S::oQ + i + NX * j] + ((j == i) ? a.eps : 0.0));
+      for (int j = 0; j < NX; ++j) Trow[j] = dot_col<NX>(acol, sm + S::sSA + S::XP * j, rec[S::oQ + i + NX * j] + ((j == i && !ev) ? a.eps : 0.0));
       const double tvi = dot_col<NX>(acol, sm + S::sW, rec[S::oq + i]);
 
       // ---- G'_i = P(:,i)' + SA(:,i)' B (row i of G') ----
@@ -193,20 +200,29 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       {
         double sacol[NX];
 #pragma unroll
-        for (int kk = 0; kk < NX; ++kk) sacol[kk] = sm[S::sSA + kk + S::XP * i];
+        for (int kk = 0; kk < NX; ++kk) sacol[kk] = ev ? Trow[kk] : sm[S::sSA + kk + S::XP * i];  // event: row i of S- (symmetric)
 #pragma unroll
         for (int l = 0; l < NU; ++l) gt[l] = dot_col<NX>(sacol, B + NX * l, rec[S::oP + l + NU * i], (NX * l) & 1);
       }
 
       // ---- Hm_l = R_l + B(:,l)' SB and Gv_l = r_l + B(:,l)' w on lanes l < nu; Cholesky by shuffles inside the group ----
       double h[NU];
+      if (EV) {  // Sv- replaces w for the event groups (every lane has read w by now)
+        __syncwarp();
+        if (ev) sm[S::sW + i] = tvi;
+        __syncwarp();
+      }
       {
         const int l = i < NU ? i : NU - 1;
         double bcol[NX];
 #pragma unroll
         for (int kk = 0; kk < NX; ++kk) bcol[kk] = B[kk + NX * l];
 #pragma unroll
-        for (int l2 = 0; l2 < NU; ++l2) h[l2] = dot_col<NX>(bcol, sm + S::sSB + S::XP * l2, rec[S::oR + l + NU * l2]);
+        for (int l2 = 0; l2 < NU; ++l2) {
+          const double rl = rec[S::oR + l + NU * l2];
+          const double hl = dot_col<NX>(bcol, sm + S::sSB + S::XP * l2, rl);
+          h[l2] = ev ? rl : hl;
+        }
         const double gv = dot_col<NX>(bcol, sm + S::sW, rec[S::or_ + l]);
         if (i < NU) sm[S::sGv + i] = gv;
       }
@@ -402,6 +418,11 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       for (int l = 0; l < NU; ++l) Svi = fma(-yt[l], yv[l], Svi);
 #pragma unroll
       for (int c1 = 0; c1 < NC; ++c1) Svi = fma(vx[c1], vv[c1], Svi);
+      if (ev) {
+        Svi = tvi;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) Srow[j] = Trow[j];
+      }
       // s: rows sum their shares inside the group (xor butterflies stay inside aligned power-of-two blocks only when nx is one,
       // so the group sum goes through shared memory)
       sm[S::sX + i] = spart;
@@ -415,7 +436,7 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
         for (int l = 0; l < NU; ++l) yy = fma(yv[l], yv[l], yy);
 #pragma unroll
         for (int c1 = 0; c1 < NC; ++c1) yy = fma(-vv[c1], vv[c1], yy);
-        sval = sval + rec[S::oc] + sh - 0.5 * yy;
+        sval = sval + rec[S::oc] + sh - (ev ? 0.0 : 0.5 * yy);
       }
       if (valid) {
 #pragma unroll
@@ -504,8 +525,11 @@ __global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
       double xn = rec[S::oHv + i];
 #pragma unroll
       for (int j = 0; j < NX; ++j) xn = fma(rec[S::oA + i + NX * j], sm[S::sX + j], xn);
+      const bool jump = EV && __ldg(evp + k) != 0;  // pre-event node: x+ = A_e x + Hv_e, the input does not enter the jump map
+      if (!jump) {
 #pragma unroll
-      for (int l = 0; l < NU; ++l) xn = fma(rec[S::oB + i + NX * l], sm[S::sU + l], xn);
+        for (int l = 0; l < NU; ++l) xn = fma(rec[S::oB + i + NX * l], sm[S::sU + l], xn);
+      }
       __syncwarp();
       x = xn;
     }
@@ -1132,13 +1156,13 @@ bool layout_matches(const Layout& L) {
          L.oQf == S::oQf && L.oqf == S::oqf && L.ocf == S::ocf;
 }
 
-template <int NX, int NU, int NC, bool NOM>
+template <int NX, int NU, int NC, bool NOM, bool EV>
 cudaError_t launch(const Args& a, cudaStream_t stream) {
   using S = Shape<NX, NU, NC>;
   static int num_sms = 0;
   constexpr int wpb = 2;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU, NC, NOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU, NC, NOM, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (num_sms == 0) {
     int dev = 0;
@@ -1146,19 +1170,19 @@ cudaError_t launch(const Args& a, cudaStream_t stream) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ilqr_rpl_kernel<NX, NU, NC, NOM>, wpb * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ilqr_rpl_kernel<NX, NU, NC, NOM, EV>, wpb * 32, smem);
   if (e != cudaSuccess) return e;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int per_cta = wpb * S::P;
   const int needed = (a.count + per_cta - 1) / per_cta;
   const int cap = num_sms * ctas_per_sm;  // persistent warps: one resident wave, static stride over the problem index
-  ilqr_rpl_kernel<NX, NU, NC, NOM><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
+  ilqr_rpl_kernel<NX, NU, NC, NOM, EV><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
 bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const Layout& L) {
   return st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
-         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1;
+         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1;
 }
 
 }  // namespace
@@ -1239,6 +1263,7 @@ cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const Dev
   a.xs = buf.xs;
   a.us = buf.us;
   a.status = buf.status;
+  a.event = buf.event;
   a.N = L.N;
   a.begin = begin;
   a.count = count;
@@ -1246,10 +1271,14 @@ cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const Dev
   a.eps = st.eps;
   a.alpha = alpha;
   if (launches) *launches = 1;
-  const bool nom = buf.x_nom != nullptr;
-  if (layout_matches<10, 3, 0>(L)) return nom ? launch<10, 3, 0, true>(a, stream) : launch<10, 3, 0, false>(a, stream);
-  if (layout_matches<9, 9, 3>(L)) return nom ? launch<9, 9, 3, true>(a, stream) : launch<9, 9, 3, false>(a, stream);
-  return nom ? launch<4, 1, 0, true>(a, stream) : launch<4, 1, 0, false>(a, stream);
+  const bool nom = buf.x_nom != nullptr, ev = buf.event != nullptr;
+#define O2C_RPL_DISPATCH(NX, NU, NC)                                                                                  \
+  return ev ? (nom ? launch<NX, NU, NC, true, true>(a, stream) : launch<NX, NU, NC, false, true>(a, stream))         \
+            : (nom ? launch<NX, NU, NC, true, false>(a, stream) : launch<NX, NU, NC, false, false>(a, stream))
+  if (layout_matches<10, 3, 0>(L)) O2C_RPL_DISPATCH(10, 3, 0);
+  if (layout_matches<9, 9, 3>(L)) O2C_RPL_DISPATCH(9, 9, 3);
+  O2C_RPL_DISPATCH(4, 1, 0);
+#undef O2C_RPL_DISPATCH
 }
 
 }  // namespace o2c

@@ -516,7 +516,8 @@ def test_eigenvalue_modification_matches_oracle(algorithm, n, m, nc):
     assert clamped > 0, "the test data should contain indefinite state costs"
 
 
-@pytest.mark.parametrize("n,m,nc,nominal", [(5, 3, 0, False), (6, 4, 2, True), (24, 24, 0, False), (24, 24, 0, True), (10, 3, 0, True)])
+@pytest.mark.parametrize("n,m,nc,nominal", [(5, 3, 0, False), (6, 4, 2, True), (24, 24, 0, False), (24, 24, 0, True), (10, 3, 0, True), (10, 3, 0, False),
+                                               (9, 9, 3, True), (9, 9, 3, False), (4, 1, 0, False)])
 def test_ilqr_events_match_oracle(n, m, nc, nominal):
     """Pre-event nodes (ILQR.cpp:263-295): value function through riccatiTransversalityConditions on the jump model data, controller
     entry from the regular data with Sm = 0, rollout through the jump map."""
@@ -537,8 +538,8 @@ def test_ilqr_events_match_oracle(n, m, nc, nominal):
     ls = o2.LineSearchSettings()
     with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=nominal, max_alphas=6) as solver:
         solver.upload(lq)
-        # the legged-shape kernel carries the event branch itself; the other shapes go through the generic kernels
-        assert ("ilqr_wpp" if n == 24 else "generic") in solver.kernel_variant
+        # the shape-specialised kernels carry the event branch themselves; every other shape goes through the generic kernels
+        assert {24: "ilqr_wpp", 10: "ilqr_rpl", 9: "ilqr_rpl", 4: "ilqr_rpl"}.get(n, "generic") in solver.kernel_variant
         solver.solve(alpha=0.7)
         sol = solver.download()
         assert (sol.status == 0).all()
@@ -556,7 +557,7 @@ def test_ilqr_events_match_oracle(n, m, nc, nominal):
         # a later upload without events clears them: the specialised kernels come back where they exist
         lq.event = None
         solver.upload(lq)
-        assert ("generic" in solver.kernel_variant) == (n not in (24, 10))
+        assert ("generic" in solver.kernel_variant) == (n not in (24, 10, 9, 4))
         solver.solve(alpha=0.7)
         sol = solver.download()
         check_against_oracle(st, _oracle_problem(lq, 2, N), lq.x0[2], sol, 2, (0.7,), what=f"events cleared n={n}")
@@ -564,7 +565,7 @@ def test_ilqr_events_match_oracle(n, m, nc, nominal):
         solver.upload(lq)
         lq.event = None
         sol_h = solver.solve_host(lq, alpha=0.7, chunk=2)
-        assert ("generic" in solver.kernel_variant) == (n not in (24, 10))
+        assert ("generic" in solver.kernel_variant) == (n not in (24, 10, 9, 4))
         for name in ("K", "dbias", "Sm", "Sv", "s", "x", "u"):
             assert rel_err(getattr(sol_h, name), getattr(sol, name)) <= 1e-12, f"solve_host after events were cleared: {name}"
 
