@@ -99,8 +99,10 @@ __device__ __forceinline__ double dot_col(const double (&a)[LEN], const double* 
   return acc;
 }
 
+// Two warps per CTA. Ballbot: capping the registers at 170 (6 CTAs = 12 warps per SM instead of 10) is worth +7 % (8.4 -> 9.0 M solves/s);
+// the manipulator kernel (252 registers, nc = 3) loses 17 % to spills under the same cap and keeps the default.
 template <int NX, int NU, int NC, bool NOM, bool EV>
-__global__ void __launch_bounds__(128) ilqr_rpl_kernel(const Args a) {
+__global__ void __launch_bounds__(64, (NX == 10 ? 6 : 1)) ilqr_rpl_kernel(const Args a) {
   using S = Shape<NX, NU, NC>;
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
