@@ -1044,15 +1044,53 @@ __global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
         }
       }
     };
+    // The rows this lane works with — row i of A, B, Hv and (lanes < nu) row l of K, bias, dbias — of the two nodes of the current time
+    // segment live in REGISTERS: the segment index never decreases along the schedule, so each node's rows cross the shared-memory pipe
+    // once (when the segment advances, lo <- hi and hi <- node idx + 1) instead of once per RK4 stage; the lerp runs on registers.
+    const int lrow = i < NU ? i : NU - 1;
+    double alo[NX], ahi[NX], blo[NU], bhi[NU], klo[NX], khi[NX];
+    double hvlo = 0.0, hvhi = 0.0, fflo = 0.0, ffhi = 0.0;  // ff = bias + alpha dbias
+    int cur = -2;                                            // node held in the lo registers
+    auto load_rows = [&](int q, double (&ar)[NX], double (&br)[NU], double (&kr)[NX], double& hv, double& ff) {
+      const double* d = sm + S::sDyn + (q % 3) * S::dyn;
+      const double* p = sm + S::sPol + (q % 3) * S::pol;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        ar[j] = d[R::oA + i + NX * j];
+        kr[j] = p[R::oK + lrow + NU * j];
+      }
+#pragma unroll
+      for (int l = 0; l < NU; ++l) br[l] = d[R::oB + i + NX * l];
+      hv = d[R::oHv + i];
+      ff = p[R::obias + lrow] + alpha * p[R::odb + lrow];
+    };
+    auto seek = [&](int idx) {  // warp-uniform: idx comes from the schedule shared by the batch
+      if (idx == cur) return;
+      ensure(idx + 1);
+      const int hi = idx + 1 < N ? idx + 1 : N;
+      if (idx == cur + 1) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          alo[j] = ahi[j];
+          klo[j] = khi[j];
+        }
+#pragma unroll
+        for (int l = 0; l < NU; ++l) blo[l] = bhi[l];
+        hvlo = hvhi;
+        fflo = ffhi;
+      } else {
+        load_rows(idx, alo, blo, klo, hvlo, fflo);
+      }
+      load_rows(hi, ahi, bhi, khi, hvhi, ffhi);
+      cur = idx;
+    };
     // u(t, x) on lanes < nu from the x in shared memory; result broadcast through shared memory
     auto policy = [&](int idx, double w0) {
+      seek(idx);
       const double w1 = 1.0 - w0;
-      const double* p0 = sm + S::sPol + (idx % 3) * S::pol;
-      const double* p1 = sm + S::sPol + ((idx + 1) % 3) * S::pol;
-      const int l = i < NU ? i : NU - 1;
-      double u = w0 * (p0[R::obias + l] + alpha * p0[R::odb + l]) + w1 * (p1[R::obias + l] + alpha * p1[R::odb + l]);
+      double u = w0 * fflo + w1 * ffhi;
 #pragma unroll
-      for (int j = 0; j < NX; ++j) u = fma(fma(w0, p0[R::oK + l + NU * j], w1 * p1[R::oK + l + NU * j]), sm[S::sX + j], u);
+      for (int j = 0; j < NX; ++j) u = fma(fma(w0, klo[j], w1 * khi[j]), sm[S::sX + j], u);
       if (i < NU) sm[S::sU + i] = u;
       __syncwarp();
     };
@@ -1060,8 +1098,6 @@ __global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
     auto flow = [&](int idx, double w0) -> double {
       policy(idx, w0);
       const double w1 = 1.0 - w0;
-      const double* d0 = sm + S::sDyn + (idx % 3) * S::dyn;
-      const double* d1 = sm + S::sDyn + ((idx + 1) % 3) * S::dyn;
       const double* xv = sm + S::sX;
       if (a.x_nom) {  // deviations from the lerped nominal trajectories (TimeTriggeredRollout on the LQ model of an SLQ iteration)
         const double* xn = a.x_nom + ((size_t)prob * (N + 1) + idx) * NX;
@@ -1072,11 +1108,11 @@ __global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
         __syncwarp();
         xv = sm + S::sDx;
       }
-      double acc = fma(w0, d0[R::oHv + i], w1 * d1[R::oHv + i]);
+      double acc = fma(w0, hvlo, w1 * hvhi);
 #pragma unroll
-      for (int j = 0; j < NX; ++j) acc = fma(fma(w0, d0[R::oA + i + NX * j], w1 * d1[R::oA + i + NX * j]), xv[j], acc);
+      for (int j = 0; j < NX; ++j) acc = fma(fma(w0, alo[j], w1 * ahi[j]), xv[j], acc);
 #pragma unroll
-      for (int l = 0; l < NU; ++l) acc = fma(fma(w0, d0[R::oB + i + NX * l], w1 * d1[R::oB + i + NX * l]), sm[S::sU + l], acc);
+      for (int l = 0; l < NU; ++l) acc = fma(fma(w0, blo[l], w1 * bhi[l]), sm[S::sU + l], acc);
       __syncwarp();  // x, u in shared memory are dead
       return acc;
     };
@@ -1084,7 +1120,6 @@ __global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
     double x = a.x0[(size_t)prob * NX + i];
     bool finite = true;
     auto observe = [&](int o, int idx, double w0) {
-      ensure(idx + 1);
       sm[S::sX + i] = x;
       __syncwarp();
       policy(idx, w0);
@@ -1103,7 +1138,6 @@ __global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
       double acc = x, xs = x;
 #pragma unroll 1
       for (int stg = 0; stg < 4; ++stg) {
-        ensure(sp.idx[stg] + 1);
         sm[S::sX + i] = xs;
         __syncwarp();
         const double kx = flow(sp.idx[stg], sp.alpha[stg]);
