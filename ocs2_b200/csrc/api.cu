@@ -834,6 +834,9 @@ o2c_error o2c_import_device(o2c_handle* h, const o2c_lq_view* v, int32_t begin, 
   o2c_error e = check_range(h, begin, count);
   if (e != O2C_OK) return e;
   if (!v) return fail(O2C_ERR_INVALID_ARGUMENT, "null view");
+  if (!v->A.ptr || !v->B.ptr || !v->Q.ptr || !v->R.ptr || !v->Qf.ptr)
+    return fail(O2C_ERR_INVALID_ARGUMENT, "A, B, Q, R and Qf are required (absent Hv, P, q, r, c, qf, cf are taken as zero)");
+  if (h->L.ncmax > 0 && (!v->C.ptr || !v->D.ptr || !v->e.ptr)) return fail(O2C_ERR_INVALID_ARGUMENT, "C, D, e are required when nc_max > 0");
   O2C_CUDA(cudaSetDevice(h->cfg.device));
   if (v->time) {
     std::vector<double> t(h->L.N + 1);
@@ -862,7 +865,10 @@ o2c_error o2c_import_device(o2c_handle* h, const o2c_lq_view* v, int32_t begin, 
   d.u_nom = cv(v->u_nom);
   d.x0 = cv(v->x0);
   d.nc = v->nc;
-  if (v->nc && h->L.ncmax > 0) h->nc_ragged = true;
+  if (h->L.ncmax > 0) {  // device-side counts cannot be inspected here: any supplied array may be ragged
+    if (v->nc) h->nc_ragged = true;
+    else if (begin == 0 && count == h->cfg.batch) h->nc_ragged = false;  // pack_kernel rewrites every count to nc_max
+  }
   d.nc_ps = v->nc_problem_stride;
   d.nc_ns = v->nc_node_stride;
   if ((e = install_events(h, h->lanes[0].stream, v->event, v->event_problem_stride, v->event_node_stride, true, begin, count)) != O2C_OK) return e;

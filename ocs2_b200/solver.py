@@ -246,6 +246,12 @@ class BatchedLqSolver:
         _l.check(self._lib.o2c_upload(self._h, C.byref(view), problem_begin, lq.batch))
         self.sync()
 
+    def import_device(self, view: _l.LqView, problem_begin: int = 0, problem_count: Optional[int] = None):
+        """o2c_import_device: LQ data that already live in device memory, in any strided SoA layout (pointers of `view` are device
+        pointers; `view.time`, if set, too)."""
+        cnt = self.batch - problem_begin if problem_count is None else problem_count
+        _l.check(self._lib.o2c_import_device(self._h, C.byref(view), problem_begin, cnt))
+
     def set_time(self, time: Sequence[float]):
         t = np.ascontiguousarray(time, dtype=np.float64)
         assert t.shape == (self.N + 1,)
