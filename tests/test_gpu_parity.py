@@ -671,3 +671,37 @@ def test_import_device_matches_host_upload(alg, n, m, nc, events):
             else:
                 assert rel_err(getattr(got, name), getattr(want, name)) <= 1e-10, f"{name} differs between import_device and upload"
         assert hv is not None
+
+
+def test_device_views_and_config_round_trip():
+    """o2c_get_config returns what o2c_create took; o2c_device_lq_view describes the resident records well enough that another handle can
+    import them device-to-device; o2c_device_solution_view points at the resident controller (checked with a raw cudaMemcpy)."""
+    import ctypes as C
+    from ocs2_b200 import lib as o2lib
+    n, m, N, batch = 10, 3, 20, 9
+    st = o2.Settings(hessianCorrectionMultiple=1e-3)
+    with o2.BatchedLqSolver(st, n, m, N, batch) as a, o2.BatchedLqSolver(st, n, m, N, batch) as b:
+        cfg = o2lib.Config()
+        o2lib.check(a._lib.o2c_get_config(a.handle, C.byref(cfg)))
+        assert (cfg.nx, cfg.nu, cfg.nc_max, cfg.num_stages, cfg.batch, cfg.algorithm) == (n, m, 0, N, batch, o2.ALG_ILQR)
+        assert cfg.hessian_multiple == 1e-3 and cfg.time_step == st.timeStep
+        assert a.compute_stream != 0
+        a.generate_synthetic(seed=99, first_problem_index=1000)
+        a.solve()
+        want = a.download()
+        b.import_device(a.device_lq_view())
+        b.solve()
+        got = b.download()
+        for name in ("K", "dbias", "Sm", "Sv", "s", "x", "u"):
+            assert np.array_equal(getattr(got, name), getattr(want, name)), name
+        sv = a.device_solution_view()
+        try:
+            cudart = C.CDLL("libcudart.so")
+        except OSError:
+            cudart = C.CDLL("/usr/local/cuda/lib64/libcudart.so")
+        for p in (2, batch - 1):
+            for node in (0, N):
+                host = np.zeros(m * n)
+                src = sv.K.ptr + 8 * (p * sv.K.problem_stride + node * sv.K.node_stride)
+                assert cudart.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(src), C.c_size_t(host.nbytes), 2) == 0
+                assert np.array_equal(host.reshape(n, m).T, want.K[p, node])
