@@ -116,6 +116,7 @@ __global__ void select_kernel(Layout L, DeviceBuffers buf, const double* __restr
 cudaError_t launch_merit(const Layout& L, const DeviceBuffers& buf, int out_nodes, int n_alpha, int batch, int begin, int count, double* merit,
                          cudaStream_t stream) {
   const long long tasks = (long long)count * n_alpha;
+  if (tasks == 0) return cudaSuccess;
   const int grid = (int)((tasks + kWarpsPerBlock - 1) / kWarpsPerBlock);
   merit_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(L, buf, out_nodes, n_alpha, batch, begin, count, merit);
   return cudaGetLastError();
@@ -124,6 +125,7 @@ cudaError_t launch_merit(const Layout& L, const DeviceBuffers& buf, int out_node
 cudaError_t launch_select(const Layout& L, const DeviceBuffers& buf, const double* merit, const double* alphas_dev, int n_alpha, int batch,
                           int begin, int count, double armijo, const double* baseline_in_dev, double* baseline_out, double* update_is,
                           double* step, int* index, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
   select_kernel<<<(count + 127) / 128, 128, 0, stream>>>(L, buf, merit, alphas_dev, n_alpha, batch, begin, count, armijo, baseline_in_dev,
                                                         baseline_out, update_is, step, index);
   return cudaGetLastError();

@@ -705,3 +705,27 @@ def test_device_views_and_config_round_trip():
                 src = sv.K.ptr + 8 * (p * sv.K.problem_stride + node * sv.K.node_stride)
                 assert cudart.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(src), C.c_size_t(host.nbytes), 2) == 0
                 assert np.array_equal(host.reshape(n, m).T, want.K[p, node])
+
+
+@pytest.mark.parametrize("alg,n,m,nc", [(o2.ALG_ILQR, 24, 24, 0), (o2.ALG_ILQR, 10, 3, 0), (o2.ALG_ILQR, 5, 2, 1), (o2.ALG_SLQ, 12, 4, 0), (o2.ALG_SLQ, 5, 2, 1)])
+def test_empty_problem_range_is_a_no_op(alg, n, m, nc):
+    """An empty problem range (count = 0) is accepted by every entry point and leaves the resident solution untouched."""
+    rng = np.random.default_rng(3)
+    batch, N = 4, 6
+    lq = _random_batch(rng, batch, n, m, N, nc, alg, ragged_nc=False)
+    st = o2.Settings(algorithm=alg, hessianCorrectionMultiple=1e-4)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=True, max_alphas=6) as solver:
+        solver.upload(lq)
+        solver.solve()
+        want = solver.download()
+        solver.solveSequentialRiccatiEquations(problem_begin=2, problem_count=0)
+        solver.rolloutTrajectory((1.0,), problem_begin=batch, problem_count=0)
+        solver.solve(problem_begin=1, problem_count=0)
+        if alg == o2.ALG_ILQR:
+            assert solver.lineSearch(problem_begin=1, problem_count=0).stepLength.shape == (0,)
+            solver.solve()
+        assert solver.flatten(1.0, problem_begin=3, problem_count=0).shape[0] == 0
+        assert solver.download(problem_begin=0, problem_count=0).K.shape[0] == 0
+        got = solver.download()
+        for name in ("K", "dbias", "Sm", "Sv", "s", "x", "u"):
+            assert np.array_equal(getattr(got, name), getattr(want, name)), name
