@@ -572,7 +572,7 @@ struct SlqShape {
   using R = Shape<NX, NU, 0>;
   static constexpr int P = 32 / NX;
   static constexpr int rec = R::rec;
-  static constexpr int sRec = 0, sBt = 3 * rec, sLm = sBt + 2 * cpad2(NX * NU), sAl = sLm + 2 * cpad2(NU * NU), sBl = sAl + cpad2(NX * NX),
+  static constexpr int sRec = 0, sAl = 3 * rec, sBl = sAl + cpad2(NX * NX),
                        sMs = sBl + cpad2(NX * NU), sGs = sMs + cpad2(NX * NX), sSv = sGs + cpad2(NX * NU), sHv = sSv + cpad2(NX),
                        sGv = sHv + cpad2(NX), slot = sGv + cpad2(NU);
   static constexpr int warp_doubles = P * slot + 2;
@@ -655,9 +655,10 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
         if (i == 0) out[R::os] = sval;
       }
     };
-    // projection of node k (record in its ring slot) into set 0; B~ and L go to shared memory slot k & 1
+    // projection of node k (record in its ring slot) into set 0; B~ and L replace B and R inside the record (both are dead once
+    // projected), which keeps the warp at 27 KB of shared memory: 8 one-warp CTAs per SM
     auto project_node = [&](int k) {
-      const double* rec = sm + S::sRec + (k % 3) * S::rec;
+      double* rec = sm + S::sRec + (k % 3) * S::rec;
       double Lr[NU][NU];
 #pragma unroll
       for (int l = 0; l < NU; ++l)
@@ -676,9 +677,10 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
 #pragma unroll
           for (int l2 = j + 1; l2 <= l; ++l2) Lr[l][l2] = fma(-Lr[l][j], Lr[l2][j], Lr[l][l2]);
       }
-      double* Lm = sm + S::sLm + (k & 1) * cpad2(NU * NU);
-      double* Bt = sm + S::sBt + (k & 1) * cpad2(NX * NU);
-      if (i == 0) {
+      double* Lm = rec + R::oR;
+      double* Bt = rec + R::oB;
+      __syncwarp();  // every lane has read R
+      if (in_group && i == 0) {
 #pragma unroll
         for (int l = 0; l < NU; ++l)
 #pragma unroll
@@ -697,7 +699,7 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
         bt[l] = vb * Lr[l][l];
         pt0[l] = vp * Lr[l][l];
         rt0[l] = vr * Lr[l][l];
-        Bt[i + NX * l] = bt[l];
+        if (in_group) Bt[i + NX * l] = bt[l];  // row i in place (the left-over lanes mirror a row and must not race with its owner)
       }
 #pragma unroll
       for (int j = 0; j < NX; ++j) qr0[j] = rec[R::oQ + ((i <= j) ? i + NX * j : j + NX * i)];
@@ -708,8 +710,8 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
     };
     // SLQ::calculateControllerWorker at node k (whose projection is set 0) from the current state
     auto controller = [&](int k) {
-      const double* Lm = sm + S::sLm + (k & 1) * cpad2(NU * NU);
-      const double* Bt = sm + S::sBt + (k & 1) * cpad2(NX * NU);
+      const double* Lm = sm + S::sRec + (k % 3) * S::rec + R::oR;
+      const double* Bt = sm + S::sRec + (k % 3) * S::rec + R::oB;
       sm[S::sSv + i] = Svi;
       __syncwarp();
       double kt[NU], db[NU], g[NU], gv[NU];
@@ -799,8 +801,8 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
       }
       const double* A0 = sm + S::sRec + (i0 % 3) * S::rec + R::oA;
       const double* A1 = sm + S::sRec + ((i0 + 1) % 3) * S::rec + R::oA;
-      const double* Bt0 = sm + S::sBt + (i0 & 1) * cpad2(NX * NU);
-      const double* Bt1 = sm + S::sBt + ((i0 + 1) & 1) * cpad2(NX * NU);
+      const double* Bt0 = sm + S::sRec + (i0 % 3) * S::rec + R::oB;
+      const double* Bt1 = sm + S::sRec + ((i0 + 1) % 3) * S::rec + R::oB;
       const double h = sp.h;
       // classic RK4 (boost::odeint runge_kutta4): k_s = f(y + c_s h k_{s-1}), y += h (k1 + 2 k2 + 2 k3 + k4) / 6
       double ys[NX], ysv = Svi, acc[NX], accv = Svi, accs = sval;
@@ -926,7 +928,7 @@ template <int NX, int NU>
 cudaError_t launch_slq(const SlqArgs& a, cudaStream_t stream) {
   using S = SlqShape<NX, NU>;
   static int num_sms = 0;
-  constexpr int wpb = 2;
+  constexpr int wpb = 1;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(slq_rpl_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
