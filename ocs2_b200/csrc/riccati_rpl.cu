@@ -1198,7 +1198,7 @@ template <int NX, int NU, int NC, bool NOM, bool EV>
 cudaError_t launch(const Args& a, cudaStream_t stream) {
   using S = Shape<NX, NU, NC>;
   static int num_sms = 0;
-  constexpr int wpb = 2;
+  constexpr int wpb = (NX == 10) ? 1 : 2;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU, NC, NOM, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
