@@ -729,3 +729,29 @@ def test_empty_problem_range_is_a_no_op(alg, n, m, nc):
         got = solver.download()
         for name in ("K", "dbias", "Sm", "Sv", "s", "x", "u"):
             assert np.array_equal(getattr(got, name), getattr(want, name)), name
+
+
+@pytest.mark.parametrize("n,m,nc", [(24, 24, 0), (10, 3, 0), (9, 9, 3), (7, 2, 0)])
+@pytest.mark.parametrize("N", [1, 2, 9])
+def test_ilqr_events_dense_and_short_horizons(n, m, nc, N):
+    """Event nodes everywhere (problem 0), at the first and last node only (problem 1), alternating (problem 2), none (problem 3):
+    every kernel family against the oracle, horizons down to a single stage."""
+    rng = np.random.default_rng(41 + n + N)
+    batch = 4
+    lq = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=False)
+    event = np.zeros((batch, N), dtype=np.int32)
+    event[0, :] = 1
+    event[1, 0] = event[1, N - 1] = 1
+    event[2, ::2] = 1
+    for b in range(batch):
+        for k in np.nonzero(event[b])[0]:
+            lq.A[b, k] = np.eye(n) + 0.2 * rng.uniform(-1, 1, (n, n))
+            lq.Hv[b, k] = 0.1 * rng.uniform(-1, 1, n)
+    lq.event = event
+    st = o2.Settings(hessianCorrectionMultiple=1e-4)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=True) as solver:
+        solver.upload(lq)
+        solver.solve(alpha=0.6)
+        sol = solver.download()
+        for i in range(batch):
+            check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, (0.6,), what=f"dense events n={n} N={N} #{i}")
