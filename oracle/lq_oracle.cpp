@@ -690,6 +690,30 @@ int backward_slq(const orc_settings& st, const orc_problem& pb, orc_solution* so
       orc_unflatten(n, y.data(), sol->Sm + (size_t)(N - j) * n * n, sol->Sv + (size_t)(N - j) * n, &sol->s[N - j]);
     }
     if (j == N) break;
+    const int lower = N - 1 - j;  // the interval [node lower, node lower + 1]
+    if (pb.event && pb.event[lower]) {
+      // node `lower` is a pre-event node, node lower + 1 the post-event node: the segments are integrated separately and joined by
+      // ContinuousTimeRiccatiEquations::computeJumpMap (SLQ.cpp:286-296, ContinuousTimeRiccatiEquations.cpp:135-147) =
+      // riccatiTransversalityConditions on modelDataEventTimes[i] (RiccatiTransversalityConditions.h:40-56)
+      int ord = 0;
+      for (int q = 0; q < lower; ++q) ord += pb.event[q] != 0;
+      const double* Ae = pb.jA + (size_t)ord * n * n;
+      const double* Hve = pb.jHv + (size_t)ord * n;
+      vec Sp((size_t)n * n), Svp(n), Sm((size_t)n * n), Sv(n), SmTransAm((size_t)n * n), SmHv(n), tmpv(n);
+      double sp;
+      orc_unflatten(n, y.data(), Sp.data(), Svp.data(), &sp);
+      gemm_tn(n, n, n, 1.0, Sp.data(), n, Ae, n, 0.0, SmTransAm.data(), n);
+      std::copy(pb.jQ + (size_t)ord * n * n, pb.jQ + (size_t)(ord + 1) * n * n, Sm.begin());
+      gemm_tn(n, n, n, 1.0, SmTransAm.data(), n, Ae, n, 1.0, Sm.data(), n);
+      gemm_nn(n, 1, n, 1.0, Sp.data(), n, Hve, n, 0.0, SmHv.data(), n);
+      for (int i = 0; i < n; ++i) tmpv[i] = Svp[i] + SmHv[i];
+      std::copy(pb.jq + (size_t)ord * n, pb.jq + (size_t)(ord + 1) * n, Sv.begin());
+      gemm_tn(n, 1, n, 1.0, Ae, n, tmpv.data(), n, 1.0, Sv.data(), n);
+      double acc = 0.0;
+      for (int i = 0; i < n; ++i) acc += Hve[i] * (Svp[i] + 0.5 * SmHv[i]);
+      orc_flatten(n, Sm.data(), Sv.data(), sp + pb.jc[ord] + acc, y.data());
+      continue;
+    }
     double current_dt = dt;
     while (less_with_sign(current_time, z[j + 1])) {
       current_dt = std::min(dt, z[j + 1] - current_time);
@@ -970,25 +994,50 @@ int orc_rollout(const orc_settings* st, const orc_problem* pb, const orc_solutio
     }
     ++count;
   };
-  if (tStart < tf) {
-    // integrate_const (boost/numeric/odeint/integrate/detail/integrate_const.hpp, stepper_tag)
-    double t = tStart;
-    int step = 0;
-    while (less_eq_with_sign(t + dt, tf)) {
+  // RolloutBase::findActiveModesTimeInterval (RolloutBase.cpp:43-67): the event times split [t0, tf] into intervals whose start is
+  // nudged by weakEpsilon; here the event times are the stamps of the pre-event nodes
+  std::vector<double> switching{t0};
+  std::vector<int> event_node;
+  if (pb->event)
+    for (int k = 0; k < N; ++k)
+      if (pb->event[k]) {
+        switching.push_back(time[k]);
+        event_node.push_back(k);
+      }
+  switching.push_back(tf);
+  const int num_intervals = (int)switching.size() - 1;
+  for (int iv = 0; iv < num_intervals; ++iv) {
+    const double tEnd = switching[iv + 1];
+    const double tBegin = std::min(switching[iv] + 1e-9, tEnd);
+    if (tBegin < tEnd) {
+      // integrate_const (boost/numeric/odeint/integrate/detail/integrate_const.hpp, stepper_tag)
+      double t = tBegin;
+      int step = 0;
+      while (less_eq_with_sign(t + dt, tEnd)) {
+        observe(t);
+        rk4_step(flow, y, t, dt, k1, k2, k3, k4, tmp);
+        ++step;
+        t = tBegin + (double)step * dt;
+      }
       observe(t);
-      rk4_step(flow, y, t, dt, k1, k2, k3, k4, tmp);
-      ++step;
-      t = tStart + (double)step * dt;
+      // integrate_adaptive's last truncated step (integrate_adaptive.hpp, stepper_tag)
+      const double end = tBegin + dt * (double)step;
+      if (less_with_sign(end, tEnd)) {
+        rk4_step(flow, y, end, tEnd - end, k1, k2, k3, k4, tmp);
+        observe(tEnd);
+      }
+    } else {
+      observe(tEnd);
     }
-    observe(t);
-    // integrate_adaptive's last truncated step (integrate_adaptive.hpp, stepper_tag)
-    const double end = tStart + dt * (double)step;
-    if (less_with_sign(end, tf)) {
-      rk4_step(flow, y, end, tf - end, k1, k2, k3, k4, tmp);
-      observe(tf);
+    if (iv + 1 < num_intervals) {
+      // jump map of the LQ model (TimeTriggeredRollout.cpp:104-108): x+ = x_nom(post) + A_e (x - x_nom(pre)) + Hv_e
+      const int k = event_node[iv];
+      const double* Ae = pb->jA + (size_t)iv * n * n;
+      for (int i = 0; i < n; ++i) dxv[i] = y[i] - (pb->x_nom ? pb->x_nom[(size_t)k * n + i] : 0.0);
+      for (int i = 0; i < n; ++i) tmp[i] = pb->jHv[(size_t)iv * n + i] + (pb->x_nom ? pb->x_nom[(size_t)(k + 1) * n + i] : 0.0);
+      gemm_nn(n, 1, n, 1.0, Ae, n, dxv.data(), n, 1.0, tmp.data(), n);
+      y = tmp;
     }
-  } else {
-    observe(tf);
   }
   *n_out = count;
   if (count > max_out) return -1;

@@ -62,7 +62,12 @@ typedef struct orc_problem {
   const int32_t* event;             /* ILQR only, [N] or NULL: event[k] != 0 marks node k as a PRE-EVENT node (time[k] == time[k+1],
                                        k+1 in postEventIndices_). Its A, Hv, Q, q, c are the jump ModelData (modelDataEventTimes:
                                        jump map linearisation and pre-jump cost), its B, P, R, r, C, D, e the regular model data of the
-                                       node, used only for the controller (ILQR.cpp:263-295). */
+                                       node, used only for the controller (ILQR.cpp:263-295).
+                                       SLQ: [N+1] or NULL: event[k] != 0 marks node k as a pre-event node and node k + 1 as its post-event
+                                       node (time[k+1] = time[k] + weakEpsilon as the reference's rollouts stamp them, RolloutBase.cpp:62-64).
+                                       Every node keeps its own continuous-time model data; the jump ModelData of the e-th event (in
+                                       node order) are jA, jHv, jQ, jq, jc below. */
+  const double *jA, *jHv, *jQ, *jq, *jc; /* SLQ jump model data per event: [e][n*n], [e][n], [e][n*n], [e][n], [e] (modelDataEventTimes) */
 } orc_problem;
 
 typedef struct orc_solution {

@@ -38,7 +38,8 @@ class Settings(C.Structure):
 class _Problem(C.Structure):
     _fields_ = [("nx", C.c_int32), ("nu", C.c_int32), ("nc_max", C.c_int32), ("N", C.c_int32)] + [
         (name, _dp) for name in ("A", "B", "Hv", "Q", "P", "R", "q", "r", "c", "C", "D", "e")
-    ] + [("nc", _ip)] + [(name, _dp) for name in ("Qf", "qf", "cf", "x_nom", "u_nom", "time")] + [("event", _ip)]
+    ] + [("nc", _ip)] + [(name, _dp) for name in ("Qf", "qf", "cf", "x_nom", "u_nom", "time")] + [("event", _ip)] + [
+        (name, _dp) for name in ("jA", "jHv", "jQ", "jq", "jc")]
 
 
 class _Solution(C.Structure):
@@ -260,7 +261,13 @@ class Problem:
     x_nom: np.ndarray | None = None
     u_nom: np.ndarray | None = None
     time: np.ndarray | None = None
-    event: np.ndarray | None = None  # (N,) int: 1 marks a pre-event node (ILQR): jump data in A, Hv, Q, q, c
+    event: np.ndarray | None = None  # (nodes,) int: 1 marks a pre-event node. ILQR: jump data in the node's A, Hv, Q, q, c
+    # SLQ: jump model data of the e-th event (node order): jA (E,n,n), jHv (E,n), jQ (E,n,n), jq (E,n), jc (E,)
+    jA: np.ndarray | None = None
+    jHv: np.ndarray | None = None
+    jQ: np.ndarray | None = None
+    jq: np.ndarray | None = None
+    jc: np.ndarray | None = None
 
     @property
     def nx(self):
@@ -289,11 +296,18 @@ class Problem:
         keep["event"] = np.ascontiguousarray(ev, dtype=np.int32) if ev is not None else None
         if keep["time"] is None:
             keep["time"] = np.arange(self.N + 1, dtype=np.float64)
+        for name in ("jA", "jQ"):
+            v = getattr(self, name)
+            keep[name] = to_colmajor_nodes(v) if v is not None else None
+        for name in ("jHv", "jq", "jc"):
+            v = getattr(self, name)
+            keep[name] = np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
         pb = _Problem(self.nx, self.nu, self.nc_max, self.N, _p(keep["A"]), _p(keep["B"]), _p(keep["Hv"]), _p(keep["Q"]), _p(keep["P"]),
                       _p(keep["R"]), _p(keep["q"]), _p(keep["r"]), _p(keep["c"]), _p(keep["C"]), _p(keep["D"]), _p(keep["e"]),
                       keep["nc"].ctypes.data_as(_ip) if keep["nc"] is not None else _ip(), _p(keep["Qf"]), _p(keep["qf"]), _p(keep["cf"]),
                       _p(keep["x_nom"]), _p(keep["u_nom"]), _p(keep["time"]),
-                      keep["event"].ctypes.data_as(_ip) if keep["event"] is not None else _ip())
+                      keep["event"].ctypes.data_as(_ip) if keep["event"] is not None else _ip(), _p(keep["jA"]), _p(keep["jHv"]),
+                      _p(keep["jQ"]), _p(keep["jq"]), _p(keep["jc"]))
         return pb, keep
 
 
@@ -327,7 +341,8 @@ def backward(st: Settings, pb: Problem) -> Solution:
 def rollout(st: Settings, pb: Problem, sol: Solution, x0, alpha=1.0, max_out=None):
     n, m, N = pb.nx, pb.nu, pb.N
     if max_out is None:
-        max_out = N + 1 if st.algorithm == ALG_ILQR else int(np.ceil((pb.time[-1] - pb.time[0]) / st.time_step)) + 4
+        n_ev = 0 if pb.event is None else int(np.count_nonzero(pb.event))
+        max_out = N + 1 if st.algorithm == ALG_ILQR else int(np.ceil((pb.time[-1] - pb.time[0]) / st.time_step)) + 4 + 3 * n_ev
     x = np.zeros((max_out, n))
     u = np.zeros((max_out, m))
     t = np.zeros(max_out)

@@ -410,3 +410,90 @@ def test_flatten_controller_layout_and_round_trip():
     assert np.allclose(orc.unflatten_controller(inc, 3, 2)[0], bias + 0.5 * dbias, atol=1e-6)
     with pytest.raises(RuntimeError):
         orc.unflatten_controller(flat[:, :-1], 3, 2)
+
+
+def _slq_random_problem(rng, n, m, N, dt, event_nodes=()):
+    """Random continuous-time LQ data on N+1 nodes; event_nodes are PRE-event nodes k: node k+1 is stamped weakEpsilon later
+    (RolloutBase.cpp:62-64) and every event carries its own jump model data."""
+    sym = lambda M: 0.5 * (M + M.T)
+    time = np.zeros(N + 1)
+    for k in range(1, N + 1):
+        time[k] = time[k - 1] + (1e-9 if (k - 1) in event_nodes else dt)
+    A = 0.5 * rng.uniform(-1, 1, (N + 1, n, n))
+    B = rng.uniform(-1, 1, (N + 1, n, m))
+    Q = np.stack([sym(rng.uniform(-1, 1, (n, n))) + n * np.eye(n) for _ in range(N + 1)])
+    R = np.stack([sym(rng.uniform(-1, 1, (m, m))) + m * np.eye(m) for _ in range(N + 1)])
+    pb = orc.Problem(N=N, A=A, B=B, Hv=0.1 * rng.uniform(-1, 1, (N + 1, n)), Q=Q, P=0.1 * rng.uniform(-1, 1, (N + 1, m, n)), R=R,
+                     q=rng.uniform(-1, 1, (N + 1, n)), r=rng.uniform(-1, 1, (N + 1, m)), c=rng.uniform(-1, 1, N + 1),
+                     Qf=sym(rng.uniform(-1, 1, (n, n))) + n * np.eye(n), qf=rng.uniform(-1, 1, n), cf=0.3, time=time,
+                     x_nom=0.2 * rng.uniform(-1, 1, (N + 1, n)), u_nom=0.2 * rng.uniform(-1, 1, (N + 1, m)))
+    E = len(event_nodes)
+    if E:
+        ev = np.zeros(N + 1, dtype=np.int32)
+        ev[list(event_nodes)] = 1
+        pb.event = ev
+        pb.jA = np.stack([np.eye(n) + 0.3 * rng.uniform(-1, 1, (n, n)) for _ in range(E)])
+        pb.jHv = 0.1 * rng.uniform(-1, 1, (E, n))
+        pb.jQ = np.stack([sym(rng.uniform(-1, 1, (n, n))) + np.eye(n) for _ in range(E)])
+        pb.jq = 0.2 * rng.uniform(-1, 1, (E, n))
+        pb.jc = rng.uniform(-1, 1, E)
+    return pb
+
+
+def _slice_problem(pb, lo, hi, Qf, qf, cf):
+    """nodes lo..hi of an SLQ problem as a problem of its own with the given terminal value function"""
+    s = slice(lo, hi + 1)
+    return orc.Problem(N=hi - lo, A=pb.A[s], B=pb.B[s], Hv=pb.Hv[s], Q=pb.Q[s], P=pb.P[s], R=pb.R[s], q=pb.q[s], r=pb.r[s], c=pb.c[s],
+                       Qf=Qf, qf=qf, cf=cf, time=pb.time[s], x_nom=pb.x_nom[s], u_nom=pb.u_nom[s])
+
+
+@pytest.mark.parametrize("reduced", [True, False])
+def test_slq_events_compose_from_event_free_segments(reduced):
+    """SLQ with events (SLQ.cpp:256-302): the backward pass integrates the inter-event segments separately and joins them with
+    computeJumpMap = riccatiTransversalityConditions (ContinuousTimeRiccatiEquations.cpp:135-147, RiccatiTransversalityConditions.h:
+    40-56). Pinned structurally: the solution with events equals the already pinned event-free pass on each segment, chained through
+    the transversality conditions evaluated here in numpy."""
+    rng = np.random.default_rng(77)
+    n, m, N, dt = 5, 2, 14, 0.02
+    events = (4, 9)
+    pb = _slq_random_problem(rng, n, m, N, dt, events)
+    st = orc.make_settings(algorithm=orc.ALG_SLQ, reduced_form=reduced, hessian_multiple=1e-6, time_step=0.007)
+    full = orc.backward(st, pb)
+    assert full.status == 0
+    Qf, qf, cf = pb.Qf, pb.qf, pb.cf
+    hi = N
+    for ord_, k in reversed(list(enumerate(events))):
+        seg = orc.backward(st, _slice_problem(pb, k + 1, hi, Qf, qf, cf))
+        for name in ("Sm", "Sv", "s"):
+            assert np.allclose(getattr(full, name)[k + 1:hi + 1], getattr(seg, name), rtol=1e-12, atol=1e-12), (name, k)
+        assert np.allclose(full.K[k + 1:hi], seg.K[:hi - k - 1], rtol=1e-12, atol=1e-12)
+        Sm, Sv, s = seg.Sm[0], seg.Sv[0], seg.s[0]
+        Ae, Hve = pb.jA[ord_], pb.jHv[ord_]
+        SmHv = Sm @ Hve
+        Qf = pb.jQ[ord_] + (Sm.T @ Ae).T @ Ae
+        qf = pb.jq[ord_] + Ae.T @ (Sv + SmHv)
+        cf = float(s + pb.jc[ord_] + Hve @ (Sv + 0.5 * SmHv))
+        Qf = np.triu(Qf) + np.triu(Qf, 1).T  # convert2Vector keeps the upper triangle
+        hi = k
+    seg = orc.backward(st, _slice_problem(pb, 0, hi, Qf, qf, cf))
+    for name in ("Sm", "Sv", "s"):
+        assert np.allclose(getattr(full, name)[:hi + 1], getattr(seg, name), rtol=1e-12, atol=1e-12), name
+    assert np.allclose(full.K[:hi], seg.K[:hi], rtol=1e-12, atol=1e-12)
+
+    # rollout: the segments chained through the jump map of the LQ model x+ = x_nom(post) + A_e (x - x_nom(pre)) + Hv_e
+    x0 = rng.uniform(-1, 1, n)
+    x, u, t, status = orc.rollout(st, pb, full, x0, alpha=0.7)
+    assert status == 0
+    pre = [int(np.argmin(np.abs(t - pb.time[k]))) for k in events]
+    for ord_, (k, i) in enumerate(zip(events, pre)):
+        assert t[i] == pb.time[k] and t[i + 1] == pb.time[k] + 1e-9  # the segment ends on the event, the next starts weakEpsilon later
+        want = pb.x_nom[k + 1] + pb.jA[ord_] @ (x[i] - pb.x_nom[k]) + pb.jHv[ord_]
+        assert np.allclose(x[i + 1], want, rtol=1e-13, atol=1e-13)
+    # first segment: identical to the event-free rollout of nodes 0..k0 (same start nudge, same steps)
+    k0 = events[0]
+    segp = _slice_problem(pb, 0, k0, Qf, qf, cf)
+    segsol = orc.Solution(K=full.K[:k0 + 1], dbias=full.dbias[:k0 + 1], bias=full.bias[:k0 + 1], Sm=full.Sm[:k0 + 1], Sv=full.Sv[:k0 + 1],
+                          s=full.s[:k0 + 1])
+    xs, us, ts, _ = orc.rollout(st, segp, segsol, x0, alpha=0.7)
+    assert np.array_equal(ts, t[:pre[0] + 1]) and np.allclose(xs, x[:pre[0] + 1], rtol=1e-13, atol=1e-13)
+    assert np.allclose(us, u[:pre[0] + 1], rtol=1e-12, atol=1e-12)
