@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define O2C_ABI_VERSION 2
+#define O2C_ABI_VERSION 3
 
 typedef enum o2c_error {
   O2C_OK = 0,
@@ -105,9 +105,18 @@ typedef struct o2c_lq_view {
    * (time[node] == time[node+1], node+1 in postEventIndices_). Its A, Hv, Q, q, c blocks hold the jump ModelData
    * (modelDataEventTimes: jump map linearisation x+ = A_e dx + Hv_e and pre-jump cost), its B, P, R, r, C, D, e the regular model
    * data of the node, which only shape the controller entry. NULL = no events. Host memory in o2c_upload / o2c_solve_host, device
-   * memory in o2c_import_device. SLQ handles reject events (O2C_ERR_UNSUPPORTED). */
+   * memory in o2c_import_device. SLQ handles: see jump_* below. */
   const int32_t* event;
   int64_t event_problem_stride, event_node_stride;
+  /* SLQ events (SLQ.cpp:256-302, ContinuousTimeRiccatiEquations.cpp:135-147): event[problem][node] != 0 marks a pre-event node k whose
+   * successor k+1 is the post-event node (stamped time[k] + weakEpsilon by the reference's rollouts, RolloutBase.cpp:62-64; the stamps
+   * must differ). The time grid is shared by the batch, so the flags must be the same for every problem. Every node keeps its own
+   * continuous-time model data; the jump ModelData of the e-th event in node order (modelDataEventTimes[e]: dynamics.dfdx,
+   * dynamicsBias, cost.dfdxx, cost.dfdx, cost.f) are block(problem, e) = ptr + problem*problem_stride + e*node_stride of the fields
+   * below. The backward pass integrates the inter-event segments separately and joins them with riccatiTransversalityConditions; the
+   * rollout restarts weakEpsilon after every event from x+ = x_nom(k+1) + A_e (x - x_nom(k)) + Hv_e. Host memory (o2c_upload,
+   * o2c_solve_host); o2c_import_device does not take SLQ events. */
+  o2c_field jump_A, jump_Hv, jump_Q, jump_q, jump_c; /* n*n, n, n*n, n, 1; jump_A and jump_Q required with SLQ events */
 } o2c_lq_view;
 
 /* Struct-of-arrays view of the solution. Controller and value function have N+1 nodes (node N of the controller is the copy of

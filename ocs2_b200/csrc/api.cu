@@ -55,6 +55,9 @@ struct o2c_handle {
   float* d_flat = nullptr;  // flattened controllers of the whole batch (o2c_download_flattened_controller), allocated on first use
   int* d_event = nullptr;       // [batch][nodes] pre-event flags, allocated by the first upload that carries events
   bool events_present = false;
+  std::vector<int> slq_events;  // SLQ: pre-event node flags shared by the batch (empty = none)
+  double* d_jump = nullptr;     // SLQ: [batch][jump_capacity] jump records
+  int jump_capacity = 0;
   std::vector<double> ls_candidates;
   bool backward_done = false;
   int* h_status = nullptr;  // pinned bounce buffer [batch]: a caller's status array may be pageable, and an asynchronous copy into
@@ -86,6 +89,8 @@ struct o2c_handle {
     b.u_nom = d_unom;
     b.nc = nc_ragged ? d_nc : nullptr;
     b.event = events_present ? d_event : nullptr;
+    b.jump = d_jump;
+    b.jump_capacity = jump_capacity;
     b.x0 = d_x0;
     b.time = d_time;
     b.sol = d_sol;
@@ -145,8 +150,22 @@ o2c_error build_slq_schedule(o2c_handle* h, std::vector<SlqStep>& steps) {
   for (int j = 0; j <= N; ++j) z[j] = -h->time[N - j];
   steps.clear();
   const double cs[4] = {0.0, 0.5, 0.5, 1.0};
+  int n_events = 0;
+  for (int flag : h->slq_events) n_events += flag != 0;
+  int events_below = n_events;  // events at nodes < the current interval's lower node, counted while walking backwards
   for (int j = 0; j < N; ++j) {
     const int i0 = N - 1 - j;
+    if (!h->slq_events.empty() && h->slq_events[i0]) {
+      // pre-event node i0 / post-event node i0 + 1: the segments are integrated separately (SLQ.cpp:269-296); the value function
+      // crosses the event through computeJumpMap
+      events_below -= 1;
+      SlqStep s{};
+      s.interval = i0;
+      s.observe_node = i0;
+      s.jump = events_below + 1;
+      steps.push_back(s);
+      continue;
+    }
     double current_time = z[j];
     double current_dt = dt;
     const size_t first = steps.size();
@@ -196,11 +215,18 @@ o2c_error build_rollout_schedule(o2c_handle* h, std::vector<RolloutStep>& steps)
   const double dt = h->st.time_step;
   if (!(dt > 0.0)) return fail(O2C_ERR_INVALID_ARGUMENT, "time_step must be positive for the continuous rollout");
   const double t0 = h->time[0], tf = h->time[N];
-  const double tStart = std::min(t0 + 1e-9, tf);
   steps.clear();
   h->ro_times.clear();
-  time_segment(tStart, h->time, h->ro_first_idx, h->ro_first_alpha);
-  h->ro_times.push_back(tStart);
+  // RolloutBase::findActiveModesTimeInterval (RolloutBase.cpp:43-67): the event times (stamps of the pre-event nodes) split [t0, tf]
+  // into intervals whose start is nudged by weakEpsilon
+  std::vector<double> switching{t0};
+  std::vector<int> event_node;
+  for (int k = 0; k < N && !h->slq_events.empty(); ++k)
+    if (h->slq_events[k]) {
+      switching.push_back(h->time[k]);
+      event_node.push_back(k);
+    }
+  switching.push_back(tf);
   auto add = [&](double t, double hh, double tnext) {
     RolloutStep s{};
     s.h = hh;
@@ -210,30 +236,43 @@ o2c_error build_rollout_schedule(o2c_handle* h, std::vector<RolloutStep>& steps)
     steps.push_back(s);
     h->ro_times.push_back(tnext);
   };
-  if (tStart < tf) {
-    double t = tStart;
-    int step = 0;
-    while (less_eq_with_sign(t + dt, tf)) {
-      ++step;
-      const double tn = tStart + (double)step * dt;
-      add(t, dt, tn);
-      t = tn;
-      if (step > 50000000) return fail(O2C_ERR_INVALID_ARGUMENT, "rollout schedule too long (time_step too small)");
+  const int intervals = (int)switching.size() - 1;
+  for (int iv = 0; iv < intervals; ++iv) {
+    const double tEnd = switching[iv + 1];
+    const double tBegin = std::min(switching[iv] + 1e-9, tEnd);
+    if (iv == 0) {
+      time_segment(tBegin, h->time, h->ro_first_idx, h->ro_first_alpha);
+      h->ro_times.push_back(tBegin);
+    } else {  // the jump at the end of the previous interval, observed at the start of this one (TimeTriggeredRollout.cpp:104-108)
+      RolloutStep s{};
+      s.jump = iv;
+      s.pre_node = event_node[iv - 1];
+      time_segment(tBegin, h->time, s.obs_idx, s.obs_alpha);
+      for (int c = 0; c < 4; ++c) s.idx[c] = s.obs_idx, s.alpha[c] = s.obs_alpha;
+      steps.push_back(s);
+      h->ro_times.push_back(tBegin);
     }
-    const double end = tStart + dt * (double)step;
-    if (less_with_sign(end, tf)) add(end, tf - end, tf);
+    if (tBegin < tEnd) {
+      double t = tBegin;
+      int step = 0;
+      while (less_eq_with_sign(t + dt, tEnd)) {
+        ++step;
+        const double tn = tBegin + (double)step * dt;
+        add(t, dt, tn);
+        t = tn;
+        if (steps.size() > 50000000) return fail(O2C_ERR_INVALID_ARGUMENT, "rollout schedule too long (time_step too small)");
+      }
+      const double end = tBegin + dt * (double)step;
+      if (less_with_sign(end, tEnd)) add(end, tEnd - end, tEnd);
+    }
   }
   return O2C_OK;
 }
 
-o2c_error install_time(o2c_handle* h, const double* host_time) {
-  const int N = h->L.N;
-  h->time.assign(host_time, host_time + N + 1);
-  for (int k = 0; k < N; ++k)
-    if (!(h->time[k + 1] >= h->time[k])) return fail(O2C_ERR_INVALID_ARGUMENT, "time nodes must be non-decreasing");
-  O2C_CUDA(cudaMemcpyAsync(h->d_time, h->time.data(), sizeof(double) * (N + 1), cudaMemcpyHostToDevice, h->lanes[0].stream));
-  O2C_CUDA(cudaStreamSynchronize(h->lanes[0].stream));
+// (re)builds the SLQ backward and rollout step schedules from the node times and the event nodes of the handle
+o2c_error rebuild_schedules(o2c_handle* h) {
   if (h->st.algorithm == O2C_ALG_SLQ) {
+    for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));  // kernels in flight still read the old schedules
     std::vector<SlqStep> steps;
     o2c_error e = build_slq_schedule(h, steps);
     if (e != O2C_OK) return e;
@@ -267,6 +306,18 @@ o2c_error install_time(o2c_handle* h, const double* host_time) {
   } else {
     h->ro_times = h->time;
   }
+  return O2C_OK;
+}
+
+o2c_error install_time(o2c_handle* h, const double* host_time) {
+  const int N = h->L.N;
+  h->time.assign(host_time, host_time + N + 1);
+  for (int k = 0; k < N; ++k)
+    if (!(h->time[k + 1] >= h->time[k])) return fail(O2C_ERR_INVALID_ARGUMENT, "time nodes must be non-decreasing");
+  O2C_CUDA(cudaMemcpyAsync(h->d_time, h->time.data(), sizeof(double) * (N + 1), cudaMemcpyHostToDevice, h->lanes[0].stream));
+  O2C_CUDA(cudaStreamSynchronize(h->lanes[0].stream));
+  o2c_error e = rebuild_schedules(h);
+  if (e != O2C_OK) return e;
   h->time_set = true;
   return O2C_OK;
 }
@@ -371,30 +422,92 @@ o2c_error check_range(const o2c_handle* h, int begin, int count) {
   return O2C_OK;
 }
 
-// pre-event flags of problems [begin, begin+count): host (or device) array -> d_event; a view without events clears the range
-o2c_error install_events(o2c_handle* h, cudaStream_t stream, const int32_t* ev, long long ps, long long ns, bool device_memory, int begin,
-                         int count) {
-  const int nodes = h->L.nodes;
-  if (ev == nullptr) {
+// pre-event flags of problems [begin, begin+count): host (or device) array -> d_event; a view without events clears the range.
+// SLQ: the flags are shared by the batch (they shape the step schedules) and every event brings its jump record.
+o2c_error install_events(o2c_handle* h, cudaStream_t stream, const o2c_lq_view* v, bool device_memory, int begin, int count) {
+  const int nodes = h->L.nodes, n = h->L.n;
+  const bool slq = h->st.algorithm == O2C_ALG_SLQ;
+  const bool whole = begin == 0 && count == h->cfg.batch;
+  const int32_t* ev = v ? v->event : nullptr;
+  if (ev == nullptr || count == 0) {
+    if (count == 0) return O2C_OK;
     if (h->events_present) O2C_CUDA(cudaMemsetAsync(h->d_event + (size_t)begin * nodes, 0, sizeof(int) * (size_t)count * nodes, stream));
-    if (begin == 0 && count == h->cfg.batch) h->events_present = false;  // whole batch replaced: the specialised kernels serve it again
+    if (whole) {  // whole batch replaced: the specialised kernels serve it again
+      h->events_present = false;
+      if (slq && !h->slq_events.empty()) {
+        h->slq_events.clear();
+        if (h->time_set) return rebuild_schedules(h);
+      }
+    } else if (slq && !h->slq_events.empty()) {
+      return fail(O2C_ERR_INVALID_ARGUMENT, "SLQ event nodes are shared by the batch: a partial upload must carry the same events");
+    }
     return O2C_OK;
   }
-  if (h->st.algorithm != O2C_ALG_ILQR) return fail(O2C_ERR_UNSUPPORTED, "events are provided for the discrete (ILQR) backward pass only");
+  const long long ps = v->event_problem_stride, ns = v->event_node_stride;
+  if (slq && device_memory) return fail(O2C_ERR_UNSUPPORTED, "o2c_import_device does not take SLQ events (upload them from host memory)");
   if (!h->d_event) {
     O2C_CUDA(cudaMalloc(&h->d_event, sizeof(int) * (size_t)h->cfg.batch * nodes));
     O2C_CUDA(cudaMemsetAsync(h->d_event, 0, sizeof(int) * (size_t)h->cfg.batch * nodes, stream));
   }
-  h->events_present = true;
   int* dst = h->d_event + (size_t)begin * nodes;
   if (device_memory) {
     if (ns != 1) return fail(O2C_ERR_UNSUPPORTED, "device event flags must be contiguous over the nodes (event_node_stride == 1)");
+    h->events_present = true;
     O2C_CUDA(cudaMemcpy2DAsync(dst, sizeof(int) * nodes, ev, sizeof(int) * (size_t)ps, sizeof(int) * nodes, count, cudaMemcpyDeviceToDevice, stream));
     return O2C_OK;
   }
   std::vector<int> tmp((size_t)count * nodes);
   for (int p = 0; p < count; ++p)
     for (int k = 0; k < nodes; ++k) tmp[(size_t)p * nodes + k] = ev[p * ps + k * ns] != 0;
+  if (slq) {
+    std::vector<int> flags(tmp.begin(), tmp.begin() + nodes);
+    for (int p = 1; p < count; ++p)
+      if (!std::equal(flags.begin(), flags.end(), tmp.begin() + (size_t)p * nodes))
+        return fail(O2C_ERR_INVALID_ARGUMENT, "SLQ event nodes must be the same for every problem (the time grid is shared by the batch)");
+    if (flags[nodes - 1]) return fail(O2C_ERR_INVALID_ARGUMENT, "the last node cannot be a pre-event node");
+    int n_ev = 0;
+    for (int f : flags) n_ev += f;
+    if (!whole && flags != h->slq_events)
+      return fail(O2C_ERR_INVALID_ARGUMENT, "SLQ event nodes are shared by the batch: a partial upload must carry the same events");
+    if (n_ev > 0 && (!v->jump_A.ptr || !v->jump_Q.ptr)) return fail(O2C_ERR_INVALID_ARGUMENT, "jump_A and jump_Q are required with SLQ events");
+    const size_t jrec = (size_t)jump_rec(n);
+    if (n_ev > h->jump_capacity) {
+      for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));
+      if (h->d_jump) cudaFree(h->d_jump);
+      h->d_jump = nullptr;
+      h->jump_capacity = 0;
+      O2C_CUDA(cudaMalloc(&h->d_jump, sizeof(double) * jrec * n_ev * h->cfg.batch));
+      h->jump_capacity = n_ev;
+    }
+    if (n_ev > 0) {
+      std::vector<double> jr((size_t)count * n_ev * jrec, 0.0);
+      auto gather = [&](const o2c_field& f, int block, int offset) {
+        if (!f.ptr) return;
+        for (int p = 0; p < count; ++p)
+          for (int e = 0; e < n_ev; ++e) {
+            const double* src = f.ptr + (long long)p * f.problem_stride + (long long)e * f.node_stride;
+            std::copy(src, src + block, jr.begin() + ((size_t)p * n_ev + e) * jrec + offset);
+          }
+      };
+      gather(v->jump_A, n * n, 0);
+      gather(v->jump_Hv, n, jump_oHv(n));
+      gather(v->jump_Q, n * n, jump_oQ(n));
+      gather(v->jump_q, n, jump_oq(n));
+      gather(v->jump_c, 1, jump_oc(n));
+      O2C_CUDA(cudaMemcpy2DAsync(h->d_jump + (size_t)begin * h->jump_capacity * jrec, sizeof(double) * h->jump_capacity * jrec, jr.data(),
+                                 sizeof(double) * n_ev * jrec, sizeof(double) * n_ev * jrec, count, cudaMemcpyHostToDevice, stream));
+      O2C_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (flags != h->slq_events) {
+      h->slq_events = flags;
+      if (h->time_set) {
+        o2c_error e = rebuild_schedules(h);
+        if (e != O2C_OK) return e;
+      }
+    }
+    if (n_ev == 0) h->slq_events.clear();
+  }
+  h->events_present = true;
   O2C_CUDA(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
   O2C_CUDA(cudaStreamSynchronize(stream));  // tmp is pageable and about to go out of scope
   return O2C_OK;
@@ -444,7 +557,7 @@ o2c_error upload_chunk(o2c_handle* h, Lane& lane, const o2c_lq_view& v, int begi
   } else if (ncm > 0 && begin == 0 && count == h->cfg.batch) {
     h->nc_ragged = false;  // pack_kernel rewrites every count to nc_max
   }
-  if ((e = install_events(h, lane.stream, v.event, v.event_problem_stride, v.event_node_stride, false, begin, count)) != O2C_OK) return e;
+  if ((e = install_events(h, lane.stream, &v, false, begin, count)) != O2C_OK) return e;
   O2C_CUDA(launch_pack(L, d, h->d_lq, h->d_term, h->d_xnom, h->d_unom, h->d_nc, h->d_x0, begin, count, lane.stream));
   h->launches += 1;
   return O2C_OK;
@@ -594,7 +707,7 @@ void release(o2c_handle* h) {
   }
   void* ptrs[] = {h->d_lq,  h->d_term, h->d_xnom, h->d_unom,   h->d_x0,        h->d_time,    h->d_sol,
                   h->d_xs,  h->d_us,   h->d_alphas, h->d_nc,   h->d_status,    h->d_slq_steps, h->d_ro_steps,
-                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event, h->d_flat};
+                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event, h->d_flat, h->d_jump};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
@@ -821,6 +934,7 @@ o2c_error o2c_upload(o2c_handle* h, const o2c_lq_view* v, int32_t begin, int32_t
     o2c_lq_view sub = *v;
 #define OFF(field) sub.field = offset_field(v->field, off);
     OFF(A) OFF(B) OFF(Hv) OFF(Q) OFF(P) OFF(R) OFF(q) OFF(r) OFF(c) OFF(C) OFF(D) OFF(e) OFF(Qf) OFF(qf) OFF(cf) OFF(x_nom) OFF(u_nom) OFF(x0)
+    OFF(jump_A) OFF(jump_Hv) OFF(jump_Q) OFF(jump_q) OFF(jump_c)
 #undef OFF
     if (v->nc) sub.nc = v->nc + (long long)off * v->nc_problem_stride;
     if (v->event) sub.event = v->event + (long long)off * v->event_problem_stride;
@@ -871,7 +985,7 @@ o2c_error o2c_import_device(o2c_handle* h, const o2c_lq_view* v, int32_t begin, 
   }
   d.nc_ps = v->nc_problem_stride;
   d.nc_ns = v->nc_node_stride;
-  if ((e = install_events(h, h->lanes[0].stream, v->event, v->event_problem_stride, v->event_node_stride, true, begin, count)) != O2C_OK) return e;
+  if ((e = install_events(h, h->lanes[0].stream, v, true, begin, count)) != O2C_OK) return e;
   O2C_CUDA(launch_pack(h->L, d, h->d_lq, h->d_term, h->d_xnom, h->d_unom, h->d_nc, h->d_x0, begin, count, h->lanes[0].stream));
   h->launches += 1;
   return O2C_OK;
@@ -1041,7 +1155,9 @@ o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solutio
   // lanes run [H2D -> pack -> sweep+rollout -> unpack -> D2H] for alternating chunks; copies of one lane overlap the kernels of another
   for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));
   if (!lq->event && count == h->cfg.batch)  // whole batch replaced by problems without events (chunk uploads alone cannot tell)
-    if ((e = install_events(h, h->lanes[0].stream, nullptr, 0, 0, false, 0, count)) != O2C_OK) return e;
+    if ((e = install_events(h, h->lanes[0].stream, nullptr, false, 0, count)) != O2C_OK) return e;
+  if (lq->event && h->st.algorithm == O2C_ALG_SLQ && count == h->cfg.batch)  // SLQ event nodes shape the schedules: install them (and the
+    if ((e = install_events(h, h->lanes[0].stream, lq, false, 0, count)) != O2C_OK) return e;  // jump records) before the chunked uploads
   int li = 0;
   for (int off = 0; off < count; off += chunk, li = (li + 1) % kLanes) {
     const int c = std::min(chunk, count - off);
@@ -1049,6 +1165,7 @@ o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solutio
     o2c_lq_view sub = *lq;
 #define OFF(field) sub.field = offset_field(lq->field, off);
     OFF(A) OFF(B) OFF(Hv) OFF(Q) OFF(P) OFF(R) OFF(q) OFF(r) OFF(c) OFF(C) OFF(D) OFF(e) OFF(Qf) OFF(qf) OFF(cf) OFF(x_nom) OFF(u_nom) OFF(x0)
+    OFF(jump_A) OFF(jump_Hv) OFF(jump_Q) OFF(jump_q) OFF(jump_c)
 #undef OFF
     if (lq->nc) sub.nc = lq->nc + (long long)off * lq->nc_problem_stride;
     if (lq->event) sub.event = lq->event + (long long)off * lq->event_problem_stride;
@@ -1071,6 +1188,7 @@ o2c_error o2c_generate_synthetic(o2c_handle* h, uint64_t seed, int64_t first_pro
   O2C_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t s = h->lanes[0].stream;
   h->events_present = false;
+  h->slq_events.clear();  // the generated family has no events; the schedules are rebuilt with the generated time grid below
   O2C_CUDA(launch_generate(h->L, h->st.algorithm, h->d_lq, h->d_term, h->d_x0, seed, first_problem_index, dt, h->cfg.batch, s));
   h->launches += 1;
   if (h->d_nc) {

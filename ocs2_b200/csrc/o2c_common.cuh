@@ -89,7 +89,9 @@ struct DeviceBuffers {
   const double* x_nom;  // [batch][N+1][n] or nullptr
   const double* u_nom;  // [batch][N+1][m] or nullptr
   const int* nc;        // [batch][nodes] or nullptr
-  const int* event;     // [batch][nodes] pre-event node flags (ILQR) or nullptr: no events anywhere
+  const int* event;     // [batch][nodes] pre-event node flags or nullptr: no events anywhere
+  const double* jump;   // SLQ: [batch][jump_capacity] jump records { A_e | Hv_e | Q_e | q_e | c_e } (offsets jump_offsets), or nullptr
+  int jump_capacity;    // events per problem the jump array has room for
   const double* x0;     // [batch][n]
   const double* time;   // [N+1]
   double* sol;
@@ -102,6 +104,8 @@ struct DeviceBuffers {
 struct SlqStep {
   int interval;      // data interval i: lerp between nodes i and i+1
   int observe_node;  // >= 0: after this step the state is the value function of this node
+  int jump;          // > 0: node `interval` is a pre-event node; instead of integrating, apply the jump record jump - 1
+                     // (ContinuousTimeRiccatiEquations::computeJumpMap, riccatiTransversalityConditions)
   double h;
   double alpha[4];   // weight of node i at the four RK4 stage times (1 - alpha on node i+1)
 };
@@ -112,7 +116,15 @@ struct RolloutStep {
   double alpha[4];
   int obs_idx;      // timeSegment of the observation time after the step
   double obs_alpha;
+  int jump;         // > 0: before observing, the state jumps through record jump - 1 at pre-event node pre_node (h == 0: no integration)
+  int pre_node;
 };
+// jump record layout for state dimension n (doubles): A_e n*n | Hv_e n | Q_e n*n | q_e n | c_e 1, padded to an even count
+__host__ __device__ inline int jump_oHv(int n) { return n * n; }
+__host__ __device__ inline int jump_oQ(int n) { return n * n + n; }
+__host__ __device__ inline int jump_oq(int n) { return 2 * n * n + n; }
+__host__ __device__ inline int jump_oc(int n) { return 2 * n * n + 2 * n; }
+__host__ __device__ inline int jump_rec(int n) { return (2 * n * n + 2 * n + 2) & ~1; }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // launchers implemented in the .cu files

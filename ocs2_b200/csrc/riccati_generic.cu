@@ -942,6 +942,44 @@ __global__ void __launch_bounds__(128) slq_generic_kernel(Layout L, SolverSettin
     const ProjSet& Lh = node[i0 & 1];
     const ProjSet& Rh = node[(i0 + 1) & 1];
     const double h = sp.h;
+    if (sp.jump > 0) {
+      // node i0 is a pre-event node: the segments on either side are integrated separately and joined by
+      // ContinuousTimeRiccatiEquations::computeJumpMap = riccatiTransversalityConditions on the event's jump model data
+      // (SLQ.cpp:286-296, ContinuousTimeRiccatiEquations.cpp:135-147, RiccatiTransversalityConditions.h:40-56)
+      const double* jr = buf.jump + ((size_t)prob * buf.jump_capacity + (sp.jump - 1)) * jump_rec(n);
+      const double* Ae = jr;
+      const double* Hve = jr + jump_oHv(n);
+      for (int idx = lane; idx < n * n; idx += 32) {
+        const int i = idx % n, j = idx / n;
+        F.Sm[idx] = (i <= j) ? y[tri_index(i, j)] : y[tri_index(j, i)];
+      }
+      __syncwarp();
+      wgemm<true, false>(n, n, n, 1.0, F.Sm, n, Ae, n, 0.0, F.StA, n);   // SmTransAm = Sm' A_e
+      wgemm<false, false>(n, 1, n, 1.0, F.Sm, n, Hve, n, 0.0, k1, n);    // SmHv
+      double part = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        part += Hve[i] * (y[ntri + i] + 0.5 * k1[i]);
+        k1[n + i] = y[ntri + i] + k1[i];                                  // Sv + SmHv
+      }
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      __syncwarp();
+      wcopy(n * n, jr + jump_oQ(n), F.Sm);
+      wgemm<true, false>(n, n, n, 1.0, F.StA, n, Ae, n, 1.0, F.Sm, n);   // Sm- = Q_e + SmTransAm' A_e
+      wcopy(n, jr + jump_oq(n), k2);
+      wgemm<true, false>(n, 1, n, 1.0, Ae, n, k1 + n, n, 1.0, k2, n);    // Sv- = q_e + A_e' (Sv + SmHv)
+      for (int idx = lane; idx < n * n; idx += 32) {
+        const int i = idx % n, j = idx / n;
+        if (i <= j) y[tri_index(i, j)] = F.Sm[idx];                       // convert2Vector keeps the upper triangle
+      }
+      for (int i = lane; i < n; i += 32) y[ntri + i] = k2[i];
+      if (lane == 0) y[ntri + n] = y[ntri + n] + jr[jump_oc(n)] + part;
+      __syncwarp();
+      if (sp.observe_node >= 0) {
+        write_value(sp.observe_node);
+        controller(sp.observe_node, node[sp.observe_node & 1]);
+      }
+      continue;
+    }
     // classic RK4 (boost::odeint runge_kutta4)
     lerp_proj(L, full, lm, gersh, sp.alpha[0], Lh, Rh, cur);
     flow_map(L, st, cur, F, y, k1);

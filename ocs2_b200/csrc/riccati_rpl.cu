@@ -1227,8 +1227,8 @@ bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const La
 
 bool rpl_slq_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   if (!(st.algorithm == O2C_ALG_SLQ && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
-        (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.nodes == L.N + 1))
-    return false;
+        (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1 && L.nodes == L.N + 1))
+    return false;  // SLQ events (jump steps in the schedule) go through the generic kernels
   return layout_matches<12, 4, 0>(L);
 }
 
@@ -1252,8 +1252,8 @@ cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const Devi
 }
 
 bool rpl_rollout_cont_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
-  return st.algorithm == O2C_ALG_SLQ && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.nodes == L.N + 1 &&
-         layout_matches<12, 4, 0>(L);
+  return st.algorithm == O2C_ALG_SLQ && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1 &&
+         L.nodes == L.N + 1 && layout_matches<12, 4, 0>(L);
 }
 
 cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,

@@ -152,6 +152,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   for (int s = 0; s < nsteps; ++s) {
     const RolloutStep sp = steps[s];
     const double h = sp.h;
+    if (sp.jump > 0) {
+      // an event (TimeTriggeredRollout.cpp:104-108): the LQ model's jump map x+ = x_nom(post) + A_e (x - x_nom(pre)) + Hv_e
+      const double* jr = buf.jump + ((size_t)prob * buf.jump_capacity + (sp.jump - 1)) * jump_rec(n);
+      for (int i = lane; i < n; i += 32) W.dx[i] = W.x[i] - (xnom ? xnom[(size_t)sp.pre_node * n + i] : 0.0);
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) {
+        double acc = jr[jump_oHv(n) + i] + (xnom ? xnom[(size_t)(sp.pre_node + 1) * n + i] : 0.0);
+        for (int k = 0; k < n; ++k) acc = fma(jr[i + (size_t)k * n], W.dx[k], acc);
+        W.xt[i] = acc;
+      }
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) W.x[i] = W.xt[i];
+      __syncwarp();
+    }
+    if (h == 0.0) {  // a jump or a degenerate interval: no integration
+      observe(s + 1, sp.obs_idx, sp.obs_alpha);
+      continue;
+    }
     cont_flow(L, buf, lqp, solp, xnom, unom, sp.idx[0], sp.alpha[0], alpha, W.x, W.k1, W);
     for (int i = lane; i < n; i += 32) W.xt[i] = W.x[i] + (h * 0.5) * W.k1[i];
     __syncwarp();

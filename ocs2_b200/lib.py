@@ -49,7 +49,8 @@ class LqView(C.Structure):
     _fields_ = [(n, Field) for n in ("A", "B", "Hv", "Q", "P", "R", "q", "r", "c", "C", "D", "e")] + [
         ("nc", C.c_void_p), ("nc_problem_stride", C.c_int64), ("nc_node_stride", C.c_int64)] + [
         (n, Field) for n in ("Qf", "qf", "cf", "x_nom", "u_nom", "x0")] + [("time", C.c_void_p)] + [
-        ("event", C.c_void_p), ("event_problem_stride", C.c_int64), ("event_node_stride", C.c_int64)]
+        ("event", C.c_void_p), ("event_problem_stride", C.c_int64), ("event_node_stride", C.c_int64)] + [
+        (n, Field) for n in ("jump_A", "jump_Hv", "jump_Q", "jump_q", "jump_c")]
 
 
 class SolutionView(C.Structure):
@@ -117,7 +118,7 @@ def load_library():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    if lib.o2c_abi_version() != 2:
+    if lib.o2c_abi_version() != 3:
         raise RuntimeError("libocs2_ddp_cuda.so ABI version mismatch")
     _lib = lib
     return lib

@@ -73,7 +73,13 @@ class LqBatch:
     u_nom: Optional[np.ndarray] = None
     x0: Optional[np.ndarray] = None
     time: Optional[np.ndarray] = None
-    event: Optional[np.ndarray] = None   # (B, nodes) int: 1 marks a pre-event node of ILQR (jump data in A, Hv, Q, q, c)
+    event: Optional[np.ndarray] = None   # (B, nodes) int: 1 marks a pre-event node. ILQR: jump data in the node's A, Hv, Q, q, c
+    # SLQ: jump ModelData of the e-th event in node order (the same event nodes for every problem: the time grid is shared)
+    jump_A: Optional[np.ndarray] = None   # (B, E, n, n)
+    jump_Hv: Optional[np.ndarray] = None  # (B, E, n)
+    jump_Q: Optional[np.ndarray] = None   # (B, E, n, n)
+    jump_q: Optional[np.ndarray] = None   # (B, E, n)
+    jump_c: Optional[np.ndarray] = None   # (B, E)
     _keep: dict = field(default_factory=dict, repr=False)
 
     @property
@@ -123,6 +129,15 @@ class LqBatch:
             lv.event = k["event"].ctypes.data
             lv.event_problem_stride = nodes
             lv.event_node_stride = 1
+        if self.jump_A is not None:
+            E = self.jump_A.shape[1]
+            for name in ("jump_A", "jump_Q"):
+                k[name] = _colmajor(getattr(self, name))
+            for name in ("jump_Hv", "jump_q", "jump_c"):
+                v = getattr(self, name)
+                k[name] = np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
+            lv.jump_A, lv.jump_Q = _field(k["jump_A"], n * n, E), _field(k["jump_Q"], n * n, E)
+            lv.jump_Hv, lv.jump_q, lv.jump_c = _field(k["jump_Hv"], n, E), _field(k["jump_q"], n, E), _field(k["jump_c"], 1, E)
         return lv
 
 

@@ -43,14 +43,14 @@ def test_struct_layouts_match_the_header():
     # o2c_config: 12 int32 + 3 double; o2c_field: ptr + 2 int64; views are arrays of fields plus a few scalars
     assert C.sizeof(_l.Config) == 12 * 4 + 3 * 8
     assert C.sizeof(_l.Field) == 24
-    assert C.sizeof(_l.LqView) == 12 * 24 + 8 + 16 + 6 * 24 + 8 + 8 + 16
+    assert C.sizeof(_l.LqView) == 12 * 24 + 8 + 16 + 6 * 24 + 8 + 8 + 16 + 5 * 24
     assert C.sizeof(_l.SolutionView) == 8 * 24 + 16 + 8
     assert [f[0] for f in _l.Config._fields_][:5] == ["nx", "nu", "nc_max", "num_stages", "batch"]
 
 
 def test_abi_version_and_error_strings_without_a_device(libpath):
     lib = _l.load_library()
-    assert lib.o2c_abi_version() == 2
+    assert lib.o2c_abi_version() == 3
     # argument validation happens before any CUDA call
     h = C.c_void_p()
     assert lib.o2c_create(None, C.byref(h)) == 1  # O2C_ERR_INVALID_ARGUMENT

@@ -166,7 +166,7 @@ def _oracle_problem(lq, i, N):
     g = lambda a: None if a is None else a[i]  # noqa: E731
     return orc.Problem(N=N, A=lq.A[i], B=lq.B[i], Hv=lq.Hv[i], Q=lq.Q[i], P=lq.P[i], R=lq.R[i], q=lq.q[i], r=lq.r[i], c=lq.c[i], Qf=lq.Qf[i],
                        qf=lq.qf[i], cf=float(lq.cf[i]), C=g(lq.C), D=g(lq.D), e=g(lq.e), nc=g(lq.nc), x_nom=g(lq.x_nom), u_nom=g(lq.u_nom),
-                       time=lq.time, event=g(lq.event))
+                       time=lq.time, event=g(lq.event), jA=g(lq.jump_A), jHv=g(lq.jump_Hv), jQ=g(lq.jump_Q), jq=g(lq.jump_q), jc=g(lq.jump_c))
 
 
 @pytest.mark.parametrize("algorithm", [o2.ALG_ILQR, o2.ALG_SLQ])
@@ -755,3 +755,62 @@ def test_ilqr_events_dense_and_short_horizons(n, m, nc, N):
         sol = solver.download()
         for i in range(batch):
             check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, (0.6,), what=f"dense events n={n} N={N} #{i}")
+
+
+@pytest.mark.parametrize("n,m,nc,variant", [(12, 4, 0, "ls_reduced"), (5, 3, 2, "ls_full"), (6, 2, 0, "lm_full")])
+def test_slq_events_match_oracle(n, m, nc, variant):
+    """SLQ with events (SLQ.cpp:256-302): inter-event segments integrated separately, joined by computeJumpMap =
+    riccatiTransversalityConditions on the event's jump model data; the continuous rollout restarts weakEpsilon after every event from
+    the LQ jump map (TimeTriggeredRollout.cpp:46-115). Event nodes are shared by the batch, jump data are per problem. Handles with
+    SLQ events use the generic kernels; a later upload without events returns to the specialised ones."""
+    rng = np.random.default_rng(53 + n)
+    batch, N, dt = 5, 13, 0.02
+    events = (3, 8)
+    lq = _random_batch(rng, batch, n, m, N, nc, o2.ALG_SLQ, ragged_nc=False, dt=dt)
+    time = np.zeros(N + 1)
+    for k in range(1, N + 1):
+        time[k] = time[k - 1] + (1e-9 if (k - 1) in events else dt)
+    lq.time = time
+    ev = np.zeros((batch, N + 1), dtype=np.int32)
+    ev[:, list(events)] = 1
+    E = len(events)
+    lq.event = ev
+    lq.jump_A = np.eye(n) + 0.3 * rng.uniform(-1, 1, (batch, E, n, n))
+    lq.jump_Hv = 0.1 * rng.uniform(-1, 1, (batch, E, n))
+    Mq = rng.uniform(-1, 1, (batch, E, n, n))
+    lq.jump_Q = np.einsum("beij,beil->bejl", Mq, Mq) / n + 0.1 * np.eye(n)
+    lq.jump_q = 0.2 * rng.uniform(-1, 1, (batch, E, n))
+    lq.jump_c = rng.uniform(-1, 1, (batch, E))
+    st = o2.Settings(algorithm=o2.ALG_SLQ, hessianCorrectionMultiple=1e-4, timeStep=0.007, preComputeRiccatiTerms=variant == "ls_reduced",
+                     strategy=o2.STRATEGY_LEVENBERG_MARQUARDT if variant == "lm_full" else o2.STRATEGY_LINE_SEARCH,
+                     riccatiMultiple=0.3 if variant == "lm_full" else 0.0)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=True, max_alphas=2) as solver:
+        solver.upload(lq)
+        assert "generic" in solver.kernel_variant
+        solver.solveSequentialRiccatiEquations()
+        solver.rolloutTrajectory((1.0, 0.4))
+        sol = solver.download()
+        assert (sol.status == 0).all()
+        for i in range(batch):
+            check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, (1.0, 0.4), what=f"slq events n={n} #{i}")
+        # the host pipeline (chunked uploads) takes the same path
+        sol_h = solver.solve_host(lq, alpha=1.0, chunk=2)
+        for name in ("K", "dbias", "Sm", "Sv", "s"):
+            assert np.array_equal(getattr(sol_h, name), getattr(sol, name)), name
+        assert np.array_equal(sol_h.x[0], sol.x[0])
+        # event flags that differ between problems are rejected: the time grid (and with it the step schedule) is shared
+        bad = ev.copy()
+        bad[2, events[0]] = 0
+        bad[2, events[0] + 1] = 1
+        lq.event = bad
+        with pytest.raises(o2.O2cError):
+            solver.upload(lq)
+        # without events the schedules are rebuilt and the shape-specialised kernels return where they exist
+        lq.event = None
+        lq.jump_A = lq.jump_Hv = lq.jump_Q = lq.jump_q = lq.jump_c = None
+        lq.time = dt * np.arange(N + 1)
+        solver.upload(lq)
+        assert ("generic" in solver.kernel_variant) == (n != 12)
+        solver.solve()
+        sol = solver.download()
+        check_against_oracle(st, _oracle_problem(lq, 1, N), lq.x0[1], sol, 1, (1.0,), what=f"slq events cleared n={n}")
