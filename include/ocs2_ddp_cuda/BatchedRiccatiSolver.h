@@ -52,8 +52,9 @@ struct HostField {
 
 class BatchedRiccatiSolver {
  public:
-  /** Throws std::runtime_error (message of o2c_last_error) when the configuration is rejected or no CUDA device exists. */
-  explicit BatchedRiccatiSolver(const o2c_config& config) : cfg_(config) {
+  /** Throws std::runtime_error (message of o2c_last_error) when the configuration is rejected or no CUDA device exists.
+   * maxEvents: room for that many events per instance (only SLQ keeps separate jump model data). */
+  explicit BatchedRiccatiSolver(const o2c_config& config, int maxEvents = 0) : cfg_(config), maxEvents_(maxEvents) {
     check(o2c_abi_version() == O2C_ABI_VERSION ? O2C_OK : O2C_ERR_INVALID_ARGUMENT, "ABI version mismatch");
     check(o2c_create(&cfg_, &h_), "o2c_create");
     const std::size_t n = cfg_.nx, m = cfg_.nu, nc = cfg_.nc_max, N = cfg_.num_stages;
@@ -71,7 +72,12 @@ class BatchedRiccatiSolver {
       alloc(K_, m * n, N + 1), alloc(dbias_, m, N + 1), alloc(bias_, m, N + 1);
       alloc(Sm_, n * n, N + 1), alloc(Sv_, n, N + 1), alloc(s_, 1, N + 1);
       status_.assign(cfg_.batch, 0);
-      if (cfg_.algorithm == O2C_ALG_ILQR) event_.assign(static_cast<std::size_t>(cfg_.batch) * nodes_, 0);
+      if (cfg_.algorithm == O2C_ALG_ILQR || maxEvents_ > 0) event_.assign(static_cast<std::size_t>(cfg_.batch) * nodes_, 0);
+      if (cfg_.algorithm == O2C_ALG_SLQ && maxEvents_ > 0) {
+        alloc(jA_, n * n, maxEvents_), alloc(jHv_, n, maxEvents_), alloc(jQ_, n * n, maxEvents_), alloc(jq_, n, maxEvents_), alloc(jc_, 1, maxEvents_);
+        eventCount_.assign(cfg_.batch, 0);
+        lastEventNode_.assign(cfg_.batch, -1);
+      }
       time_.resize(N + 1);
       for (std::size_t k = 0; k <= N; ++k) time_[k] = cfg_.time_step * static_cast<double>(k);
     } catch (...) {
@@ -107,21 +113,36 @@ class BatchedRiccatiSolver {
       if (cfg_.nc_max > 0) copyConstraint(md.stateInputEqConstraint, b, k);
       if (!event_.empty()) event_[static_cast<std::size_t>(b) * nodes_ + k] = 0;
     }
+    if (!eventCount_.empty()) eventCount_[b] = 0, lastEventNode_[b] = -1;
     copyRaw(finalValueFunction.dfdxx, Qf_.at(b, 0), Qf_.block, "finalValueFunction.dfdxx");
     copyRaw(finalValueFunction.dfdx, qf_.at(b, 0), qf_.block, "finalValueFunction.dfdx");
     *cf_.at(b, 0) = finalValueFunction.f;
   }
 
   /**
-   * Marks node `preEventNode` of instance b (ILQR: postEventIndex - 1) as a pre-event node and installs the jump model data
-   * (nominalPrimalData_.modelDataEventTimes[i]: dynamics.dfdx, dynamicsBias, cost.{dfdxx, dfdx, f}); the node keeps the
-   * input-side blocks of setModelData, which shape its controller entry (ILQR.cpp:263-295). Call after setModelData.
+   * Marks node `preEventNode` of instance b (postEventIndex - 1) as a pre-event node and installs the jump model data
+   * (nominalPrimalData_.modelDataEventTimes[i]: dynamics.dfdx, dynamicsBias, cost.{dfdxx, dfdx, f}). Call after setModelData.
+   * ILQR: the node keeps the input-side blocks of setModelData, which shape its controller entry (ILQR.cpp:263-295).
+   * SLQ: the node keeps all of its continuous-time model data; the jump data are stored per event (SLQ.cpp:256-302) — call in
+   * increasing node order; the instances run in lock-step on one time grid, so every instance must mark the same nodes.
    */
   template <class ModelDataT>
   void setEvent(int b, int preEventNode, const ModelDataT& modelDataEventTime) {
     checkInstance(b);
-    if (cfg_.algorithm != O2C_ALG_ILQR) throw std::runtime_error("[BatchedRiccatiSolver] events are provided for ILQR only");
     if (preEventNode < 0 || static_cast<std::size_t>(preEventNode) >= nodes_) throw std::runtime_error("[BatchedRiccatiSolver] event node out of range");
+    if (cfg_.algorithm == O2C_ALG_SLQ) {
+      if (maxEvents_ <= 0 || eventCount_[b] >= maxEvents_) throw std::runtime_error("[BatchedRiccatiSolver] more events than maxEvents");
+      if (preEventNode <= lastEventNode_[b]) throw std::runtime_error("[BatchedRiccatiSolver] SLQ events must be set in increasing node order");
+      const int e = eventCount_[b]++;
+      lastEventNode_[b] = preEventNode;
+      copyBlock(modelDataEventTime.dynamics.dfdx, jA_, b, e, "event dynamics.dfdx");
+      copyBlock(modelDataEventTime.dynamicsBias, jHv_, b, e, "event dynamicsBias");
+      copyBlock(modelDataEventTime.cost.dfdxx, jQ_, b, e, "event cost.dfdxx");
+      copyBlock(modelDataEventTime.cost.dfdx, jq_, b, e, "event cost.dfdx");
+      *jc_.at(b, e) = modelDataEventTime.cost.f;
+      event_[static_cast<std::size_t>(b) * nodes_ + preEventNode] = 1;
+      return;
+    }
     const int k = preEventNode;
     copyBlock(modelDataEventTime.dynamics.dfdx, A_, b, k, "event dynamics.dfdx");
     copyBlock(modelDataEventTime.dynamicsBias, Hv_, b, k, "event dynamicsBias");
@@ -411,6 +432,8 @@ class BatchedRiccatiSolver {
     bool any = false;
     for (int32_t flag : event_) any = any || flag != 0;
     if (any) v.event = event_.data(), v.event_problem_stride = static_cast<int64_t>(nodes_), v.event_node_stride = 1;
+    if (any && cfg_.algorithm == O2C_ALG_SLQ)
+      v.jump_A = jA_.field(), v.jump_Hv = jHv_.field(), v.jump_Q = jQ_.field(), v.jump_q = jq_.field(), v.jump_c = jc_.field();
     return v;
   }
   void fetchRollouts(int nAlpha) {
@@ -434,6 +457,9 @@ class BatchedRiccatiSolver {
   std::size_t nodes_ = 0;
   HostField A_, B_, Hv_, Q_, P_, R_, q_, r_, c_, C_, D_, e_, Qf_, qf_, cf_, x0_, xNom_, uNom_;
   HostField K_, dbias_, bias_, Sm_, Sv_, s_;
+  HostField jA_, jHv_, jQ_, jq_, jc_;  // SLQ jump model data [instance][event]
+  int maxEvents_ = 0;
+  std::vector<int> eventCount_, lastEventNode_;
   std::vector<int32_t> ncActive_, event_, status_;
   std::vector<double> time_, xRoll_, uRoll_;
   std::vector<void*> owned_;

@@ -649,8 +649,8 @@ void rk4_step(F&& f, vec& y, double t, double h, vec& k1, vec& k2, vec& k3, vec&
 inline bool less_with_sign(double t1, double t2) { return (t2 - t1) > std::numeric_limits<double>::epsilon(); }
 inline bool less_eq_with_sign(double t1, double t2) { return (t1 - t2) <= std::numeric_limits<double>::epsilon(); }
 
-// SLQ::solveSequentialRiccatiEquations / riccatiEquationsWorker / integrateRiccatiEquationNominalTime (SLQ.cpp:174-302, no
-// events) and SLQ::calculateControllerWorker (SLQ.cpp:127-169)
+// SLQ::solveSequentialRiccatiEquations / riccatiEquationsWorker / integrateRiccatiEquationNominalTime (SLQ.cpp:174-302, events
+// included) and SLQ::calculateControllerWorker (SLQ.cpp:127-169)
 int backward_slq(const orc_settings& st, const orc_problem& pb, orc_solution* sol) {
   const int n = pb.nx, m = pb.nu, N = pb.N;
   int status = ORC_STATUS_OK;

@@ -49,7 +49,7 @@ struct LinearController {
 // one problem in the oracle's flat layout
 struct Flat {
   int n, m, nc, N, nodes;
-  std::vector<double> A, B, Hv, Q, P, R, q, r, c, C, D, e, Qf, qf, cf, x0, xnom, unom, time;
+  std::vector<double> A, B, Hv, Q, P, R, q, r, c, C, D, e, Qf, qf, cf, x0, xnom, unom, time, jA, jHv, jQ, jq, jc;
   std::vector<int32_t> ncActive, event;
   orc_problem view(bool nominal, bool ragged, bool events) const {
     orc_problem p{};
@@ -62,6 +62,7 @@ struct Flat {
     if (nominal) p.x_nom = xnom.data(), p.u_nom = unom.data();
     p.time = time.data();
     if (events) p.event = event.data();
+    if (events && !jA.empty()) p.jA = jA.data(), p.jHv = jHv.data(), p.jQ = jQ.data(), p.jq = jq.data(), p.jc = jc.data();
     return p;
   }
 };
@@ -99,7 +100,9 @@ int runCase(const Case& cs) {
   ost.algorithm = cs.algorithm, ost.reduced_form = 1, ost.strategy = ORC_STRATEGY_LINE_SEARCH, ost.hessian_correction = ORC_HC_DIAGONAL_SHIFT;
   ost.hessian_multiple = 1e-5, ost.time_step = dt;
 
-  ocs2_ddp_cuda::BatchedRiccatiSolver solver(cfg);
+  const bool slqEvents = cs.events && cs.algorithm == ORC_ALG_SLQ;
+  const int slqEventNodes[2] = {3, 8};  // pre-event nodes, the same for every instance (one time grid)
+  ocs2_ddp_cuda::BatchedRiccatiSolver solver(cfg, slqEvents ? 2 : 0);
   std::vector<Flat> flats(cs.batch);
   uint64_t rng = 0x9e3779b97f4a7c15ull + n * 131 + m;
   for (int b = 0; b < cs.batch; ++b) {
@@ -114,6 +117,8 @@ int runCase(const Case& cs) {
                          f.q.data(), f.r.data(), f.c.data(), f.C.data(), f.D.data(), f.e.data(), f.Qf.data(), f.qf.data(), f.cf.data(), f.x0.data());
     f.time.resize(N + 1);
     for (int k = 0; k <= N; ++k) f.time[k] = dt * k;
+    if (slqEvents)  // the post-event node is stamped weakEpsilon after the pre-event node (RolloutBase.cpp:62-64)
+      for (int k = 1; k <= N; ++k) f.time[k] = f.time[k - 1] + ((k - 1 == slqEventNodes[0] || k - 1 == slqEventNodes[1]) ? 1e-9 : dt);
     f.xnom.resize((size_t)(N + 1) * n), f.unom.resize((size_t)(N + 1) * m);
     for (auto& x : f.xnom) x = 0.3 * uni(rng);
     for (auto& u : f.unom) u = 0.3 * uni(rng);
@@ -144,8 +149,8 @@ int runCase(const Case& cs) {
     fin.dfdxx.set(f.Qf.data(), n, n), fin.dfdx.set(f.qf.data(), n, 1), fin.f = f.cf[0];
     solver.setModelData(b, traj, fin);
     if (cs.events) {
-      for (int j = 0; j < (b % 3); ++j) {  // 0, 1 or 2 events per instance
-        const int k = (int)(lcg(rng) >> 33) % nodes;
+      for (int j = 0; j < (slqEvents ? 2 : b % 3); ++j) {  // ILQR: 0, 1 or 2 events per instance at random nodes
+        const int k = slqEvents ? slqEventNodes[j] : (int)(lcg(rng) >> 33) % nodes;
         ModelData jump;
         jump.stateDim = n, jump.inputDim = m;
         jump.dynamics.dfdx.resize(n, n), jump.dynamicsBias.resize(n), jump.cost.dfdxx.resize(n, n), jump.cost.dfdx.resize(n);
@@ -156,7 +161,16 @@ int runCase(const Case& cs) {
         }
         jump.cost.f = 0.4 * uni(rng);
         solver.setEvent(b, k, jump);
-        f.event[k] = 1;  // the oracle reads the jump data from the node's own A, Hv, Q, q, c
+        f.event[k] = 1;
+        if (slqEvents) {  // SLQ keeps the jump data per event
+          f.jA.insert(f.jA.end(), jump.dynamics.dfdx.v.begin(), jump.dynamics.dfdx.v.end());
+          f.jHv.insert(f.jHv.end(), jump.dynamicsBias.v.begin(), jump.dynamicsBias.v.end());
+          f.jQ.insert(f.jQ.end(), jump.cost.dfdxx.v.begin(), jump.cost.dfdxx.v.end());
+          f.jq.insert(f.jq.end(), jump.cost.dfdx.v.begin(), jump.cost.dfdx.v.end());
+          f.jc.push_back(jump.cost.f);
+          continue;
+        }
+        // ILQR: the oracle reads the jump data from the node's own A, Hv, Q, q, c
         std::copy(jump.dynamics.dfdx.v.begin(), jump.dynamics.dfdx.v.end(), &f.A[(size_t)k * n * n]);
         std::copy(jump.dynamicsBias.v.begin(), jump.dynamicsBias.v.end(), &f.Hv[(size_t)k * n]);
         std::copy(jump.cost.dfdxx.v.begin(), jump.cost.dfdxx.v.end(), &f.Q[(size_t)k * n * n]);
@@ -321,6 +335,7 @@ int main(int argc, char** argv) {
       {"generic slq nc=2", ORC_ALG_SLQ, 6, 4, 2, 16, 3, false, false, false, "generic"},
       {"ilqr events", ORC_ALG_ILQR, 6, 4, 0, 14, 6, true, false, true, "generic"},
       {"legged ilqr events", ORC_ALG_ILQR, 24, 24, 0, 12, 4, false, false, true, "ilqr_wpp"},
+      {"quadrotor slq events", ORC_ALG_SLQ, 12, 4, 0, 14, 4, true, false, true, "generic"},
   };
   int failures = 0;
   try {
