@@ -808,27 +808,31 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
       double ys[NX], ysv = Svi, acc[NX], accv = Svi, accs = sval;
 #pragma unroll
       for (int j = 0; j < NX; ++j) ys[j] = acc[j] = Srow[j];
+      double prev_al = -1.0;  // lerp weights lie in [0, 1]
 #pragma unroll 1
       for (int stg = 0; stg < 4; ++stg) {
         const double al = sp.alpha[stg], be = 1.0 - al;
-        // lerped data: column i of A, row i of B~ -> shared (broadcast operands); lane-private pieces stay in registers
-        if (NX % 2 == 0) {
+        // lerped data: column i of A, row i of B~ -> shared (broadcast operands); lane-private pieces stay in registers. Stages 2 and 3 of
+        // RK4 share their time, hence their data: the shared operands are still in place (warp-uniform test on the schedule)
+        if (al != prev_al) {
+          if (NX % 2 == 0) {
 #pragma unroll
-          for (int kk = 0; kk < NX; kk += 2) {
-            const double2 v0 = ld2(A0 + kk + NX * i), v1 = ld2(A1 + kk + NX * i);
-            *reinterpret_cast<double2*>(sm + S::sAl + kk + NX * i) = make_double2(fma(al, v0.x, be * v1.x), fma(al, v0.y, be * v1.y));
+            for (int kk = 0; kk < NX; kk += 2) {
+              const double2 v0 = ld2(A0 + kk + NX * i), v1 = ld2(A1 + kk + NX * i);
+              *reinterpret_cast<double2*>(sm + S::sAl + kk + NX * i) = make_double2(fma(al, v0.x, be * v1.x), fma(al, v0.y, be * v1.y));
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < NX; ++kk) sm[S::sAl + kk + NX * i] = fma(al, A0[kk + NX * i], be * A1[kk + NX * i]);
           }
-        } else {
 #pragma unroll
-          for (int kk = 0; kk < NX; ++kk) sm[S::sAl + kk + NX * i] = fma(al, A0[kk + NX * i], be * A1[kk + NX * i]);
+          for (int l = 0; l < NU; ++l) sm[S::sBl + i + NX * l] = fma(al, Bt0[i + NX * l], be * Bt1[i + NX * l]);
+          sm[S::sHv + i] = fma(al, hv0, be * hv1);
+          prev_al = al;
         }
         double ptl[NU];
 #pragma unroll
-        for (int l = 0; l < NU; ++l) {
-          sm[S::sBl + i + NX * l] = fma(al, Bt0[i + NX * l], be * Bt1[i + NX * l]);
-          ptl[l] = fma(al, pt0[l], be * pt1[l]);
-        }
-        sm[S::sHv + i] = fma(al, hv0, be * hv1);
+        for (int l = 0; l < NU; ++l) ptl[l] = fma(al, pt0[l], be * pt1[l]);
         sm[S::sSv + i] = ysv;
         __syncwarp();
         // M_i = S_i A, G'_i = P~(:,i)' + S_i B~, G~v on lanes < nu
