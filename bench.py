@@ -397,7 +397,7 @@ def run_e2e(o2, np, torch, solver, st, n, m, nc, alg, eb, args, dist, world, bar
     def step():
         _l.check(lib.o2c_solve_host(solver.handle, C.byref(lv), C.byref(sv), 1.0, eb, 0))  # returns after the last D2H completed
 
-    for _ in range(2):
+    for _ in range(max(2, args.warmup)):
         step()
     barrier()
     t0 = time.perf_counter()
@@ -412,6 +412,9 @@ def run_e2e(o2, np, torch, solver, st, n, m, nc, alg, eb, args, dist, world, bar
     secs = float(tt.item())
     return {"value": world * eb * args.steps / secs, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "problems_per_step": eb, "ms_per_step": 1e3 * secs / args.steps,
+            "h2d_gb_per_s": h2d * args.steps / secs / 1e9, "d2h_gb_per_s": d2h * args.steps / secs / 1e9,
+            "bound": "PCIe: the host->device copy of the LQ data runs at the link rate measured on this pool (tools/pcie_bw.py: 55.6 GB/s one "
+                     "way, about 45 GB/s each way with both directions busy); the kernels are hidden behind it",
             "how": "o2c_solve_host: pinned host SoA buffers -> chunked H2D, pack, sweep+rollout, unpack, D2H on 3 overlapping stream lanes; "
                    "host wall clock around the blocking call (it returns after the last D2H)"}
 
