@@ -130,7 +130,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     threads = args.cpu_threads or cores
     st = orc.make_settings(algorithm=alg, reduced_form=True, hessian_multiple=eps, time_step=DT)
-    sample = args.cpu_sample or max(threads * 4, 32)
+    sample = args.cpu_sample or max(threads * 64, 256)  # ~0.4 s of CPU work per step on 16 threads: long enough to keep every thread busy
     for w in range(args.warmup):
         orc.baseline_run(st, 1, w * sample, min(sample, threads), n, m, nc, N_STAGES, DT, threads)
     total_s = 0.0
