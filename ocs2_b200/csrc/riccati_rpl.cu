@@ -1233,7 +1233,8 @@ bool rpl_slq_supported(const Layout& L, const SolverSettings& st, const DeviceBu
   if (!(st.algorithm == O2C_ALG_SLQ && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1 && L.nodes == L.N + 1))
     return false;  // SLQ events (jump steps in the schedule) go through the generic kernels
-  return layout_matches<12, 4, 0>(L);
+  if (L.ncmax != 0) return false;
+  return layout_matches<12, 4, 0>(L) || layout_matches<10, 3, 0>(L) || layout_matches<4, 1, 0>(L);
 }
 
 cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin,
@@ -1252,12 +1253,14 @@ cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const Devi
   a.begin = begin;
   a.count = count;
   a.eps = st.eps;
-  return launch_slq<12, 4>(a, stream);
+  if (layout_matches<12, 4, 0>(L)) return launch_slq<12, 4>(a, stream);
+  if (layout_matches<10, 3, 0>(L)) return launch_slq<10, 3>(a, stream);
+  return launch_slq<4, 1>(a, stream);
 }
 
 bool rpl_rollout_cont_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   return st.algorithm == O2C_ALG_SLQ && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1 &&
-         L.nodes == L.N + 1 && layout_matches<12, 4, 0>(L);
+         L.nodes == L.N + 1 && L.ncmax == 0 && (layout_matches<12, 4, 0>(L) || layout_matches<10, 3, 0>(L) || layout_matches<4, 1, 0>(L));
 }
 
 cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,
@@ -1283,13 +1286,15 @@ cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, c
   a.batch = batch;
   a.begin = begin;
   a.count = count;
-  return launch_ro<12, 4>(a, n_alpha, stream);
+  if (layout_matches<12, 4, 0>(L)) return launch_ro<12, 4>(a, n_alpha, stream);
+  if (layout_matches<10, 3, 0>(L)) return launch_ro<10, 3>(a, n_alpha, stream);
+  return launch_ro<4, 1>(a, n_alpha, stream);
 }
 
 bool rpl_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   if (!settings_match(st, buf, L)) return false;
   if (L.ncmax > 0 && buf.nc != nullptr) return false;  // ragged per-node constraint counts: the generic kernel handles those
-  return layout_matches<10, 3, 0>(L) || layout_matches<4, 1, 0>(L) || layout_matches<9, 9, 3>(L);
+  return layout_matches<10, 3, 0>(L) || layout_matches<4, 1, 0>(L) || layout_matches<9, 9, 3>(L) || layout_matches<12, 4, 0>(L);
 }
 
 cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int begin,
@@ -1319,6 +1324,7 @@ cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const Dev
             : (nom ? launch<NX, NU, NC, true, false>(a, stream) : launch<NX, NU, NC, false, false>(a, stream))
   if (layout_matches<10, 3, 0>(L)) O2C_RPL_DISPATCH(10, 3, 0);
   if (layout_matches<9, 9, 3>(L)) O2C_RPL_DISPATCH(9, 9, 3);
+  if (layout_matches<12, 4, 0>(L)) O2C_RPL_DISPATCH(12, 4, 0);
   O2C_RPL_DISPATCH(4, 1, 0);
 #undef O2C_RPL_DISPATCH
 }

@@ -327,7 +327,9 @@ def test_legged_dmma_kernel_uploaded_data_subrange_and_status():
 
 # ---- the row-per-lane kernels (small shapes: several problems per warp) ----
 @pytest.mark.parametrize("shape,algorithm,variant", [("ballbot", o2.ALG_ILQR, "ilqr_rpl_kernel"), ("manipulator", o2.ALG_ILQR, "ilqr_rpl_kernel"),
-                                                     ("cartpole", o2.ALG_ILQR, "ilqr_rpl_kernel"), ("quadrotor", o2.ALG_SLQ, "slq_rpl_kernel")])
+                                                     ("cartpole", o2.ALG_ILQR, "ilqr_rpl_kernel"), ("quadrotor", o2.ALG_SLQ, "slq_rpl_kernel"),
+                                                     ("quadrotor", o2.ALG_ILQR, "ilqr_rpl_kernel"), ("ballbot", o2.ALG_SLQ, "slq_rpl_kernel"),
+                                                     ("cartpole", o2.ALG_SLQ, "slq_rpl_kernel")])
 @pytest.mark.parametrize("batch,begin,count", [(1, 0, 1), (2, 1, 1), (7, 0, 7), (11, 3, 5)])
 def test_rpl_kernels_partial_warps_and_subranges(shape, algorithm, variant, batch, begin, count):
     """A warp carries 32 // nx problems: batches that do not fill the last warp, and sub-range solves, must not touch neighbours."""
@@ -455,7 +457,8 @@ def test_line_search_argument_checks():
 
 @pytest.mark.parametrize("shape,algorithm,variant", [("legged", o2.ALG_ILQR, "ilqr_wpp_kernel"), ("ballbot", o2.ALG_ILQR, "ilqr_rpl_kernel"),
                                                      ("manipulator", o2.ALG_ILQR, "ilqr_rpl_kernel"), ("cartpole", o2.ALG_ILQR, "ilqr_rpl_kernel"),
-                                                     ("quadrotor", o2.ALG_SLQ, "slq_rpl_kernel")])
+                                                     ("quadrotor", o2.ALG_SLQ, "slq_rpl_kernel"), ("quadrotor", o2.ALG_ILQR, "ilqr_rpl_kernel"),
+                                                     ("ballbot", o2.ALG_SLQ, "slq_rpl_kernel"), ("cartpole", o2.ALG_SLQ, "slq_rpl_kernel")])
 def test_fast_kernels_with_nominal_trajectories(shape, algorithm, variant):
     """The real DDP iteration linearises about a nominal trajectory: bias = u_nom - K x_nom and the rollout is
     x_{k+1} = x_nom_{k+1} + A dx + B du + Hv (xdot = A (x - x_nom(t)) + B (u - u_nom(t)) + Hv for SLQ). The specialised kernels keep
@@ -731,7 +734,7 @@ def test_empty_problem_range_is_a_no_op(alg, n, m, nc):
             assert np.array_equal(getattr(got, name), getattr(want, name)), name
 
 
-@pytest.mark.parametrize("n,m,nc", [(24, 24, 0), (10, 3, 0), (9, 9, 3), (7, 2, 0)])
+@pytest.mark.parametrize("n,m,nc", [(24, 24, 0), (10, 3, 0), (9, 9, 3), (12, 4, 0), (7, 2, 0)])
 @pytest.mark.parametrize("N", [1, 2, 9])
 def test_ilqr_events_dense_and_short_horizons(n, m, nc, N):
     """Event nodes everywhere (problem 0), at the first and last node only (problem 1), alternating (problem 2), none (problem 3):
