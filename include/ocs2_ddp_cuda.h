@@ -212,6 +212,23 @@ o2c_error o2c_line_search_result(o2c_handle* handle, double* step_length, int32_
 o2c_error o2c_download_flattened_controller(o2c_handle* handle, float* host_out, double step_length, int32_t problem_begin,
                                             int32_t problem_count);
 
+/* ---- the step before: ILQR discretisation of continuous-time linearisations ----
+ * ILQR::discreteLQWorker (ocs2_ddp/src/ILQR.cpp:137-157) with rk4SensitivityDiscretization
+ * (ocs2_core/src/integration/SensitivityIntegratorImpl.cpp:130-169): the discrete A, B of the interval after node k are assembled from
+ * the four stage linearisations (dfdx, dfdu) of one RK4 step of length dt_k — k1 at (t, x), k2 at (t + dt/2, x + dt/2 f1), k3 at
+ * (t + dt/2, x + dt/2 f2), k4 at (t + dt, x + dt f3). The stage evaluations need the caller's system dynamics; this call does the
+ * batched dense part on the device: the input sensitivity chain (k2.dfdu += dt/2 k2.dfdx k1.dfdu, ...), the state sensitivity chain
+ * (k2.dfdx += dt/2 k2.dfdx k1.dfdx, ...), the assembly A = I + dt/6 k1 + dt/3 k2 + dt/3 k3 + dt/6 k4 (B alike), Hv := 0, and
+ * (scale_cost != 0) modelData.cost *= dt_k on the resident Q, P, R, q, r, c of the node. A node with dt_k == 0 keeps the
+ * continuous-time data (k1) unscaled (ILQR.cpp:123-130). ILQR handles only; all pointers of the view are DEVICE memory except dt. */
+typedef struct o2c_discretization_view {
+  o2c_field dfdx[4], dfdu[4]; /* n*n and n*m blocks per (problem, node) of the stages k1..k4; with stages == 1 only [0] is read */
+  const double* dt;           /* HOST array of num_stages step lengths, or NULL = time[k+1] - time[k] of the handle's time grid */
+  int32_t stages;             /* 4, or 1 for a model that is constant over the step (k1 = k2 = k3 = k4) */
+} o2c_discretization_view;
+o2c_error o2c_discretize(o2c_handle* handle, const o2c_discretization_view* device_view, int32_t scale_cost, int32_t problem_begin,
+                         int32_t problem_count);
+
 /* ---- end-to-end convenience: host buffers in, host buffers out, chunked H2D / compute / D2H pipeline ---- */
 o2c_error o2c_solve_host(o2c_handle* handle, const o2c_lq_view* host_lq, const o2c_solution_view* host_solution, double alpha,
                          int32_t problem_count, int32_t chunk);

@@ -52,6 +52,7 @@ struct o2c_handle {
   int *d_nc = nullptr, *d_status = nullptr;
   double *d_ls_merit = nullptr, *d_ls_base = nullptr, *d_ls_is = nullptr, *d_ls_step = nullptr, *d_ls_basein = nullptr;  // line search
   int* d_ls_index = nullptr;
+  double* d_dt = nullptr;  // step lengths of o2c_discretize [N], allocated on first use
   float* d_flat = nullptr;  // flattened controllers of the whole batch (o2c_download_flattened_controller), allocated on first use
   int* d_event = nullptr;       // [batch][nodes] pre-event flags, allocated by the first upload that carries events
   bool events_present = false;
@@ -707,7 +708,7 @@ void release(o2c_handle* h) {
   }
   void* ptrs[] = {h->d_lq,  h->d_term, h->d_xnom, h->d_unom,   h->d_x0,        h->d_time,    h->d_sol,
                   h->d_xs,  h->d_us,   h->d_alphas, h->d_nc,   h->d_status,    h->d_slq_steps, h->d_ro_steps,
-                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event, h->d_flat, h->d_jump};
+                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event, h->d_flat, h->d_jump, h->d_dt};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
@@ -1122,6 +1123,45 @@ o2c_error o2c_download_flattened_controller(o2c_handle* h, float* host_out, doub
   h->launches += 1;
   O2C_CUDA(cudaMemcpyAsync(host_out, dev, sizeof(float) * per * count, cudaMemcpyDeviceToHost, stream));
   O2C_CUDA(cudaStreamSynchronize(stream));
+  return O2C_OK;
+}
+
+o2c_error o2c_discretize(o2c_handle* h, const o2c_discretization_view* v, int32_t scale_cost, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  if (!v) return fail(O2C_ERR_INVALID_ARGUMENT, "null view");
+  if (h->st.algorithm != O2C_ALG_ILQR) return fail(O2C_ERR_UNSUPPORTED, "discretisation belongs to the ILQR path (SLQ consumes continuous-time data)");
+  if (v->stages != 1 && v->stages != 4) return fail(O2C_ERR_INVALID_ARGUMENT, "stages must be 1 or 4");
+  for (int s = 0; s < v->stages; ++s)
+    if (!v->dfdx[s].ptr || !v->dfdu[s].ptr) return fail(O2C_ERR_INVALID_ARGUMENT, "dfdx / dfdu of every stage are required");
+  const int N = h->L.N;
+  std::vector<double> dt(N);
+  if (v->dt) {
+    std::copy(v->dt, v->dt + N, dt.begin());
+  } else {
+    if (!h->time_set) return fail(O2C_ERR_NOT_READY, "no step lengths: pass dt or set the node times first");
+    for (int k = 0; k < N; ++k) dt[k] = h->time[k + 1] - h->time[k];
+  }
+  for (double d : dt)
+    if (!(d >= 0.0) || !std::isfinite(d)) return fail(O2C_ERR_INVALID_ARGUMENT, "step lengths must be finite and non-negative");
+  if (5 * (size_t)h->L.n * h->L.n + 4 * (size_t)h->L.n * h->L.m > 227 * 1024 / sizeof(double))
+    return fail(O2C_ERR_UNSUPPORTED, "state / input dimensions too large for the discretisation kernel");
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t stream = h->lanes[0].stream;
+  if (!h->d_dt) O2C_CUDA(cudaMalloc(&h->d_dt, sizeof(double) * (size_t)N));
+  O2C_CUDA(cudaMemcpyAsync(h->d_dt, dt.data(), sizeof(double) * N, cudaMemcpyHostToDevice, stream));
+  O2C_CUDA(cudaStreamSynchronize(stream));  // dt is pageable and about to go out of scope
+  DiscretizeArgs a{};
+  for (int s = 0; s < 4; ++s) {
+    const int src = v->stages == 4 ? s : 0;
+    a.dfdx[s] = FieldDev{v->dfdx[src].ptr, (long long)v->dfdx[src].problem_stride, (long long)v->dfdx[src].node_stride};
+    a.dfdu[s] = FieldDev{v->dfdu[src].ptr, (long long)v->dfdu[src].problem_stride, (long long)v->dfdu[src].node_stride};
+  }
+  a.dt = h->d_dt;
+  a.stages = v->stages;
+  a.scale_cost = scale_cost != 0;
+  O2C_CUDA(launch_discretize(h->L, a, h->d_lq, begin, count, stream));
+  h->launches += 1;
   return O2C_OK;
 }
 

@@ -162,6 +162,14 @@ cudaError_t launch_pack(const Layout& L, const LqViewDev& v, double* lq, double*
 cudaError_t launch_unpack(const Layout& L, const SolViewDev& v, const double* sol, const double* xs, const double* us, const int* status,
                           int out_nodes, int n_alpha, int batch, int begin, int count, cudaStream_t stream);
 
+// ILQR::discreteLQWorker on caller-supplied stage linearisations (device, strided): A, B, Hv of the records, cost blocks scaled by dt
+struct DiscretizeArgs {
+  FieldDev dfdx[4], dfdu[4];
+  const double* dt;  // device, [N]
+  int stages, scale_cost;
+};
+cudaError_t launch_discretize(const Layout& L, const DiscretizeArgs& a, double* lq, int begin, int count, cudaStream_t stream);
+
 // controller records -> float wire format of LinearController::flatten, out[count][N+1][m*(n+1)] (device)
 cudaError_t launch_flatten(const Layout& L, const double* sol, float* out, double alpha, int begin, int count, cudaStream_t stream);
 

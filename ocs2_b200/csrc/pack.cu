@@ -105,7 +105,82 @@ __global__ void __launch_bounds__(128) flatten_kernel(Layout L, const double* __
   }
 }
 
+// rk4SensitivityDiscretization (SensitivityIntegratorImpl.cpp:130-169) + ILQR::discreteLQWorker (ILQR.cpp:137-157); one CTA per
+// (problem, node), all eight stage matrices in shared memory
+__device__ __forceinline__ void cta_gemm_acc(int M, int N, int K, double alpha, const double* A, const double* B, double* C) {
+  // C(MxN) += alpha * A(MxK) * B(KxN), column-major, leading dimensions = rows
+  for (int idx = threadIdx.x; idx < M * N; idx += blockDim.x) {
+    const int i = idx % M, j = idx / M;
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) acc = fma(A[i + k * M], B[k + j * K], acc);
+    C[idx] += alpha * acc;
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(128) discretize_kernel(Layout L, DiscretizeArgs a, double* __restrict__ lq, int begin, int count) {
+  extern __shared__ __align__(16) double dsm[];
+  const int lp = blockIdx.x / L.N, node = blockIdx.x % L.N;
+  if (lp >= count) return;
+  const int n = L.n, m = L.m, nn = n * n, nm = n * m;
+  double* A[4] = {dsm, dsm + nn, dsm + 2 * nn, dsm + 3 * nn};
+  double* B[4] = {dsm + 4 * nn, dsm + 4 * nn + nm, dsm + 4 * nn + 2 * nm, dsm + 4 * nn + 3 * nm};
+  double* tmp = dsm + 4 * nn + 4 * nm;
+  for (int s = 0; s < 4; ++s) {
+    const int src = a.stages == 4 ? s : 0;
+    const double* pa = a.dfdx[src].ptr + (long long)lp * a.dfdx[src].ps + (long long)node * a.dfdx[src].ns;
+    const double* pb = a.dfdu[src].ptr + (long long)lp * a.dfdu[src].ps + (long long)node * a.dfdu[src].ns;
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) A[s][i] = pa[i];
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) B[s][i] = pb[i];
+  }
+  __syncthreads();
+  const double dt = a.dt[node];
+  double* rec = lq + ((size_t)(begin + lp) * L.nodes + node) * L.rec;
+  if (dt == 0.0) {  // zero-length interval: the node keeps its continuous-time model data (ILQR.cpp:123-130)
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) rec[L.oA + i] = A[0][i];
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) rec[L.oB + i] = B[0][i];
+    return;
+  }
+  const double h2 = dt / 2.0, h6 = dt / 6.0, h3 = dt / 3.0;
+  // input sensitivity: dk2/du += dt/2 k2.dfdx dk1/du, dk3/du += dt/2 k3.dfdx dk2/du, dk4/du += dt k4.dfdx dk3/du
+  cta_gemm_acc(n, m, n, h2, A[1], B[0], B[1]);
+  cta_gemm_acc(n, m, n, h2, A[2], B[1], B[2]);
+  cta_gemm_acc(n, m, n, dt, A[3], B[2], B[3]);
+  // state sensitivity: one temporary per product to avoid aliasing, as the reference does
+  for (int s = 1; s < 4; ++s) {
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) tmp[i] = 0.0;
+    __syncthreads();
+    cta_gemm_acc(n, n, n, s == 3 ? dt : h2, A[s], A[s - 1], tmp);
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) A[s][i] += tmp[i];
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+    const double v = h6 * A[0][idx] + h3 * A[1][idx] + h3 * A[2][idx] + h6 * A[3][idx];
+    rec[L.oA + idx] = v + ((idx % n == idx / n) ? 1.0 : 0.0);
+  }
+  for (int idx = threadIdx.x; idx < nm; idx += blockDim.x) rec[L.oB + idx] = h6 * B[0][idx] + h3 * B[1][idx] + h3 * B[2][idx] + h6 * B[3][idx];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) rec[L.oHv + i] = 0.0;  // dynamicsBias.setZero (ILQR.cpp:144)
+  if (a.scale_cost) {  // modelData.cost *= timeStep (ILQR.cpp:149-150)
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) rec[L.oQ + i] *= dt;
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) rec[L.oP + i] *= dt;
+    for (int i = threadIdx.x; i < m * m; i += blockDim.x) rec[L.oR + i] *= dt;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) rec[L.oq + i] *= dt;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) rec[L.or_ + i] *= dt;
+    if (threadIdx.x == 0) rec[L.oc] *= dt;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_discretize(const Layout& L, const DiscretizeArgs& a, double* lq, int begin, int count, cudaStream_t stream) {
+  const long long blocks = (long long)count * L.N;
+  if (blocks > 2147483647LL) return cudaErrorInvalidValue;
+  if (blocks == 0) return cudaSuccess;
+  const size_t smem = sizeof(double) * (size_t)(5 * L.n * L.n + 4 * L.n * L.m);
+  cudaError_t e = cudaFuncSetAttribute(discretize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  discretize_kernel<<<(unsigned)blocks, 128, smem, stream>>>(L, a, lq, begin, count);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_flatten(const Layout& L, const double* sol, float* out, double alpha, int begin, int count, cudaStream_t stream) {
   const long long blocks = (long long)count * (L.N + 1);

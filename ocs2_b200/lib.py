@@ -53,6 +53,10 @@ class LqView(C.Structure):
         (n, Field) for n in ("jump_A", "jump_Hv", "jump_Q", "jump_q", "jump_c")]
 
 
+class DiscretizationView(C.Structure):
+    _fields_ = [("dfdx", Field * 4), ("dfdu", Field * 4), ("dt", C.c_void_p), ("stages", C.c_int32)]
+
+
 class SolutionView(C.Structure):
     _fields_ = [(n, Field) for n in ("K", "dbias", "bias", "Sm", "Sv", "s", "x", "u")] + [
         ("x_alpha_stride", C.c_int64), ("u_alpha_stride", C.c_int64), ("status", C.c_void_p)]
@@ -63,7 +67,7 @@ EXPORTED_SYMBOLS = [
     "o2c_device_lq_view", "o2c_device_solution_view", "o2c_rollout_num_nodes", "o2c_rollout_times", "o2c_upload", "o2c_import_device",
     "o2c_download", "o2c_set_time", "o2c_backward", "o2c_rollout", "o2c_solve", "o2c_launch_count", "o2c_kernel_variant",
     "o2c_solve_host", "o2c_generate_synthetic", "o2c_host_alloc", "o2c_host_free", "o2c_line_search", "o2c_line_search_result",
-    "o2c_download_flattened_controller",
+    "o2c_download_flattened_controller", "o2c_discretize",
 ]
 
 
@@ -113,6 +117,7 @@ def load_library():
         "o2c_line_search": [hp, C.POINTER(LineSearchSettings), _dp, C.c_int32, C.c_int32],
         "o2c_line_search_result": [hp, _dp, _ip, _dp, _dp, _dp, _dp, _ip, C.c_int32, C.c_int32],
         "o2c_download_flattened_controller": [hp, C.POINTER(C.c_float), C.c_double, C.c_int32, C.c_int32],
+        "o2c_discretize": [hp, C.POINTER(DiscretizationView), C.c_int32, C.c_int32, C.c_int32],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

@@ -267,6 +267,12 @@ class BatchedLqSolver:
         cnt = self.batch - problem_begin if problem_count is None else problem_count
         _l.check(self._lib.o2c_import_device(self._h, C.byref(view), problem_begin, cnt))
 
+    def discretize(self, view: "_l.DiscretizationView", scale_cost: bool = True, problem_begin: int = 0, problem_count: Optional[int] = None):
+        """o2c_discretize: ILQR::discreteLQWorker on caller-supplied stage linearisations in device memory (rk4SensitivityDiscretization):
+        writes A, B, Hv = 0 of the resident records and scales the resident cost blocks by the step length."""
+        cnt = self.batch - problem_begin if problem_count is None else problem_count
+        _l.check(self._lib.o2c_discretize(self._h, C.byref(view), 1 if scale_cost else 0, problem_begin, cnt))
+
     def set_time(self, time: Sequence[float]):
         t = np.ascontiguousarray(time, dtype=np.float64)
         assert t.shape == (self.N + 1,)

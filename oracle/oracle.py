@@ -436,6 +436,28 @@ def unflatten_controller(flat, n, m):
     return rows[:, :, 0].copy(), rows[:, :, 1:].copy()
 
 
+def rk4_sensitivity_discretization(dfdx, dfdu, dt):
+    """rk4SensitivityDiscretization (ocs2_core/src/integration/SensitivityIntegratorImpl.cpp:130-169) on the four stage linearisations
+    k1..k4 (dfdx[s] (n,n), dfdu[s] (n,m)) of one RK4 step: the input sensitivity chain, the state sensitivity chain (one temporary per
+    product), and the assembly dfdx = I + dt/6 k1 + dt/3 k2 + dt/3 k3 + dt/6 k4 (dfdu alike). Returns (A, B) of the discrete model."""
+    A = [np.array(a, dtype=np.float64) for a in dfdx]
+    B = [np.array(b, dtype=np.float64) for b in dfdu]
+    h2, h6, h3 = dt / 2.0, dt / 6.0, dt / 3.0
+    B[1] = B[1] + h2 * (A[1] @ B[0])
+    B[2] = B[2] + h2 * (A[2] @ B[1])
+    B[3] = B[3] + dt * (A[3] @ B[2])
+    tmp = h2 * (A[1] @ A[0])
+    A[1] = A[1] + tmp
+    tmp = h2 * (A[2] @ A[1])
+    A[2] = A[2] + tmp
+    tmp = dt * (A[3] @ A[2])
+    A[3] = A[3] + tmp
+    Ad = h6 * A[0] + h3 * A[1] + h3 * A[2] + h6 * A[3]
+    Ad[np.diag_indices_from(Ad)] += 1.0
+    Bd = h6 * B[0] + h3 * B[1] + h3 * B[2] + h6 * B[3]
+    return Ad, Bd
+
+
 def generate_problem(seed, problem, algorithm, n, m, nc, N, dt):
     """One problem of the seeded synthetic family (bit-identical to the CUDA generator). Returns (Problem, x0)."""
     nodes = N if algorithm == ALG_ILQR else N + 1

@@ -817,3 +817,64 @@ def test_slq_events_match_oracle(n, m, nc, variant):
         solver.solve()
         sol = solver.download()
         check_against_oracle(st, _oracle_problem(lq, 1, N), lq.x0[1], sol, 1, (1.0,), what=f"slq events cleared n={n}")
+
+
+@pytest.mark.parametrize("n,m,stages", [(4, 1, 4), (24, 24, 4), (10, 3, 1), (7, 5, 4)])
+def test_discretize_matches_oracle(n, m, stages):
+    """o2c_discretize = ILQR::discreteLQWorker on caller-supplied stage linearisations (rk4SensitivityDiscretization,
+    SensitivityIntegratorImpl.cpp:130-169; cost *= dt, Hv := 0, ILQR.cpp:137-157): A, B of the resident records against the oracle's
+    restatement, cost blocks scaled by the step length, a zero-length interval keeps the continuous-time data; then the discretised
+    batch solves like the same data uploaded from the host."""
+    import torch
+    from ocs2_b200 import lib as o2lib
+    rng = np.random.default_rng(61 + n)
+    batch, N = 4, 8
+    lq = _random_batch(rng, batch, n, m, N, 0, o2.ALG_ILQR, ragged_nc=False)
+    dts = rng.uniform(0.005, 0.03, N)
+    dts[5] = 0.0
+    Ac = rng.uniform(-1, 1, (4, batch, N, n, n))
+    Bc = rng.uniform(-1, 1, (4, batch, N, n, m))
+    dev = torch.device("cuda:0")
+    keep = []
+
+    def dfield(arr, block):  # (batch, N, rows, cols) natural -> column-major blocks on the device, padded strides
+        host = np.zeros((batch, N + 1, block + 2))
+        host[:, :N, :block] = np.swapaxes(arr, -1, -2).reshape(batch, N, block)
+        t = torch.from_numpy(host).to(dev)
+        keep.append(t)
+        return o2lib.Field(t.data_ptr(), (N + 1) * (block + 2), block + 2)
+
+    dv = o2lib.DiscretizationView()
+    for s in range(stages):
+        dv.dfdx[s], dv.dfdu[s] = dfield(Ac[s], n * n), dfield(Bc[s], n * m)
+    dv.dt = dts.ctypes.data
+    dv.stages = stages
+    st = o2.Settings(hessianCorrectionMultiple=1e-4)
+    with o2.BatchedLqSolver(st, n, m, N, batch, has_nominal=True) as a, o2.BatchedLqSolver(st, n, m, N, batch, has_nominal=True) as b:
+        a.upload(lq)
+        torch.cuda.synchronize()
+        a.discretize(dv)
+        # the same thing on the host: oracle discretisation + cost * dt, uploaded
+        want = o2.LqBatch(**{f: getattr(lq, f) for f in ("A", "B", "Q", "R", "Qf", "Hv", "P", "q", "r", "c", "qf", "cf", "x_nom", "u_nom", "x0", "time")})
+        want.A, want.B, want.Hv = lq.A.copy(), lq.B.copy(), np.zeros_like(lq.Hv)
+        want.Q, want.P, want.R, want.q, want.r, want.c = (getattr(lq, f).copy() for f in ("Q", "P", "R", "q", "r", "c"))
+        for p in range(batch):
+            for k in range(N):
+                src = [s if stages == 4 else 0 for s in range(4)]
+                if dts[k] == 0.0:
+                    want.A[p, k], want.B[p, k], want.Hv[p, k] = Ac[0, p, k], Bc[0, p, k], lq.Hv[p, k]
+                    continue
+                want.A[p, k], want.B[p, k] = orc.rk4_sensitivity_discretization([Ac[s, p, k] for s in src], [Bc[s, p, k] for s in src], dts[k])
+                for f in ("Q", "P", "R", "q", "r", "c"):
+                    getattr(want, f)[p, k] *= dts[k]
+        b.upload(want)
+        a.solve(alpha=0.9)
+        b.solve(alpha=0.9)
+        sa, sb = a.download(), b.download()
+        for name in ("K", "dbias", "bias", "Sm", "Sv", "s", "x", "u"):
+            assert rel_err(getattr(sa, name), getattr(sb, name)) <= 1e-10, name
+        ref = orc.backward(orc_settings(st), _oracle_problem(want, 1, N))
+        assert rel_err(sa.K[1], ref.K) <= REL_TOL and rel_err(sa.Sm[1], ref.Sm) <= REL_TOL
+    with o2.BatchedLqSolver(o2.Settings(algorithm=o2.ALG_SLQ), n, m, N, batch) as slq:
+        with pytest.raises(o2.O2cError):
+            slq.discretize(dv)

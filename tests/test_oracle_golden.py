@@ -497,3 +497,33 @@ def test_slq_events_compose_from_event_free_segments(reduced):
     xs, us, ts, _ = orc.rollout(st, segp, segsol, x0, alpha=0.7)
     assert np.array_equal(ts, t[:pre[0] + 1]) and np.allclose(xs, x[:pre[0] + 1], rtol=1e-13, atol=1e-13)
     assert np.allclose(us, u[:pre[0] + 1], rtol=1e-12, atol=1e-12)
+
+
+def test_rk4_sensitivity_discretization_reproduces_the_cartpole_fixture():
+    """ILQR::discreteLQWorker / rk4SensitivityDiscretization (ILQR.cpp:137-157, SensitivityIntegratorImpl.cpp:130-169): the oracle's
+    restatement on the four stage linearisations of the analytic cartpole model reproduces the discrete A, B stored in the committed
+    fixture (tests/golden/cartpole_ilqr.npz, generated by make_cartpole_fixture.py)."""
+    sympy = pytest.importorskip("sympy")  # the analytic model of the generator
+    assert sympy is not None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_cartpole_fixture", os.path.join(os.path.dirname(__file__), "golden", "make_cartpole_fixture.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "cartpole_ilqr.npz"))
+    dt = float(fx["dt"])
+    for k in (0, 17, 63, 99):
+        x, u = fx["x_nom"][k], float(fx["u_nom"][k, 0])
+        f1, A1, B1 = gen.lin(x, u)
+        f2, A2, B2 = gen.lin(x + dt / 2 * f1, u)
+        f3, A3, B3 = gen.lin(x + dt / 2 * f2, u)
+        f4, A4, B4 = gen.lin(x + dt * f3, u)
+        Ad, Bd = orc.rk4_sensitivity_discretization([A1, A2, A3, A4], [B1, B2, B3, B4], dt)
+        assert np.allclose(Ad, fx["A"][k], rtol=1e-13, atol=1e-13) and np.allclose(Bd, fx["B"][k], rtol=1e-13, atol=1e-13)
+    # a model that is constant over the step: the chain collapses to the 4th-order Taylor polynomial of the matrix exponential
+    rng = np.random.default_rng(2)
+    A, B, h = rng.uniform(-1, 1, (3, 3)), rng.uniform(-1, 1, (3, 2)), 0.05
+    Ad, Bd = orc.rk4_sensitivity_discretization([A] * 4, [B] * 4, h)
+    hA = h * A
+    taylor = np.eye(3) + hA + hA @ hA / 2 + hA @ hA @ hA / 6 + hA @ hA @ hA @ hA / 24
+    assert np.allclose(Ad, taylor, rtol=1e-13, atol=1e-14)
+    assert np.allclose(Bd, h * (np.eye(3) + hA / 2 + hA @ hA / 6 + hA @ hA @ hA / 24) @ B, rtol=1e-13, atol=1e-14)
