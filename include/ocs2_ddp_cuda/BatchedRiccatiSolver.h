@@ -152,6 +152,46 @@ class BatchedRiccatiSolver {
     event_[static_cast<std::size_t>(b) * nodes_ + k] = 1;
   }
 
+  /**
+   * The same LQ arrays as another in-tree consumer hands them over: HpipmInterface::solve (ocs2_sqp/hpipm_catkin/include/hpipm_catkin/
+   * HpipmInterface.h:85-87, called from SqpSolver.cpp:287-293) takes x0, N dynamics {f, dfdx, dfdu} (x+ = dfdx x + dfdu u + f) and
+   * N+1 costs {f, dfdx, dfdu, dfdxx, dfdux, dfduu}, the last one being the terminal cost. Without inequality / equality constraints
+   * the QP solution is this class's backward pass + rollout with step length 1 (create the handle with hessian_multiple = 0 and
+   * has_nominal = 0): solveQps() then getQpSolution(), getValueFunctionTrajectory() (= getRiccatiCostToGo, with f filled in) and
+   * calculateController() (gainArray_ = getRiccatiFeedback, deltaBiasArray_ = getRiccatiFeedforward).
+   */
+  template <class Vector, class LinearArray, class QuadraticArray>
+  void setQp(int b, const Vector& x0, const LinearArray& dynamics, const QuadraticArray& cost) {
+    checkInstance(b);
+    if (cfg_.algorithm != O2C_ALG_ILQR || cfg_.has_nominal) throw std::runtime_error("[BatchedRiccatiSolver] setQp needs a discrete (ILQR) handle without nominal trajectories");
+    const std::size_t N = cfg_.num_stages;
+    if (dynamics.size() < N || cost.size() < N + 1) throw std::runtime_error("[BatchedRiccatiSolver] setQp: N dynamics and N+1 costs are required");
+    for (std::size_t k = 0; k < N; ++k) {
+      copyBlock(dynamics[k].dfdx, A_, b, k, "dynamics.dfdx");
+      copyBlock(dynamics[k].dfdu, B_, b, k, "dynamics.dfdu");
+      copyBlock(dynamics[k].f, Hv_, b, k, "dynamics.f");
+      copyCost(cost[k], b, k);
+      if (cfg_.nc_max > 0) ncActive_[static_cast<std::size_t>(b) * nodes_ + k] = 0;
+      if (!event_.empty()) event_[static_cast<std::size_t>(b) * nodes_ + k] = 0;
+    }
+    copyRaw(cost[N].dfdxx, Qf_.at(b, 0), Qf_.block, "terminal cost.dfdxx");
+    copyRaw(cost[N].dfdx, qf_.at(b, 0), qf_.block, "terminal cost.dfdx");
+    *cf_.at(b, 0) = cost[N].f;
+    copyRaw(x0, x0_.at(b, 0), x0_.block, "x0");
+  }
+  /** solves every QP of the batch: backward pass + rollout with step length 1 */
+  void solveQps() {
+    solveSequentialRiccatiEquations();
+    const double one[1] = {1.0};
+    rolloutTrajectory(std::vector<double>(one, one + 1));
+  }
+  /** HpipmInterface::solve outputs: N+1 states and N inputs of the optimal trajectory of instance b */
+  template <class VectorArray>
+  void getQpSolution(int b, VectorArray& stateTrajectory, VectorArray& inputTrajectory) const {
+    getRollout(b, 0, stateTrajectory, inputTrajectory);
+    inputTrajectory.resize(cfg_.num_stages);
+  }
+
   /** primalSolution.stateTrajectory_ / inputTrajectory_ of instance b (N+1 nodes); requires config.has_nominal. */
   template <class VectorArray>
   void setNominalTrajectories(int b, const VectorArray& stateTrajectory, const VectorArray& inputTrajectory) {

@@ -309,6 +309,72 @@ int runCase(const Case& cs) {
   return worst <= tol ? 0 : 1;
 }
 
+// HpipmInterface::solve-style hand-over (HpipmInterface.h:85-87): x0, N dynamics {f, dfdx, dfdu}, N+1 costs. The QP solution must satisfy
+// the optimality conditions of the equality-constrained QP: with the costates lambda_k = dV_k/dx (x_k) = Sm_k x_k + Sv_k,
+//   r_k + P_k x_k + R_k u_k + B_k' lambda_{k+1} = 0   (stationarity in u_k),   x_{k+1} = A_k x_k + B_k u_k + b_k   (feasibility)
+int qpCase() {
+  const int n = 10, m = 3, N = 15, batch = 4;
+  o2c_config cfg{};
+  cfg.nx = n, cfg.nu = m, cfg.num_stages = N, cfg.batch = batch, cfg.algorithm = O2C_ALG_ILQR, cfg.riccati_form = O2C_FORM_REDUCED;
+  cfg.max_alphas = 1, cfg.hessian_multiple = 0.0, cfg.time_step = 0.01;
+  ocs2_ddp_cuda::BatchedRiccatiSolver solver(cfg);
+  std::vector<std::vector<VectorFunctionLinearApproximation>> dyn(batch);
+  std::vector<std::vector<ScalarFunctionQuadraticApproximation>> cost(batch);
+  for (int b = 0; b < batch; ++b) {
+    std::vector<double> A((size_t)N * n * n), B((size_t)N * n * m), Hv((size_t)N * n), Q((size_t)N * n * n), P((size_t)N * m * n), R((size_t)N * m * m),
+        q((size_t)N * n), r((size_t)N * m), c(N), C(1), D(1), e(1), Qf((size_t)n * n), qf(n), cf(1), x0(n);
+    orc_generate_problem(99, b, ORC_ALG_ILQR, n, m, 0, N, 0.01, A.data(), B.data(), Hv.data(), Q.data(), P.data(), R.data(), q.data(), r.data(),
+                         c.data(), C.data(), D.data(), e.data(), Qf.data(), qf.data(), cf.data(), x0.data());
+    dyn[b].resize(N), cost[b].resize(N + 1);
+    for (int k = 0; k < N; ++k) {
+      dyn[b][k].dfdx.set(&A[(size_t)k * n * n], n, n), dyn[b][k].dfdu.set(&B[(size_t)k * n * m], n, m), dyn[b][k].f.set(&Hv[(size_t)k * n], n, 1);
+      cost[b][k].dfdxx.set(&Q[(size_t)k * n * n], n, n), cost[b][k].dfdux.set(&P[(size_t)k * m * n], m, n), cost[b][k].dfduu.set(&R[(size_t)k * m * m], m, m);
+      cost[b][k].dfdx.set(&q[(size_t)k * n], n, 1), cost[b][k].dfdu.set(&r[(size_t)k * m], m, 1), cost[b][k].f = c[k];
+    }
+    cost[b][N].dfdxx.set(Qf.data(), n, n), cost[b][N].dfdx.set(qf.data(), n, 1), cost[b][N].f = cf[0];
+    Dense x0v;
+    x0v.set(x0.data(), n, 1);
+    solver.setQp(b, x0v, dyn[b], cost[b]);
+  }
+  solver.solveQps();
+  double worst = 0.0;
+  for (int b = 0; b < batch; ++b) {
+    std::vector<Dense> xs, us;
+    solver.getQpSolution(b, xs, us);
+    std::vector<ScalarFunctionQuadraticApproximation> vf;
+    solver.getValueFunctionTrajectory(b, vf);
+    if ((int)xs.size() != N + 1 || (int)us.size() != N) {
+      std::printf("FAIL qp: trajectory sizes %zu, %zu\n", xs.size(), us.size());
+      return 1;
+    }
+    for (int k = 0; k < N; ++k) {
+      const auto& d = dyn[b][k];
+      const auto& cs = cost[b][k];
+      for (int i = 0; i < n; ++i) {  // feasibility
+        double v = d.f.v[i];
+        for (int j = 0; j < n; ++j) v += d.dfdx.v[i + (size_t)n * j] * xs[k].v[j];
+        for (int j = 0; j < m; ++j) v += d.dfdu.v[i + (size_t)n * j] * us[k].v[j];
+        worst = std::max(worst, std::fabs(v - xs[k + 1].v[i]));
+      }
+      std::vector<double> lam(n);  // costate at k+1
+      for (int i = 0; i < n; ++i) {
+        double v = vf[k + 1].dfdx.v[i];
+        for (int j = 0; j < n; ++j) v += vf[k + 1].dfdxx.v[i + (size_t)n * j] * xs[k + 1].v[j];
+        lam[i] = v;
+      }
+      for (int l = 0; l < m; ++l) {  // stationarity
+        double v = cs.dfdu.v[l];
+        for (int j = 0; j < n; ++j) v += cs.dfdux.v[l + (size_t)m * j] * xs[k].v[j];
+        for (int j = 0; j < m; ++j) v += cs.dfduu.v[l + (size_t)m * j] * us[k].v[j];
+        for (int i = 0; i < n; ++i) v += d.dfdu.v[i + (size_t)n * l] * lam[i];
+        worst = std::max(worst, std::fabs(v));
+      }
+    }
+  }
+  std::printf("%s %-28s kernel %-22s max KKT residual %.3e\n", worst <= 1e-9 ? "ok  " : "FAIL", "hpipm-style qp hand-over", solver.kernelVariant().c_str(), worst);
+  return worst <= 1e-9 ? 0 : 1;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -340,6 +406,7 @@ int main(int argc, char** argv) {
   int failures = 0;
   try {
     for (const Case& cs : cases) failures += runCase(cs);
+    failures += qpCase();
   } catch (const std::exception& err) {
     std::printf("FAIL exception: %s\n", err.what());
     return 2;

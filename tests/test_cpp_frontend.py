@@ -46,4 +46,4 @@ def test_frontend_matches_oracle():
     done = subprocess.run([exe, "--gpu"], capture_output=True, text=True, timeout=600)
     print(done.stdout)
     assert done.returncode == 0, done.stdout + done.stderr
-    assert done.stdout.count("ok  ") == 10
+    assert done.stdout.count("ok  ") == 11
