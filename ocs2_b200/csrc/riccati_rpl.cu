@@ -586,11 +586,13 @@ struct SlqArgs {
   double* sol;
   int* status;
   const SlqStep* steps;
+  const double* jump;  // [batch][jump_capacity] jump records (o2c_common.cuh: jump_rec) or nullptr
+  int jump_capacity;
   int nsteps, N, begin, count;
   double eps;
 };
 
-template <int NX, int NU>
+template <int NX, int NU, bool EV>
 __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
   using S = SlqShape<NX, NU>;
   using R = typename S::R;
@@ -804,6 +806,58 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
       const double* Bt0 = sm + S::sRec + (i0 % 3) * S::rec + R::oB;
       const double* Bt1 = sm + S::sRec + ((i0 + 1) % 3) * S::rec + R::oB;
       const double h = sp.h;
+      if (EV && sp.jump > 0) {  // (template variant: the event-free kernel is at its register limit)
+        // node i0 is a pre-event node: instead of integrating, the value function crosses the event through
+        // ContinuousTimeRiccatiEquations::computeJumpMap = riccatiTransversalityConditions on the event's jump model data
+        // (SLQ.cpp:286-296, RiccatiTransversalityConditions.h:40-56): S- = Q_e + (S A_e)' A_e, Sv- = q_e + A_e'(Sv + S Hv_e),
+        // s- = s + c_e + Hv_e.(Sv + S Hv_e / 2). Row i of S A_e per lane, columns through shared memory.
+        const double* jr = a.jump + ((size_t)prob * a.jump_capacity + (sp.jump - 1)) * jump_rec(NX);
+        const double* Ae = jr;
+        const double* Hve = jr + jump_oHv(NX);
+        double shv = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < NX; ++kk) shv = fma(Srow[kk], __ldg(Hve + kk), shv);
+        sm[S::sSv + i] = Svi + shv;                               // w = Sv + S Hv_e
+        sm[S::sHv + i] = __ldg(Hve + i) * (Svi + 0.5 * shv);      // this row's share of Hv_e.(Sv + S Hv_e / 2)
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          double v = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < NX; ++kk) v = fma(Srow[kk], __ldg(Ae + kk + NX * j), v);
+          sm[S::sMs + i + NX * j] = v;                            // (S A_e)(i, j)
+        }
+        __syncwarp();
+        double mcol[NX];
+#pragma unroll
+        for (int kk = 0; kk < NX; ++kk) mcol[kk] = sm[S::sMs + kk + NX * i];  // column i of S A_e
+        double svn = __ldg(jr + jump_oq(NX) + i), ssum = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < NX; ++kk) {
+          svn = fma(__ldg(Ae + kk + NX * i), sm[S::sSv + kk], svn);
+          ssum += sm[S::sHv + kk];
+        }
+        __syncwarp();  // sMs is read; it now takes the upper triangle of S- so that both triangles carry the same numbers
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          if (j >= i) {  // convert2Vector keeps the upper triangle (row <= column)
+            double v = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < NX; ++kk) v = fma(mcol[kk], __ldg(Ae + kk + NX * j), v);
+            sm[S::sMs + i + NX * j] = __ldg(jr + jump_oQ(NX) + i + NX * j) + v;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < NX; ++j) Srow[j] = (j >= i) ? sm[S::sMs + i + NX * j] : sm[S::sMs + j + NX * i];
+        Svi = svn;
+        sval = sval + __ldg(jr + jump_oc(NX)) + ssum;
+        __syncwarp();
+        if (sp.observe_node >= 0) {
+          write_value(sp.observe_node);
+          controller(sp.observe_node);
+        }
+        continue;
+      }
       // classic RK4 (boost::odeint runge_kutta4): k_s = f(y + c_s h k_{s-1}), y += h (k1 + 2 k2 + 2 k3 + k4) / 6
       double ys[NX], ysv = Svi, acc[NX], accv = Svi, accs = sval;
 #pragma unroll
@@ -928,13 +982,13 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
   }
 }
 
-template <int NX, int NU>
+template <int NX, int NU, bool EV>
 cudaError_t launch_slq(const SlqArgs& a, cudaStream_t stream) {
   using S = SlqShape<NX, NU>;
   static int num_sms = 0;
   constexpr int wpb = 1;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(slq_rpl_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(slq_rpl_kernel<NX, NU, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (num_sms == 0) {
     int dev = 0;
@@ -942,13 +996,13 @@ cudaError_t launch_slq(const SlqArgs& a, cudaStream_t stream) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, slq_rpl_kernel<NX, NU>, wpb * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, slq_rpl_kernel<NX, NU, EV>, wpb * 32, smem);
   if (e != cudaSuccess) return e;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int per_cta = wpb * S::P;
   const int needed = (a.count + per_cta - 1) / per_cta;
   const int cap = num_sms * ctas_per_sm;
-  slq_rpl_kernel<NX, NU><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
+  slq_rpl_kernel<NX, NU, EV><<<needed < cap ? needed : cap, wpb * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -981,6 +1035,8 @@ struct RoArgs {
   int* status;
   const RolloutStep* steps;
   const double* alphas;
+  const double* jump;  // [batch][jump_capacity] jump records or nullptr
+  int jump_capacity;
   int nsteps, first_idx, out_nodes, N, batch, begin, count;
   double first_alpha;
 };
@@ -1141,6 +1197,20 @@ __global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
     for (int sidx = 0; sidx < a.nsteps; ++sidx) {
       const RolloutStep sp = a.steps[sidx];
       const double h = sp.h;
+      if (sp.jump > 0) {  // an event (TimeTriggeredRollout.cpp:104-108): x+ = x_nom(post) + A_e (x - x_nom(pre)) + Hv_e
+        const double* jr = a.jump + ((size_t)prob * a.jump_capacity + (sp.jump - 1)) * jump_rec(NX);
+        sm[S::sX + i] = x - (a.x_nom ? __ldg(a.x_nom + ((size_t)prob * (N + 1) + sp.pre_node) * NX + i) : 0.0);
+        __syncwarp();
+        double xn = __ldg(jr + jump_oHv(NX) + i) + (a.x_nom ? __ldg(a.x_nom + ((size_t)prob * (N + 1) + sp.pre_node + 1) * NX + i) : 0.0);
+#pragma unroll
+        for (int kk = 0; kk < NX; ++kk) xn = fma(__ldg(jr + i + NX * kk), sm[S::sX + kk], xn);
+        __syncwarp();
+        x = xn;
+      }
+      if (h == 0.0) {  // a jump or a degenerate interval: no integration
+        observe(sidx + 1, sp.obs_idx, sp.obs_alpha);
+        continue;
+      }
       double acc = x, xs = x;
 #pragma unroll 1
       for (int stg = 0; stg < 4; ++stg) {
@@ -1231,8 +1301,8 @@ bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const La
 
 bool rpl_slq_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   if (!(st.algorithm == O2C_ALG_SLQ && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
-        (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1 && L.nodes == L.N + 1))
-    return false;  // SLQ events (jump steps in the schedule) go through the generic kernels
+        (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.nodes == L.N + 1))
+    return false;
   if (L.ncmax != 0) return false;
   return layout_matches<12, 4, 0>(L) || layout_matches<10, 3, 0>(L) || layout_matches<4, 1, 0>(L);
 }
@@ -1248,18 +1318,21 @@ cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const Devi
   a.sol = buf.sol;
   a.status = buf.status;
   a.steps = steps;
+  a.jump = buf.jump;
+  a.jump_capacity = buf.jump_capacity;
   a.nsteps = nsteps;
   a.N = L.N;
   a.begin = begin;
   a.count = count;
   a.eps = st.eps;
-  if (layout_matches<12, 4, 0>(L)) return launch_slq<12, 4>(a, stream);
-  if (layout_matches<10, 3, 0>(L)) return launch_slq<10, 3>(a, stream);
-  return launch_slq<4, 1>(a, stream);
+  const bool ev = buf.event != nullptr;
+  if (layout_matches<12, 4, 0>(L)) return ev ? launch_slq<12, 4, true>(a, stream) : launch_slq<12, 4, false>(a, stream);
+  if (layout_matches<10, 3, 0>(L)) return ev ? launch_slq<10, 3, true>(a, stream) : launch_slq<10, 3, false>(a, stream);
+  return ev ? launch_slq<4, 1, true>(a, stream) : launch_slq<4, 1, false>(a, stream);
 }
 
 bool rpl_rollout_cont_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
-  return st.algorithm == O2C_ALG_SLQ && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && buf.event == nullptr && L.N >= 1 &&
+  return st.algorithm == O2C_ALG_SLQ && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 &&
          L.nodes == L.N + 1 && L.ncmax == 0 && (layout_matches<12, 4, 0>(L) || layout_matches<10, 3, 0>(L) || layout_matches<4, 1, 0>(L));
 }
 
@@ -1278,6 +1351,8 @@ cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, c
   a.status = buf.status;
   a.steps = steps;
   a.alphas = alphas_dev;
+  a.jump = buf.jump;
+  a.jump_capacity = buf.jump_capacity;
   a.nsteps = nsteps;
   a.first_idx = first_idx;
   a.first_alpha = first_alpha;

@@ -401,7 +401,7 @@ int main(int argc, char** argv) {
       {"generic slq nc=2", ORC_ALG_SLQ, 6, 4, 2, 16, 3, false, false, false, "generic"},
       {"ilqr events", ORC_ALG_ILQR, 6, 4, 0, 14, 6, true, false, true, "generic"},
       {"legged ilqr events", ORC_ALG_ILQR, 24, 24, 0, 12, 4, false, false, true, "ilqr_wpp"},
-      {"quadrotor slq events", ORC_ALG_SLQ, 12, 4, 0, 14, 4, true, false, true, "generic"},
+      {"quadrotor slq events", ORC_ALG_SLQ, 12, 4, 0, 14, 4, true, false, true, "slq_rpl"},
   };
   int failures = 0;
   try {

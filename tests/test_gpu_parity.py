@@ -760,12 +760,11 @@ def test_ilqr_events_dense_and_short_horizons(n, m, nc, N):
             check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, (0.6,), what=f"dense events n={n} N={N} #{i}")
 
 
-@pytest.mark.parametrize("n,m,nc,variant", [(12, 4, 0, "ls_reduced"), (5, 3, 2, "ls_full"), (6, 2, 0, "lm_full")])
+@pytest.mark.parametrize("n,m,nc,variant", [(12, 4, 0, "ls_reduced"), (10, 3, 0, "ls_reduced"), (4, 1, 0, "ls_reduced"), (5, 3, 2, "ls_full"), (6, 2, 0, "lm_full")])
 def test_slq_events_match_oracle(n, m, nc, variant):
     """SLQ with events (SLQ.cpp:256-302): inter-event segments integrated separately, joined by computeJumpMap =
     riccatiTransversalityConditions on the event's jump model data; the continuous rollout restarts weakEpsilon after every event from
-    the LQ jump map (TimeTriggeredRollout.cpp:46-115). Event nodes are shared by the batch, jump data are per problem. Handles with
-    SLQ events use the generic kernels; a later upload without events returns to the specialised ones."""
+    the LQ jump map (TimeTriggeredRollout.cpp:46-115). Event nodes are shared by the batch, jump data are per problem."""
     rng = np.random.default_rng(53 + n)
     batch, N, dt = 5, 13, 0.02
     events = (3, 8)
@@ -789,7 +788,7 @@ def test_slq_events_match_oracle(n, m, nc, variant):
                      riccatiMultiple=0.3 if variant == "lm_full" else 0.0)
     with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=True, max_alphas=2) as solver:
         solver.upload(lq)
-        assert "generic" in solver.kernel_variant
+        assert ("slq_rpl" if n in (12, 10, 4) else "generic") in solver.kernel_variant  # the quadrotor shape keeps its row-per-lane kernels
         solver.solveSequentialRiccatiEquations()
         solver.rolloutTrajectory((1.0, 0.4))
         sol = solver.download()
@@ -813,7 +812,7 @@ def test_slq_events_match_oracle(n, m, nc, variant):
         lq.jump_A = lq.jump_Hv = lq.jump_Q = lq.jump_q = lq.jump_c = None
         lq.time = dt * np.arange(N + 1)
         solver.upload(lq)
-        assert ("generic" in solver.kernel_variant) == (n != 12)
+        assert ("generic" in solver.kernel_variant) == (n not in (12, 10, 4))
         solver.solve()
         sol = solver.download()
         check_against_oracle(st, _oracle_problem(lq, 1, N), lq.x0[1], sol, 1, (1.0,), what=f"slq events cleared n={n}")
