@@ -1293,14 +1293,15 @@ cudaError_t launch(const Args& a, cudaStream_t stream) {
 }
 
 bool settings_match(const SolverSettings& st, const DeviceBuffers& buf, const Layout& L) {
-  return st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
+  // reduced and full Riccati form alike: under LINE_SEARCH they are the same map (RiccatiTest.cpp:87-105 holds them equal to 1e-9)
+  return st.algorithm == O2C_ALG_ILQR && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
          (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1;
 }
 
 }  // namespace
 
 bool rpl_slq_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
-  if (!(st.algorithm == O2C_ALG_SLQ && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
+  if (!(st.algorithm == O2C_ALG_SLQ && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.nodes == L.N + 1))
     return false;
   if (L.ncmax != 0) return false;

@@ -878,7 +878,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 }  // namespace
 
 bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
-  return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && st.reduced && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
+  // Both Riccati forms are served: under LINE_SEARCH the full form (preComputeRiccatiTerms = false) is the same map written with
+  // K~'G~ + G~'K~ + K~'H~K~ in place of -G~'G~ (H~ = Pu'Hm Pu = I); the reference's own RiccatiTest.cpp:87-105 holds them equal to 1e-9.
+  return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
          st.hc == O2C_HC_DIAGONAL_SHIFT && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
          L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb && L.obias == kObias && L.oSm == kOSm &&
          L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat;

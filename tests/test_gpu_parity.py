@@ -74,6 +74,10 @@ def test_ilqr_generated_batch_matches_oracle(shape, variant):
         st.riccatiMultiple = 0.37
     with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, max_alphas=2) as solver:
         solver.generate_synthetic(seed, first_problem_index=1000, dt=dt)
+        # LINE_SEARCH + DIAGONAL_SHIFT in either Riccati form runs the shape's specialised kernel (the forms are the same map, the oracle
+        # below is evaluated in the form asked for); every other variant goes through the generic kernel
+        fast = variant in ("ls_reduced_diag", "ls_full_diag") and shape != "test32c"
+        assert ("generic" in solver.kernel_variant) != fast
         solver.solveSequentialRiccatiEquations()
         alphas = (1.0, 0.35)
         solver.rolloutTrajectory(alphas)
@@ -96,6 +100,15 @@ def test_slq_rk4_generated_batch_matches_oracle(shape, substeps, variant):
     elif variant == "lm_full":
         st.strategy = o2.STRATEGY_LEVENBERG_MARQUARDT
         st.riccatiMultiple = 0.2
+    if shape == "quadrotor" and variant == "ls_reduced_diag":  # the full form of the same settings takes the same kernel
+        st_full = o2.Settings(algorithm=o2.ALG_SLQ, hessianCorrectionMultiple=1e-3, timeStep=dt / substeps, preComputeRiccatiTerms=False)
+        with o2.BatchedLqSolver(st_full, n, m, N, batch, nc_max=nc) as solver:
+            assert solver.kernel_variant == "slq_rpl_kernel"
+            solver.generate_synthetic(seed, first_problem_index=50, dt=dt)
+            solver.solve(alpha=1.0)
+            sol = solver.download()
+            pb, x0 = orc.generate_problem(seed, 50, orc.ALG_SLQ, n, m, nc, N, dt)
+            check_against_oracle(st_full, pb, x0, sol, 0, what="slq quadrotor full form")
     with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
         solver.generate_synthetic(seed, first_problem_index=50, dt=dt)
         solver.solve(alpha=1.0)
