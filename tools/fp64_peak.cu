@@ -2,6 +2,8 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fp64_peak tools/fp64_peak.cu
 #include <cstdio>
 #include <cstdlib>
+#include <string>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); exit(1);} }while(0)
 
@@ -90,7 +92,33 @@ float timeit(F f, int reps = 3) {
   return best;
 }
 
-int main() {
+// sustained mode: `fp64_peak sustained [seconds]` keeps the best DMMA configuration running back to back for that long (default 4 s) and
+// prints the throughput of consecutive half-second windows: the figure under the board's power cap, for kernels timed inside long steps
+int sustained(double seconds) {
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+  const int sms = p.multiProcessorCount, threads = 256, iters = 20000;
+  double* out; CK(cudaMalloc(&out, sizeof(double) * sms * 64 * 1024));
+  const double fl = 2.0 * 256 * 8 * iters * (double)(threads / 32) * sms;
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) k_dmma884<8><<<sms, threads>>>(out, iters, 1.0000001, 1e-9);
+  CK(cudaDeviceSynchronize());
+  double elapsed = 0.0;
+  int window = 0;
+  while (elapsed < seconds) {
+    int launches = 0;
+    CK(cudaEventRecord(e0));
+    for (; launches < 190; ++launches) k_dmma884<8><<<sms, threads>>>(out, iters, 1.0000001, 1e-9);  // about half a second
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    elapsed += ms * 1e-3;
+    printf("sustained DMMA m8n8k4 window %d (%.2f s .. %.2f s): %.2f TFLOP/s\n", window++, elapsed - ms * 1e-3, elapsed, fl * launches / ms * 1e-9);
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "sustained") return sustained(argc > 2 ? atof(argv[2]) : 4.0);
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   printf("device %s SMs %d clock %d kHz\n", p.name, p.multiProcessorCount, clk);
