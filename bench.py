@@ -152,6 +152,37 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(device_index):
+    """One process per GPU: run on the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers of the end-to-end path
+    (first-touch allocation) and the copy engines' reads stay on that socket. Returns the node, or None when it cannot be determined."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:  # noqa: BLE001 - placement is an optimisation, never a requirement
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,6 +214,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (ocs2_b200 has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch places the host buffers next to the GPU
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -305,7 +337,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": (f"{args.workload} ILQR nx={n} nu={m} nc={nc} N={N_STAGES} LINE_SEARCH reduced DIAGONAL_SHIFT {eps}" if alg == 0
                                     else f"{args.workload} SLQ-RK4 nx={n} nu={m} N={N_STAGES} timeStep={DT}"),
-                       "batch_per_gpu": batch, "global_batch": world * batch, "sharding": "by problem index, no collective",
+                       "batch_per_gpu": batch, "global_batch": world * batch, "sharding": "by problem index, no collective", "host_numa_node": numa,
                        "l2": "inputs larger than L2 (per-GPU LQ data %.1f GB >> 126 MB), no flush needed" % (bytes_solve * batch / 1e9),
                        "kernel": solver.kernel_variant},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
