@@ -244,11 +244,48 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor pipe: lane (r = lane / 4, c = lane % 4) supplies a = A[r][c], b = B[c][r] and owns
+// d.x = D[r][2c], d.y = D[r][2c + 1]
+__device__ __forceinline__ void dmma_m8n8k4(double2& d, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d.x), "+d"(d.y) : "d"(a), "d"(b));
+}
+
 // C(MxN) = beta*C + alpha * op(A)*op(B); op(A) is MxK, op(B) is KxN. TA: A stored KxM; TB: B stored NxK.
+// Shapes made of whole 8x8x4 tiles (the legged shape in every configuration the specialised kernel does not serve: LM, Gershgorin,
+// eigenvalue correction, SLQ) go through DMMA, three column tiles per A fragment; everything else one output element per lane.
 template <bool TA, bool TB>
 __device__ __forceinline__ void wgemm(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
                                       const double* __restrict__ B, int ldb, double beta, double* C, int ldc) {
   const int lane = lane_id();
+  if (((M | N) & 7) == 0 && (K & 3) == 0) {
+    const int r = lane >> 2, c = lane & 3;
+    for (int ti = 0; ti < M; ti += 8) {
+      for (int tj = 0; tj < N; tj += 24) {
+        double2 acc[3] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+        const int ntile = (N - tj) >= 24 ? 3 : (N - tj) / 8;
+        for (int k0 = 0; k0 < K; k0 += 4) {
+          const double a = TA ? A[(k0 + c) + (ti + r) * lda] : A[(ti + r) + (k0 + c) * lda];
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+            if (t < ntile) {
+              const int j = tj + 8 * t + r;
+              const double b = TB ? B[j + (k0 + c) * ldb] : B[(k0 + c) + j * ldb];
+              dmma_m8n8k4(acc[t], a, b);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (t < ntile) {
+            double* c0 = C + (ti + r) + (tj + 8 * t + 2 * c) * ldc;
+            double* c1 = c0 + ldc;
+            *c0 = (beta == 0.0 ? 0.0 : beta * (*c0)) + alpha * acc[t].x;
+            *c1 = (beta == 0.0 ? 0.0 : beta * (*c1)) + alpha * acc[t].y;
+          }
+      }
+    }
+    __syncwarp();
+    return;
+  }
   const int total = M * N;
   for (int idx = lane; idx < total; idx += 32) {
     const int i = idx % M, j = idx / M;
