@@ -135,10 +135,10 @@ __device__ __forceinline__ bool warp_cholesky(int m, double* H) {
     for (int i = j + 1 + lane; i < m; i += 32) H[i + j * m] *= rs;
     if (lane == 0) H[j + j * m] = ljj;
     __syncwarp();
-    const int rem = m - 1 - j;
-    for (int idx = lane; idx < rem * rem; idx += 32) {
-      const int i = j + 1 + idx % rem, k = j + 1 + idx / rem;
-      if (i >= k) H[i + k * m] = fma(-H[i + j * m], H[k + j * m], H[i + k * m]);
+    // trailing update of the lower triangle: four columns at a time, eight row lanes per column (no index divisions)
+    for (int k = j + 1 + (lane >> 3); k < m; k += 4) {
+      const double lkj = H[k + j * m];
+      for (int i = k + (lane & 7); i < m; i += 8) H[i + k * m] = fma(-H[i + j * m], lkj, H[i + k * m]);
     }
     __syncwarp();
   }
@@ -557,23 +557,20 @@ __global__ void __launch_bounds__(128) ilqr_generic_kernel(Layout L, SolverSetti
       wgemm<false, false>(p, n, p, 1.0, W.Rt, p, W.Km, p, 0.0, HmKm, p);
       wgemm<false, false>(p, 1, p, 1.0, W.Rt, p, W.Lv, p, 0.0, W.HmLv, p);
     }
-    // Sm
-    for (int idx = lane; idx < n * n; idx += 32) {
-      const int i = idx % n, j = idx / n;
-      double acc = W.Q[idx] + dq_at(W, st, n, i, j);
-      for (int kk = 0; kk < n; ++kk) acc = fma(W.SA[kk + i * n], W.A[kk + j * n], acc);
-      double kg = 0.0;
-      for (int l = 0; l < p; ++l) kg = fma(W.Km[l + i * p], W.Gm[l + j * p], kg);
-      acc += kg;
-      if (full) {
-        double kgT = 0.0, khk = 0.0;
-        for (int l = 0; l < p; ++l) {
-          kgT = fma(W.Km[l + j * p], W.Gm[l + i * p], kgT);
-          khk = fma(W.Km[l + i * p], HmKm[l + j * p], khk);
-        }
-        acc += kgT + khk;
+    // Sm = Q + dQ + (S A)'A + K~'G~ [+ (K~'G~)' + K~'(H~ K~)] through the warp GEMM (tensor pipe when the shape is made of whole tiles)
+    for (int idx = lane; idx < n * n; idx += 32) Sb[idx] = W.Q[idx] + dq_at(W, st, n, idx % n, idx / n);
+    __syncwarp();
+    wgemm<true, false>(n, n, n, 1.0, W.SA, n, W.A, n, 1.0, Sb, n);
+    if (!full) {
+      wgemm<true, false>(n, n, p, 1.0, W.Km, p, W.Gm, p, 1.0, Sb, n);
+    } else {
+      wgemm<true, false>(n, n, p, 1.0, W.Km, p, W.Gm, p, 0.0, W.SA, n);  // K~'G~ (S A is dead from here on)
+      for (int idx = lane; idx < n * n; idx += 32) {
+        const int i = idx % n, j = idx / n;
+        Sb[idx] += W.SA[idx] + W.SA[j + i * n];
       }
-      Sb[idx] = acc;
+      __syncwarp();
+      wgemm<true, false>(n, n, p, 1.0, W.Km, p, HmKm, p, 1.0, Sb, n);
     }
     // Sv
     for (int i = lane; i < n; i += 32) {
