@@ -423,11 +423,11 @@ __device__ __forceinline__ bool emit_controller(const Work& W, const Layout& L, 
                                 const double* unom, double* out) {
   const int n = L.n, m = L.m, p = W.p, lane = lane_id();
   bool finite = true;
+  for (int idx = lane; idx < m * n; idx += 32) W.Kout[idx] = (nc > 0) ? W.Px[idx] : 0.0;
+  __syncwarp();
+  wgemm<false, false>(m, n, p, 1.0, W.Pu, m, Km, p, 1.0, W.Kout, m);
   for (int idx = lane; idx < m * n; idx += 32) {
-    const int i = idx % m, j = idx / m;
-    double acc = (nc > 0) ? W.Px[idx] : 0.0;
-    for (int k = 0; k < p; ++k) acc = fma(W.Pu[i + k * m], Km[k + j * p], acc);
-    W.Kout[idx] = acc;
+    const double acc = W.Kout[idx];
     out[L.oK + idx] = acc;
     finite = finite && isfinite(acc);
   }
