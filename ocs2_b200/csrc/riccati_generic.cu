@@ -775,26 +775,7 @@ __device__ __forceinline__ void flow_map(const Layout& L, const SolverSettings& 
     wgemm<false, false>(p, n, p, 1.0, P.Rt, p, F.Km, p, 0.0, F.RmKm, p);
     wgemm<false, false>(p, 1, p, 1.0, P.Rt, p, F.Lv, p, 0.0, F.RmLv, p);
   }
-  // dSm (upper triangle only is packed)
-  for (int idx = lane; idx < n * n; idx += 32) {
-    const int i = idx % n, j = idx / n;
-    if (i > j) continue;
-    double dq = gersh ? P.dQ[idx] : ((i == j) ? P.dQ[i] : 0.0);
-    double acc = P.Qt[idx] + (dq + F.StA[i + j * n] + F.StA[j + i * n]);
-    double kg = 0.0;
-    for (int l = 0; l < p; ++l) kg = fma(F.Km[l + i * p], F.Gm[l + j * p], kg);
-    if (full) {
-      double kgT = 0.0, khk = 0.0;
-      for (int l = 0; l < p; ++l) {
-        kgT = fma(F.Km[l + j * p], F.Gm[l + i * p], kgT);
-        khk = fma(F.Km[l + i * p], F.RmKm[l + j * p], khk);
-      }
-      acc += (kg + kgT) + khk;
-    } else {
-      acc += kg;
-    }
-    dy[tri_index(i, j)] = acc;
-  }
+  // dSv first: it is the last reader of S, whose storage then takes K~'G~ (+ K~'(R~ K~) / 2 in the full form)
   for (int i = lane; i < n; i += 32) {
     double acc = P.qt[i];
     for (int k = 0; k < n; ++k) acc = fma(F.Sm[k + i * n], P.Hvt[k], acc);
@@ -803,6 +784,18 @@ __device__ __forceinline__ void flow_map(const Layout& L, const SolverSettings& 
     if (full)
       for (int l = 0; l < p; ++l) acc += F.Km[l + i * p] * F.Gv[l] + F.RmKm[l + i * p] * F.Lv[l];
     dy[ntri + i] = acc;
+  }
+  __syncwarp();
+  wgemm<true, false>(n, n, p, 1.0, F.Km, p, F.Gm, p, 0.0, F.Sm, n);
+  if (full) wgemm<true, false>(n, n, p, 0.5, F.Km, p, F.RmKm, p, 1.0, F.Sm, n);  // symmetric: its two halves re-join in T + T' below
+  // dSm (upper triangle only is packed)
+  for (int idx = lane; idx < n * n; idx += 32) {
+    const int i = idx % n, j = idx / n;
+    if (i > j) continue;
+    const double dq = gersh ? P.dQ[idx] : ((i == j) ? P.dQ[i] : 0.0);
+    double acc = P.Qt[idx] + (dq + F.StA[i + j * n] + F.StA[j + i * n]);
+    acc += full ? (F.Sm[i + j * n] + F.Sm[j + i * n]) : F.Sm[i + j * n];
+    dy[tri_index(i, j)] = acc;
   }
   double ds = P.ct + wdot(n, P.Hvt, Sv);
   if (st.reduced)
