@@ -123,6 +123,34 @@ __device__ __forceinline__ void carve(Work& W, double* base, const Layout& L, bo
 __device__ __forceinline__ bool warp_cholesky(int m, double* H) {
   const int lane = lane_id();
   bool ok = true;
+  if ((m & 7) == 0 && m >= 16) {
+    // blocked right-looking variant for tile-aligned sizes: eight columns are factorised with their panel by rank-1 updates restricted to
+    // the block, the trailing matrix takes ONE rank-8 update through the warp GEMM (FP64 tensor pipe). Same pivots, same NaN propagation;
+    // the strictly upper triangle of the trailing blocks is scratch (nothing reads it: U = L' is taken from the lower triangle).
+    for (int b0 = 0; b0 < m; b0 += 8) {
+      const int b1 = b0 + 8;
+      for (int j = b0; j < b1; ++j) {
+        double d = H[j + j * m];
+        if (!(d > 0.0)) {
+          ok = false;
+          d = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        const double rs = rsqrt(d);
+        const double ljj = d * rs;
+        __syncwarp();
+        for (int i = j + 1 + lane; i < m; i += 32) H[i + j * m] *= rs;
+        if (lane == 0) H[j + j * m] = ljj;
+        __syncwarp();
+        for (int k = j + 1 + (lane >> 3); k < b1; k += 4) {
+          const double lkj = H[k + j * m];
+          for (int i = k + (lane & 7); i < m; i += 8) H[i + k * m] = fma(-H[i + j * m], lkj, H[i + k * m]);
+        }
+        __syncwarp();
+      }
+      if (b1 < m) wgemm<false, true>(m - b1, m - b1, 8, -1.0, H + b1 + b0 * m, m, H + b1 + b0 * m, m, 1.0, H + b1 + b1 * m, m);
+    }
+    return ok;
+  }
   for (int j = 0; j < m; ++j) {
     double d = H[j + j * m];
     if (!(d > 0.0)) {
