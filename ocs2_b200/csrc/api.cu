@@ -1116,13 +1116,17 @@ o2c_error o2c_download_flattened_controller(o2c_handle* h, float* host_out, doub
   if (!std::isfinite(step_length)) return fail(O2C_ERR_INVALID_ARGUMENT, "step_length must be finite");
   O2C_CUDA(cudaSetDevice(h->cfg.device));
   const size_t per = (size_t)(h->L.N + 1) * h->L.m * (h->L.n + 1);
-  if (!h->d_flat) O2C_CUDA(cudaMalloc(&h->d_flat, sizeof(float) * per * h->cfg.batch));
+  // converted in slices of at most 256 MiB of device scratch (the whole legged batch would be 4 GB of floats)
+  const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)h->cfg.batch, ((size_t)256 << 20) / (per * sizeof(float))));
+  if (!h->d_flat) O2C_CUDA(cudaMalloc(&h->d_flat, sizeof(float) * per * slice));
   cudaStream_t stream = h->lanes[0].stream;
-  float* dev = h->d_flat + per * begin;
-  O2C_CUDA(launch_flatten(h->L, h->d_sol, dev, step_length, begin, count, stream));
-  h->launches += 1;
-  O2C_CUDA(cudaMemcpyAsync(host_out, dev, sizeof(float) * per * count, cudaMemcpyDeviceToHost, stream));
-  O2C_CUDA(cudaStreamSynchronize(stream));
+  for (int off = 0; off < count; off += slice) {
+    const int c = std::min(slice, count - off);
+    O2C_CUDA(launch_flatten(h->L, h->d_sol, h->d_flat, step_length, begin + off, c, stream));
+    h->launches += 1;
+    O2C_CUDA(cudaMemcpyAsync(host_out + per * off, h->d_flat, sizeof(float) * per * c, cudaMemcpyDeviceToHost, stream));
+    O2C_CUDA(cudaStreamSynchronize(stream));  // the scratch is reused by the next slice
+  }
   return O2C_OK;
 }
 

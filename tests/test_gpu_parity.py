@@ -890,3 +890,17 @@ def test_discretize_matches_oracle(n, m, stages):
     with o2.BatchedLqSolver(o2.Settings(algorithm=o2.ALG_SLQ), n, m, N, batch) as slq:
         with pytest.raises(o2.O2cError):
             slq.discretize(dv)
+
+
+def test_flattened_controller_in_slices():
+    """The float conversion runs through a bounded device scratch: a batch larger than one slice comes back identical to the per-problem
+    conversion."""
+    n, m, N, batch = 24, 24, 100, 1300  # 1300 * 101 * 600 floats = 315 MB > one 256 MiB slice
+    st = o2.Settings(hessianCorrectionMultiple=1e-5)
+    with o2.BatchedLqSolver(st, n, m, N, batch) as solver:
+        solver.generate_synthetic(4, 0)
+        solver.solveSequentialRiccatiEquations()
+        flat = solver.flatten(1.0)
+        assert flat.shape == (batch, N + 1, m * (n + 1)) and np.isfinite(flat).all()
+        for p in (0, 1107, 1108, batch - 1):  # both sides of the slice boundary
+            assert np.array_equal(flat[p], solver.flatten(1.0, problem_begin=p, problem_count=1)[0])
