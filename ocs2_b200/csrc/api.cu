@@ -460,6 +460,8 @@ o2c_error install_events(o2c_handle* h, cudaStream_t stream, const o2c_lq_view* 
   std::vector<int> tmp((size_t)count * nodes);
   for (int p = 0; p < count; ++p)
     for (int k = 0; k < nodes; ++k) tmp[(size_t)p * nodes + k] = ev[p * ps + k * ns] != 0;
+  if (std::find(tmp.begin(), tmp.end(), 1) == tmp.end())  // an all-zero flag array is "no events": keep the event-free kernels
+    return install_events(h, stream, nullptr, false, begin, count);
   if (slq) {
     std::vector<int> flags(tmp.begin(), tmp.begin() + nodes);
     for (int p = 1; p < count; ++p)

@@ -570,7 +570,10 @@ def test_ilqr_events_match_oracle(n, m, nc, nominal):
         sol_h = solver.solve_host(lq, alpha=0.7, chunk=2)
         for name in ("K", "dbias", "Sm", "Sv", "s", "x", "u"):
             assert np.array_equal(getattr(sol_h, name), getattr(sol, name)), f"solve_host with events: {name}"
-        # a later upload without events clears them: the specialised kernels come back where they exist
+        # a later upload without events (or with an all-zero flag array) clears them: the specialised kernels come back where they exist
+        lq.event = np.zeros_like(event)
+        solver.upload(lq)
+        assert ("generic" in solver.kernel_variant) == (n not in (24, 10, 9, 4))
         lq.event = None
         solver.upload(lq)
         assert ("generic" in solver.kernel_variant) == (n not in (24, 10, 9, 4))
