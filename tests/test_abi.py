@@ -70,3 +70,21 @@ def test_no_cpu_fallback():
 def test_unsupported_settings_are_rejected_in_the_host_mirror():
     with pytest.raises(o2.O2cError):
         o2.BatchedLqSolver(o2.Settings(algorithm=o2.ALG_SLQ, backwardPassIntegratorType="ODE45"), 4, 1, 10, 2)
+
+
+def test_headers_compile_as_c99_and_cxx14():
+    """The ABI header is plain C (a cgo / JNI / ctypes binding can include it); the front-end header is dependency-free C++14."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    c = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(root, "include", "ocs2_ddp_cuda.h")], capture_output=True, text=True)
+    assert c.returncode == 0, c.stderr
+    cxx = subprocess.run(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++",
+                          os.path.join(root, "include", "ocs2_ddp_cuda", "BatchedRiccatiSolver.h")], capture_output=True, text=True)
+    assert cxx.returncode == 0, cxx.stderr
+
+
+def test_discretization_view_layout():
+    """o2c_discretization_view: 8 fields of 24 bytes, the dt pointer, the stage count (padded to 8)."""
+    import ctypes as C
+    assert C.sizeof(_l.DiscretizationView) == 8 * 24 + 8 + 8
