@@ -177,6 +177,33 @@ __device__ __forceinline__ bool warp_cholesky(int m, double* H) {
 __device__ __forceinline__ void warp_upper_inverse(int dim, const double* Ub, int si, int sk, double* X, double* dinv) {
   for (int i = lane_id(); i < dim; i += 32) dinv[i] = 1.0 / Ub[i * si + i * sk];  // the divisions, once and in parallel
   __syncwarp();
+  if (sk == 1 && (dim & 7) == 0 && dim >= 16 && dim <= 32) {
+    // blocked variant for tile-aligned sizes (U = L' of a Cholesky factor stored lower, ld si): the 8x8 diagonal blocks are inverted side by
+    // side by back substitution (one column per lane: a chain of at most 28 fmas instead of dim^2 / 2), the off-diagonal blocks follow from
+    // X_ab = -X_aa (sum_{a < c <= b} U_ac X_cb) through the warp GEMM; the (zero) lower block (b, a) serves as the scratch of the sum
+    const int lane = lane_id(), nb = dim >> 3;
+    if (lane < dim) {
+      const int j = lane, b0 = j & ~7;
+      for (int i = j; i >= b0; --i) {
+        double v = (i == j) ? 1.0 : 0.0;
+        for (int k = i + 1; k <= j; ++k) v = fma(-Ub[i * si + k], X[k + j * dim], v);
+        X[i + j * dim] = v * dinv[i];
+      }
+      for (int i = j + 1; i < b0 + 8; ++i) X[i + j * dim] = 0.0;  // the diagonal blocks enter the products below as full 8x8 tiles
+    }
+    __syncwarp();
+    for (int b = 1; b < nb; ++b)
+      for (int a = b - 1; a >= 0; --a) {
+        double* S = X + 8 * b + 8 * a * dim;
+        for (int c = a + 1; c <= b; ++c)
+          wgemm<true, false>(8, 8, 8, 1.0, Ub + 8 * c + 8 * a * si, si, X + 8 * c + 8 * b * dim, dim, c == a + 1 ? 0.0 : 1.0, S, dim);
+        wgemm<false, false>(8, 8, 8, -1.0, X + 8 * a + 8 * a * dim, dim, S, dim, 0.0, X + 8 * a + 8 * b * dim, dim);
+      }
+    for (int idx = lane; idx < dim * dim; idx += 32)
+      if ((idx % dim) > (idx / dim)) X[idx] = 0.0;
+    __syncwarp();
+    return;
+  }
   for (int j = lane_id(); j < dim; j += 32) {
     for (int i = j; i >= 0; --i) {
       double v = (i == j) ? 1.0 : 0.0;
