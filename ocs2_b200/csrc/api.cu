@@ -81,7 +81,18 @@ struct o2c_handle {
   bool nc_ragged = false;  // a caller supplied per-node constraint counts (otherwise every node has nc_max: the kernels skip the lookup)
   int64_t launches = 0;
   int stage_chunk = 0;
+  int* d_counter = nullptr;  // [kLanes] work counters of the persistent kernels' dynamic problem fetch, one per stream lane
 
+  int lane_of(cudaStream_t s) const {
+    for (int i = 0; i < kLanes; ++i)
+      if (lanes[i].stream == s) return i;
+    return 0;
+  }
+  DeviceBuffers buffers(cudaStream_t s) const {
+    DeviceBuffers b = buffers();
+    b.work_counter = d_counter ? d_counter + lane_of(s) : nullptr;
+    return b;
+  }
   DeviceBuffers buffers() const {
     DeviceBuffers b{};
     b.lq = d_lq;
@@ -98,6 +109,7 @@ struct o2c_handle {
     b.xs = d_xs;
     b.us = d_us;
     b.status = d_status;
+    b.work_counter = nullptr;
     return b;
   }
 };
@@ -640,7 +652,7 @@ void flush_status(o2c_handle* h) {
 o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) {
   if (count == 0) return O2C_OK;
   h->backward_done = true;
-  const DeviceBuffers buf = h->buffers();
+  const DeviceBuffers buf = h->buffers(stream);
   if (h->st.algorithm == O2C_ALG_ILQR) {
     if (h->use_fast && wpp_ilqr_supported(h->L, h->st, buf)) {  // (handles with events fall through to the generic kernel)
       int l = 0;
@@ -690,9 +702,9 @@ o2c_error solve_on(o2c_handle* h, cudaStream_t stream, double* alpha_slot_dev, d
     int l = 0;
     h->backward_done = true;
     if (h->use_fast)
-      O2C_CUDA(launch_ilqr_wpp(h->L, h->st, h->buffers(), true, alpha, h->cfg.batch, begin, count, stream, &l));
+      O2C_CUDA(launch_ilqr_wpp(h->L, h->st, h->buffers(stream), true, alpha, h->cfg.batch, begin, count, stream, &l));
     else
-      O2C_CUDA(launch_ilqr_rpl(h->L, h->st, h->buffers(), true, alpha, begin, count, stream, &l));
+      O2C_CUDA(launch_ilqr_rpl(h->L, h->st, h->buffers(stream), true, alpha, begin, count, stream, &l));
     h->launches += l;
     return O2C_OK;
   }
@@ -710,7 +722,7 @@ void release(o2c_handle* h) {
   }
   void* ptrs[] = {h->d_lq,  h->d_term, h->d_xnom, h->d_unom,   h->d_x0,        h->d_time,    h->d_sol,
                   h->d_xs,  h->d_us,   h->d_alphas, h->d_nc,   h->d_status,    h->d_slq_steps, h->d_ro_steps,
-                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event, h->d_flat, h->d_jump, h->d_dt};
+                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event, h->d_flat, h->d_jump, h->d_dt, h->d_counter};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
@@ -791,6 +803,7 @@ o2c_error o2c_create(const o2c_config* cfg, o2c_handle** out) {
   ALLOC(h->d_us, sizeof(double) * (size_t)cfg->max_alphas * B * h->out_nodes * L.m);
   ALLOC(h->d_alphas, sizeof(double) * (cfg->max_alphas + kLanes));
   ALLOC(h->d_status, sizeof(int) * B);
+  ALLOC(h->d_counter, sizeof(int) * kLanes);
   if (cfg->has_nominal) {
     ALLOC(h->d_xnom, sizeof(double) * B * (L.N + 1) * L.n);
     ALLOC(h->d_unom, sizeof(double) * B * (L.N + 1) * L.m);

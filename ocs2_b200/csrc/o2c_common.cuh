@@ -98,7 +98,17 @@ struct DeviceBuffers {
   double* xs;
   double* us;
   int* status;
+  int* work_counter;  // one int owned by the launching stream lane (dynamic problem fetch of the persistent kernels), or nullptr
 };
+
+// SM count of the CURRENT device, queried per call: nothing is cached in function-local statics, so handles on different devices
+// and launches from different host threads never share launcher state
+inline int device_sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return sms;
+}
 
 // one RK4 step of the SLQ backward integration (host-precomputed, mirrors boost::odeint integrate_times)
 struct SlqStep {

@@ -985,16 +985,12 @@ __global__ void __launch_bounds__(64) slq_rpl_kernel(const SlqArgs a) {
 template <int NX, int NU, bool EV>
 cudaError_t launch_slq(const SlqArgs& a, cudaStream_t stream) {
   using S = SlqShape<NX, NU>;
-  static int num_sms = 0;
   constexpr int wpb = 1;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(slq_rpl_kernel<NX, NU, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_sm_count();
+  if (num_sms <= 0) return cudaErrorInvalidDevice;
   int ctas_per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, slq_rpl_kernel<NX, NU, EV>, wpb * 32, smem);
   if (e != cudaSuccess) return e;
@@ -1237,16 +1233,12 @@ __global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
 template <int NX, int NU>
 cudaError_t launch_ro(const RoArgs& a, int n_alpha, cudaStream_t stream) {
   using S = RoShape<NX, NU>;
-  static int num_sms = 0;
   constexpr int wpb = 4;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(rollout_cont_rpl_kernel<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_sm_count();
+  if (num_sms <= 0) return cudaErrorInvalidDevice;
   int ctas_per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, rollout_cont_rpl_kernel<NX, NU>, wpb * 32, smem);
   if (e != cudaSuccess) return e;
@@ -1271,16 +1263,12 @@ bool layout_matches(const Layout& L) {
 template <int NX, int NU, int NC, bool NOM, bool EV>
 cudaError_t launch(const Args& a, cudaStream_t stream) {
   using S = Shape<NX, NU, NC>;
-  static int num_sms = 0;
   constexpr int wpb = (NX == 10) ? 1 : 2;
   const size_t smem = (size_t)S::warp_doubles * wpb * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(ilqr_rpl_kernel<NX, NU, NC, NOM, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_sm_count();
+  if (num_sms <= 0) return cudaErrorInvalidDevice;
   int ctas_per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ilqr_rpl_kernel<NX, NU, NC, NOM, EV>, wpb * 32, smem);
   if (e != cudaSuccess) return e;

@@ -32,6 +32,7 @@
 //   to one rounding of M_ii + eps (<= 1e-16 |M_ii|).
 // Rollout (fused, same warp): du_k = K_k dx_k + alpha dbias_k ; dx_{k+1} = A_k dx_k + B_k du_k + Hv_k
 //                                            DDP_HelperFunctions.cpp:125-138, 296-304; LinearController.cpp:79-87
+#include <cstdio>
 #include <cstdlib>
 
 #include "o2c_common.cuh"
@@ -42,9 +43,9 @@ namespace {
 constexpr int kN = 24;            // nx == nu
 constexpr int kMat = kN * kN;     // 576
 constexpr int kLd = 26;           // leading dimension of the scratch matrix (conflict-free 8-byte transposed access)
-constexpr int kWarps = 4;         // problems per CTA
-constexpr int kThreads = 32 * kWarps;
-constexpr int kCtasPerSm = 3;
+// Residency: one CTA per SM whose warp count is chosen per launch (1..12: 168 registers per thread and 15.9 KB of shared memory per warp
+// allow three warps on each of the four schedulers; a fourth would need <= 128 registers: 4 x 32 x 144 > the 16 K registers of a scheduler).
+constexpr int kMaxWarps = 12;
 constexpr int kOperand = 2 * kMat + 3 * kN + 2 + 6;  // {A|B|Hv|q|r|c,pad} doubles staged by TMA (= Layout::oQ for n = m = 24, 128-byte aligned)
 constexpr unsigned kFull = 0xffffffffu;
 // record offsets of make_layout(24, 24, 0, N, ILQR) as compile-time constants (address arithmetic folds into the instructions'
@@ -121,6 +122,8 @@ struct Args {
   int N;
   int oQf, oqf, ocf, trec;
   int begin, count, with_rollout;
+  int* counter;  // dynamic problem fetch: zeroed before the launch; nullptr = static stride
+  int dyn_limit;  // problems [resident slots, dyn_limit) are fetched dynamically, [dyn_limit, count) = the last partial wave, static
   double eps, alpha;
 };
 
@@ -295,13 +298,14 @@ __device__ __forceinline__ bool factor_hm(double* W, int lane, int li, int r, in
 
 // L2 prefetch of the cost Hessians a stage reads: all of P and Q (they are copied to shared memory whole by TMA), and the tiles of R on
 // or above the block diagonal (R is symmetric; the sweep reads R[8jb+2c..][8ib+r] for jb <= ib). One 16-byte touch per lane and tile.
+template <bool QPD>
 __device__ __forceinline__ void prefetch_hessians(const double* rec, const Args& a, int lo24) {
 #pragma unroll
   for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
     for (int jb = 0; jb < 3; ++jb) {
       l2_touch(rec + kOP + lo24 + t24(jb, ib));
-      l2_touch(rec + kOQ + lo24 + t24(jb, ib));
+      if (!QPD || jb <= ib) l2_touch(rec + kOQ + lo24 + t24(jb, ib));  // QPD reads Q like R: only the tiles on or above the block diagonal
       if (jb <= ib) l2_touch(rec + kOR + lo24 + t24(jb, ib));
     }
 }
@@ -309,8 +313,25 @@ __device__ __forceinline__ void prefetch_hessians(const double* rec, const Args&
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool NOM, bool EV>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Args a) {
+// next problem of this warp. The first problem is static (warp-major over the CTAs: CTA b gets b, b + grid, b + 2 grid, ... so that a
+// batch smaller than the resident slots still spreads evenly over the SMs). The problems of the following FULL waves come from a global
+// counter, so a warp that finishes early picks up the next problem instead of idling until the slowest warp of a static schedule is
+// done. The last, partial wave is static again (warp-major): handed out dynamically it would be grabbed by the SMs that finished
+// first, twelve problems each, and run at full-machine contention on a few SMs while the others idle (measured: 3.4 ms instead of 2.5 ms
+// for 2048 problems, profiles/r02_wpp_residency.jsonl).
+__device__ __forceinline__ int next_problem(const Args& a, int lane, int total_warps, int pi, int slot, bool& tail_taken) {
+  if (a.counter == nullptr) return pi + total_warps;
+  if (tail_taken) return a.count;
+  int nx = 0;
+  if (lane == 0) nx = atomicAdd(a.counter, 1) + total_warps;
+  nx = __shfl_sync(kFull, nx, 0);
+  if (nx < a.dyn_limit) return nx;
+  tail_taken = true;
+  return a.dyn_limit + slot;  // >= count when this warp has no problem in the last wave
+}
+
+template <bool NOM, bool EV, bool QPD>
+__global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
@@ -332,7 +353,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
   __syncwarp();
   uint32_t phase = 0, hphase = 0, bphase = 0;  // bphase: bit q = parity to wait for on bfull[q]
 
-  for (int pi = blockIdx.x * kWarps + warp; pi < a.count; pi += gridDim.x * kWarps) {
+  const int total_warps = gridDim.x * (blockDim.x >> 5);
+  const int slot = warp * gridDim.x + blockIdx.x;
+  bool tail_taken = false;
+  for (int pi = slot; pi < a.count; pi = next_problem(a, lane, total_warps, pi, slot, tail_taken)) {
     const int prob = a.begin + pi;
     const double* lqp = a.lq + (size_t)prob * N * kRec;
     const double* term = a.term + (size_t)prob * a.trec;
@@ -345,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       mbar_expect_tx(&ws.full, opBytes);
       tma_load(ws.in, lqp + (size_t)(N - 1) * kRec, opBytes, &ws.full);
     }
-    prefetch_hessians(lqp + (size_t)(N - 1) * kRec, a, lo24);
+    prefetch_hessians<QPD>(lqp + (size_t)(N - 1) * kRec, a, lo24);
     // terminal condition: valueFunctionTrajectory.back() = finalValueFunction (GaussNewtonDDP.cpp:526)
     {
       double* outN = solp + (size_t)N * kORec;
@@ -384,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       const bool ev = EV && __ldg(evp + k) != 0;
       mbar_wait(&ws.full, phase);
       phase ^= 1u;
-      if (k < N - 1) prefetch_hessians(rec, a, lo24);  // this node's Q, P, R into L2 now: first needed a third of a stage from here
+      if (k < N - 1) prefetch_hessians<QPD>(rec, a, lo24);  // this node's Q, P, R into L2 now: first needed a third of a stage from here
                                                         // (node N-1's were touched in the prologue); prefetching any earlier only
                                                         // loses lines to L2 capacity misses with 1776 problems in flight
 
@@ -460,10 +484,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 
       // The cost Hessians Q and P ride through shared memory too, each in a slot that is dead for exactly as long as the copy needs:
       // Q (4.6 KB, one TMA copy) into the scratch while Hm and T are being contracted, P into A's slot while G' is.
-      if (lane == 0) {
+      if (!QPD && lane == 0) {
         fence_proxy_async();
         mbar_expect_tx(&ws.hfull, matBytes);
         tma_load(ws.W, rec + kOQ, matBytes, &ws.hfull);
+      }
+      // QPD: Q (its six tiles on or below the block diagonal) and P go from L2 straight into the accumulators of T and G', each issued
+      // one contraction (576 pipe cycles) ahead of its first use, like R at the top of the stage
+      if (QPD) {
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) t[lt(ib, jb)] = ldg2(rec + kOQ + lo24 + t24(jb, ib));  // Q[8ib+r][8jb+2c..] = Q[8jb+2c..][8ib+r]
       }
 
       // ---- Hm = R + SB'B (lower tiles) ----
@@ -481,8 +513,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
       }
 
       // ---- T = Q + eps I + SA'A (lower tiles) ----
+      double2 g[3][3];
+      if (QPD) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) t[i] = zero2();
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) g[ib][jb] = ldg2(rec + kOP + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) t[i] = zero2();
+      }
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) {
         double2 af[3];
@@ -493,29 +533,34 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
 #pragma unroll
           for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], zA[ib][kb], af[jb]);
       }
-      __syncwarp();  // A is dead: its slot takes P
-      if (lane == 0) {
-        mbar_expect_tx(&ws.hfull2, matBytes);
-        tma_load(ws.in, rec + kOP, matBytes, &ws.hfull2);
+      if (!QPD) {
+        __syncwarp();  // A is dead: its slot takes P
+        if (lane == 0) {
+          mbar_expect_tx(&ws.hfull2, matBytes);
+          tma_load(ws.in, rec + kOP, matBytes, &ws.hfull2);
+        }
+        mbar_wait(&ws.hfull, hphase);
       }
-      mbar_wait(&ws.hfull, hphase);
 #pragma unroll
       for (int ib = 0; ib < 3; ++ib) {
+        if (!QPD) {
 #pragma unroll
-        for (int jb = 0; jb <= ib; ++jb) {
-          const double2 qq = ld2(ws.W + lo24 + t24(jb, ib));  // Q[8ib+r][8jb+2c..] = Q[8jb+2c..][8ib+r], dense ld 24 as copied
-          t[lt(ib, jb)].x += qq.x;
-          t[lt(ib, jb)].y += qq.y;
+          for (int jb = 0; jb <= ib; ++jb) {
+            const double2 qq = ld2(ws.W + lo24 + t24(jb, ib));  // Q[8ib+r][8jb+2c..] = Q[8jb+2c..][8ib+r], dense ld 24 as copied
+            t[lt(ib, jb)].x += qq.x;
+            t[lt(ib, jb)].y += qq.y;
+          }
         }
         t[lt(ib, ib)].x += (2 * c == r) ? epsk : 0.0;
         t[lt(ib, ib)].y += (2 * c + 1 == r) ? epsk : 0.0;
       }
-      __syncwarp();  // Q is consumed: the scratch takes Hm (lower triangle)
-      double2 g[3][3];
+      if (!QPD) {
+        __syncwarp();  // Q is consumed: the scratch takes Hm (lower triangle)
 #pragma unroll
-      for (int ib = 0; ib < 3; ++ib)
+        for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-        for (int jb = 0; jb < 3; ++jb) g[ib][jb] = zero2();
+          for (int jb = 0; jb < 3; ++jb) g[ib][jb] = zero2();
+      }
       if (ev) {
         // S- = T and Sv- = tv are final: through the scratch once more for G' = P' + S-B and Gv = r + B'Sv-
 #pragma unroll
@@ -567,16 +612,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) ilqr_wpp_kernel(const Ar
             for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], zA[ib][kb], bf[jb]);
         }
       }
-      mbar_wait(&ws.hfull2, hphase);
-      hphase ^= 1u;
+      if (!QPD) {
+        mbar_wait(&ws.hfull2, hphase);
+        hphase ^= 1u;
 #pragma unroll
-      for (int ib = 0; ib < 3; ++ib)
+        for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-        for (int jb = 0; jb < 3; ++jb) {
-          const double2 pp = ld2(ws.in + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
-          g[ib][jb].x += pp.x;
-          g[ib][jb].y += pp.y;
-        }
+          for (int jb = 0; jb < 3; ++jb) {
+            const double2 pp = ld2(ws.in + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
+            g[ib][jb].x += pp.x;
+            g[ib][jb].y += pp.y;
+          }
+      }
       __syncwarp();  // all lanes are done with the staged operand block: refill it for node k-1 while this stage finishes
       if (lane == 0 && k >= 1) {
         mbar_expect_tx(&ws.full, opBytes);
@@ -886,25 +933,63 @@ bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceB
          L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat;
 }
 
+// Resident problems (warps) per SM for a launch of `count` problems on `sms` SMs. The time one problem takes depends on how many
+// problems share its SM's FP64 pipe: t(w) in ms for ONE full wave of w warps per SM (N = 100; measured on B200,
+// profiles/r02_wpp_residency.jsonl; the steps at 4 -> 5 and 8 -> 9 are a scheduler taking its second / third warp).
+// A full machine (w = 12) has the best steady-state throughput, but a batch that is not a multiple of 12 x sms ends in a ragged
+// wave: 2048 problems on 148 SMs (BASELINE.json config 5: 16384 over 8 GPUs) are 1776 + 272, and the 272 stragglers cost another
+// t(2). Two even waves of 7 per SM take 2 t(7) instead of t(12) + t(2). The choice minimises the modelled makespan
+// full_waves(w) x t(w) + t(warps of the last, partial wave); only the ratios of t matter. Batches of many waves (>= 4 at w = 12)
+// keep w = 12: with the dynamic fetch the waves de-synchronise and the steady-state throughput is what counts.
+int choose_resident_warps(int count, int sms) {
+  static const double t[kMaxWarps + 1] = {0.0, 0.82, 0.83, 0.86, 0.89, 1.18, 1.21, 1.27, 1.34, 1.61, 1.63, 1.72, 1.87};
+  if (count >= 4 * kMaxWarps * sms) return kMaxWarps;
+  int best = kMaxWarps;
+  double best_time = 1e300;
+  for (int w = kMaxWarps; w >= 1; --w) {
+    const long slots = (long)w * sms;
+    const long full = count / slots, rem = count % slots;
+    const int tail_warps = (int)((rem + sms - 1) / sms);  // warps per SM in the last wave (problems spread warp-major over the SMs)
+    const double time = (double)full * t[w] + (tail_warps ? t[tail_warps] : 0.0);
+    if (time < best_time - 1e-9) {
+      best_time = time;
+      best = w;
+    }
+  }
+  return best;
+}
+
 cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, bool with_rollout, double alpha, int batch,
                             int begin, int count, cudaStream_t stream, int* launches) {
   if (!wpp_ilqr_supported(L, st, buf)) return cudaErrorNotSupported;
-  static bool configured = false;
-  static int num_sms = 0;
-  const size_t smem = sizeof(WarpSmem) * kWarps;
   const bool nom = buf.x_nom != nullptr, ev = buf.event != nullptr;
-  void (*const kernels[4])(const Args) = {ilqr_wpp_kernel<false, false>, ilqr_wpp_kernel<true, false>, ilqr_wpp_kernel<false, true>,
-                                          ilqr_wpp_kernel<true, true>};
-  void (*const kernel)(const Args) = kernels[(nom ? 1 : 0) + (ev ? 2 : 0)];
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  if (!configured) {
-    for (auto fn : kernels) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
+  using Kernel = void (*)(const Args);
+  const Kernel kernels[8] = {ilqr_wpp_kernel<false, false, false>, ilqr_wpp_kernel<true, false, false>, ilqr_wpp_kernel<false, true, false>,
+                             ilqr_wpp_kernel<true, true, false>,   ilqr_wpp_kernel<false, false, true>, ilqr_wpp_kernel<true, false, true>,
+                             ilqr_wpp_kernel<false, true, true>,   ilqr_wpp_kernel<true, true, true>};
+  // QPD (default): Q and P go from L2 straight into the accumulators instead of through TMA-staged shared-memory slots: Q is read
+  // like R (six tiles instead of nine: -1.5 KB of DRAM traffic per stage) and two mbarrier round trips per stage disappear
+  // (+0.8 % at 16384 problems, profiles/r02_wpp_variants.jsonl). O2C_WPP_QPD=0 selects the round-1 staging for comparison.
+  bool qpd = true;
+  if (const char* e = getenv("O2C_WPP_QPD")) qpd = atoi(e) != 0;
+  const Kernel kernel = kernels[(nom ? 1 : 0) + (ev ? 2 : 0) + (qpd ? 4 : 0)];
+  const int num_sms = device_sm_count();
+  if (num_sms <= 0) return cudaErrorInvalidDevice;
+  // profiling knobs, read per launch (no state is cached in statics: launches from several host threads / on several devices are
+  // independent): O2C_WPP_RESIDENT = warps per SM (1..12), O2C_WPP_DYNAMIC = 0 switches the dynamic problem fetch off
+  int warps = choose_resident_warps(count, num_sms);
+  if (const char* e = getenv("O2C_WPP_RESIDENT")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= kMaxWarps) warps = v;
   }
+  bool dynamic = true;
+  if (const char* e = getenv("O2C_WPP_DYNAMIC")) dynamic = atoi(e) != 0;
+  const size_t smem = sizeof(WarpSmem) * warps;
+  // function attributes are per device: set on every launch (sub-microsecond) instead of caching "configured" in a static
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * kMaxWarps));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   Args a{};
   a.lq = buf.lq;
   a.term = buf.term;
@@ -927,14 +1012,19 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   a.eps = st.eps;
   a.alpha = alpha;
   (void)batch;
-  const int ctas_needed = (count + kWarps - 1) / kWarps;
-  int ctas_per_sm = kCtasPerSm;
-  if (const char* e = getenv("O2C_WPP_CTAS_PER_SM")) {  // profiling knob: fewer resident problems per SM
-    const int v = atoi(e);
-    if (v >= 1 && v < kCtasPerSm) ctas_per_sm = v;
+  // warp-major problem order (CTA b starts with problems b, b + grid, ...): the grid is as wide as the machine even when the batch
+  // does not fill every warp slot, so a small batch spreads evenly over the SMs
+  const int grid = count < num_sms ? count : num_sms;
+  a.counter = nullptr;
+  if (dynamic && buf.work_counter != nullptr && count > grid * warps) {
+    e = cudaMemsetAsync(buf.work_counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    a.counter = buf.work_counter;
+    a.dyn_limit = count - count % (grid * warps);
   }
-  const int grid = ctas_needed < num_sms * ctas_per_sm ? ctas_needed : num_sms * ctas_per_sm;
-  kernel<<<grid, kThreads, smem, stream>>>(a);
+  if (getenv("O2C_WPP_VERBOSE"))
+    fprintf(stderr, "ilqr_wpp launch: warps/SM %d grid %d count %d dynamic %d\n", warps, grid, count, a.counter != nullptr);
+  kernel<<<grid, 32 * warps, smem, stream>>>(a);
   if (launches) *launches = 1;
   return cudaGetLastError();
 }
