@@ -21,8 +21,15 @@
  * in a struct-of-arrays batch layout; every matrix block is column-major (Eigen default) and contiguous.
  *
  * Conventions: all functions return an o2c_error (0 = success) and never throw; o2c_last_error() gives the message of the
- * last failure on the calling thread. Calls on one handle must be serialised by the caller; different handles are independent.
+ * last failure on the calling thread. Calls on one handle must be serialised by the caller; different handles are independent:
+ * they may live on different devices and be driven from different host threads at the same time (the library keeps no
+ * process-wide launch state; include/ocs2_ddp_cuda/ShardedRiccatiSolver.h shards one batch over several devices that way).
  * There is NO CPU fallback: without a CUDA device o2c_create fails with O2C_ERR_CUDA.
+ *
+ * Riccati form: under LINE_SEARCH the shape-specialised kernels evaluate the REDUCED form for both O2C_FORM_* values. The full form
+ * (preComputeRiccatiTerms = false) is the same map written with K~'G~ + G~'K~ + K~'H~K~ in place of -G~'G~ (H~ = Pu'Hm Pu = I); the
+ * reference's own RiccatiTest.cpp:87-105 holds the two equal to 1e-9. They differ only in rounding, which matters when Hm is barely
+ * positive definite. Configurations served by the generic kernels (see o2c_kernel_variant) evaluate the form that was asked for.
  */
 #ifndef OCS2_DDP_CUDA_H_
 #define OCS2_DDP_CUDA_H_
@@ -33,7 +40,7 @@
 extern "C" {
 #endif
 
-#define O2C_ABI_VERSION 3
+#define O2C_ABI_VERSION 4
 
 typedef enum o2c_error {
   O2C_OK = 0,
@@ -60,7 +67,18 @@ enum {
   O2C_STATUS_OK = 0,
   O2C_STATUS_CHOL_NOT_PD = 1,    /* Hm = R + B'SB not positive definite (LinearAlgebra.cpp:119-124 would silently continue) */
   O2C_STATUS_NONFINITE = 2,      /* non-finite gains / value function / rollout (GaussNewtonDDP.cpp:621-636, DDP_HelperFunctions.cpp:132-134) */
-  O2C_STATUS_CONSTRAINT_RANK = 4 /* |Rc_ii| clamped to 1e-9 in the constraint QR (LinearAlgebra.cpp:38-47) */
+  O2C_STATUS_CONSTRAINT_RANK = 4, /* |Rc_ii| clamped to 1e-9 in the constraint QR (LinearAlgebra.cpp:38-47) */
+  O2C_STATUS_NOT_PSD = 8          /* set by o2c_check_numerical_stability only: some S_k fails checkBeingPSD (GaussNewtonDDP.cpp:555-579) */
+};
+
+/* o2c_lq_view.flags */
+enum {
+  /* Q, R and Qf hold only their upper triangle, packed column by column (element (i, j), i <= j, at j (j + 1) / 2 + i; blocks of
+   * n (n + 1) / 2 and m (m + 1) / 2 doubles): the order of ContinuousTimeRiccatiEquations::convert2Vector
+   * (ocs2_ddp/src/riccati_equations/ContinuousTimeRiccatiEquations.cpp:55-108) and of Eigen's triangularView<Upper> traversal. The
+   * cost Hessians are symmetric, so a host caller moves 19 % fewer bytes over PCIe for the legged shape. Strides are in doubles of
+   * the packed blocks. Honoured by o2c_upload, o2c_import_device and o2c_solve_host. */
+  O2C_LQ_SYMMETRIC_PACKED = 1
 };
 
 typedef struct o2c_config {
@@ -105,7 +123,11 @@ typedef struct o2c_lq_view {
    * (time[node] == time[node+1], node+1 in postEventIndices_). Its A, Hv, Q, q, c blocks hold the jump ModelData
    * (modelDataEventTimes: jump map linearisation x+ = A_e dx + Hv_e and pre-jump cost), its B, P, R, r, C, D, e the regular model
    * data of the node, which only shape the controller entry. NULL = no events. Host memory in o2c_upload / o2c_solve_host, device
-   * memory in o2c_import_device. SLQ handles: see jump_* below. */
+   * memory in o2c_import_device. With a pre-event node at the last stage (node N-1) the controller entry of node N is still
+   * the copy of node N-1: the reference keeps the entry built from node N's OWN ModelData in that case (GaussNewtonDDP.cpp:609-618,
+   * ILQR.cpp:196-209), which an ILQR handle does not carry (stage data of nodes 0..N-1 only). LEVENBERG_MARQUARDT handles
+   * do not take ILQR events (O2C_ERR_UNSUPPORTED from o2c_backward): deltaGm / deltaGv of a pre-event node are built from the node's
+   * regular dynamics (ILQR.cpp:263-295), which this layout replaces by the jump map. SLQ handles: see jump_* below. */
   const int32_t* event;
   int64_t event_problem_stride, event_node_stride;
   /* SLQ events (SLQ.cpp:256-302, ContinuousTimeRiccatiEquations.cpp:135-147): event[problem][node] != 0 marks a pre-event node k whose
@@ -117,6 +139,7 @@ typedef struct o2c_lq_view {
    * rollout restarts weakEpsilon after every event from x+ = x_nom(k+1) + A_e (x - x_nom(k)) + Hv_e. Host memory (o2c_upload,
    * o2c_solve_host); o2c_import_device does not take SLQ events. */
   o2c_field jump_A, jump_Hv, jump_Q, jump_q, jump_c; /* n*n, n, n*n, n, 1; jump_A and jump_Q required with SLQ events */
+  int32_t flags;                                      /* O2C_LQ_* bits, 0 = dense blocks everywhere */
 } o2c_lq_view;
 
 /* Struct-of-arrays view of the solution. Controller and value function have N+1 nodes (node N of the controller is the copy of
@@ -173,6 +196,11 @@ o2c_error o2c_backward(o2c_handle* handle, int32_t problem_begin, int32_t proble
 o2c_error o2c_rollout(o2c_handle* handle, const double* alphas, int32_t n_alpha, int32_t problem_begin, int32_t problem_count);
 /* backward + one rollout with step length alpha (one "LQ solve" of the benchmark metric) */
 o2c_error o2c_solve(o2c_handle* handle, double alpha, int32_t problem_begin, int32_t problem_count);
+/* ddp::Settings::checkNumericalStability_ for problems [begin, begin+count) after o2c_backward: every S_k of the value function goes
+ * through the reference's checkBeingPSD (ocs2_core/src/Types.cpp:206-236 as called from GaussNewtonDDP.cpp:555-579): finite,
+ * self-adjoint to 1e-6 (Eigen isApprox), smallest eigenvalue >= -epsilon. A failing problem gets O2C_STATUS_NOT_PSD (non-finite
+ * entries: O2C_STATUS_NONFINITE) or-ed into its status word, where the reference would throw. Asynchronous on the compute stream. */
+o2c_error o2c_check_numerical_stability(o2c_handle* handle, int32_t problem_begin, int32_t problem_count);
 /* number of kernel launches enqueued by this handle so far (bench.py's gpu_launches) */
 o2c_error o2c_launch_count(const o2c_handle* handle, int64_t* launches);
 /* name of the sweep kernel variant that o2c_backward dispatches to for this config (diagnostics / profiles) */

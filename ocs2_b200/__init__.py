@@ -7,13 +7,14 @@ arrays. There is no CPU fallback: importing works anywhere, but creating a solve
 device raises.
 """
 from .lib import (ALG_ILQR, ALG_SLQ, FORM_FULL, FORM_REDUCED, HC_CHOLESKY_MODIFICATION, HC_DIAGONAL_SHIFT, HC_EIGENVALUE_MODIFICATION,
-                  HC_GERSHGORIN_MODIFICATION, STATUS_CHOL_NOT_PD, STATUS_CONSTRAINT_RANK, STATUS_NONFINITE, STRATEGY_LEVENBERG_MARQUARDT,
+                  HC_GERSHGORIN_MODIFICATION, LQ_SYMMETRIC_PACKED, STATUS_CHOL_NOT_PD, STATUS_CONSTRAINT_RANK, STATUS_NONFINITE,
+                  STATUS_NOT_PSD, STRATEGY_LEVENBERG_MARQUARDT,
                   STRATEGY_LINE_SEARCH, O2cError, library_path, load_library)
-from .solver import BatchedLqSolver, LinearController, LineSearchResult, LineSearchSettings, LqBatch, Settings, Solution
+from .solver import BatchedLqSolver, LinearController, LineSearchResult, LineSearchSettings, LqBatch, Settings, Solution, pack_upper
 
 __all__ = [
     "ALG_ILQR", "ALG_SLQ", "FORM_FULL", "FORM_REDUCED", "HC_DIAGONAL_SHIFT", "HC_CHOLESKY_MODIFICATION", "HC_EIGENVALUE_MODIFICATION",
     "HC_GERSHGORIN_MODIFICATION", "STRATEGY_LINE_SEARCH", "STRATEGY_LEVENBERG_MARQUARDT", "STATUS_CHOL_NOT_PD", "STATUS_NONFINITE",
-    "STATUS_CONSTRAINT_RANK", "O2cError", "library_path", "load_library", "BatchedLqSolver", "LinearController", "LqBatch", "Settings",
-    "Solution", "LineSearchSettings", "LineSearchResult",
+    "STATUS_CONSTRAINT_RANK", "STATUS_NOT_PSD", "LQ_SYMMETRIC_PACKED", "O2cError", "library_path", "load_library", "BatchedLqSolver", "LinearController", "LqBatch", "Settings",
+    "Solution", "LineSearchSettings", "LineSearchResult", "pack_upper",
 ]

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -38,6 +39,9 @@ struct Lane {
   double* stage_out = nullptr;
   size_t stage_in_doubles = 0, stage_out_doubles = 0;
   std::vector<double> bounce;  // host bounce buffer for irregular strides
+  int* h_nc = nullptr;         // pinned staging of the per-node constraint counts of one chunk (asynchronous H2D without a lane sync)
+  size_t h_nc_count = 0;
+  cudaEvent_t nc_copied = nullptr;  // recorded after the last H2D out of h_nc: the next chunk on this lane waits for it before refilling
 };
 
 }  // namespace
@@ -528,6 +532,22 @@ o2c_error install_events(o2c_handle* h, cudaStream_t stream, const o2c_lq_view* 
   return O2C_OK;
 }
 
+// Bookkeeping of an upload that replaces the WHOLE batch, done once before its chunks (a chunk alone cannot tell that the batch is
+// being replaced): stale event flags and the "ragged constraint counts" mark of the previous contents are dropped, so that the
+// shape-specialised kernels serve the new data again, and SLQ event nodes (they shape the step schedules) and their jump records are
+// installed up front. The chunks then only add what they carry.
+o2c_error begin_whole_upload(o2c_handle* h, const o2c_lq_view* lq) {
+  cudaStream_t stream = h->lanes[0].stream;
+  h->nc_ragged = false;
+  const bool slq = h->st.algorithm == O2C_ALG_SLQ;
+  if (!lq->event || !slq) {  // no events, or ILQR flags that the chunks install range by range: start from a clean slate
+    o2c_error e = install_events(h, stream, nullptr, false, 0, h->cfg.batch);
+    if (e != O2C_OK) return e;
+  }
+  if (lq->event && slq) return install_events(h, stream, lq, false, 0, h->cfg.batch);
+  return O2C_OK;
+}
+
 // host view (already offset so that index 0 is the first problem of the chunk) -> records of problems [begin, begin+count)
 o2c_error upload_chunk(o2c_handle* h, Lane& lane, const o2c_lq_view& v, int begin, int count) {
   const Layout& L = h->L;
@@ -539,33 +559,45 @@ o2c_error upload_chunk(o2c_handle* h, Lane& lane, const o2c_lq_view& v, int begi
   const int n = L.n, m = L.m, ncm = L.ncmax, nodes = L.nodes;
 #define H2D(field, block, nn)                                                   \
   if ((e = field_h2d(lane, v.field, block, nn, count, cur, d.field)) != O2C_OK) return e;
-  H2D(A, n * n, nodes) H2D(B, n * m, nodes) H2D(Hv, n, nodes) H2D(Q, n * n, nodes) H2D(P, m * n, nodes) H2D(R, m * m, nodes)
+  const bool packed = (v.flags & O2C_LQ_SYMMETRIC_PACKED) != 0;
+  const int qblock = packed ? n * (n + 1) / 2 : n * n, rblock = packed ? m * (m + 1) / 2 : m * m;
+  d.sym_packed = packed ? 1 : 0;
+  H2D(A, n * n, nodes) H2D(B, n * m, nodes) H2D(Hv, n, nodes) H2D(Q, qblock, nodes) H2D(P, m * n, nodes) H2D(R, rblock, nodes)
   H2D(q, n, nodes) H2D(r, m, nodes) H2D(c, 1, nodes)
   if (ncm > 0) {
     H2D(C, ncm * n, nodes) H2D(D, ncm * m, nodes) H2D(e, ncm, nodes)
   }
-  H2D(Qf, n * n, 1) H2D(qf, n, 1) H2D(cf, 1, 1) H2D(x0, n, 1)
+  H2D(Qf, qblock, 1) H2D(qf, n, 1) H2D(cf, 1, 1) H2D(x0, n, 1)
   if (nominal) {
     H2D(x_nom, n, L.N + 1) H2D(u_nom, m, L.N + 1)
   }
 #undef H2D
   int* nc_stage = nullptr;
   if (ncm > 0 && v.nc != nullptr) {
-    // int32 per (problem, node): gathered densely on the host, staged after the doubles
-    std::vector<int> tmp((size_t)count * nodes);
+    // int32 per (problem, node): gathered densely into the lane's pinned staging, copied after the doubles without blocking the host
+    const size_t cnt = (size_t)count * nodes;
+    if (lane.nc_copied) O2C_CUDA(cudaEventSynchronize(lane.nc_copied));  // the previous chunk of this lane has left the staging
+    if (cnt > lane.h_nc_count) {
+      if (lane.h_nc) cudaFreeHost(lane.h_nc);
+      lane.h_nc = nullptr;
+      lane.h_nc_count = 0;
+      O2C_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&lane.h_nc), cnt * sizeof(int), cudaHostAllocDefault));
+      lane.h_nc_count = cnt;
+    }
+    if (!lane.nc_copied) O2C_CUDA(cudaEventCreateWithFlags(&lane.nc_copied, cudaEventDisableTiming));
     bool ragged = false;
     for (int p = 0; p < count; ++p)
       for (int k = 0; k < nodes; ++k) {
         const int c = v.nc[p * v.nc_problem_stride + k * v.nc_node_stride];
         if (c < 0 || c > ncm) return fail(O2C_ERR_INVALID_ARGUMENT, "nc[problem][node] must lie in [0, nc_max]");
         ragged = ragged || c != ncm;
-        tmp[(size_t)p * nodes + k] = c;
+        lane.h_nc[(size_t)p * nodes + k] = c;
       }
     nc_stage = reinterpret_cast<int*>(cur);
-    O2C_CUDA(cudaMemcpyAsync(nc_stage, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, lane.stream));
-    O2C_CUDA(cudaStreamSynchronize(lane.stream));
+    O2C_CUDA(cudaMemcpyAsync(nc_stage, lane.h_nc, cnt * sizeof(int), cudaMemcpyHostToDevice, lane.stream));
+    O2C_CUDA(cudaEventRecord(lane.nc_copied, lane.stream));
     d.nc = nc_stage;
-    // counts that all equal nc_max keep the kernels that skip the lookup; a whole-batch upload resets the flag
+    // counts that all equal nc_max keep the kernels that skip the lookup; a whole-batch upload resets the flag first (begin_whole_upload)
     h->nc_ragged = (begin == 0 && count == h->cfg.batch) ? ragged : (h->nc_ragged || ragged);
     d.nc_ps = nodes;
     d.nc_ns = 1;
@@ -651,6 +683,10 @@ void flush_status(o2c_handle* h) {
 
 o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) {
   if (count == 0) return O2C_OK;
+  if (h->st.algorithm == O2C_ALG_ILQR && h->events_present && h->st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT)
+    return fail(O2C_ERR_UNSUPPORTED,
+                "ILQR events under LEVENBERG_MARQUARDT: deltaGm / deltaGv of a pre-event node need the node's regular dynamics "
+                "(ILQR.cpp:263-295), which the record layout replaces by the jump map");
   h->backward_done = true;
   const DeviceBuffers buf = h->buffers(stream);
   if (h->st.algorithm == O2C_ALG_ILQR) {
@@ -729,6 +765,8 @@ void release(o2c_handle* h) {
   for (auto& lane : h->lanes) {
     if (lane.stage_in) cudaFree(lane.stage_in);
     if (lane.stage_out) cudaFree(lane.stage_out);
+    if (lane.h_nc) cudaFreeHost(lane.h_nc);
+    if (lane.nc_copied) cudaEventDestroy(lane.nc_copied);
     if (lane.stream) cudaStreamDestroy(lane.stream);
   }
   delete h;
@@ -944,7 +982,14 @@ o2c_error o2c_upload(o2c_handle* h, const o2c_lq_view* v, int32_t begin, int32_t
   }
   Lane& lane = h->lanes[0];
   const size_t per = stage_in_per_problem(h->L, h->cfg.has_nominal != 0) * sizeof(double);
-  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)count, ((size_t)1 << 30) / per));
+  size_t chunk_bytes = (size_t)1 << 30;
+  if (const char* env = getenv("O2C_UPLOAD_CHUNK_BYTES")) {  // test knob: split small uploads like the 38.8 GB legged batch is split
+    const long long v = atoll(env);
+    if (v > 0) chunk_bytes = (size_t)v;
+  }
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)count, chunk_bytes / per));
+  if (begin == 0 && count == h->cfg.batch && chunk < count)  // a whole-batch upload that is split: do the whole-range bookkeeping once
+    if ((e = begin_whole_upload(h, v)) != O2C_OK) return e;
   for (int off = 0; off < count; off += chunk) {
     const int c = std::min(chunk, count - off);
     o2c_lq_view sub = *v;
@@ -1001,6 +1046,7 @@ o2c_error o2c_import_device(o2c_handle* h, const o2c_lq_view* v, int32_t begin, 
   }
   d.nc_ps = v->nc_problem_stride;
   d.nc_ns = v->nc_node_stride;
+  d.sym_packed = (v->flags & O2C_LQ_SYMMETRIC_PACKED) ? 1 : 0;
   if ((e = install_events(h, h->lanes[0].stream, v, true, begin, count)) != O2C_OK) return e;
   O2C_CUDA(launch_pack(h->L, d, h->d_lq, h->d_term, h->d_xnom, h->d_unom, h->d_nc, h->d_x0, begin, count, h->lanes[0].stream));
   h->launches += 1;
@@ -1042,6 +1088,7 @@ o2c_error o2c_rollout(o2c_handle* h, const double* alphas, int32_t n_alpha, int3
   o2c_error e = check_range(h, begin, count);
   if (e != O2C_OK) return e;
   if (!alphas || n_alpha < 1 || n_alpha > h->cfg.max_alphas) return fail(O2C_ERR_INVALID_ARGUMENT, "n_alpha outside [1, max_alphas]");
+  if (!h->backward_done) return fail(O2C_ERR_NOT_READY, "o2c_rollout needs the controller of o2c_backward");
   O2C_CUDA(cudaSetDevice(h->cfg.device));
   O2C_CUDA(cudaMemcpyAsync(h->d_alphas, alphas, sizeof(double) * n_alpha, cudaMemcpyHostToDevice, h->lanes[0].stream));
   return rollout_on(h, h->lanes[0].stream, h->d_alphas, n_alpha, begin, count);
@@ -1184,6 +1231,17 @@ o2c_error o2c_discretize(o2c_handle* h, const o2c_discretization_view* v, int32_
   return O2C_OK;
 }
 
+o2c_error o2c_check_numerical_stability(o2c_handle* h, int32_t begin, int32_t count) {
+  o2c_error e = check_range(h, begin, count);
+  if (e != O2C_OK) return e;
+  if (!h->backward_done) return fail(O2C_ERR_NOT_READY, "o2c_check_numerical_stability needs the value function of o2c_backward");
+  if (count == 0) return O2C_OK;
+  O2C_CUDA(cudaSetDevice(h->cfg.device));
+  O2C_CUDA(launch_check_psd(h->L, h->d_sol, h->d_status, begin, count, h->lanes[0].stream));
+  h->launches += 1;
+  return O2C_OK;
+}
+
 o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {
   if (!h || !launches) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
   *launches = h->launches;
@@ -1213,12 +1271,11 @@ o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solutio
   }
   // lanes run [H2D -> pack -> sweep+rollout -> unpack -> D2H] for alternating chunks; copies of one lane overlap the kernels of another
   for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));
-  if (!lq->event && count == h->cfg.batch)  // whole batch replaced by problems without events (chunk uploads alone cannot tell)
-    if ((e = install_events(h, h->lanes[0].stream, nullptr, false, 0, count)) != O2C_OK) return e;
-  if (lq->event && h->st.algorithm == O2C_ALG_SLQ && count == h->cfg.batch)  // SLQ event nodes shape the schedules: install them (and the
-    if ((e = install_events(h, h->lanes[0].stream, lq, false, 0, count)) != O2C_OK) return e;  // jump records) before the chunked uploads
+  if (count == h->cfg.batch)  // whole batch replaced: whole-range bookkeeping once, before the chunks (a chunk alone cannot tell)
+    if ((e = begin_whole_upload(h, lq)) != O2C_OK) return e;
   int li = 0;
-  for (int off = 0; off < count; off += chunk, li = (li + 1) % kLanes) {
+  o2c_error failed = O2C_OK;
+  for (int off = 0; off < count && failed == O2C_OK; off += chunk, li = (li + 1) % kLanes) {
     const int c = std::min(chunk, count - off);
     Lane& lane = h->lanes[li];
     o2c_lq_view sub = *lq;
@@ -1228,16 +1285,30 @@ o2c_error o2c_solve_host(o2c_handle* h, const o2c_lq_view* lq, const o2c_solutio
 #undef OFF
     if (lq->nc) sub.nc = lq->nc + (long long)off * lq->nc_problem_stride;
     if (lq->event) sub.event = lq->event + (long long)off * lq->event_problem_stride;
-    if ((e = upload_chunk(h, lane, sub, off, c)) != O2C_OK) return e;
-    if ((e = solve_on(h, lane.stream, h->d_alphas + h->cfg.max_alphas + li, alpha, off, c)) != O2C_OK) return e;
     o2c_solution_view ss = *sol;
 #define OFF(field) ss.field = offset_field(sol->field, off);
     OFF(K) OFF(dbias) OFF(bias) OFF(Sm) OFF(Sv) OFF(s) OFF(x) OFF(u)
 #undef OFF
     if (sol->status) ss.status = sol->status + off;
-    if ((e = download_chunk(h, lane, ss, off, c, 1)) != O2C_OK) return e;
+    if ((failed = upload_chunk(h, lane, sub, off, c)) != O2C_OK) break;
+    if ((failed = solve_on(h, lane.stream, h->d_alphas + h->cfg.max_alphas + li, alpha, off, c)) != O2C_OK) break;
+    if ((failed = download_chunk(h, lane, ss, off, c, 1)) != O2C_OK) break;
   }
-  for (auto& lane : h->lanes) O2C_CUDA(cudaStreamSynchronize(lane.stream));
+  // success or not, every lane is drained before returning: the caller's host buffers are no longer touched by copies in flight
+  const std::string first_error = failed != O2C_OK ? g_last_error : std::string();
+  cudaError_t drain = cudaSuccess;
+  for (auto& lane : h->lanes) {
+    const cudaError_t se = cudaStreamSynchronize(lane.stream);
+    if (se != cudaSuccess && drain == cudaSuccess) drain = se;
+  }
+  if (failed != O2C_OK) {
+    h->pending_status.clear();
+    return fail(failed, first_error);
+  }
+  if (drain != cudaSuccess) {
+    h->pending_status.clear();
+    return fail(O2C_ERR_CUDA, std::string("o2c_solve_host: ") + cudaGetErrorString(drain));
+  }
   flush_status(h);
   return O2C_OK;
 }
@@ -1247,6 +1318,9 @@ o2c_error o2c_generate_synthetic(o2c_handle* h, uint64_t seed, int64_t first_pro
   O2C_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t s = h->lanes[0].stream;
   h->events_present = false;
+  if (h->d_event)  // stale flags of an earlier upload must not come back to life with a later partial upload that carries events
+    O2C_CUDA(cudaMemsetAsync(h->d_event, 0, sizeof(int) * (size_t)h->cfg.batch * h->L.nodes, s));
+  h->nc_ragged = false;
   h->slq_events.clear();  // the generated family has no events; the schedules are rebuilt with the generated time grid below
   O2C_CUDA(launch_generate(h->L, h->st.algorithm, h->d_lq, h->d_term, h->d_x0, seed, first_problem_index, dt, h->cfg.batch, s));
   h->launches += 1;

@@ -159,6 +159,7 @@ struct LqViewDev {
   FieldDev A, B, Hv, Q, P, R, q, r, c, C, D, e, Qf, qf, cf, x_nom, u_nom, x0;
   const int* nc;
   long long nc_ps, nc_ns;
+  int sym_packed;  // O2C_LQ_SYMMETRIC_PACKED: Q, R, Qf are packed upper triangles
 };
 struct SolViewDev {
   FieldDev K, dbias, bias, Sm, Sv, s, x, u;
@@ -201,6 +202,9 @@ bool rpl_rollout_cont_supported(const Layout& L, const SolverSettings& st, const
 cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,
                                     int first_idx, double first_alpha, int out_nodes, const double* alphas_dev, int n_alpha, int batch,
                                     int begin, int count, cudaStream_t stream);
+
+// checkBeingPSD of every S_k (stability.cu): ors O2C_STATUS_NOT_PSD / O2C_STATUS_NONFINITE into status[problem]
+cudaError_t launch_check_psd(const Layout& L, const double* sol, int* status, int begin, int count, cudaStream_t stream);
 
 // batched Armijo line search on the LQ model (line_search.cu)
 cudaError_t launch_merit(const Layout& L, const DeviceBuffers& buf, int out_nodes, int n_alpha, int batch, int begin, int count, double* merit,

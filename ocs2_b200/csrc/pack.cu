@@ -12,6 +12,19 @@ __device__ __forceinline__ void copy_in(const FieldDev& f, long long p, long lon
   const double* src = f.ptr + p * f.ps + node * f.ns;
   for (int i = tid; i < count; i += nt) dst[i] = src[i];
 }
+// symmetric dim x dim block from its packed upper triangle (column by column: (i, j), i <= j, at j (j + 1) / 2 + i)
+__device__ __forceinline__ void copy_in_sym(const FieldDev& f, long long p, long long node, int dim, double* dst, int tid, int nt) {
+  if (f.ptr == nullptr) {
+    for (int i = tid; i < dim * dim; i += nt) dst[i] = 0.0;
+    return;
+  }
+  const double* src = f.ptr + p * f.ps + node * f.ns;
+  for (int idx = tid; idx < dim * dim; idx += nt) {
+    const int i = idx % dim, j = idx / dim;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    dst[idx] = src[hi * (hi + 1) / 2 + lo];
+  }
+}
 __device__ __forceinline__ void copy_out(const FieldDev& f, long long p, long long node, int count, const double* src, int tid, int nt) {
   if (f.ptr == nullptr) return;
   double* dst = f.ptr + p * f.ps + node * f.ns;
@@ -29,9 +42,14 @@ __global__ void __launch_bounds__(128) pack_kernel(Layout L, LqViewDev v, double
     double* rec = lq + ((size_t)prob * L.nodes + node) * L.rec;
     copy_in(v.A, lp, node, n * n, rec + L.oA, tid, nt);
     copy_in(v.B, lp, node, n * m, rec + L.oB, tid, nt);
-    copy_in(v.Q, lp, node, n * n, rec + L.oQ, tid, nt);
+    if (v.sym_packed) {
+      copy_in_sym(v.Q, lp, node, n, rec + L.oQ, tid, nt);
+      copy_in_sym(v.R, lp, node, m, rec + L.oR, tid, nt);
+    } else {
+      copy_in(v.Q, lp, node, n * n, rec + L.oQ, tid, nt);
+      copy_in(v.R, lp, node, m * m, rec + L.oR, tid, nt);
+    }
     copy_in(v.P, lp, node, m * n, rec + L.oP, tid, nt);
-    copy_in(v.R, lp, node, m * m, rec + L.oR, tid, nt);
     copy_in(v.Hv, lp, node, n, rec + L.oHv, tid, nt);
     copy_in(v.q, lp, node, n, rec + L.oq, tid, nt);
     copy_in(v.r, lp, node, m, rec + L.or_, tid, nt);
@@ -49,7 +67,10 @@ __global__ void __launch_bounds__(128) pack_kernel(Layout L, LqViewDev v, double
   }
   if (node == 0) {
     double* t = term + (size_t)prob * L.trec;
-    copy_in(v.Qf, lp, 0, n * n, t + L.oQf, tid, nt);
+    if (v.sym_packed)
+      copy_in_sym(v.Qf, lp, 0, n, t + L.oQf, tid, nt);
+    else
+      copy_in(v.Qf, lp, 0, n * n, t + L.oQf, tid, nt);
     copy_in(v.qf, lp, 0, n, t + L.oqf, tid, nt);
     copy_in(v.cf, lp, 0, 1, t + L.ocf, tid, nt);
     if (v.x0.ptr) copy_in(v.x0, lp, 0, n, x0 + (size_t)prob * n, tid, nt);

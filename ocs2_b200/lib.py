@@ -11,7 +11,8 @@ ALG_ILQR, ALG_SLQ = 0, 1
 FORM_FULL, FORM_REDUCED = 0, 1
 STRATEGY_LINE_SEARCH, STRATEGY_LEVENBERG_MARQUARDT = 0, 1
 HC_DIAGONAL_SHIFT, HC_CHOLESKY_MODIFICATION, HC_EIGENVALUE_MODIFICATION, HC_GERSHGORIN_MODIFICATION = 0, 1, 2, 3
-STATUS_CHOL_NOT_PD, STATUS_NONFINITE, STATUS_CONSTRAINT_RANK = 1, 2, 4
+STATUS_CHOL_NOT_PD, STATUS_NONFINITE, STATUS_CONSTRAINT_RANK, STATUS_NOT_PSD = 1, 2, 4, 8
+LQ_SYMMETRIC_PACKED = 1
 
 _ERR_NAMES = {1: "INVALID_ARGUMENT", 2: "UNSUPPORTED", 3: "CUDA", 4: "OUT_OF_MEMORY", 5: "NOT_READY"}
 
@@ -50,7 +51,7 @@ class LqView(C.Structure):
         ("nc", C.c_void_p), ("nc_problem_stride", C.c_int64), ("nc_node_stride", C.c_int64)] + [
         (n, Field) for n in ("Qf", "qf", "cf", "x_nom", "u_nom", "x0")] + [("time", C.c_void_p)] + [
         ("event", C.c_void_p), ("event_problem_stride", C.c_int64), ("event_node_stride", C.c_int64)] + [
-        (n, Field) for n in ("jump_A", "jump_Hv", "jump_Q", "jump_q", "jump_c")]
+        (n, Field) for n in ("jump_A", "jump_Hv", "jump_Q", "jump_q", "jump_c")] + [("flags", C.c_int32)]
 
 
 class DiscretizationView(C.Structure):
@@ -67,7 +68,7 @@ EXPORTED_SYMBOLS = [
     "o2c_device_lq_view", "o2c_device_solution_view", "o2c_rollout_num_nodes", "o2c_rollout_times", "o2c_upload", "o2c_import_device",
     "o2c_download", "o2c_set_time", "o2c_backward", "o2c_rollout", "o2c_solve", "o2c_launch_count", "o2c_kernel_variant",
     "o2c_solve_host", "o2c_generate_synthetic", "o2c_host_alloc", "o2c_host_free", "o2c_line_search", "o2c_line_search_result",
-    "o2c_download_flattened_controller", "o2c_discretize",
+    "o2c_download_flattened_controller", "o2c_discretize", "o2c_check_numerical_stability",
 ]
 
 
@@ -118,12 +119,13 @@ def load_library():
         "o2c_line_search_result": [hp, _dp, _ip, _dp, _dp, _dp, _dp, _ip, C.c_int32, C.c_int32],
         "o2c_download_flattened_controller": [hp, C.POINTER(C.c_float), C.c_double, C.c_int32, C.c_int32],
         "o2c_discretize": [hp, C.POINTER(DiscretizationView), C.c_int32, C.c_int32, C.c_int32],
+        "o2c_check_numerical_stability": [hp, C.c_int32, C.c_int32],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    if lib.o2c_abi_version() != 3:
+    if lib.o2c_abi_version() != 4:
         raise RuntimeError("libocs2_ddp_cuda.so ABI version mismatch")
     _lib = lib
     return lib

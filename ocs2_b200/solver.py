@@ -40,6 +40,15 @@ def _colmajor(a: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(np.swapaxes(np.asarray(a, dtype=np.float64), -1, -2))
 
 
+def pack_upper(a: np.ndarray) -> np.ndarray:
+    """(..., k, k) symmetric -> (..., k (k + 1) / 2): upper triangle column by column, element (i, j), i <= j, at j (j + 1) / 2 + i
+    (O2C_LQ_SYMMETRIC_PACKED; the order of ContinuousTimeRiccatiEquations::convert2Vector)."""
+    k = a.shape[-1]
+    rows = np.concatenate([np.arange(j + 1) for j in range(k)])
+    cols = np.concatenate([np.full(j + 1, j) for j in range(k)])
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64)[..., rows, cols])
+
+
 def _field(arr: Optional[np.ndarray], block: int, nodes: int) -> _l.Field:
     if arr is None:
         return _l.Field(None, 0, 0)
@@ -86,15 +95,19 @@ class LqBatch:
     def batch(self) -> int:
         return self.A.shape[0]
 
-    def view(self, N: int) -> _l.LqView:
-        """Builds the o2c_lq_view over column-major copies of the arrays (kept alive in self._keep)."""
+    def view(self, N: int, symmetric_packed: bool = False) -> _l.LqView:
+        """Builds the o2c_lq_view over column-major copies of the arrays (kept alive in self._keep). symmetric_packed: Q, R, Qf travel
+        as packed upper triangles (O2C_LQ_SYMMETRIC_PACKED)."""
         k = self._keep
         nodes = self.A.shape[1]
         n, m = self.B.shape[-2], self.B.shape[-1]
         ncm = 0 if self.D is None else self.D.shape[-2]
         for name in ("A", "B", "Q", "P", "R", "C", "D", "Qf"):
             v = getattr(self, name)
-            k[name] = _colmajor(v) if v is not None else None
+            if symmetric_packed and name in ("Q", "R", "Qf"):
+                k[name] = pack_upper(v)
+            else:
+                k[name] = _colmajor(v) if v is not None else None
         for name in ("Hv", "q", "r", "c", "e", "qf", "cf", "x_nom", "u_nom", "x0", "time"):
             v = getattr(self, name)
             k[name] = np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
@@ -103,9 +116,10 @@ class LqBatch:
         lv.A = _field(k["A"], n * n, nodes)
         lv.B = _field(k["B"], n * m, nodes)
         lv.Hv = _field(k["Hv"], n, nodes)
-        lv.Q = _field(k["Q"], n * n, nodes)
+        lv.Q = _field(k["Q"], n * (n + 1) // 2 if symmetric_packed else n * n, nodes)
         lv.P = _field(k["P"], m * n, nodes)
-        lv.R = _field(k["R"], m * m, nodes)
+        lv.R = _field(k["R"], m * (m + 1) // 2 if symmetric_packed else m * m, nodes)
+        lv.flags = _l.LQ_SYMMETRIC_PACKED if symmetric_packed else 0
         lv.q = _field(k["q"], n, nodes)
         lv.r = _field(k["r"], m, nodes)
         lv.c = _field(k["c"], 1, nodes)
@@ -117,7 +131,7 @@ class LqBatch:
                 lv.nc = k["nc"].ctypes.data
                 lv.nc_problem_stride = nodes
                 lv.nc_node_stride = 1
-        lv.Qf = _field(k["Qf"], n * n, 1)
+        lv.Qf = _field(k["Qf"], n * (n + 1) // 2 if symmetric_packed else n * n, 1)
         lv.qf = _field(k["qf"], n, 1)
         lv.cf = _field(k["cf"], 1, 1)
         lv.x_nom = _field(k["x_nom"], n, N + 1)
@@ -256,8 +270,8 @@ class BatchedLqSolver:
         _l.check(self._lib.o2c_sync(self._h))
 
     # ---- data -------------------------------------------------------------------------------------------------------
-    def upload(self, lq: LqBatch, problem_begin: int = 0):
-        view = lq.view(self.N)
+    def upload(self, lq: LqBatch, problem_begin: int = 0, symmetric_packed: bool = False):
+        view = lq.view(self.N, symmetric_packed)
         _l.check(self._lib.o2c_upload(self._h, C.byref(view), problem_begin, lq.batch))
         self.sync()
 
@@ -318,6 +332,12 @@ class BatchedLqSolver:
         cnt = self.batch - problem_begin if problem_count is None else problem_count
         _l.check(self._lib.o2c_rollout(self._h, a.ctypes.data_as(C.POINTER(C.c_double)), len(a), problem_begin, cnt))
         self._n_alpha = len(a)
+
+    def checkNumericalStability(self, problem_begin: int = 0, problem_count: Optional[int] = None):
+        """ddp::Settings::checkNumericalStability_ for the value function (GaussNewtonDDP.cpp:555-579): checkBeingPSD of every S_k; a
+        failing problem gets STATUS_NOT_PSD in its status word (the reference throws). Run after the backward pass."""
+        cnt = self.batch - problem_begin if problem_count is None else problem_count
+        _l.check(self._lib.o2c_check_numerical_stability(self._h, problem_begin, cnt))
 
     def solve(self, alpha: float = 1.0, problem_begin: int = 0, problem_count: Optional[int] = None):
         """backward pass + one rollout: one 'LQ solve' per problem (the benchmark metric)."""
@@ -390,9 +410,10 @@ class BatchedLqSolver:
         _l.check(self._lib.o2c_download(self._h, C.byref(sv), problem_begin, cnt, na))
         return self._to_solution(bufs, na)
 
-    def solve_host(self, lq: LqBatch, alpha: float = 1.0, chunk: int = 0) -> Solution:
-        """End to end through host buffers: chunked H2D -> sweep + rollout -> D2H pipeline (o2c_solve_host)."""
-        view = lq.view(self.N)
-        bufs, sv = self._solution_buffers(lq.batch, 1)
+    def solve_host(self, lq: LqBatch, alpha: float = 1.0, chunk: int = 0, symmetric_packed: bool = False, want_value: bool = True) -> Solution:
+        """End to end through host buffers: chunked H2D -> sweep + rollout -> D2H pipeline (o2c_solve_host). symmetric_packed: the cost
+        Hessians travel as packed upper triangles; want_value = False skips the value function (Sm, Sv, s) on the way back."""
+        view = lq.view(self.N, symmetric_packed)
+        bufs, sv = self._solution_buffers(lq.batch, 1, want_value)
         _l.check(self._lib.o2c_solve_host(self._h, C.byref(view), C.byref(sv), alpha, lq.batch, chunk))
         return self._to_solution(bufs, 1)

@@ -1236,4 +1236,69 @@ double orc_baseline_run(const orc_settings* st, uint64_t seed, int64_t first, in
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+int orc_batch_solve(const orc_settings* st, uint64_t seed, int64_t first, int64_t count, int n, int m, int nc, int N, double dt, double alpha,
+                    int threads, double* K, double* dbias, double* bias, double* Sm, double* Sv, double* s, double* x, double* u,
+                    int max_out, int32_t* status) {
+  const bool discrete = st->algorithm == ORC_ALG_ILQR;
+  const int nodes = discrete ? N : N + 1;
+  std::atomic<int64_t> next{0};
+  std::atomic<int> out_nodes{0};
+  auto work = [&]() {
+    const int ncm = std::max(nc, 1);
+    vec A((size_t)nodes * n * n), B((size_t)nodes * n * m), Hv((size_t)nodes * n), Q((size_t)nodes * n * n), P((size_t)nodes * m * n),
+        R((size_t)nodes * m * m), q((size_t)nodes * n), r((size_t)nodes * m), c(nodes), C((size_t)nodes * ncm * n), D((size_t)nodes * ncm * m),
+        e((size_t)nodes * ncm), Qf((size_t)n * n), qf(n), cf(1), x0(n), time(N + 1);
+    vec lK((size_t)(N + 1) * m * n), ldb((size_t)(N + 1) * m), lbias((size_t)(N + 1) * m), lSm((size_t)(N + 1) * n * n), lSv((size_t)(N + 1) * n),
+        ls(N + 1), lx((size_t)max_out * n), lu((size_t)max_out * m);
+    for (int k = 0; k <= N; ++k) time[k] = dt * (double)k;
+    int64_t i;
+    while ((i = next++) < count) {
+      orc_generate_problem(seed, first + i, st->algorithm, n, m, nc, N, dt, A.data(), B.data(), Hv.data(), Q.data(), P.data(), R.data(), q.data(),
+                           r.data(), c.data(), C.data(), D.data(), e.data(), Qf.data(), qf.data(), cf.data(), x0.data());
+      orc_problem pb{};
+      pb.nx = n;
+      pb.nu = m;
+      pb.nc_max = nc;
+      pb.N = N;
+      pb.A = A.data();
+      pb.B = B.data();
+      pb.Hv = Hv.data();
+      pb.Q = Q.data();
+      pb.P = P.data();
+      pb.R = R.data();
+      pb.q = q.data();
+      pb.r = r.data();
+      pb.c = c.data();
+      pb.C = C.data();
+      pb.D = D.data();
+      pb.e = e.data();
+      pb.Qf = Qf.data();
+      pb.qf = qf.data();
+      pb.cf = cf.data();
+      pb.time = time.data();
+      orc_solution sol{lK.data(), ldb.data(), lbias.data(), lSm.data(), lSv.data(), ls.data(), 0};
+      const int stat = orc_backward(st, &pb, &sol);
+      int nOut = 0;
+      orc_rollout(st, &pb, &sol, x0.data(), alpha, lx.data(), lu.data(), nullptr, max_out, &nOut);
+      out_nodes = nOut;
+      auto put = [&](double* dst, const vec& src, size_t per) {
+        if (dst) std::copy(src.begin(), src.begin() + per, dst + (size_t)i * per);
+      };
+      put(K, lK, (size_t)(N + 1) * m * n);
+      put(dbias, ldb, (size_t)(N + 1) * m);
+      put(bias, lbias, (size_t)(N + 1) * m);
+      put(Sm, lSm, (size_t)(N + 1) * n * n);
+      put(Sv, lSv, (size_t)(N + 1) * n);
+      put(s, ls, (size_t)(N + 1));
+      if (x) std::copy(lx.begin(), lx.begin() + (size_t)nOut * n, x + (size_t)i * max_out * n);
+      if (u) std::copy(lu.begin(), lu.begin() + (size_t)nOut * m, u + (size_t)i * max_out * m);
+      if (status) status[i] = stat;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < std::max(threads, 1); ++t) pool.emplace_back(work);
+  for (auto& th : pool) th.join();
+  return out_nodes;
+}
+
 }  // extern "C"

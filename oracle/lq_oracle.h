@@ -132,6 +132,16 @@ void orc_generate_problem(uint64_t seed, int64_t problem, int algorithm, int n, 
 double orc_baseline_run(const orc_settings* st, uint64_t seed, int64_t first, int64_t count, int n, int m, int nc, int N, double dt,
                         int threads, double* checksum);
 
+/* ---- batched solve with the results kept: problems [first, first+count) of the seeded family, backward + one rollout with step
+ * length alpha, one problem per task on `threads` std::threads. Caller-allocated outputs (any may be NULL), indexed
+ * [problem][node][block] with column-major blocks like orc_solution: K [count][N+1][m*n], dbias/bias [count][N+1][m],
+ * Sm [count][N+1][n*n], Sv [count][N+1][n], s [count][N+1], x [count][out_nodes][n], u [count][out_nodes][m] (out_nodes = N+1 for
+ * ILQR; SLQ: the rollout step schedule, capacity max_out, the count actually written is returned), status [count]. Used by the
+ * all-problems GPU parity test. */
+int orc_batch_solve(const orc_settings* st, uint64_t seed, int64_t first, int64_t count, int n, int m, int nc, int N, double dt, double alpha,
+                    int threads, double* K, double* dbias, double* bias, double* Sm, double* Sv, double* s, double* x, double* u,
+                    int max_out, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -492,3 +492,22 @@ def baseline_run(st: Settings, seed, first, count, n, m, nc, N, dt, threads):
     secs = lib().orc_baseline_run(C.byref(st), C.c_uint64(seed), C.c_int64(first), C.c_int64(count), n, m, nc, N, C.c_double(dt), threads,
                                   C.byref(chk))
     return secs, chk.value
+
+
+def batch_solve(st: Settings, seed, first, count, n, m, nc, N, dt, alpha=1.0, threads=None, max_out=None):
+    """backward + one rollout of `count` generated problems on `threads` CPU threads, results kept. Returns a dict of arrays in the
+    natural layout of Solution: K (count,N+1,m,n), dbias, bias (count,N+1,m), Sm (count,N+1,n,n), Sv (count,N+1,n), s (count,N+1),
+    x (count,out_nodes,n), u (count,out_nodes,m), status (count,)."""
+    threads = threads or (os.cpu_count() or 1)
+    if max_out is None:
+        max_out = N + 1 if st.algorithm == ALG_ILQR else int(np.ceil(N * dt / st.time_step)) + 4
+    Kc = np.zeros((count, N + 1, n, m))
+    db, bias = np.zeros((count, N + 1, m)), np.zeros((count, N + 1, m))
+    Smc, Sv, s = np.zeros((count, N + 1, n, n)), np.zeros((count, N + 1, n)), np.zeros((count, N + 1))
+    x, u = np.zeros((count, max_out, n)), np.zeros((count, max_out, m))
+    status = np.zeros(count, dtype=np.int32)
+    fn = lib().orc_batch_solve
+    fn.restype = C.c_int
+    k = fn(C.byref(st), C.c_uint64(seed), C.c_int64(first), C.c_int64(count), n, m, nc, N, C.c_double(dt), C.c_double(alpha), threads, _p(Kc),
+           _p(db), _p(bias), _p(Smc), _p(Sv), _p(s), _p(x), _p(u), max_out, status.ctypes.data_as(_ip))
+    return dict(K=np.swapaxes(Kc, -1, -2), dbias=db, bias=bias, Sm=np.swapaxes(Smc, -1, -2), Sv=Sv, s=s, x=x[:, :k], u=u[:, :k], status=status)

@@ -39,18 +39,37 @@ def test_library_exports_every_declared_symbol_and_nothing_else(libpath):
         assert getattr(lib, name) is not None
 
 
-def test_struct_layouts_match_the_header():
+def test_struct_layouts_match_the_header(tmp_path):
     # o2c_config: 12 int32 + 3 double; o2c_field: ptr + 2 int64; views are arrays of fields plus a few scalars
     assert C.sizeof(_l.Config) == 12 * 4 + 3 * 8
     assert C.sizeof(_l.Field) == 24
-    assert C.sizeof(_l.LqView) == 12 * 24 + 8 + 16 + 6 * 24 + 8 + 8 + 16 + 5 * 24
+    assert C.sizeof(_l.LqView) == 12 * 24 + 8 + 16 + 6 * 24 + 8 + 8 + 16 + 5 * 24 + 8  # + flags (int32, padded)
     assert C.sizeof(_l.SolutionView) == 8 * 24 + 16 + 8
     assert [f[0] for f in _l.Config._fields_][:5] == ["nx", "nu", "nc_max", "num_stages", "batch"]
+    # sizes and the offsets of the scalar members as the C compiler lays the header's structs out
+    src = tmp_path / "layout.c"
+    src.write_text('''#include <stddef.h>
+#include <stdio.h>
+#include "ocs2_ddp_cuda.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(o2c_config), sizeof(o2c_field), sizeof(o2c_lq_view), sizeof(o2c_solution_view),
+         sizeof(o2c_discretization_view), offsetof(o2c_lq_view, nc), offsetof(o2c_lq_view, time), offsetof(o2c_lq_view, event),
+         offsetof(o2c_lq_view, jump_A), offsetof(o2c_lq_view, flags), offsetof(o2c_solution_view, status));
+  return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(_l.Config), C.sizeof(_l.Field), C.sizeof(_l.LqView), C.sizeof(_l.SolutionView), C.sizeof(_l.DiscretizationView),
+            _l.LqView.nc.offset, _l.LqView.time.offset, _l.LqView.event.offset, _l.LqView.jump_A.offset, _l.LqView.flags.offset,
+            _l.SolutionView.status.offset]
+    assert got == want
 
 
 def test_abi_version_and_error_strings_without_a_device(libpath):
     lib = _l.load_library()
-    assert lib.o2c_abi_version() == 3
+    assert lib.o2c_abi_version() == 4
     # argument validation happens before any CUDA call
     h = C.c_void_p()
     assert lib.o2c_create(None, C.byref(h)) == 1  # O2C_ERR_INVALID_ARGUMENT

@@ -527,3 +527,20 @@ def test_rk4_sensitivity_discretization_reproduces_the_cartpole_fixture():
     taylor = np.eye(3) + hA + hA @ hA / 2 + hA @ hA @ hA / 6 + hA @ hA @ hA @ hA / 24
     assert np.allclose(Ad, taylor, rtol=1e-13, atol=1e-14)
     assert np.allclose(Bd, h * (np.eye(3) + hA / 2 + hA @ hA / 6 + hA @ hA @ hA / 24) @ B, rtol=1e-13, atol=1e-14)
+
+
+def test_batch_solve_is_the_single_problem_path_run_in_threads():
+    """orc_batch_solve (the all-problems checker of the GPU parity tests) returns bit for bit what backward + rollout return per problem."""
+    for alg, (n, m, nc) in ((orc.ALG_ILQR, (24, 24, 0)), (orc.ALG_ILQR, (9, 9, 3)), (orc.ALG_SLQ, (12, 4, 0))):
+        N, dt, seed, first, count = 20, 0.01, 5, 1771, 9
+        st = orc.make_settings(algorithm=alg, hessian_multiple=1e-4, time_step=dt)
+        got = orc.batch_solve(st, seed, first, count, n, m, nc, N, dt, alpha=0.7, threads=4)
+        assert (got["status"] == 0).all()
+        for i in (0, 4, count - 1):
+            pb, x0 = orc.generate_problem(seed, first + i, alg, n, m, nc, N, dt)
+            ref = orc.backward(st, pb)
+            x, u, _, _ = orc.rollout(st, pb, ref, x0, alpha=0.7)
+            for name in ("K", "dbias", "bias", "Sm", "Sv", "s"):
+                assert np.array_equal(got[name][i], getattr(ref, name)), name
+            assert got["x"].shape[1] == len(x)
+            assert np.array_equal(got["x"][i], x) and np.array_equal(got["u"][i], u)
