@@ -124,7 +124,7 @@ struct Args {
   int begin, count, with_rollout;
   int* counter;  // dynamic problem fetch: zeroed before the launch; nullptr = static stride
   int dyn_limit;  // problems [resident slots, dyn_limit) are fetched dynamically, [dyn_limit, count) = the last partial wave, static
-  double eps, alpha;
+  double eps, alpha, mu;
 };
 
 __device__ __forceinline__ double quad_sum(double v) {
@@ -330,8 +330,23 @@ __device__ __forceinline__ int next_problem(const Args& a, int lane, int total_w
   return a.dyn_limit + slot;  // >= count when this warp has no problem in the last wave
 }
 
-template <bool NOM, bool EV, bool QPD>
+// MODE: the Riccati modification (search strategy) the stage carries, everything else is shared:
+//   kModeLS    LINE_SEARCH + DIAGONAL_SHIFT: dQ = eps I                                   LineSearchStrategy.cpp:294-312, HessianCorrection.cpp:53-74
+//   kModeGersh LINE_SEARCH + GERSHGORIN_MODIFICATION: dQ = diag(max(0, R_i + eps - M_ii)), M = Q - P'Hm^-1 P, R_i = sum_{j != i} |M_ji|
+//                                                                                        LinearAlgebra.cpp:77-85 (the off-diagonal part of dQ,
+//              (M' - M) / 2, is rounding noise of a symmetric M and is not formed)
+//   kModeLM    LEVENBERG_MARQUARDT (full Riccati form): Hm += mu B'B, dGm = mu B~'A~, dGv = mu B~'Hv~, dQ = 0
+//                                                                                        LevenbergMarquardtStrategy.cpp:230-249
+//              With S' = S + mu I this is the LINE_SEARCH stage evaluated on S' (which yields Hm, K, dbias exactly) minus mu times the Gram
+//              terms of the closed loop: S = T(S') - Y'Y - mu Acl'Acl, Sv = tv(S') - Y'Yv - mu Acl'hcl, s = s(S') - mu/2 |hcl|^2 with
+//              Acl = A + B K, hcl = Hv + B dbias (expand the full-form map of DiscreteTimeRiccatiEquations.cpp:91-153 with
+//              H~m = I - mu B~'B~: the cross terms cancel).
+constexpr int kModeLS = 0, kModeLM = 1, kModeGersh = 2;
+
+template <bool NOM, bool EV, int MODE>
 __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args a) {
+  constexpr bool QPD = true;  // Q and P straight from L2 into the accumulators (the TMA-staged round-1 path is kept for reference only)
+  static_assert(!(EV && MODE == kModeLM), "ILQR events under LEVENBERG_MARQUARDT are refused by the API");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
@@ -437,6 +452,10 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
 #pragma unroll
         for (int jb = 0; jb < 3; ++jb) {
           s[jb] = ld2(ws.W + lo26 + t26(kb, jb));
+          if (MODE == kModeLM && kb == jb) {  // S' = S + mu I: rows 8kb + 2c, 2c + 1 of column 8jb + r
+            s[jb].x += (2 * c == r) ? a.mu : 0.0;
+            s[jb].y += (2 * c + 1 == r) ? a.mu : 0.0;
+          }
           pSH[jb] = fma(s[jb].x, hvf[kb].x, pSH[jb]);
           pSH[jb] = fma(s[jb].y, hvf[kb].y, pSH[jb]);
         }
@@ -479,7 +498,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
         }
       }
       const double cval = ws.in[2 * kMat + 3 * kN];
-      const double epsk = ev ? 0.0 : a.eps;  // the transversality condition carries no Hessian correction
+      const double epsk = (ev || MODE != kModeLS) ? 0.0 : a.eps;  // the transversality condition carries no Hessian correction; LM: dQ = 0;
+                                                                   // Gershgorin: dQ is added to S at the end of the stage
       __syncwarp();  // S (scratch) is dead from here on
 
       // The cost Hessians Q and P ride through shared memory too, each in a slot that is dead for exactly as long as the copy needs:
@@ -625,7 +645,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
           }
       }
       __syncwarp();  // all lanes are done with the staged operand block: refill it for node k-1 while this stage finishes
-      if (lane == 0 && k >= 1) {
+      if (MODE != kModeLM && lane == 0 && k >= 1) {  // (LM needs A, B, Hv once more after the gains: its refill follows Acl)
         mbar_expect_tx(&ws.full, opBytes);
         tma_load(ws.in, lqp + (size_t)(k - 1) * kRec, opBytes, &ws.full);
       }
@@ -662,6 +682,16 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
           const int j = 8 * c + r;
           __stcg(out + kOdb + j, -pick3(z, c));
           if (!NOM) __stcg(out + kObias + j, 0.0);
+          if (MODE == kModeLM) ws.ub[j] = -pick3(z, c);
+        }
+        if (MODE == kModeLM) {  // hcl = Hv + B dbias (one row per lane), kept in xb for Sv; s -= mu/2 |hcl|^2
+          __syncwarp();
+          const double hcl = Hv[li] + matvec_rows(B, ws.ub, li);
+          if (lane < kN) {
+            ws.xb[lane] = hcl;
+            spart = fma(-0.5 * a.mu * hcl, hcl, spart);
+          }
+          __syncwarp();
         }
         sval = sval + cval + warp_sum_all(spart);
         if (lane == 0) __stcg(out + kOs, sval);
@@ -683,6 +713,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
         }
 
       // ---- K' = -Y' L^-1 (op fragments of K -> 16-byte global stores); L^-1 is block lower triangular ----
+      double2 zc[3][3];  // LM: -Acl' = -(A + B K)' as accumulators = operand fragments of -Acl
       {
         double2 kk[3][3];
 #pragma unroll
@@ -728,6 +759,31 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
             }
           }
         }
+        if (MODE == kModeLM) {
+          // -Acl' = -A' - K'B' = -A' + (-K)'B': X = -K (the accumulators kk are its operand fragments), Y = B' (transposed reads of B)
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+            for (int jb = 0; jb < 3; ++jb) zc[ib][jb] = neg2(ld2(A + lo24 + t24(jb, ib)));  // A'[8ib+r][8jb+2c..] = A[8jb+2c..][8ib+r]
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            double2 bt[3];
+#pragma unroll
+            for (int jb = 0; jb < 3; ++jb) {  // B'[8kb+2c..2c+1][8jb+r] = B[8jb+r][8kb+2c..2c+1]
+              const double* bp = B + (8 * jb + r) + kN * (8 * kb + 2 * c);
+              bt[jb] = make_double2(bp[0], bp[kN]);
+            }
+#pragma unroll
+            for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+              for (int jb = 0; jb < 3; ++jb) dmma2(zc[ib][jb], kk[ib][kb], bt[jb]);
+          }
+          __syncwarp();  // A, B, Hv are consumed: the operand slot takes node k-1
+          if (lane == 0 && k >= 1) {
+            mbar_expect_tx(&ws.full, opBytes);
+            tma_load(ws.in, lqp + (size_t)(k - 1) * kRec, opBytes, &ws.full);
+          }
+        }
       }
 
       // ---- Sv = tv - Y'Yv ----
@@ -745,6 +801,21 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
             p = fma(y[cb][kb].y, vf[kb].y, p);
           }
           z[cb] = quad_sum(p);
+        }
+        if (MODE == kModeLM) {  // - mu Acl'hcl: the fragments hold -Acl
+          double2 hf[3];
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) hf[kb] = ld2(ws.xb + 8 * kb + 2 * c);
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+            double p = 0.0;
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) {
+              p = fma(zc[cb][kb].x, hf[kb].x, p);
+              p = fma(zc[cb][kb].y, hf[kb].y, p);
+            }
+            z[cb] = fma(-a.mu, quad_sum(p), z[cb]);
+          }
         }
         if (c < 3) {
           const int j = 8 * c + r;
@@ -764,6 +835,91 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
           for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
             for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], y[ib][kb], y[jb][kb]);
+      }
+      if (MODE == kModeLM) {  // + mu Acl'Acl
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+            const double2 zs = make_double2(a.mu * zc[ib][kb].x, a.mu * zc[ib][kb].y);
+#pragma unroll
+            for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], zs, zc[jb][kb]);
+          }
+      }
+      if (MODE == kModeGersh && !ev) {
+        // dQ = makePsdGershgorin(M) - M on M = Q~ - P~'P~ = Q - Yp'Yp, Yp = L^-1 P (LineSearchStrategy.cpp:294-312): only its diagonal
+        // max(0, R_i + eps - M_ii) differs from rounding noise. Yp' = P'L^-T like Y', M like S; P and Q come from L2 once more.
+        double2 yp[3][3];
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) {
+          double2 pf[3];
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) pf[kb] = ldg2(rec + kOP + lo24 + t24(kb, ib));
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            yp[ib][jb] = zero2();
+#pragma unroll
+            for (int kb = 0; kb <= jb; ++kb) dmma2(yp[ib][jb], pf[kb], ld2(ws.W + lo26 + t26(kb, jb)));
+          }
+        }
+        double2 mq[6];
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) mq[lt(ib, jb)] = ldg2(rec + kOQ + lo24 + t24(jb, ib));
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+            const double2 ny = neg2(yp[ib][kb]);
+#pragma unroll
+            for (int jb = 0; jb <= ib; ++jb) dmma2(mq[lt(ib, jb)], ny, yp[jb][kb]);
+          }
+        // Gershgorin radii: lane (r,c) holds M[8ib+r][8jb+2c..2c+1] of the lower tiles; a row's sum takes the row sums of its own
+        // tiles (over c) and, by symmetry, the column sums of the tiles below it (over r)
+        double rowp[3] = {0.0, 0.0, 0.0};
+        double2 colp[2] = {zero2(), zero2()};
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) {
+            const double ax = fabs(mq[lt(ib, jb)].x), ay = fabs(mq[lt(ib, jb)].y);
+            rowp[ib] += ax + ay;
+            if (ib != jb) {
+              colp[jb].x += ax;
+              colp[jb].y += ay;
+            }
+          }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rowp[i] = quad_sum(rowp[i]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            colp[j].x += __shfl_xor_sync(kFull, colp[j].x, o);
+            colp[j].y += __shfl_xor_sync(kFull, colp[j].y, o);
+          }
+        if (c == 0) {
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) ws.Gv[8 * ib + r] = rowp[ib];  // Gv is free between the gain computation and the next stage
+        }
+        __syncwarp();
+        if (r == 0) {
+#pragma unroll
+          for (int jb = 0; jb < 2; ++jb) {
+            ws.Gv[8 * jb + 2 * c] += colp[jb].x;
+            ws.Gv[8 * jb + 2 * c + 1] += colp[jb].y;
+          }
+        }
+        __syncwarp();
+        if (2 * c == r || 2 * c + 1 == r) {  // this lane holds the diagonal element of row 8ib + r in its diagonal tiles
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+            const double mii = (2 * c == r) ? mq[lt(ib, ib)].x : mq[lt(ib, ib)].y;
+            const double dq = fmax(0.0, ws.Gv[8 * ib + r] - fabs(mii) + a.eps - mii);
+            if (2 * c == r) t[lt(ib, ib)].x -= dq; else t[lt(ib, ib)].y -= dq;  // t holds Y'Y - T here: S = -t gains + dq
+          }
+        }
       }
       __syncwarp();  // every lane is done reading L^-T from the scratch
 #pragma unroll
@@ -927,8 +1083,10 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
 bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   // Both Riccati forms are served: under LINE_SEARCH the full form (preComputeRiccatiTerms = false) is the same map written with
   // K~'G~ + G~'K~ + K~'H~K~ in place of -G~'G~ (H~ = Pu'Hm Pu = I); the reference's own RiccatiTest.cpp:87-105 holds them equal to 1e-9.
-  return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
-         st.hc == O2C_HC_DIAGONAL_SHIFT && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
+  const bool ls = st.strategy == O2C_STRATEGY_LINE_SEARCH && (st.hc == O2C_HC_DIAGONAL_SHIFT || st.hc == O2C_HC_GERSHGORIN_MODIFICATION);
+  const bool lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT && buf.event == nullptr;  // (events under LM: refused by the API)
+  return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && (ls || lm) &&
+         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
          L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb && L.obias == kObias && L.oSm == kOSm &&
          L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat;
 }
@@ -964,15 +1122,15 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   if (!wpp_ilqr_supported(L, st, buf)) return cudaErrorNotSupported;
   const bool nom = buf.x_nom != nullptr, ev = buf.event != nullptr;
   using Kernel = void (*)(const Args);
-  const Kernel kernels[8] = {ilqr_wpp_kernel<false, false, false>, ilqr_wpp_kernel<true, false, false>, ilqr_wpp_kernel<false, true, false>,
-                             ilqr_wpp_kernel<true, true, false>,   ilqr_wpp_kernel<false, false, true>, ilqr_wpp_kernel<true, false, true>,
-                             ilqr_wpp_kernel<false, true, true>,   ilqr_wpp_kernel<true, true, true>};
-  // QPD (default): Q and P go from L2 straight into the accumulators instead of through TMA-staged shared-memory slots: Q is read
-  // like R (six tiles instead of nine: -1.5 KB of DRAM traffic per stage) and two mbarrier round trips per stage disappear
-  // (+0.8 % at 16384 problems, profiles/r02_wpp_variants.jsonl). O2C_WPP_QPD=0 selects the round-1 staging for comparison.
-  bool qpd = true;
-  if (const char* e = getenv("O2C_WPP_QPD")) qpd = atoi(e) != 0;
-  const Kernel kernel = kernels[(nom ? 1 : 0) + (ev ? 2 : 0) + (qpd ? 4 : 0)];
+  const Kernel kernels[3][4] = {
+      {ilqr_wpp_kernel<false, false, kModeLS>, ilqr_wpp_kernel<true, false, kModeLS>, ilqr_wpp_kernel<false, true, kModeLS>,
+       ilqr_wpp_kernel<true, true, kModeLS>},
+      {ilqr_wpp_kernel<false, false, kModeLM>, ilqr_wpp_kernel<true, false, kModeLM>, nullptr, nullptr},
+      {ilqr_wpp_kernel<false, false, kModeGersh>, ilqr_wpp_kernel<true, false, kModeGersh>, ilqr_wpp_kernel<false, true, kModeGersh>,
+       ilqr_wpp_kernel<true, true, kModeGersh>}};
+  const int mode = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT ? kModeLM : (st.hc == O2C_HC_GERSHGORIN_MODIFICATION ? kModeGersh : kModeLS);
+  const Kernel kernel = kernels[mode][(nom ? 1 : 0) + (ev ? 2 : 0)];
+  if (kernel == nullptr) return cudaErrorNotSupported;
   const int num_sms = device_sm_count();
   if (num_sms <= 0) return cudaErrorInvalidDevice;
   // profiling knobs, read per launch (no state is cached in statics: launches from several host threads / on several devices are
@@ -1011,6 +1169,7 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   a.with_rollout = with_rollout ? 1 : 0;
   a.eps = st.eps;
   a.alpha = alpha;
+  a.mu = st.mu;
   (void)batch;
   // warp-major problem order (CTA b starts with problems b, b + grid, ...): the grid is as wide as the machine even when the batch
   // does not fill every warp slot, so a small batch spreads evenly over the SMs

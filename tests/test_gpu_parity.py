@@ -81,7 +81,8 @@ def test_ilqr_generated_batch_matches_oracle(shape, variant):
         solver.generate_synthetic(seed, first_problem_index=1000, dt=dt)
         # LINE_SEARCH + DIAGONAL_SHIFT in either Riccati form runs the shape's specialised kernel (the forms are the same map, the oracle
         # below is evaluated in the form asked for); every other variant goes through the generic kernel
-        fast = variant in ("ls_reduced_diag", "ls_full_diag") and shape != "test32c"
+        # (the legged shape: its DMMA kernel also carries the Gershgorin and Levenberg-Marquardt modifications as template variants)
+        fast = (variant in ("ls_reduced_diag", "ls_full_diag") and shape != "test32c") or shape == "legged"
         assert ("generic" in solver.kernel_variant) != fast
         solver.solveSequentialRiccatiEquations()
         alphas = (1.0, 0.35)
