@@ -85,6 +85,7 @@ struct o2c_handle {
   bool nc_ragged = false;  // a caller supplied per-node constraint counts (otherwise every node has nc_max: the kernels skip the lookup)
   int64_t launches = 0;
   int stage_chunk = 0;
+  double* d_slq_ws = nullptr;  // projected node data of the legged SLQ kernels (slq_wpp.cu), allocated on first use
   int* d_counter = nullptr;  // [kLanes] work counters of the persistent kernels' dynamic problem fetch, one per stream lane
 
   int lane_of(cudaStream_t s) const {
@@ -704,6 +705,13 @@ o2c_error backward_on(o2c_handle* h, cudaStream_t stream, int begin, int count) 
     }
   } else {
     if (!h->time_set) return fail(O2C_ERR_NOT_READY, "SLQ needs the node times (o2c_set_time or lq_view.time) before o2c_backward");
+    if (slq_wpp_supported(h->L, h->st, buf)) {
+      if (!h->d_slq_ws) O2C_CUDA(cudaMalloc(&h->d_slq_ws, sizeof(double) * slq_wpp_workspace_doubles(h->L, h->cfg.batch)));
+      int l = 0;
+      O2C_CUDA(launch_slq_wpp(h->L, h->st, buf, h->d_slq_ws, h->d_slq_steps, h->n_slq_steps, begin, count, stream, &l));
+      h->launches += l;
+      return O2C_OK;
+    }
     if (rpl_slq_supported(h->L, h->st, buf))
       O2C_CUDA(launch_slq_rpl(h->L, h->st, buf, h->d_slq_steps, h->n_slq_steps, begin, count, stream));
     else
@@ -758,7 +766,7 @@ void release(o2c_handle* h) {
   }
   void* ptrs[] = {h->d_lq,  h->d_term, h->d_xnom, h->d_unom,   h->d_x0,        h->d_time,    h->d_sol,
                   h->d_xs,  h->d_us,   h->d_alphas, h->d_nc,   h->d_status,    h->d_slq_steps, h->d_ro_steps,
-                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event, h->d_flat, h->d_jump, h->d_dt, h->d_counter};
+                  h->d_ls_merit, h->d_ls_base, h->d_ls_is, h->d_ls_step, h->d_ls_basein, h->d_ls_index, h->d_event, h->d_flat, h->d_jump, h->d_dt, h->d_counter, h->d_slq_ws};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_status) cudaFreeHost(h->h_status);
@@ -1250,6 +1258,7 @@ o2c_error o2c_launch_count(const o2c_handle* h, int64_t* launches) {
 
 const char* o2c_kernel_variant(const o2c_handle* h) {
   if (!h) return "";
+  if (h->st.algorithm == O2C_ALG_SLQ && slq_wpp_supported(h->L, h->st, h->buffers())) return "slq_wpp_kernel";
   if (h->st.algorithm == O2C_ALG_SLQ && rpl_slq_supported(h->L, h->st, h->buffers())) return "slq_rpl_kernel";
   if (h->st.algorithm == O2C_ALG_ILQR && h->use_fast && wpp_ilqr_supported(h->L, h->st, h->buffers())) return "ilqr_wpp_kernel";
   if (h->st.algorithm == O2C_ALG_ILQR && h->use_rpl && rpl_ilqr_supported(h->L, h->st, h->buffers())) return "ilqr_rpl_kernel";

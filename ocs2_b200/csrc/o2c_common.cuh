@@ -198,6 +198,13 @@ bool rpl_slq_supported(const Layout& L, const SolverSettings& st, const DeviceBu
 cudaError_t launch_slq_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin,
                            int count, cudaStream_t stream);
 
+// SLQ backward pass of the legged shape on the FP64 tensor pipe (slq_wpp.cu): projection, RK4 flow map, controller = 3 launches; needs
+// a workspace of slq_wpp_workspace_doubles(L, batch) doubles
+bool slq_wpp_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
+size_t slq_wpp_workspace_doubles(const Layout& L, int batch);
+cudaError_t launch_slq_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, double* workspace, const SlqStep* steps, int nsteps,
+                           int begin, int count, cudaStream_t stream, int* launches);
+
 bool rpl_rollout_cont_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
 cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,
                                     int first_idx, double first_alpha, int out_nodes, const double* alphas_dev, int n_alpha, int batch,

@@ -1,0 +1,618 @@
+// slq_wpp.cu — SLQ backward pass for nx = nu = 24 (the legged-robot shape) on the FP64 tensor pipe, warp per problem, sm_100a.
+//
+// The reference's legged example runs SLQ (ocs2_robotic_examples/ocs2_legged_robot/config/mpc/task.info:85); this is its backward pass for
+// the unconstrained LINE_SEARCH / DIAGONAL_SHIFT configuration, in the three phases the reference itself has:
+//
+//   slq_project_kernel      SLQ::solveSequentialRiccatiEquations, the per-node projection loop (SLQ.cpp:174-208; node-parallel there too):
+//                           Hm = R = L L', Pu = L^-T, B~ = B Pu, P~ = Pu'P, r~ = Pu'r (GaussNewtonDDP.cpp:734-782 with nc = 0,
+//                           DDP_HelperFunctions.cpp:143-201) into a workspace record { B~ | P~ | L^-T | r~ } per (problem, node)
+//   slq_flow_kernel         SLQ::riccatiEquationsWorker / integrateRiccatiEquationNominalTime (SLQ.cpp:213-302): classic RK4 over the
+//                           host-built step schedule (boost::odeint integrate_times semantics, api.cu build_slq_schedule), four evaluations
+//                           of ContinuousTimeRiccatiEquations::computeFlowMapSLQ (ContinuousTimeRiccatiEquations.cpp:152-292) per step on
+//                           the projected data lerped between the two nodes of the interval. One warp per problem (time-sequential):
+//                               dS  = Q~ + eps I + S'A~ + (S'A~)' - G'G,  G = P~ + B~'S
+//                               dSv = q~ + S Hv + A~'Sv - G'Gv,           Gv = r~ + B~'Sv
+//                               ds  = c~ + Hv.Sv - Gv.Gv / 2
+//                           (reduced form, K~ = -G, L~ = -Gv under LINE_SEARCH; the full form is the same map). 162 DMMA per evaluation:
+//                           the lower tiles of S'A + A'S (72), G' = P~' + S B~ as operand fragments of G (54), G'G lower (36).
+//   slq_controller_kernel   SLQ::calculateControllerWorker (SLQ.cpp:127-169) + GaussNewtonDDP::calculateController (GaussNewtonDDP.cpp:588-618),
+//                           node-parallel: K = -Pu (P~ + B~'S_k), dbias = -Pu (r~ + B~'Sv_k), bias = u_nom - K x_nom, node N := node N-1
+//
+// Fragment conventions are those of riccati_wpp.cu (wpp_tiles.cuh): every product is Z = X'Y on "op" fragments, the accumulator fragment
+// of Z is the operand fragment of Z'. The value function lives in the lower tiles of accumulator layout; the stage argument of every
+// evaluation goes through the 5 KB scratch (both triangles) to be re-read as operand fragments. The reference integrates the upper
+// triangle of S (convert2Vector); this kernel integrates the lower tiles and mirrors them — dS is symmetric up to rounding.
+#include <cstdio>
+#include <cstdlib>
+
+#include "o2c_common.cuh"
+#include "wpp_tiles.cuh"
+
+namespace o2c {
+namespace {
+
+// workspace record per (problem, node), 128-byte multiple
+constexpr int kWB = 0, kWP = kMat, kWL = 2 * kMat, kWr = 3 * kMat, kWRec = 3 * kMat + 32;
+constexpr int kTail = kOperand - 2 * kMat;  // { Hv | q | r | c, pad } = 80 doubles
+constexpr int kSlot = kOperand + kN;        // { A | B~ | Hv | q | r | c, pad | r~ }
+constexpr int kFlowWarps = 8;               // per SM: two 10 KB node slots + the scratch per warp = 25.5 KB
+constexpr int kNodeWarps = 4;
+
+struct SlqWppArgs {
+  const double* lq;
+  const double* term;
+  const double* x_nom;
+  const double* u_nom;
+  double* ws;
+  double* sol;
+  int* status;
+  const SlqStep* steps;
+  int nsteps, N, begin, count;
+  int oQf, oqf, ocf, trec;
+  double eps;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// projection of every node (node-parallel)
+// ---------------------------------------------------------------------------------------------------------------------
+struct __align__(16) NodeSmem {
+  double W[kN * kLd];
+  double v[kN], y[kN];
+};
+
+__global__ void __launch_bounds__(32 * kNodeWarps) slq_project_kernel(const SlqWppArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  NodeSmem& ws = reinterpret_cast<NodeSmem*>(smem_raw)[warp];
+  const int r = lane >> 2, c = lane & 3;
+  const int lo24 = 2 * c + kN * r, lo26 = 2 * c + kLd * r;
+  const int li = lane < kN ? lane : kN - 1;
+  const int nodes = a.N + 1;
+  const long long items = (long long)a.count * nodes;
+  for (long long item = (long long)blockIdx.x * kNodeWarps + warp; item < items; item += (long long)gridDim.x * kNodeWarps) {
+    const int prob = a.begin + (int)(item / nodes), node = (int)(item % nodes);
+    const double* rec = a.lq + ((size_t)prob * nodes + node) * kRec;
+    double* out = a.ws + ((size_t)prob * nodes + node) * kWRec;
+    // Hm = R (SLQ.cpp:206-208): lower tiles into the scratch, r into shared memory
+#pragma unroll
+    for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+      for (int jb = 0; jb <= ib; ++jb) tput(ws.W, ib, jb, r, c, ldg2(rec + kOR + lo24 + t24(jb, ib)));  // R[8ib+r][8jb+2c..] = R[8jb+2c..][8ib+r]
+    if (lane < kN) ws.v[lane] = rec[2 * kMat + 2 * kN + lane];
+    __syncwarp();
+    const bool pd = factor_hm(ws.W, lane, li, r, c);  // the scratch now holds L^-T in its block upper triangle
+    // B~' = L^-1 B' = (L^-T)'B': X = L^-T, Y = B' (transposed reads of B); acc(B~')(ib, jb) = B~[8jb+2c..][8ib+r] -> column-major B~
+    // P~  = L^-1 P  = (L^-T)'P : X = L^-T, Y = P;                          acc(P~)(ib, jb)  = P~[8ib+r][8jb+2c..]
+    double2 bt[3][3], pt[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) bt[i][j] = pt[i][j] = zero2();
+#pragma unroll
+    for (int kb = 0; kb < 3; ++kb) {
+      double2 bf[3], pf[3];
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb) {
+        const double* bp = rec + kMat + (8 * jb + r) + kN * (8 * kb + 2 * c);  // B'[8kb+2c..2c+1][8jb+r] = B[8jb+r][8kb+2c..2c+1]
+        bf[jb] = make_double2(__ldcg(bp), __ldcg(bp + kN));
+        pf[jb] = ldg2(rec + kOP + lo24 + t24(kb, jb));
+      }
+#pragma unroll
+      for (int ib = kb; ib < 3; ++ib) {  // L^-T is block upper triangular: tiles (kb, ib) with kb <= ib
+        const double2 lf = ld2(ws.W + lo26 + t26(kb, ib));
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) {
+          dmma2(bt[ib][jb], lf, bf[jb]);
+          dmma2(pt[ib][jb], lf, pf[jb]);
+        }
+      }
+    }
+#pragma unroll
+    for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb) {
+        stg2(out + kWB + lo24 + t24(jb, ib), bt[ib][jb]);
+        double* pq = out + kWP + (8 * ib + r) + kN * (8 * jb + 2 * c);
+        __stcg(pq, pt[ib][jb].x);
+        __stcg(pq + kN, pt[ib][jb].y);
+        if (ib <= jb) stg2(out + kWL + lo24 + t24(ib, jb), ld2(ws.W + lo26 + t26(ib, jb)));  // L^-T, tiles on and above the block diagonal
+      }
+    // r~ = L^-1 r
+    {
+      double z[3];
+      matvec_cols<kLd, true>(ws.W, ws.v, r, c, z);
+      if (c < 3) __stcg(out + kWr + 8 * c + r, pick3(z, c));
+    }
+    if (!__all_sync(kFull, pd) && lane == 0) atomicOr(a.status + prob, O2C_STATUS_CHOL_NOT_PD);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the flow map under RK4 (one warp per problem)
+// ---------------------------------------------------------------------------------------------------------------------
+struct __align__(16) FlowSmem {
+  double slot[2][kSlot];  // node k lives in slot k & 1: { A | B~ | Hv | q | r | c, pad | r~ }
+  double W[kN * kLd];     // stage argument of the flow map, both triangles
+  double Sv[kN], Gv[kN];
+  unsigned long long full[2];
+};
+static_assert(sizeof(FlowSmem) % 16 == 0, "warp slots must keep 16-byte alignment");
+
+__device__ __forceinline__ double2 lerp2(double al, double be, const double2& u, const double2& v) {
+  return make_double2(fma(al, u.x, be * v.x), fma(al, u.y, be * v.y));
+}
+
+__global__ void __launch_bounds__(32 * kFlowWarps, 1) slq_flow_kernel(const SlqWppArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FlowSmem& ws = reinterpret_cast<FlowSmem*>(smem_raw)[warp];
+  const int r = lane >> 2, c = lane & 3;
+  const int lo24 = 2 * c + kN * r, lo26 = 2 * c + kLd * r;
+  const int N = a.N, nodes = N + 1;
+  const int jv = c < 3 ? 8 * c + r : 0;  // the vector element this lane owns (lanes with c < 3)
+  const bool own = c < 3;
+  if (lane == 0) {
+    mbar_init(&ws.full[0], 1);
+    mbar_init(&ws.full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phase = 0;  // bit q: parity to wait for on full[q]
+  const int total_warps = gridDim.x * (blockDim.x >> 5);
+
+  for (int pi = warp * gridDim.x + blockIdx.x; pi < a.count; pi += total_warps) {
+    const int prob = a.begin + pi;
+    const double* lqp = a.lq + (size_t)prob * nodes * kRec;
+    const double* wsp = a.ws + (size_t)prob * nodes * kWRec;
+    const double* term = a.term + (size_t)prob * a.trec;
+    double* solp = a.sol + (size_t)prob * nodes * kORec;
+
+    auto issue_node = [&](int k) {  // four bulk copies, one mbarrier
+      if (lane == 0) {
+        double* dst = ws.slot[k & 1];
+        const double* rec = lqp + (size_t)k * kRec;
+        const double* wr = wsp + (size_t)k * kWRec;
+        fence_proxy_async();
+        mbar_expect_tx(&ws.full[k & 1], (uint32_t)(sizeof(double) * kSlot));
+        tma_load(dst, rec, sizeof(double) * kMat, &ws.full[k & 1]);
+        tma_load(dst + kMat, wr + kWB, sizeof(double) * kMat, &ws.full[k & 1]);
+        tma_load(dst + 2 * kMat, rec + 2 * kMat, sizeof(double) * kTail, &ws.full[k & 1]);
+        tma_load(dst + kOperand, wr + kWr, sizeof(double) * kN, &ws.full[k & 1]);
+      }
+    };
+    auto wait_node = [&](int k) {
+      const int q = k & 1;
+      mbar_wait(&ws.full[q], (phase >> q) & 1u);
+      phase ^= 1u << q;
+    };
+    auto touch_node = [&](int k) {  // pull the pieces of node k towards L2 (operands by bulk prefetch, the accumulator inits per lane)
+      const double* rec = lqp + (size_t)k * kRec;
+      const double* wr = wsp + (size_t)k * kWRec;
+      if (lane == 0) {
+        l2_prefetch(rec, sizeof(double) * kMat);
+        l2_prefetch(wr + kWB, sizeof(double) * kMat);
+      }
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) {
+          l2_touch(wr + kWP + lo24 + t24(jb, ib));
+          if (jb <= ib) l2_touch(rec + kOQ + lo24 + t24(jb, ib));
+        }
+    };
+
+    // ---- terminal condition: valueFunctionTrajectory.back() = finalValueFunction (GaussNewtonDDP.cpp:526) ----
+    double2 S[6];  // lower tiles, accumulator layout: S[8ib+r][8jb+2c..2c+1]
+#pragma unroll
+    for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+      for (int jb = 0; jb <= ib; ++jb) S[lt(ib, jb)] = ld2(term + a.oQf + lo24 + t24(jb, ib));  // Qf[8jb+2c..][8ib+r] (symmetric)
+    double Svj = own ? term[a.oqf + jv] : 0.0;
+    double sval = term[a.ocf];
+
+    auto stage_to_scratch = [&](const double2 (&Y)[6], double svj) {  // value function -> operand layout (both triangles), Sv -> shared
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+        for (int jb = 0; jb <= ib; ++jb) {
+          st2(ws.W + lo26 + t26(jb, ib), Y[lt(ib, jb)]);
+          if (ib != jb) tput(ws.W, ib, jb, r, c, Y[lt(ib, jb)]);
+        }
+      if (own) ws.Sv[jv] = svj;
+      __syncwarp();
+    };
+    auto write_value = [&](int k) {
+      double* out = solp + (size_t)k * kORec;
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+        for (int jb = 0; jb <= ib; ++jb) {
+          const double2 sv = S[lt(ib, jb)];
+          stg2(out + kOSm + lo24 + t24(jb, ib), sv);
+          if (ib != jb) {
+            double* gq = out + kOSm + (8 * ib + r) + kN * (8 * jb + 2 * c);
+            __stcg(gq, sv.x);
+            __stcg(gq + kN, sv.y);
+          }
+        }
+      if (own) __stcg(out + kOSv + jv, Svj);
+      if (lane == 0) __stcg(out + kOs, sval);
+    };
+
+    write_value(N);
+    issue_node(N);
+    if (N >= 1) issue_node(N - 1);
+    wait_node(N);
+    if (N >= 1) wait_node(N - 1);
+    if (N >= 2) touch_node(N - 2);
+    int loaded_lo = N >= 1 ? N - 1 : N;
+    stage_to_scratch(S, Svj);
+
+#pragma unroll 1
+    for (int sidx = 0; sidx < a.nsteps; ++sidx) {
+      const SlqStep sp = a.steps[sidx];
+      const int i0 = sp.interval;
+      if (i0 < loaded_lo) {  // the interval moved one node down: node i0 takes the slot of node i0 + 2 (dead)
+        __syncwarp();
+        issue_node(i0);
+        wait_node(i0);
+        if (i0 >= 1) touch_node(i0 - 1);
+        loaded_lo = i0;
+      }
+      const double* s0 = ws.slot[i0 & 1];        // node i0
+      const double* s1 = ws.slot[(i0 + 1) & 1];  // node i0 + 1
+      const double* q0 = lqp + (size_t)i0 * kRec + kOQ;
+      const double* q1 = q0 + kRec;
+      const double* p0 = wsp + (size_t)i0 * kWRec + kWP;
+      const double* p1 = p0 + kWRec;
+      const double h = sp.h;
+      double2 acc[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) acc[i] = S[i];
+      double accv = Svj, accs = sval;
+
+#pragma unroll 1
+      for (int stg = 0; stg < 4; ++stg) {
+        const double al = sp.alpha[stg], be = 1.0 - al;
+        // Q (lower tiles, + eps I) and P~' (all tiles) come from L2, lerped; they are issued here and added to the accumulators after the
+        // contractions, so that their latency hides behind the first 126 DMMAs
+        double2 d[6], g[3][3], qd[6], pg[3][3];
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) {
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) {
+            qd[lt(ib, jb)] = lerp2(al, be, ldg2(q0 + lo24 + t24(jb, ib)), ldg2(q1 + lo24 + t24(jb, ib)));
+            d[lt(ib, jb)] = zero2();
+          }
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            pg[ib][jb] = lerp2(al, be, ldg2(p0 + lo24 + t24(jb, ib)), ldg2(p1 + lo24 + t24(jb, ib)));
+            g[ib][jb] = zero2();
+          }
+        }
+        double pSH[3] = {0.0, 0.0, 0.0}, pA[3] = {0.0, 0.0, 0.0}, pB[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) {
+          const double2 hvf = lerp2(al, be, ld2(s0 + 2 * kMat + 8 * kb + 2 * c), ld2(s1 + 2 * kMat + 8 * kb + 2 * c));
+          const double2 svf = ld2(ws.Sv + 8 * kb + 2 * c);
+          double2 s[3], af[3], bf[3];
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            s[jb] = ld2(ws.W + lo26 + t26(kb, jb));
+            pSH[jb] = fma(s[jb].x, hvf.x, pSH[jb]);
+            pSH[jb] = fma(s[jb].y, hvf.y, pSH[jb]);
+            af[jb] = lerp2(al, be, ld2(s0 + lo24 + t24(kb, jb)), ld2(s1 + lo24 + t24(kb, jb)));
+            bf[jb] = lerp2(al, be, ld2(s0 + kMat + lo24 + t24(kb, jb)), ld2(s1 + kMat + lo24 + t24(kb, jb)));
+            pA[jb] = fma(af[jb].x, svf.x, pA[jb]);
+            pA[jb] = fma(af[jb].y, svf.y, pA[jb]);
+            pB[jb] = fma(bf[jb].x, svf.x, pB[jb]);
+            pB[jb] = fma(bf[jb].y, svf.y, pB[jb]);
+          }
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+#pragma unroll
+            for (int jb = 0; jb <= ib; ++jb) {
+              dmma2(d[lt(ib, jb)], s[ib], af[jb]);  // (S'A)(ib, jb)
+              dmma2(d[lt(ib, jb)], af[ib], s[jb]);  // (A'S)(ib, jb)
+            }
+#pragma unroll
+            for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], s[ib], bf[jb]);  // G' = P~' + S B~: operand fragments of G
+          }
+        }
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) {
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) {
+            d[lt(ib, jb)].x += qd[lt(ib, jb)].x;
+            d[lt(ib, jb)].y += qd[lt(ib, jb)].y;
+          }
+          d[lt(ib, ib)].x += (2 * c == r) ? a.eps : 0.0;
+          d[lt(ib, ib)].y += (2 * c + 1 == r) ? a.eps : 0.0;
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            g[ib][jb].x += pg[ib][jb].x;
+            g[ib][jb].y += pg[ib][jb].y;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          pSH[i] = quad_sum(pSH[i]);
+          pA[i] = quad_sum(pA[i]);
+          pB[i] = quad_sum(pB[i]);
+        }
+        double kv = 0.0, spart = 0.0;
+        if (own) {
+          const double hvj = fma(al, s0[2 * kMat + jv], be * s1[2 * kMat + jv]);
+          const double gvj = fma(al, s0[kOperand + jv], be * s1[kOperand + jv]) + pick3(pB, c);  // Gv = r~ + B~'Sv
+          ws.Gv[jv] = gvj;
+          kv = fma(al, s0[2 * kMat + kN + jv], be * s1[2 * kMat + kN + jv]) + pick3(pSH, c) + pick3(pA, c);  // q~ + S Hv + A'Sv
+          spart = fma(hvj, ws.Sv[jv], -0.5 * gvj * gvj);                                                     // Hv.Sv - Gv.Gv / 2
+        }
+        const double cl = fma(al, s0[2 * kMat + 3 * kN], be * s1[2 * kMat + 3 * kN]);
+        __syncwarp();  // Gv is in shared memory; every lane is done reading the stage argument from the scratch
+        // dS -= G'G (lower tiles); dSv -= G'Gv
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+            const double2 ng = neg2(g[ib][kb]);
+#pragma unroll
+            for (int jb = 0; jb <= ib; ++jb) dmma2(d[lt(ib, jb)], ng, g[jb][kb]);
+          }
+        {
+          double2 gvf[3];
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) gvf[kb] = ld2(ws.Gv + 8 * kb + 2 * c);
+          double z[3];
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+            double p = 0.0;
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) {
+              p = fma(g[cb][kb].x, gvf[kb].x, p);
+              p = fma(g[cb][kb].y, gvf[kb].y, p);
+            }
+            z[cb] = quad_sum(p);
+          }
+          if (own) kv -= pick3(z, c);
+        }
+        const double ks = cl + warp_sum_all(spart);
+        // classic RK4 (boost::odeint runge_kutta4): y += h (k1 + 2 k2 + 2 k3 + k4) / 6, next argument y + c_s h k_s
+        const double bw = h * ((stg == 0 || stg == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
+        const double cw = h * ((stg == 2) ? 1.0 : 0.5);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          acc[i].x = fma(bw, d[i].x, acc[i].x);
+          acc[i].y = fma(bw, d[i].y, acc[i].y);
+        }
+        accv = fma(bw, kv, accv);
+        accs = fma(bw, ks, accs);
+        if (stg < 3) {
+          double2 ys[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) ys[i] = make_double2(fma(cw, d[i].x, S[i].x), fma(cw, d[i].y, S[i].y));
+          stage_to_scratch(ys, fma(cw, kv, Svj));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) S[i] = acc[i];
+      Svj = accv;
+      sval = accs;
+      stage_to_scratch(S, Svj);
+      if (sp.observe_node >= 0) write_value(sp.observe_node);
+    }
+
+    bool finite = finite_bits(sval) && finite_bits(Svj);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) finite = finite && finite2(S[i]);
+    if (!__all_sync(kFull, finite) && lane == 0) atomicOr(a.status + prob, O2C_STATUS_NONFINITE);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// controller of every node (node-parallel)
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool NOM>
+__global__ void __launch_bounds__(32 * kNodeWarps) slq_controller_kernel(const SlqWppArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  NodeSmem& ws = reinterpret_cast<NodeSmem*>(smem_raw)[warp];
+  const int r = lane >> 2, c = lane & 3;
+  const int lo24 = 2 * c + kN * r, lo26 = 2 * c + kLd * r;
+  const int N = a.N, nodes = N + 1;
+  const long long items = (long long)a.count * N;  // nodes 0 .. N-1; node N is the copy of node N-1 (GaussNewtonDDP.cpp:609-618)
+  for (long long item = (long long)blockIdx.x * kNodeWarps + warp; item < items; item += (long long)gridDim.x * kNodeWarps) {
+    const int prob = a.begin + (int)(item / N), node = (int)(item % N);
+    const double* wr = a.ws + ((size_t)prob * nodes + node) * kWRec;
+    double* out = a.sol + ((size_t)prob * nodes + node) * kORec;
+    double* outN = (node == N - 1) ? a.sol + ((size_t)prob * nodes + N) * kORec : nullptr;
+    // L^-T into the scratch (tiles on and above the block diagonal), Sv into shared memory
+#pragma unroll
+    for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+      for (int jb = ib; jb < 3; ++jb) st2(ws.W + lo26 + t26(ib, jb), ldg2(wr + kWL + lo24 + t24(ib, jb)));
+    if (lane < kN) ws.v[lane] = out[kOSv + lane];
+    __syncwarp();
+    // Yc' = P~' + S B~ (operand fragments of Yc = P~ + B~'S_k), Gv = r~ + B~'Sv_k
+    double2 y[3][3];
+#pragma unroll
+    for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb) y[ib][jb] = ldg2(wr + kWP + lo24 + t24(jb, ib));
+    double pB[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int kb = 0; kb < 3; ++kb) {
+      const double2 svf = ld2(ws.v + 8 * kb + 2 * c);
+      double2 s[3], bf[3];
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb) {
+        s[jb] = ldg2(out + kOSm + lo24 + t24(kb, jb));
+        bf[jb] = ldg2(wr + kWB + lo24 + t24(kb, jb));
+        pB[jb] = fma(bf[jb].x, svf.x, pB[jb]);
+        pB[jb] = fma(bf[jb].y, svf.y, pB[jb]);
+      }
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) dmma2(y[ib][jb], s[ib], bf[jb]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pB[i] = quad_sum(pB[i]);
+    if (c < 3) ws.y[8 * c + r] = __ldcg(wr + kWr + 8 * c + r) + pick3(pB, c);
+    __syncwarp();
+    // dbias = -L^-T Gv
+    {
+      double2 vf[3];
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb) vf[kb] = ld2(ws.y + 8 * kb + 2 * c);
+      double z[3];
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb) {
+        double p = 0.0;
+#pragma unroll
+        for (int kb = jb; kb < 3; ++kb) {
+          const double2 mv = tfrag(ws.W, jb, kb, r, c);
+          p = fma(mv.x, vf[kb].x, p);
+          p = fma(mv.y, vf[kb].y, p);
+        }
+        z[jb] = quad_sum(p);
+      }
+      if (c < 3) {
+        const int j = 8 * c + r;
+        __stcg(out + kOdb + j, -pick3(z, c));
+        if (outN) __stcg(outN + kOdb + j, -pick3(z, c));
+        if (!NOM) {
+          __stcg(out + kObias + j, 0.0);
+          if (outN) __stcg(outN + kObias + j, 0.0);
+        }
+      }
+    }
+    // K' = -Yc' L^-1 (operand fragments of K -> 16-byte stores)
+    double2 kk[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) kk[i][j] = zero2();
+#pragma unroll
+    for (int jb = 0; jb < 3; ++jb)
+#pragma unroll
+      for (int kb = jb; kb < 3; ++kb) {
+        const double2 lf = tfrag(ws.W, jb, kb, r, c);  // L^-1[8kb+2c..][8jb+r] = L^-T[8jb+r][8kb+2c..]
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) dmma2(kk[ib][jb], y[ib][kb], lf);
+      }
+#pragma unroll
+    for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb) {
+        stg2(out + kOK + lo24 + t24(jb, ib), neg2(kk[ib][jb]));
+        if (outN) stg2(outN + kOK + lo24 + t24(jb, ib), neg2(kk[ib][jb]));
+      }
+    if (NOM) {  // bias = u_nom - K x_nom (GaussNewtonDDP.cpp:604-606): the accumulators hold -K'
+      const double* xn = a.x_nom + ((size_t)prob * nodes + node) * kN;
+      const double* un = a.u_nom + ((size_t)prob * nodes + node) * kN;
+      double xr[3];
+#pragma unroll
+      for (int ib = 0; ib < 3; ++ib) xr[ib] = __ldg(xn + 8 * ib + r);
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb) {
+        double px = 0.0, py = 0.0;
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) {
+          px = fma(kk[ib][jb].x, xr[ib], px);
+          py = fma(kk[ib][jb].y, xr[ib], py);
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          px += __shfl_xor_sync(kFull, px, o);
+          py += __shfl_xor_sync(kFull, py, o);
+        }
+        if (r == 0) {
+          const double2 u2 = *reinterpret_cast<const double2*>(un + 8 * jb + 2 * c);
+          const double2 b2 = make_double2(u2.x + px, u2.y + py);
+          stg2(out + kObias + 8 * jb + 2 * c, b2);
+          if (outN) stg2(outN + kObias + 8 * jb + 2 * c, b2);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+size_t slq_wpp_workspace_doubles(const Layout& L, int batch) { return (size_t)batch * (L.N + 1) * kWRec; }
+
+bool slq_wpp_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
+  return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_SLQ && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
+         st.hc == O2C_HC_DIAGONAL_SHIFT && buf.event == nullptr && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 &&
+         L.rec == kRec && L.oQ == kOQ && L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb &&
+         L.obias == kObias && L.oSm == kOSm && L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat &&
+         L.oq == 2 * kMat + kN && L.or_ == 2 * kMat + 2 * kN && L.oc == 2 * kMat + 3 * kN;
+}
+
+cudaError_t launch_slq_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, double* workspace, const SlqStep* steps, int nsteps,
+                           int begin, int count, cudaStream_t stream, int* launches) {
+  if (!slq_wpp_supported(L, st, buf) || workspace == nullptr) return cudaErrorNotSupported;
+  const int sms = device_sm_count();
+  if (sms <= 0) return cudaErrorInvalidDevice;
+  SlqWppArgs a{};
+  a.lq = buf.lq;
+  a.term = buf.term;
+  a.x_nom = buf.x_nom;
+  a.u_nom = buf.u_nom;
+  a.ws = workspace;
+  a.sol = buf.sol;
+  a.status = buf.status;
+  a.steps = steps;
+  a.nsteps = nsteps;
+  a.N = L.N;
+  a.begin = begin;
+  a.count = count;
+  a.oQf = L.oQf;
+  a.oqf = L.oqf;
+  a.ocf = L.ocf;
+  a.trec = L.trec;
+  a.eps = st.eps;
+  cudaError_t e = cudaMemsetAsync(buf.status + begin, 0, sizeof(int) * (size_t)count, stream);  // the three kernels or their bits in
+  if (e != cudaSuccess) return e;
+  const size_t node_smem = sizeof(NodeSmem) * kNodeWarps;
+  {
+    const long long items = (long long)count * (L.N + 1);
+    const long long ctas = (items + kNodeWarps - 1) / kNodeWarps;
+    const int grid = (int)(ctas < (long long)sms * 16 ? ctas : (long long)sms * 16);
+    slq_project_kernel<<<grid, 32 * kNodeWarps, node_smem, stream>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  {
+    int warps = kFlowWarps;
+    if (const char* env = getenv("O2C_SLQ_WPP_RESIDENT")) {  // profiling knob
+      const int v = atoi(env);
+      if (v >= 1 && v <= kFlowWarps) warps = v;
+    }
+    const size_t smem = sizeof(FlowSmem) * warps;
+    e = cudaFuncSetAttribute(slq_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FlowSmem) * kFlowWarps));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(slq_flow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    const int grid = count < sms ? count : sms;
+    slq_flow_kernel<<<grid, 32 * warps, smem, stream>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  {
+    const long long items = (long long)count * L.N;
+    const long long ctas = (items + kNodeWarps - 1) / kNodeWarps;
+    const int grid = (int)(ctas < (long long)sms * 16 ? ctas : (long long)sms * 16);
+    if (buf.x_nom)
+      slq_controller_kernel<true><<<grid, 32 * kNodeWarps, node_smem, stream>>>(a);
+    else
+      slq_controller_kernel<false><<<grid, 32 * kNodeWarps, node_smem, stream>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (launches) *launches = 3;
+  return cudaSuccess;
+}
+
+}  // namespace o2c

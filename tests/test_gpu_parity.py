@@ -94,7 +94,7 @@ def test_ilqr_generated_batch_matches_oracle(shape, variant):
             check_against_oracle(st, pb, x0, sol, i, alphas, what=f"{shape}/{variant}")
 
 
-@pytest.mark.parametrize("shape,substeps", [("quadrotor", 1.0), ("test32c", 2.5), ("cartpole", 1.0)])
+@pytest.mark.parametrize("shape,substeps", [("quadrotor", 1.0), ("test32c", 2.5), ("cartpole", 1.0), ("legged", 1.0), ("legged", 2.5)])
 @pytest.mark.parametrize("variant", ["ls_reduced_diag", "ls_full_gershgorin", "lm_full"])
 def test_slq_rk4_generated_batch_matches_oracle(shape, substeps, variant):
     n, m, nc = SHAPES[shape]
@@ -116,6 +116,8 @@ def test_slq_rk4_generated_batch_matches_oracle(shape, substeps, variant):
             pb, x0 = orc.generate_problem(seed, 50, orc.ALG_SLQ, n, m, nc, N, dt)
             check_against_oracle(st_full, pb, x0, sol, 0, what="slq quadrotor full form")
     with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
+        if shape == "legged":  # projection / RK4 flow map / controller on the FP64 tensor pipe for the line-search configuration
+            assert solver.kernel_variant == ("slq_wpp_kernel" if variant == "ls_reduced_diag" else "slq_generic_kernel")
         solver.generate_synthetic(seed, first_problem_index=50, dt=dt)
         solver.solve(alpha=1.0)
         sol = solver.download()
@@ -518,7 +520,8 @@ def test_line_search_argument_checks():
 @pytest.mark.parametrize("shape,algorithm,variant", [("legged", o2.ALG_ILQR, "ilqr_wpp_kernel"), ("ballbot", o2.ALG_ILQR, "ilqr_rpl_kernel"),
                                                      ("manipulator", o2.ALG_ILQR, "ilqr_rpl_kernel"), ("cartpole", o2.ALG_ILQR, "ilqr_rpl_kernel"),
                                                      ("quadrotor", o2.ALG_SLQ, "slq_rpl_kernel"), ("quadrotor", o2.ALG_ILQR, "ilqr_rpl_kernel"),
-                                                     ("ballbot", o2.ALG_SLQ, "slq_rpl_kernel"), ("cartpole", o2.ALG_SLQ, "slq_rpl_kernel")])
+                                                     ("ballbot", o2.ALG_SLQ, "slq_rpl_kernel"), ("cartpole", o2.ALG_SLQ, "slq_rpl_kernel"),
+                                                     ("legged", o2.ALG_SLQ, "slq_wpp_kernel")])
 def test_fast_kernels_with_nominal_trajectories(shape, algorithm, variant):
     """The real DDP iteration linearises about a nominal trajectory: bias = u_nom - K x_nom and the rollout is
     x_{k+1} = x_nom_{k+1} + A dx + B du + Hv (xdot = A (x - x_nom(t)) + B (u - u_nom(t)) + Hv for SLQ). The specialised kernels keep
