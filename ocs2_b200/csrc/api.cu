@@ -728,7 +728,10 @@ o2c_error rollout_on(o2c_handle* h, cudaStream_t stream, const double* alphas_de
     O2C_CUDA(launch_rollout_discrete(h->L, buf, alphas_dev, n_alpha, h->cfg.batch, begin, count, stream));
   } else {
     if (!h->time_set) return fail(O2C_ERR_NOT_READY, "continuous rollout needs the node times");
-    if (rpl_rollout_cont_supported(h->L, h->st, buf))
+    if (rollout_cont24_supported(h->L, h->st, buf))
+      O2C_CUDA(launch_rollout_cont24(h->L, h->st, buf, h->d_ro_steps, h->n_ro_steps, h->ro_first_idx, h->ro_first_alpha, h->out_nodes, alphas_dev,
+                                     n_alpha, h->cfg.batch, begin, count, stream));
+    else if (rpl_rollout_cont_supported(h->L, h->st, buf))
       O2C_CUDA(launch_rollout_cont_rpl(h->L, h->st, buf, h->d_ro_steps, h->n_ro_steps, h->ro_first_idx, h->ro_first_alpha, h->out_nodes,
                                        alphas_dev, n_alpha, h->cfg.batch, begin, count, stream));
     else

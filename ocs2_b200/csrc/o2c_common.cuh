@@ -205,6 +205,12 @@ size_t slq_wpp_workspace_doubles(const Layout& L, int batch);
 cudaError_t launch_slq_wpp(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, double* workspace, const SlqStep* steps, int nsteps,
                            int begin, int count, cudaStream_t stream, int* launches);
 
+// continuous LQ rollout of the legged shape (slq_wpp.cu)
+bool rollout_cont24_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
+cudaError_t launch_rollout_cont24(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,
+                                  int first_idx, double first_alpha, int out_nodes, const double* alphas_dev, int n_alpha, int batch, int begin,
+                                  int count, cudaStream_t stream);
+
 bool rpl_rollout_cont_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf);
 cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,
                                     int first_idx, double first_alpha, int out_nodes, const double* alphas_dev, int n_alpha, int batch,

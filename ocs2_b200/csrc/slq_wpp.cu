@@ -541,6 +541,195 @@ __global__ void __launch_bounds__(32 * kNodeWarps) slq_controller_kernel(const S
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// continuous rollout of the LQ model under the LinearController for nx = nu = 24 (TimeTriggeredRollout::run on the linearised model,
+// ocs2_oc/src/rollout/TimeTriggeredRollout.cpp:46-115; LinearController::computeInput, ocs2_core/src/control/LinearController.cpp:79-87):
+// xdot = A(t) (x - x_nom(t)) + B(t) (u - u_nom(t)) + Hv(t), u(t, x) = bias_alpha(t) + K(t) x, every quantity lerped between the two nodes
+// of its time segment, classic RK4 over the host-built step schedule (api.cu build_rollout_schedule). One warp per (problem, step
+// length), one state row per lane; {A | B | Hv} and {K | dbias | bias} of the nodes stream through a three-slot TMA ring and are lerped
+// on the fly from shared memory (the row-per-lane kernels of the small shapes keep them in registers: 6 x 24 doubles do not fit here).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kDyn = 2 * kMat + kN;  // { A | B | Hv }
+constexpr int kPol = kMat + 2 * kN;  // { K | dbias | bias }
+constexpr int kRoWarps = 4;
+
+struct __align__(16) RoSmem {
+  double dyn[3][kDyn];
+  double pol[3][kPol];
+  double x[kN], u[kN], dx[kN];
+  unsigned long long bar;
+  unsigned long long pad;
+};
+static_assert(sizeof(RoSmem) % 16 == 0, "warp slots must keep 16-byte alignment");
+
+struct Ro24Args {
+  const double* lq;
+  const double* sol;
+  const double* x0;
+  const double* x_nom;
+  const double* u_nom;
+  double* xs;
+  double* us;
+  int* status;
+  const RolloutStep* steps;
+  const double* alphas;
+  const double* jump;
+  int jump_capacity;
+  int nsteps, first_idx, out_nodes, N, batch, begin, count;
+  double first_alpha;
+};
+
+__global__ void __launch_bounds__(32 * kRoWarps) rollout_cont24_kernel(const Ro24Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RoSmem& ws = reinterpret_cast<RoSmem*>(smem_raw)[warp];
+  const bool valid = lane < kN;
+  const int i = valid ? lane : kN - 1;
+  const int N = a.N, nodes = N + 1;
+  const int ia = blockIdx.y;
+  const double alpha = a.alphas[ia];
+  if (lane == 0) {
+    mbar_init(&ws.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  const int warps_total = gridDim.x * kRoWarps;
+  for (int pi = blockIdx.x * kRoWarps + warp; pi < a.count; pi += warps_total) {
+    const int prob = a.begin + pi;
+    double* xo = a.xs + ((size_t)ia * a.batch + prob) * (size_t)a.out_nodes * kN;
+    double* uo = a.us + ((size_t)ia * a.batch + prob) * (size_t)a.out_nodes * kN;
+    auto issue_node = [&](int k) {
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&ws.bar, (uint32_t)(sizeof(double) * (kDyn + kPol)));
+        tma_load(ws.dyn[k % 3], a.lq + ((size_t)prob * nodes + k) * kRec, sizeof(double) * kDyn, &ws.bar);
+        tma_load(ws.pol[k % 3], a.sol + ((size_t)prob * nodes + k) * kORec, sizeof(double) * kPol, &ws.bar);
+      }
+    };
+    int loaded_hi = -1, issued_hi = -1;
+    // make nodes <= q resident (the segment index never decreases along the schedule: when node q has landed node q - 2 is dead and its
+    // slot takes the prefetch of node q + 1)
+    auto ensure = [&](int q) {
+      q = q < N ? q : N;
+      while (loaded_hi < q) {
+        if (issued_hi == loaded_hi) {
+          issue_node(loaded_hi + 1);
+          issued_hi = loaded_hi + 1;
+        }
+        mbar_wait(&ws.bar, parity);
+        parity ^= 1u;
+        loaded_hi += 1;
+        if (loaded_hi >= q && loaded_hi + 1 <= N) {
+          __syncwarp();
+          issue_node(loaded_hi + 1);
+          issued_hi = loaded_hi + 1;
+        }
+      }
+    };
+    // u(t, x) for the x in shared memory (row i of K per lane), broadcast through shared memory
+    auto policy = [&](int idx, double w0) {
+      ensure(idx + 1);
+      const int hi = idx + 1 < N ? idx + 1 : N;
+      const double* plo = ws.pol[idx % 3];
+      const double* phi = ws.pol[hi % 3];
+      const double w1 = 1.0 - w0;
+      double u0 = w0 * (plo[kMat + kN + i] + alpha * plo[kMat + i]) + w1 * (phi[kMat + kN + i] + alpha * phi[kMat + i]), u1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < kN; j += 2) {
+        const double2 xv = ld2(ws.x + j);
+        u0 = fma(fma(w0, plo[i + kN * j], w1 * phi[i + kN * j]), xv.x, u0);
+        u1 = fma(fma(w0, plo[i + kN * (j + 1)], w1 * phi[i + kN * (j + 1)]), xv.y, u1);
+      }
+      if (valid) ws.u[lane] = u0 + u1;
+      __syncwarp();
+    };
+    auto flow = [&](int idx, double w0) -> double {
+      policy(idx, w0);
+      const int hi = idx + 1 < N ? idx + 1 : N;
+      const double* dlo = ws.dyn[idx % 3];
+      const double* dhi = ws.dyn[hi % 3];
+      const double w1 = 1.0 - w0;
+      const double* xv = ws.x;
+      if (a.x_nom) {  // deviations from the lerped nominal trajectories
+        const double* xn = a.x_nom + ((size_t)prob * nodes + idx) * kN;
+        const double* un = a.u_nom + ((size_t)prob * nodes + idx) * kN;
+        const int step = hi > idx ? kN : 0;
+        const double dxi = ws.x[i] - fma(w0, __ldg(xn + i), w1 * __ldg(xn + step + i));
+        const double dui = ws.u[i] - fma(w0, __ldg(un + i), w1 * __ldg(un + step + i));
+        __syncwarp();
+        if (valid) {
+          ws.dx[lane] = dxi;
+          ws.u[lane] = dui;
+        }
+        __syncwarp();
+        xv = ws.dx;
+      }
+      double a0 = fma(w0, dlo[2 * kMat + i], w1 * dhi[2 * kMat + i]), a1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < kN; j += 2) {
+        const double2 x2 = ld2(xv + j), u2 = ld2(ws.u + j);
+        a0 = fma(fma(w0, dlo[i + kN * j], w1 * dhi[i + kN * j]), x2.x, a0);
+        a1 = fma(fma(w0, dlo[i + kN * (j + 1)], w1 * dhi[i + kN * (j + 1)]), x2.y, a1);
+        a0 = fma(fma(w0, dlo[kMat + i + kN * j], w1 * dhi[kMat + i + kN * j]), u2.x, a0);
+        a1 = fma(fma(w0, dlo[kMat + i + kN * (j + 1)], w1 * dhi[kMat + i + kN * (j + 1)]), u2.y, a1);
+      }
+      __syncwarp();  // x, u in shared memory are dead
+      return a0 + a1;
+    };
+    double x = a.x0[(size_t)prob * kN + i];
+    bool finite = true;
+    auto observe = [&](int o, int idx, double w0) {
+      if (valid) ws.x[lane] = x;
+      __syncwarp();
+      policy(idx, w0);
+      if (valid) {
+        __stcg(xo + (size_t)o * kN + lane, x);
+        __stcg(uo + (size_t)o * kN + lane, ws.u[lane]);
+      }
+      finite = finite && finite_bits(x);
+      __syncwarp();
+    };
+    observe(0, a.first_idx, a.first_alpha);
+#pragma unroll 1
+    for (int sidx = 0; sidx < a.nsteps; ++sidx) {
+      const RolloutStep sp = a.steps[sidx];
+      const double h = sp.h;
+      if (sp.jump > 0) {  // an event (TimeTriggeredRollout.cpp:104-108): x+ = x_nom(post) + A_e (x - x_nom(pre)) + Hv_e
+        const double* jr = a.jump + ((size_t)prob * a.jump_capacity + (sp.jump - 1)) * jump_rec(kN);
+        if (valid) ws.x[lane] = x - (a.x_nom ? __ldg(a.x_nom + ((size_t)prob * nodes + sp.pre_node) * kN + i) : 0.0);
+        __syncwarp();
+        double xn = __ldg(jr + jump_oHv(kN) + i) + (a.x_nom ? __ldg(a.x_nom + ((size_t)prob * nodes + sp.pre_node + 1) * kN + i) : 0.0);
+#pragma unroll
+        for (int kk = 0; kk < kN; ++kk) xn = fma(__ldg(jr + i + kN * kk), ws.x[kk], xn);
+        __syncwarp();
+        x = xn;
+      }
+      if (h == 0.0) {  // a jump or a degenerate interval: no integration
+        observe(sidx + 1, sp.obs_idx, sp.obs_alpha);
+        continue;
+      }
+      double acc = x, xs = x;
+#pragma unroll 1
+      for (int stg = 0; stg < 4; ++stg) {
+        if (valid) ws.x[lane] = xs;
+        __syncwarp();
+        const double kx = flow(sp.idx[stg], sp.alpha[stg]);
+        acc = fma(h * ((stg == 0 || stg == 3) ? (1.0 / 6.0) : (1.0 / 3.0)), kx, acc);
+        xs = fma(h * ((stg == 2) ? 1.0 : 0.5), kx, x);
+      }
+      x = acc;
+      observe(sidx + 1, sp.obs_idx, sp.obs_alpha);
+    }
+    if (issued_hi > loaded_hi) {  // drain a prefetch that is still in flight before the ring is reused
+      mbar_wait(&ws.bar, parity);
+      parity ^= 1u;
+    }
+    if (!__all_sync(kFull, finite) && lane == 0) atomicOr(a.status + prob, O2C_STATUS_NONFINITE);
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 size_t slq_wpp_workspace_doubles(const Layout& L, int batch) { return (size_t)batch * (L.N + 1) * kWRec; }
@@ -613,6 +802,53 @@ cudaError_t launch_slq_wpp(const Layout& L, const SolverSettings& st, const Devi
   }
   if (launches) *launches = 3;
   return cudaSuccess;
+}
+
+bool rollout_cont24_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
+  return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_SLQ && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) &&
+         L.N >= 1 && L.nodes == L.N + 1 && L.rec == kRec && L.orec == kORec && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat && L.oK == kOK &&
+         L.odb == kOdb && L.obias == kObias;
+}
+
+cudaError_t launch_rollout_cont24(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const RolloutStep* steps, int nsteps,
+                                  int first_idx, double first_alpha, int out_nodes, const double* alphas_dev, int n_alpha, int batch, int begin,
+                                  int count, cudaStream_t stream) {
+  if (!rollout_cont24_supported(L, st, buf)) return cudaErrorNotSupported;
+  Ro24Args a{};
+  a.lq = buf.lq;
+  a.sol = buf.sol;
+  a.x0 = buf.x0;
+  a.x_nom = buf.x_nom;
+  a.u_nom = buf.u_nom;
+  a.xs = buf.xs;
+  a.us = buf.us;
+  a.status = buf.status;
+  a.steps = steps;
+  a.alphas = alphas_dev;
+  a.jump = buf.jump;
+  a.jump_capacity = buf.jump_capacity;
+  a.nsteps = nsteps;
+  a.first_idx = first_idx;
+  a.first_alpha = first_alpha;
+  a.out_nodes = out_nodes;
+  a.N = L.N;
+  a.batch = batch;
+  a.begin = begin;
+  a.count = count;
+  const size_t smem = sizeof(RoSmem) * kRoWarps;
+  cudaError_t e = cudaFuncSetAttribute(rollout_cont24_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int sms = device_sm_count();
+  if (sms <= 0) return cudaErrorInvalidDevice;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, rollout_cont24_kernel, 32 * kRoWarps, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int needed = (count + kRoWarps - 1) / kRoWarps;
+  const int cap = sms * ctas_per_sm;
+  dim3 grid(needed < cap ? needed : cap, n_alpha);
+  rollout_cont24_kernel<<<grid, 32 * kRoWarps, smem, stream>>>(a);
+  return cudaGetLastError();
 }
 
 }  // namespace o2c

@@ -826,7 +826,8 @@ def test_ilqr_events_dense_and_short_horizons(n, m, nc, N):
             check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, (0.6,), what=f"dense events n={n} N={N} #{i}")
 
 
-@pytest.mark.parametrize("n,m,nc,variant", [(12, 4, 0, "ls_reduced"), (10, 3, 0, "ls_reduced"), (4, 1, 0, "ls_reduced"), (5, 3, 2, "ls_full"), (6, 2, 0, "lm_full")])
+@pytest.mark.parametrize("n,m,nc,variant", [(12, 4, 0, "ls_reduced"), (10, 3, 0, "ls_reduced"), (4, 1, 0, "ls_reduced"), (5, 3, 2, "ls_full"), (6, 2, 0, "lm_full"),
+                                            (24, 24, 0, "ls_reduced")])
 def test_slq_events_match_oracle(n, m, nc, variant):
     """SLQ with events (SLQ.cpp:256-302): inter-event segments integrated separately, joined by computeJumpMap =
     riccatiTransversalityConditions on the event's jump model data; the continuous rollout restarts weakEpsilon after every event from
@@ -878,7 +879,7 @@ def test_slq_events_match_oracle(n, m, nc, variant):
         lq.jump_A = lq.jump_Hv = lq.jump_Q = lq.jump_q = lq.jump_c = None
         lq.time = dt * np.arange(N + 1)
         solver.upload(lq)
-        assert ("generic" in solver.kernel_variant) == (n not in (12, 10, 4))
+        assert ("generic" in solver.kernel_variant) == (n not in (12, 10, 4, 24))
         solver.solve()
         sol = solver.download()
         check_against_oracle(st, _oracle_problem(lq, 1, N), lq.x0[1], sol, 1, (1.0,), what=f"slq events cleared n={n}")
