@@ -164,6 +164,11 @@ const char* o2c_last_error(void);
 o2c_error o2c_create(const o2c_config* config, o2c_handle** handle);
 o2c_error o2c_destroy(o2c_handle* handle);
 o2c_error o2c_get_config(const o2c_handle* handle, o2c_config* config);
+/* number of CUDA devices visible to the process (0 and O2C_ERR_CUDA when there is none): the valid range of o2c_config.device */
+o2c_error o2c_device_count(int32_t* count);
+/* levenbergMarquardt riccatiMultiple of the NEXT backward pass. The reference's strategy adapts it from iteration to iteration
+ * (LevenbergMarquardtStrategy.cpp: lmModule_.riccatiMultiple); the handle otherwise keeps o2c_config.lm_riccati_multiple. */
+o2c_error o2c_set_lm_riccati_multiple(o2c_handle* handle, double riccati_multiple);
 o2c_error o2c_sync(o2c_handle* handle);
 /* the CUDA stream (cudaStream_t) all compute of this handle is enqueued on; time it with CUDA events on this stream */
 o2c_error o2c_compute_stream(o2c_handle* handle, void** stream);

@@ -213,6 +213,13 @@ class BatchedRiccatiSolver {
     copyRaw(initState, x0_.at(b, 0), x0_.block, "initState");
   }
 
+  /** levenbergMarquardt riccatiMultiple of the next backward pass: the reference's strategy adapts it after every iteration
+   * (LevenbergMarquardtStrategy.cpp:131-147), the handle otherwise keeps config.lm_riccati_multiple */
+  void setRiccatiMultiple(double riccatiMultiple) {
+    check(o2c_set_lm_riccati_multiple(h_, riccatiMultiple), "o2c_set_lm_riccati_multiple");
+    cfg_.lm_riccati_multiple = riccatiMultiple;
+  }
+
   /** primalSolution.timeTrajectory_ (N+1 node times, shared by the batch: the instances run in lock-step) */
   template <class ScalarArray>
   void setTimeTrajectory(const ScalarArray& timeTrajectory) {

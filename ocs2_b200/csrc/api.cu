@@ -894,6 +894,26 @@ o2c_error o2c_get_config(const o2c_handle* h, o2c_config* cfg) {
   return O2C_OK;
 }
 
+o2c_error o2c_device_count(int32_t* count) {
+  if (!count) return fail(O2C_ERR_INVALID_ARGUMENT, "null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    *count = 0;
+    return fail(O2C_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  }
+  *count = n;
+  return O2C_OK;
+}
+
+o2c_error o2c_set_lm_riccati_multiple(o2c_handle* h, double mu) {
+  if (!h) return fail(O2C_ERR_INVALID_ARGUMENT, "null handle");
+  if (!(mu >= 0.0) || !std::isfinite(mu)) return fail(O2C_ERR_INVALID_ARGUMENT, "riccati_multiple must be finite and non-negative");
+  h->cfg.lm_riccati_multiple = mu;
+  h->st.mu = mu;  // kernel parameter blocks are built per launch: in-flight launches keep the value they were enqueued with
+  return O2C_OK;
+}
+
 o2c_error o2c_sync(o2c_handle* h) {
   if (!h) return fail(O2C_ERR_INVALID_ARGUMENT, "null handle");
   O2C_CUDA(cudaSetDevice(h->cfg.device));

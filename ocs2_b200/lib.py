@@ -69,6 +69,7 @@ EXPORTED_SYMBOLS = [
     "o2c_download", "o2c_set_time", "o2c_backward", "o2c_rollout", "o2c_solve", "o2c_launch_count", "o2c_kernel_variant",
     "o2c_solve_host", "o2c_generate_synthetic", "o2c_host_alloc", "o2c_host_free", "o2c_line_search", "o2c_line_search_result",
     "o2c_download_flattened_controller", "o2c_discretize", "o2c_check_numerical_stability",
+    "o2c_device_count", "o2c_set_lm_riccati_multiple",
 ]
 
 
@@ -120,6 +121,8 @@ def load_library():
         "o2c_download_flattened_controller": [hp, C.POINTER(C.c_float), C.c_double, C.c_int32, C.c_int32],
         "o2c_discretize": [hp, C.POINTER(DiscretizationView), C.c_int32, C.c_int32, C.c_int32],
         "o2c_check_numerical_stability": [hp, C.c_int32, C.c_int32],
+        "o2c_device_count": [_ip],
+        "o2c_set_lm_riccati_multiple": [hp, C.c_double],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

@@ -333,6 +333,11 @@ class BatchedLqSolver:
         _l.check(self._lib.o2c_rollout(self._h, a.ctypes.data_as(C.POINTER(C.c_double)), len(a), problem_begin, cnt))
         self._n_alpha = len(a)
 
+    def setRiccatiMultiple(self, riccatiMultiple: float):
+        """levenbergMarquardt riccatiMultiple of the next backward pass (the reference's strategy adapts it every iteration)."""
+        _l.check(self._lib.o2c_set_lm_riccati_multiple(self._h, float(riccatiMultiple)))
+        self.settings.riccatiMultiple = float(riccatiMultiple)
+
     def checkNumericalStability(self, problem_begin: int = 0, problem_count: Optional[int] = None):
         """ddp::Settings::checkNumericalStability_ for the value function (GaussNewtonDDP.cpp:555-579): checkBeingPSD of every S_k; a
         failing problem gets STATUS_NOT_PSD in its status word (the reference throws). Run after the backward pass."""

@@ -1,0 +1,2 @@
+#pragma once
+#include "../ocs2_standins.h"  // stand-in of ocs2_ddp/include/ocs2_ddp/SLQ.h

@@ -1113,3 +1113,37 @@ def test_chunked_whole_batch_upload_does_the_whole_range_bookkeeping(alg, monkey
         sol = solver.download()
         for i in (1, 4):
             check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, what=f"chunked upload, events cleared #{i}")
+
+
+@pytest.mark.parametrize("shape,alg", [("legged", "ilqr"), ("ballbot", "ilqr"), ("quadrotor", "slq")])
+def test_riccati_multiple_can_change_between_backward_passes(shape, alg):
+    """LevenbergMarquardtStrategy adapts riccatiMultiple after every iteration (LevenbergMarquardtStrategy.cpp:131-147): the handle takes
+    the new value without being rebuilt and the next pass equals the oracle evaluated with it."""
+    n, m, nc = SHAPES[shape]
+    algorithm = o2.ALG_ILQR if alg == "ilqr" else o2.ALG_SLQ
+    N, batch, dt, seed = 30, 6, 0.01, 11
+    st = o2.Settings(algorithm=algorithm, hessianCorrectionMultiple=1e-4, timeStep=dt, strategy=o2.STRATEGY_LEVENBERG_MARQUARDT, riccatiMultiple=0.05)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
+        solver.generate_synthetic(seed, first_problem_index=3, dt=dt)
+        for mu in (0.05, 0.8, 0.0):
+            solver.setRiccatiMultiple(mu)
+            assert solver.settings.riccatiMultiple == mu
+            solver.solve(alpha=1.0)
+            sol = solver.download()
+            for i in (0, batch - 1):
+                pb, x0 = orc.generate_problem(seed, 3 + i, algorithm, n, m, nc, N, dt)
+                check_against_oracle(solver.settings, pb, x0, sol, i, what=f"{shape} mu={mu}")
+        with pytest.raises(o2.O2cError):
+            solver.setRiccatiMultiple(-1.0)
+
+
+def test_device_count_matches_torch():
+    import ctypes as C
+
+    import torch
+
+    from ocs2_b200 import lib as o2lib
+
+    count = C.c_int32(-1)
+    o2lib.check(o2lib.load_library().o2c_device_count(C.byref(count)))
+    assert count.value == torch.cuda.device_count() >= 1
