@@ -46,8 +46,8 @@ struct __align__(16) WarpSmem {
   double W[kN * kLd];    // S of node k+1 (both triangles) -> Hm (lower) -> L -> L^-T (upper)
   double Sv[kN], Gv[kN], Yv[kN], xb[kN], ub[kN];
   unsigned long long full;   // operand block landed (sweep)
-  unsigned long long bfull[2];  // rollout: B_k landed in slot k & 1
   unsigned long long hfull, hfull2;  // sweep: Q landed in the scratch / P landed in A's slot
+  unsigned long long pad_;
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp slots must keep 16-byte alignment");
 
@@ -65,6 +65,9 @@ struct Args {
   int N;
   int oQf, oqf, ocf, trec;
   int begin, count, with_rollout;
+  int sweep_count;  // problems [0, sweep_count) belong to the sweepers; [sweep_count, count) are swept by the rollers before their first rollout
+  int ring_depth;  // stage sets in a roller's ring (the rollers' rings follow the sweepers' slots in dynamic shared memory)
+  int nsweep;    // warps [0, nsweep) of a CTA sweep; the others only roll out (0 < nsweep <= warps per CTA)
   int* counter;  // dynamic problem fetch: zeroed before the launch; nullptr = static stride
   int dyn_limit;  // problems [resident slots, dyn_limit) are fetched dynamically, [dyn_limit, count) = the last partial wave, static
   double eps, alpha, mu;
@@ -95,13 +98,13 @@ __device__ __forceinline__ void prefetch_hessians(const double* rec, const Args&
 // for 2048 problems, profiles/r02_wpp_residency.jsonl).
 __device__ __forceinline__ int next_problem(const Args& a, int lane, int total_warps, int pi, int slot, bool& tail_taken) {
   if (a.counter == nullptr) return pi + total_warps;
-  if (tail_taken) return a.count;
+  if (tail_taken) return a.sweep_count;
   int nx = 0;
   if (lane == 0) nx = atomicAdd(a.counter, 1) + total_warps;
   nx = __shfl_sync(kFull, nx, 0);
   if (nx < a.dyn_limit) return nx;
   tail_taken = true;
-  return a.dyn_limit + slot;  // >= count when this warp has no problem in the last wave
+  return a.dyn_limit + slot;  // >= sweep_count when this warp has no problem in the last wave
 }
 
 // MODE: the Riccati modification (search strategy) the stage carries, everything else is shared:
@@ -117,13 +120,38 @@ __device__ __forceinline__ int next_problem(const Args& a, int lane, int total_w
 //              H~m = I - mu B~'B~: the cross terms cancel).
 constexpr int kModeLS = 0, kModeLM = 1, kModeGersh = 2;
 
+// Profiling builds only (tools/wpp_ablate.py): -DO2C_WPP_ABLATE=<bits> removes one cost at a time from the kernel to measure what it is
+// worth at full residency. The results of such a build are WRONG by construction; the product is always built with 0.
+//   1 no factorisation   2 every stage reads the record of node N-1 (no DRAM reads in the sweep)   4 every stage writes node 0's record
+//   8 no K / S global stores   16 the rollout reads node 0's records at every stage (no DRAM reads in the rollout)
+#ifndef O2C_WPP_ABLATE
+#define O2C_WPP_ABLATE 0
+#endif
+constexpr int kAblate = O2C_WPP_ABLATE;
+constexpr int kQueue = 64;  // finished problems waiting for a roller, per CTA
+constexpr int kDefaultRollers = 1;
+#ifndef O2C_WPP_CTA_WARPS
+#define O2C_WPP_CTA_WARPS 12
+#endif
+constexpr int kMaxCtaWarps = O2C_WPP_CTA_WARPS;  // sweepers + rollers of a CTA (the register file holds 12 warps at 168 registers, 13 at 152)
+constexpr int kRingK = 2 * kMat + kN;        // stage set of the rollout ring: { A | B | Hv } then { K | dbias }
+constexpr int kRing = kRingK + kMat + kN;    // 1776 doubles = 14.2 KB
+constexpr int kMaxRingDepth = 4;
+#ifndef O2C_WPP_ROLL_AHEAD
+#define O2C_WPP_ROLL_AHEAD 3
+#endif
+constexpr int kRollAhead = O2C_WPP_ROLL_AHEAD;  // rollout: L2 prefetch distance in stages
+
 template <bool NOM, bool EV, int MODE>
-__global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args a) {
+__global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Args a) {
   constexpr bool QPD = true;  // Q and P straight from L2 into the accumulators (the TMA-staged round-1 path is kept for reference only)
   static_assert(!(EV && MODE == kModeLM), "ILQR events under LEVENBERG_MARQUARDT are refused by the API");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+  // a roller's ring doubles as the WarpSmem of the one sweep it does before its first rollout
+  WarpSmem& ws = warp < a.nsweep ? reinterpret_cast<WarpSmem*>(smem_raw)[warp]
+                                 : *reinterpret_cast<WarpSmem*>(smem_raw + (size_t)a.nsweep * sizeof(WarpSmem) +
+                                                                (size_t)(warp - a.nsweep) * a.ring_depth * kRing * sizeof(double));
   const int r = lane >> 2, c = lane & 3;
   const int lo24 = 2 * c + kN * r, lo26 = 2 * c + kLd * r;
   const int li = lane < kN ? lane : kN - 1;
@@ -131,21 +159,71 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
   const uint32_t opBytes = kOperand * sizeof(double);
   const uint32_t matBytes = kMat * sizeof(double);
 
+  const int nwarps = blockDim.x >> 5, nsweep = a.nsweep, nroll = nwarps - nsweep;
+  __shared__ unsigned long long ring_full[kMaxCtaWarps][kMaxRingDepth];  // rollout ring: stage set landed
+  __shared__ __align__(16) double rvec[kMaxCtaWarps][2][kN];               // rollout: x, u of the current node
   if (lane == 0) {
-    mbar_init(&ws.full, 1);
-    mbar_init(&ws.bfull[0], 1);
-    mbar_init(&ws.bfull[1], 1);
-    mbar_init(&ws.hfull, 1);
-    mbar_init(&ws.hfull2, 1);
+    if (warp < nsweep || a.sweep_count < a.count) {
+      mbar_init(&ws.full, 1);
+      mbar_init(&ws.hfull, 1);
+      mbar_init(&ws.hfull2, 1);
+    }
+    for (int d = 0; d < kMaxRingDepth; ++d) mbar_init(&ring_full[warp][d], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t phase = 0, hphase = 0, bphase = 0;  // bphase: bit q = parity to wait for on bfull[q]
+  uint32_t phase = 0, hphase = 0, rphase = 0;  // rphase: bit d = parity to wait for on ring_full[warp][d]
 
-  const int total_warps = gridDim.x * (blockDim.x >> 5);
+  // Warp roles. Warps [0, nsweep) are SWEEPERS: backward pass after backward pass, the FP64 pipe never waits for a rollout. The
+  // remaining warps are ROLLERS: they take finished problems from a queue in shared memory and run the forward rollout, which is
+  // 1.6 % of the flops but streams {A|B|Hv} and {K|dbias} once more (1.4 MB per problem) and is bound by DRAM latency and bandwidth:
+  // fused behind each sweep in the same warp it took 21 % of the kernel time at full residency (profiles/r02_wpp_ablation.jsonl). A
+  // sweeper that runs out of problems becomes a roller, so the tail of a launch drains on every warp of the CTA. With no rollers
+  // (nsweep == warps per CTA) every sweeper rolls its own problem out, as before.
+  // queue entry = (ticket + 1) << 32 | problem, 0 = empty. A producer writes its slot once the ticket one lap earlier has been claimed
+  // AND its entry consumed (slot back to 0); a consumer claims a ticket by CAS on the head and takes exactly that ticket's entry.
+  __shared__ unsigned long long queue[kQueue];
+  __shared__ unsigned q_tail, q_head, sweepers_done;
+  if (threadIdx.x < kQueue) queue[threadIdx.x] = 0ull;
+  if (threadIdx.x == 0) q_tail = q_head = sweepers_done = 0;
+  __syncthreads();
+  const int total_warps = gridDim.x * nsweep;
   const int slot = warp * gridDim.x + blockIdx.x;
   bool tail_taken = false;
-  for (int pi = slot; pi < a.count; pi = next_problem(a, lane, total_warps, pi, slot, tail_taken)) {
+  // The rollers have nothing to roll out until the first sweeps finish (1.4 ms): each of them first sweeps one problem from the end of
+  // the batch itself (its ring is the scratch), which is what keeps a launch from ending in a nearly empty extra round when the batch
+  // is a little more than a whole number of rounds (16384 problems = 10.06 rounds of 148 x 11 sweepers).
+  const int init_pi = a.sweep_count + (warp - nsweep) * (int)gridDim.x + (int)blockIdx.x;
+  bool sweeping = warp < nsweep || init_pi < a.count;
+  int pi = warp < nsweep ? slot : init_pi;
+  int done_target = nsweep;
+  for (int q = 0; q < nroll; ++q) done_target += a.sweep_count + q * (int)gridDim.x + (int)blockIdx.x < a.count ? 1 : 0;
+#ifdef O2C_WPP_STATS
+  long long st_t0 = clock64(), st_sweep = 0, st_roll = 0, st_wait = 0, st_mark = 0;
+  int st_nsweep = 0, st_nroll = 0;
+#endif
+  for (;;) {
+    int job = -1;
+#ifdef O2C_WPP_STATS
+    st_mark = clock64();
+#endif
+    if (sweeping) {
+      if (pi >= (warp < nsweep ? a.sweep_count : a.count)) {
+        sweeping = false;
+        if (nroll == 0) break;
+        __syncwarp();
+        if (lane == 0 && warp >= nsweep) {  // the scratch of the roller's own sweep becomes its ring
+          mbar_inval(&ws.full);
+          mbar_inval(&ws.hfull);
+          mbar_inval(&ws.hfull2);
+        }
+        if (lane == 0) {
+          __threadfence_block();
+          atomicAdd(&sweepers_done, 1u);
+        }
+      }
+    }
+    if (sweeping) {
     const int prob = a.begin + pi;
     const double* lqp = a.lq + (size_t)prob * N * kRec;
     const double* term = a.term + (size_t)prob * a.trec;
@@ -188,8 +266,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
       const double* Hv = ws.in + 2 * kMat;
       const double* qv = Hv + kN;
       const double* rv = qv + kN;
-      const double* rec = lqp + (size_t)k * kRec;
-      double* out = solp + (size_t)k * kORec;
+      const double* rec = lqp + (size_t)((kAblate & 2) ? N - 1 : k) * kRec;
+      double* out = solp + (size_t)((kAblate & 4) ? 0 : k) * kORec;
       // pre-event node (ILQR.cpp:263-295): the staged A, Hv, q, c and Q are the jump map and the pre-jump cost. The value function goes
       // through riccatiTransversalityConditions (S- = Q_e + A_e'S A_e, Sv- = q_e + A_e'(Sv + S Hv), s- = s + c_e + Hv.(Sv + S Hv / 2));
       // the controller entry comes from the node's B, P, R, r against a zero next value function (Hm = R) and S-, Sv-:
@@ -421,11 +499,11 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
       __syncwarp();  // all lanes are done with the staged operand block: refill it for node k-1 while this stage finishes
       if (MODE != kModeLM && lane == 0 && k >= 1) {  // (LM needs A, B, Hv once more after the gains: its refill follows Acl)
         mbar_expect_tx(&ws.full, opBytes);
-        tma_load(ws.in, lqp + (size_t)(k - 1) * kRec, opBytes, &ws.full);
+        tma_load(ws.in, lqp + (size_t)((kAblate & 2) ? N - 1 : k - 1) * kRec, opBytes, &ws.full);
       }
 
       // ---- blocked Cholesky of Hm and L^-T into the scratch ----
-      pd = factor_hm(ws.W, lane, li, r, c) && pd;
+      if (!(kAblate & 1)) pd = factor_hm(ws.W, lane, li, r, c) && pd;
 
       // ---- Yv = L^-1 Gv, dbias = -L^-T Yv, s ----
       {
@@ -505,7 +583,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
 #pragma unroll
         for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb < 3; ++jb) stg2(out + kOK + lo24 + t24(jb, ib), neg2(kk[ib][jb]));
+          for (int jb = 0; jb < 3; ++jb)
+            if (!(kAblate & 8)) stg2(out + kOK + lo24 + t24(jb, ib), neg2(kk[ib][jb]));
         if (NOM) {
           // bias = u_nom - K x_nom (GaussNewtonDDP.cpp:604-606). The accumulators hold -K' = Y'L^-1: lane (r,c) owns the terms of
           // state 8ib + r for inputs 8jb + 2c, 2c+1; the sum over the states is a butterfly over r
@@ -703,12 +782,14 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
           const double2 sv = neg2(t[lt(ib, jb)]);  // S[8ib+r][8jb+2c..] = S[8jb+2c..][8ib+r]
           t[lt(ib, jb)] = sv;
           st2(ws.W + lo26 + t26(jb, ib), sv);
-          stg2(out + kOSm + lo24 + t24(jb, ib), sv);
+          if (!(kAblate & 8)) stg2(out + kOSm + lo24 + t24(jb, ib), sv);
           if (ib != jb) {
             tput(ws.W, ib, jb, r, c, sv);
             double* gq = out + kOSm + (8 * ib + r) + kN * (8 * jb + 2 * c);
-            __stcg(gq, sv.x);
-            __stcg(gq + kN, sv.y);
+            if (!(kAblate & 8)) {
+              __stcg(gq, sv.x);
+              __stcg(gq + kN, sv.y);
+            }
           }
         }
       __syncwarp();
@@ -731,22 +812,87 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
       if (!__all_sync(kFull, pd)) bits |= O2C_STATUS_CHOL_NOT_PD;
       if (!__all_sync(kFull, finite)) bits |= O2C_STATUS_NONFINITE;
     }
-    if (!a.with_rollout) {
-      if (lane == 0) a.status[prob] = bits;
+    if (lane == 0) a.status[prob] = bits;
+#ifdef O2C_WPP_STATS
+    st_sweep += clock64() - st_mark, ++st_nsweep, st_mark = clock64();
+#endif
+    const int done_pi = pi;
+    pi = warp < nsweep ? next_problem(a, lane, total_warps, pi, slot, tail_taken) : a.count;  // (a roller sweeps one problem only)
+    if (!a.with_rollout) continue;
+    if (nroll == 0) {
+      job = done_pi;
+    } else {
+      // hand the problem to the rollers: every lane's K / dbias / bias stores are ordered before the queue entry becomes visible
+      __threadfence();
+      fence_proxy_async_global();  // ... and before the rollers' TMA reads of them
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned ticket = atomicAdd(&q_tail, 1u);
+        volatile unsigned long long* entry = &queue[ticket % kQueue];
+        while ((int)(ticket - *(volatile unsigned*)&q_head) >= kQueue || *entry != 0ull) {  // ring full: the rollers are behind (the head may
+                                                                                           // already be past this ticket: a roller claims it first)
+          __nanosleep(100);
+        }
+        *entry = ((unsigned long long)(ticket + 1u) << 32) | (unsigned)done_pi;
+      }
       continue;
     }
+    }  // sweeping
 
-    // ---- fused forward rollout of the LQ model: du_k = K_k dx_k + alpha dbias_k, dx_{k+1} = A_k dx_k + B_k du_k + Hv_k. One row per lane.
-    // K_k and A_k live in registers and are re-loaded for node k+1 right after their last use (one stage of load latency hidden behind
-    // the other half of the stage); B_k comes through a two-slot TMA ring over the (now free) operand slot, two stages ahead. ----
-    if (lane == 0) {
-      fence_proxy_async();
-      for (int k = 0; k < 2 && k < N; ++k) {
-        mbar_expect_tx(&ws.bfull[k], matBytes);
-        tma_load(ws.in + kMat * k, lqp + (size_t)k * kRec + kMat, matBytes, &ws.bfull[k]);
+    if (job < 0) {
+      // roller: next finished problem of this CTA, or -1 once every sweeper is done and the queue is empty
+      if (lane == 0) {
+        for (;;) {
+          const unsigned done = *(volatile unsigned*)&sweepers_done;  // read before the tail: every push precedes its sweeper's done
+          const unsigned h = *(volatile unsigned*)&q_head, t = *(volatile unsigned*)&q_tail;
+          if (h != t) {
+            if (atomicCAS(&q_head, h, h + 1u) != h) continue;
+            volatile unsigned long long* entry = &queue[h % kQueue];
+            unsigned long long v;
+            while ((unsigned)((v = *entry) >> 32) != h + 1u) {
+            }
+            *entry = 0ull;
+            job = (int)(unsigned)v;
+            break;
+          }
+          if (done == (unsigned)done_target) break;
+          __nanosleep(200);
+        }
       }
-      for (int k = 1; k < 3 && k < N; ++k) l2_prefetch(lqp + (size_t)k * kRec, 2 * matBytes + kN * sizeof(double));
-      for (int k = 1; k < 3 && k < N; ++k) l2_prefetch(solp + (size_t)k * kORec + kOK, (kMat + kN) * sizeof(double));
+      job = __shfl_sync(kFull, job, 0);
+#ifdef O2C_WPP_STATS
+      st_wait += clock64() - st_mark, st_mark = clock64();
+#endif
+      if (job < 0) break;
+      __threadfence();
+    }
+    const int prob = a.begin + job;
+    const double* lqp = a.lq + (size_t)prob * N * kRec;
+    double* solp = a.sol + (size_t)prob * (N + 1) * kORec;
+    const int* evp = EV ? a.event + (size_t)prob * N : nullptr;
+
+    // ---- forward rollout of the LQ model: du_k = K_k dx_k + alpha dbias_k, dx_{k+1} = A_k dx_k + B_k du_k + Hv_k. One row per lane.
+    // Everything a stage reads — {A | B | Hv} of the LQ record and {K | dbias} of the solution record, 14.2 KB — arrives by two TMA bulk
+    // copies in a ring of `depth` stage sets in shared memory, issued `depth` stages ahead. The stage itself is a short dependent chain
+    // (two 24-term dot products per lane, ~0.3 us), so a rollout runs at DRAM latency / depth per stage: nothing waits in L2 (with 1600
+    // sweeps in flight, lines prefetched into L2 ahead of a rollout were evicted before their use and every stage paid a full DRAM round
+    // trip: 2.3 - 2.7 us per stage, profiles/r02_wpp_stats.log). Rollers own a deep ring behind the sweepers' slots; a sweeper rolling
+    // out (no rollers, or the tail of a launch) uses its own slot as a ring of one.
+    const bool own_slot = warp < nsweep;
+    const int depth = own_slot ? 1 : a.ring_depth;
+    double* ring = own_slot ? ws.in : reinterpret_cast<double*>(smem_raw + (size_t)nsweep * sizeof(WarpSmem)) + (size_t)(warp - nsweep) * a.ring_depth * kRing;
+    unsigned long long* rfull = ring_full[warp];
+    double* xb = rvec[warp][0];
+    double* ub = rvec[warp][1];
+    const uint32_t lqBytes = (2 * kMat + kN) * sizeof(double), solBytes = (kMat + kN) * sizeof(double);
+    if (lane == 0) {
+      fence_proxy_async();        // the slot was last touched through the generic proxy
+      fence_proxy_async_global();  // K, dbias were written by ordinary stores (this warp or a sweeper of this CTA) and are read by TMA
+      for (int d = 0; d < depth && d < N; ++d) {
+        mbar_expect_tx(&rfull[d], lqBytes + solBytes);
+        tma_load(ring + (size_t)d * kRing, lqp + (size_t)d * kRec, lqBytes, &rfull[d]);
+        tma_load(ring + (size_t)d * kRing + kRingK, solp + (size_t)d * kORec + kOK, solBytes, &rfull[d]);
+      }
     }
     double* xo = a.xs + (size_t)prob * (N + 1) * kN;
     double* uo = a.us + (size_t)prob * (N + 1) * kN;
@@ -754,91 +900,77 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
     // x_{k+1} = x_nom_{k+1} + A dx + B du + Hv, u = u_nom + K dx + alpha dbias) and the outputs are shifted back
     const double* xnp = NOM ? a.x_nom + (size_t)prob * (N + 1) * kN : nullptr;
     const double* unp = NOM ? a.u_nom + (size_t)prob * (N + 1) * kN : nullptr;
-    double x = a.x0[(size_t)prob * kN + li] - (NOM ? __ldg(xnp + li) : 0.0);
-    if (lane < kN) ws.xb[lane] = x;
+    double xnk = NOM ? __ldg(xnp + li) : 0.0, unk = NOM ? __ldg(unp + li) : 0.0;  // nominal state / input of the current node
+    double x = a.x0[(size_t)prob * kN + li] - xnk;
+    if (lane < kN) xb[lane] = x;
     bool xfinite = true;
-    double kreg[kN], areg[kN];
-#pragma unroll
-    for (int j = 0; j < kN; ++j) {
-      kreg[j] = __ldcg(solp + kOK + li + kN * j);
-      areg[j] = __ldcg(lqp + li + kN * j);
-    }
-    double dbk = __ldcg(solp + kOdb + li), hvk = __ldcg(lqp + 2 * kMat + li);
     bool jump = EV && __ldg(evp) != 0;  // pre-event node: x+ = A_e x + Hv_e, the input does not enter the jump map
+    int rs = 0;                         // ring slot of stage k
     __syncwarp();
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
-      const double* nsol = solp + (size_t)(k + 1) * kORec;             // node N carries the copy of node N-1
-      const double* nrec = lqp + (size_t)(k + 1 < N ? k + 1 : k) * kRec;  // (the last reload is a harmless repeat)
-      // u = alpha dbias + K x ; the gains of node k+1 take the registers over as they are consumed
-      double u0 = a.alpha * dbk, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+      const double* S = ring + (size_t)rs * kRing;
+      const double* Kk = S + kRingK;
+      mbar_wait(&rfull[rs], (rphase >> rs) & 1u);
+      rphase ^= 1u << rs;
+      // u = alpha dbias + K x ; ax = Hv + A x (independent of u)
+      double u0 = a.alpha * Kk[kMat + li], u1 = 0.0, u2 = 0.0, u3 = 0.0;
+      double a0 = S[2 * kMat + li], a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
       for (int j = 0; j < kN; j += 4) {
-        const double2 x01 = ld2(ws.xb + j), x23 = ld2(ws.xb + j + 2);
-        u0 = fma(kreg[j], x01.x, u0);
-        u1 = fma(kreg[j + 1], x01.y, u1);
-        u2 = fma(kreg[j + 2], x23.x, u2);
-        u3 = fma(kreg[j + 3], x23.y, u3);
+        const double2 x01 = ld2(xb + j), x23 = ld2(xb + j + 2);
+        u0 = fma(Kk[li + kN * j], x01.x, u0);
+        u1 = fma(Kk[li + kN * (j + 1)], x01.y, u1);
+        u2 = fma(Kk[li + kN * (j + 2)], x23.x, u2);
+        u3 = fma(Kk[li + kN * (j + 3)], x23.y, u3);
+        a0 = fma(S[li + kN * j], x01.x, a0);
+        a1 = fma(S[li + kN * (j + 1)], x01.y, a1);
+        a2 = fma(S[li + kN * (j + 2)], x23.x, a2);
+        a3 = fma(S[li + kN * (j + 3)], x23.y, a3);
       }
-#pragma unroll
-      for (int j = 0; j < kN; ++j) kreg[j] = __ldcg(nsol + kOK + li + kN * j);
-      dbk = __ldcg(nsol + kOdb + li);
       const double u = (u0 + u1) + (u2 + u3);
       if (lane < kN) {
-        ws.ub[lane] = u;
-        __stcg(xo + (size_t)k * kN + lane, x + (NOM ? __ldg(xnp + (size_t)k * kN + lane) : 0.0));
-        __stcg(uo + (size_t)k * kN + lane, u + (NOM ? __ldg(unp + (size_t)k * kN + lane) : 0.0));
+        ub[lane] = u;
+        __stcg(xo + (size_t)k * kN + lane, x + xnk);
+        __stcg(uo + (size_t)k * kN + lane, u + unk);
       }
       xfinite = xfinite && finite_bits(x);
-      // x+ = Hv + A x + B u
-      double a0 = hvk, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-      for (int j = 0; j < kN; j += 4) {
-        const double2 x01 = ld2(ws.xb + j), x23 = ld2(ws.xb + j + 2);
-        a0 = fma(areg[j], x01.x, a0);
-        a1 = fma(areg[j + 1], x01.y, a1);
-        a2 = fma(areg[j + 2], x23.x, a2);
-        a3 = fma(areg[j + 3], x23.y, a3);
+      if (NOM) {  // next node's nominal values: in flight during the second half of the stage
+        xnk = __ldg(xnp + (size_t)(k + 1) * kN + li);
+        unk = __ldg(unp + (size_t)(k + 1) * kN + li);
       }
-#pragma unroll
-      for (int j = 0; j < kN; ++j) areg[j] = __ldcg(nrec + li + kN * j);
-      hvk = __ldcg(nrec + 2 * kMat + li);
-      const int q = k & 1;
-      mbar_wait(&ws.bfull[q], (bphase >> q) & 1u);
-      bphase ^= 1u << q;
+      const bool jump_next = EV && k + 1 < N && __ldg(evp + k + 1) != 0;
       __syncwarp();  // u of every lane is in shared memory
-      const double xn = ((a0 + a1) + (a2 + a3)) + (jump ? 0.0 : matvec_rows(ws.in + kMat * q, ws.ub, li));
-      if (EV) jump = k + 1 < N && __ldg(evp + k + 1) != 0;
-      __syncwarp();  // every lane is done with x, u and slot q
+      const double xn = ((a0 + a1) + (a2 + a3)) + (jump ? 0.0 : matvec_rows(S + kMat, ub, li));
+      jump = jump_next;
+      __syncwarp();  // every lane is done with x, u and the stage set
       x = xn;
-      if (lane < kN) ws.xb[lane] = x;
-      if (lane == 0) {
-        if (k + 2 < N) {
-          mbar_expect_tx(&ws.bfull[q], matBytes);
-          tma_load(ws.in + kMat * q, lqp + (size_t)(k + 2) * kRec + kMat, matBytes, &ws.bfull[q]);
-        }
-        if (k + 3 < N) {
-          l2_prefetch(lqp + (size_t)(k + 3) * kRec, 2 * matBytes + kN * sizeof(double));  // A | B | Hv
-          l2_prefetch(solp + (size_t)(k + 3) * kORec + kOK, (kMat + kN) * sizeof(double));
-        }
+      if (lane < kN) xb[lane] = x;
+      if (lane == 0 && k + depth < N) {
+        mbar_expect_tx(&rfull[rs], lqBytes + solBytes);
+        tma_load(ring + (size_t)rs * kRing, lqp + (size_t)((kAblate & 16) ? 0 : k + depth) * kRec, lqBytes, &rfull[rs]);
+        tma_load(ring + (size_t)rs * kRing + kRingK, solp + (size_t)((kAblate & 16) ? 0 : k + depth) * kORec + kOK, solBytes, &rfull[rs]);
       }
       __syncwarp();
+      rs = rs + 1 == depth ? 0 : rs + 1;
     }
-    // node N: state, and the input of the copied last policy re-evaluated at x_N (TimeTriggeredRollout.cpp:98-102)
+    // node N: state, and the input of the copied last policy (K, dbias of node N-1, still in their ring slot) re-evaluated at x_N
+    // (TimeTriggeredRollout.cpp:98-102)
     {
-      const double xabs = x + (NOM ? __ldg(xnp + (size_t)N * kN + li) : 0.0);
-      double u0 = a.alpha * dbk, u1 = 0.0;
+      const double* Kl = ring + (size_t)((N - 1) % depth) * kRing + kRingK;
+      const double xabs = x + xnk;
+      double u0 = a.alpha * Kl[kMat + li], u1 = 0.0;
       if (NOM) {  // the copied policy of node N-1 is evaluated at the absolute state: u = bias + alpha dbias + K x
         __syncwarp();
-        if (lane < kN) ws.xb[lane] = xabs;
+        if (lane < kN) xb[lane] = xabs;
         __syncwarp();
         u0 += __ldcg(solp + (size_t)N * kORec + kObias + li);
       }
 #pragma unroll
       for (int j = 0; j < kN; j += 2) {
-        const double2 x01 = ld2(ws.xb + j);
-        u0 = fma(kreg[j], x01.x, u0);
-        u1 = fma(kreg[j + 1], x01.y, u1);
+        const double2 x01 = ld2(xb + j);
+        u0 = fma(Kl[li + kN * j], x01.x, u0);
+        u1 = fma(Kl[li + kN * (j + 1)], x01.y, u1);
       }
       if (lane < kN) {
         __stcg(xo + (size_t)N * kN + lane, xabs);
@@ -846,10 +978,17 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 1) ilqr_wpp_kernel(const Args 
       }
       xfinite = xfinite && finite_bits(x);
     }
-    if (!__all_sync(kFull, xfinite)) bits |= O2C_STATUS_NONFINITE;
-    if (lane == 0) a.status[prob] = bits;
+    if (!__all_sync(kFull, xfinite) && lane == 0) atomicOr(a.status + prob, O2C_STATUS_NONFINITE);
     __syncwarp();
+#ifdef O2C_WPP_STATS
+    st_roll += clock64() - st_mark, ++st_nroll;
+#endif
   }
+#ifdef O2C_WPP_STATS
+  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+    printf("cta %3d warp %2d: %3d sweeps %8.1f us, %3d rollouts %8.1f us, queue wait %8.1f us, total %8.1f us\n", blockIdx.x, warp, st_nsweep,
+           st_sweep / 1965.0, st_nroll, st_roll / 1965.0, st_wait / 1965.0, (clock64() - st_t0) / 1965.0);
+#endif
 }
 
 }  // namespace
@@ -865,24 +1004,30 @@ bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceB
          L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat;
 }
 
-// Resident problems (warps) per SM for a launch of `count` problems on `sms` SMs. The time one problem takes depends on how many
-// problems share its SM's FP64 pipe: t(w) in ms for ONE full wave of w warps per SM (N = 100; measured on B200,
-// profiles/r02_wpp_residency.jsonl; the steps at 4 -> 5 and 8 -> 9 are a scheduler taking its second / third warp).
-// A full machine (w = 12) has the best steady-state throughput, but a batch that is not a multiple of 12 x sms ends in a ragged
-// wave: 2048 problems on 148 SMs (BASELINE.json config 5: 16384 over 8 GPUs) are 1776 + 272, and the 272 stragglers cost another
-// t(2). Two even waves of 7 per SM take 2 t(7) instead of t(12) + t(2). The choice minimises the modelled makespan
-// full_waves(w) x t(w) + t(warps of the last, partial wave); only the ratios of t matter. Batches of many waves (>= 4 at w = 12)
-// keep w = 12: with the dynamic fetch the waves de-synchronise and the steady-state throughput is what counts.
-int choose_resident_warps(int count, int sms) {
-  static const double t[kMaxWarps + 1] = {0.0, 0.82, 0.83, 0.86, 0.89, 1.18, 1.21, 1.27, 1.34, 1.61, 1.63, 1.72, 1.87};
-  if (count >= 4 * kMaxWarps * sms) return kMaxWarps;
-  int best = kMaxWarps;
+// Sweeping warps per SM for a launch of `count` problems on `sms` SMs with `rollers` rollout warps per SM. The time a sweep takes
+// depends on how many sweeps share its SM's FP64 pipe: tb(w) in ms for ONE round of w resident sweeps per SM (N = 100; B200,
+// profiles/r02_wpp_residency2.jsonl; the steps at 4 -> 5 and 8 -> 9 are a scheduler taking its second / third warp). A full machine
+// has the best steady-state throughput, but a batch of a few rounds pays for a ragged last round: 2048 problems on 148 SMs
+// (BASELINE.json config 5: 16384 over 8 GPUs) are 13.8 per SM; with 11 sweepers + 1 roller that is a round of 12 and a round of 2,
+// tb(12) + tb(2), while 7 sweepers + 1 roller run a round of 8 and a round of 6: tb(8) + tb(6), 2.2 ms instead of 2.5 ms. The choice
+// minimises the modelled makespan (first round: w sweepers plus one sweep per roller; full rounds of w; the partial last round); only
+// the ratios of tb matter. Batches of many rounds keep the full machine: the dynamic fetch de-synchronises the rounds and the
+// steady-state throughput is what counts.
+int choose_sweepers(int count, int sms, int rollers) {
+  static const double tb[kMaxWarps + 1] = {0.0, 0.80, 0.81, 0.83, 0.86, 1.00, 1.03, 1.08, 1.12, 1.30, 1.32, 1.36, 1.40};
+  const int wmax = kMaxCtaWarps - rollers < kMaxWarps ? kMaxCtaWarps - rollers : kMaxWarps;
+  if (count >= 4L * wmax * sms) return wmax;
+  int best = wmax;
   double best_time = 1e300;
-  for (int w = kMaxWarps; w >= 1; --w) {
-    const long slots = (long)w * sms;
-    const long full = count / slots, rem = count % slots;
-    const int tail_warps = (int)((rem + sms - 1) / sms);  // warps per SM in the last wave (problems spread warp-major over the SMs)
-    const double time = (double)full * t[w] + (tail_warps ? t[tail_warps] : 0.0);
+  for (int w = wmax; w >= 1; --w) {
+    long left = count;
+    const long first = left < (long)(w + rollers) * sms ? left : (long)(w + rollers) * sms;
+    double time = tb[(first + sms - 1) / sms];
+    left -= first;
+    const long full = left / ((long)w * sms);
+    time += (double)full * tb[w];
+    left -= full * w * sms;
+    if (left > 0) time += tb[(left + sms - 1) / sms];
     if (time < best_time - 1e-9) {
       best_time = time;
       best = w;
@@ -896,29 +1041,54 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   if (!wpp_ilqr_supported(L, st, buf)) return cudaErrorNotSupported;
   const bool nom = buf.x_nom != nullptr, ev = buf.event != nullptr;
   using Kernel = void (*)(const Args);
+#ifdef O2C_WPP_ONLY_BASE  // profiling builds: one instantiation, seconds to compile
+  const Kernel base = ilqr_wpp_kernel<false, false, kModeLS>;
+  const Kernel kernels[3][4] = {{base, base, base, base}, {base, base, base, base}, {base, base, base, base}};
+#else
   const Kernel kernels[3][4] = {
       {ilqr_wpp_kernel<false, false, kModeLS>, ilqr_wpp_kernel<true, false, kModeLS>, ilqr_wpp_kernel<false, true, kModeLS>,
        ilqr_wpp_kernel<true, true, kModeLS>},
       {ilqr_wpp_kernel<false, false, kModeLM>, ilqr_wpp_kernel<true, false, kModeLM>, nullptr, nullptr},
       {ilqr_wpp_kernel<false, false, kModeGersh>, ilqr_wpp_kernel<true, false, kModeGersh>, ilqr_wpp_kernel<false, true, kModeGersh>,
        ilqr_wpp_kernel<true, true, kModeGersh>}};
+#endif
   const int mode = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT ? kModeLM : (st.hc == O2C_HC_GERSHGORIN_MODIFICATION ? kModeGersh : kModeLS);
   const Kernel kernel = kernels[mode][(nom ? 1 : 0) + (ev ? 2 : 0)];
   if (kernel == nullptr) return cudaErrorNotSupported;
   const int num_sms = device_sm_count();
   if (num_sms <= 0) return cudaErrorInvalidDevice;
   // profiling knobs, read per launch (no state is cached in statics: launches from several host threads / on several devices are
-  // independent): O2C_WPP_RESIDENT = warps per SM (1..12), O2C_WPP_DYNAMIC = 0 switches the dynamic problem fetch off
-  int warps = choose_resident_warps(count, num_sms);
+  // independent): O2C_WPP_RESIDENT = sweeping warps per SM, O2C_WPP_ROLLERS = rollout-only warps per SM (0 = every sweeper rolls its own
+  // problem out), O2C_WPP_DYNAMIC = 0 switches the dynamic problem fetch off
+  int rollers = with_rollout ? kDefaultRollers : 0;
+  if (const char* e = getenv("O2C_WPP_ROLLERS")) {
+    const int v = atoi(e);
+    if (with_rollout && v >= 0 && v < kMaxCtaWarps) rollers = v;
+  }
+  int sweepers = choose_sweepers(count, num_sms, rollers);
   if (const char* e = getenv("O2C_WPP_RESIDENT")) {
     const int v = atoi(e);
-    if (v >= 1 && v <= kMaxWarps) warps = v;
+    if (v >= 1 && v <= kMaxWarps) sweepers = v;
+  }
+  if (sweepers + rollers > kMaxCtaWarps) sweepers = kMaxCtaWarps - rollers;
+  const int warps = sweepers + rollers;
+  // shared memory: the sweepers' slots, then the rollers' rings (as deep as fits, at most kMaxRingDepth stage sets)
+  const size_t smem_cap = 227 * 1024 - 6 * 1024;  // minus the static part (queue, ring barriers, x / u vectors)
+  int ring_depth = 0;
+  if (rollers > 0) {
+    ring_depth = (int)((smem_cap - sizeof(WarpSmem) * sweepers) / (sizeof(double) * kRing * rollers));
+    if (ring_depth > kMaxRingDepth) ring_depth = kMaxRingDepth;
+    if (const char* e = getenv("O2C_WPP_RING")) {
+      const int v = atoi(e);
+      if (v >= 1 && v <= ring_depth) ring_depth = v;
+    }
+    if (ring_depth < 1) return cudaErrorInvalidConfiguration;
   }
   bool dynamic = true;
   if (const char* e = getenv("O2C_WPP_DYNAMIC")) dynamic = atoi(e) != 0;
-  const size_t smem = sizeof(WarpSmem) * warps;
+  const size_t smem = sizeof(WarpSmem) * sweepers + sizeof(double) * kRing * rollers * ring_depth;
   // function attributes are per device: set on every launch (sub-microsecond) instead of caching "configured" in a static
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * kMaxWarps));
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
@@ -941,6 +1111,9 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   a.begin = begin;
   a.count = count;
   a.with_rollout = with_rollout ? 1 : 0;
+  a.nsweep = sweepers;
+  a.sweep_count = count;
+  a.ring_depth = ring_depth;
   a.eps = st.eps;
   a.alpha = alpha;
   a.mu = st.mu;
@@ -948,15 +1121,23 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   // warp-major problem order (CTA b starts with problems b, b + grid, ...): the grid is as wide as the machine even when the batch
   // does not fill every warp slot, so a small batch spreads evenly over the SMs
   const int grid = count < num_sms ? count : num_sms;
+  // the rollers' initial sweeps: whatever exceeds the sweepers' first static round, at most one problem per roller
+  if (rollers > 0 && sizeof(double) * kRing * ring_depth >= sizeof(WarpSmem) && count > grid * sweepers) {
+    const int extra = count - grid * sweepers;
+    a.sweep_count = count - (extra < grid * rollers ? extra : grid * rollers);
+  }
+  if (const char* e = getenv("O2C_WPP_ROLLER_SWEEPS"))
+    if (atoi(e) == 0) a.sweep_count = count;
+  const int scount = a.sweep_count;
   a.counter = nullptr;
-  if (dynamic && buf.work_counter != nullptr && count > grid * warps) {
+  if (dynamic && buf.work_counter != nullptr && scount > grid * sweepers) {
     e = cudaMemsetAsync(buf.work_counter, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
     a.counter = buf.work_counter;
-    a.dyn_limit = count - count % (grid * warps);
+    a.dyn_limit = scount - scount % (grid * sweepers);
   }
   if (getenv("O2C_WPP_VERBOSE"))
-    fprintf(stderr, "ilqr_wpp launch: warps/SM %d grid %d count %d dynamic %d\n", warps, grid, count, a.counter != nullptr);
+    fprintf(stderr, "ilqr_wpp launch: sweepers/SM %d rollers/SM %d (ring %d) grid %d count %d dynamic %d\n", sweepers, rollers, ring_depth, grid, count, a.counter != nullptr);
   kernel<<<grid, 32 * warps, smem, stream>>>(a);
   if (launches) *launches = 1;
   return cudaGetLastError();
