@@ -45,7 +45,11 @@ struct Shape {
   static constexpr int sRec = 0, sSA = 2 * rec, sSB = sSA + XP * NX, sYt = sSB + XP * NU, sL = sYt + XP * NU,
                        sW = sL + cpad2(NU * NU), sGv = sW + cpad2(NX), sYv = sGv + cpad2(NU), sX = sYv + cpad2(NU), sU = sX + cpad2(NX),
                        sK = sU + cpad2(NU), sZ = sK + cpad2(NU * NX + NU), sVx = sZ + cpad2(NU * NC), slot = sVx + NC * XP;
-  static constexpr int warp_doubles = P * slot + 2;  // + the warp's mbarrier
+  // fused rollout: ring of stage sets { A | B | Hv } + { K | dbias } over the part of the slot the sweep no longer needs
+  static constexpr int dyn = oq, pol = odb + cpad2(NU), set = dyn + pol;
+  static constexpr int ring = (sX / set) < 6 ? (sX / set) : 6;
+  static_assert(ring >= 2, "the rollout ring needs at least two stage sets");
+  static constexpr int warp_doubles = P * slot + 2 + 6;  // + the warp's mbarriers: sweep, and one per ring slot
 };
 
 struct Args {
@@ -108,6 +112,7 @@ __global__ void __launch_bounds__(64, (NX == 10 ? 6 : 1)) ilqr_rpl_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* wbase = smem + (size_t)warp * S::warp_doubles;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(wbase + S::P * S::slot);
+  unsigned long long* rbar = bar + 1;  // rollout ring: stage set landed
   const int graw = lane / NX;
   const bool in_group = graw < S::P;
   const int gi = in_group ? graw : S::P - 1;   // left-over lanes shadow the last slot and never store
@@ -116,14 +121,16 @@ __global__ void __launch_bounds__(64, (NX == 10 ? 6 : 1)) ilqr_rpl_kernel(const 
   double* sm = wbase + gi * S::slot;
   const int N = a.N;
   const uint32_t recBytes = S::rec * sizeof(double);
-  const uint32_t dynBytes = S::oq * sizeof(double);  // { A | B | Hv }: all the rollout reads of a record
+  const uint32_t dynBytes = S::dyn * sizeof(double);  // { A | B | Hv }: all the rollout reads of a record
+  const uint32_t polBytes = S::pol * sizeof(double);  // { K | dbias }
 
   if (lane == 0) {
     mbar_init(bar, 1);
+    for (int d = 0; d < S::ring; ++d) mbar_init(&rbar[d], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t parity = 0;
+  uint32_t parity = 0, rphase = 0;  // rphase: bit d = parity to wait for on rbar[d]
   const int warps_total = gridDim.x * (blockDim.x >> 5);
 
   for (int base = (blockIdx.x * (blockDim.x >> 5) + warp) * S::P; base < a.count; base += warps_total * S::P) {
@@ -470,83 +477,90 @@ __global__ void __launch_bounds__(64, (NX == 10 ? 6 : 1)) ilqr_rpl_kernel(const 
     }
 
     // ---- fused forward rollout: du_k = K_k dx_k + alpha dbias_k ; dx_{k+1} = A_k dx_k + B_k du_k + Hv_k ----
+    // Everything a stage reads — { A | B | Hv } of the record and { K | dbias } of the solution — comes by TMA through a ring of
+    // S::ring stage sets per problem, issued S::ring stages ahead, so that the short dependent chain of a stage never waits for a DRAM
+    // round trip (one stage ahead for the record and plain loads for the gains cost 2.3 us per stage: profiles/r02_prof_modes.jsonl).
+    fence_proxy_async_global();  // this warp's K / dbias stores of the sweep are read back through the async proxy
     __syncwarp();
     if (lane == 0) {
       fence_proxy_async();
-      mbar_expect_tx(bar, dynBytes * nprob);
-      for (int g = 0; g < nprob; ++g) tma_load(wbase + g * S::slot + S::sRec, a.lq + (size_t)(a.begin + base + g) * N * S::rec, dynBytes, bar);
+      for (int d = 0; d < S::ring && d < N; ++d) {
+        mbar_expect_tx(&rbar[d], (dynBytes + polBytes) * nprob);
+        for (int g = 0; g < nprob; ++g) {
+          double* dst = wbase + g * S::slot + d * S::set;
+          tma_load(dst, a.lq + ((size_t)(a.begin + base + g) * N + d) * S::rec, dynBytes, &rbar[d]);
+          tma_load(dst + S::dyn, a.sol + ((size_t)(a.begin + base + g) * (N + 1) + d) * S::orec + S::oK, polBytes, &rbar[d]);
+        }
+      }
     }
     double* xo = a.xs + (size_t)prob * (N + 1) * NX;
     double* uo = a.us + (size_t)prob * (N + 1) * NU;
     // with nominal trajectories the rollout runs in deviation coordinates (dx = x - x_nom, du = u - u_nom) and shifts the outputs back
     const double* xnp = NOM ? a.x_nom + (size_t)prob * (N + 1) * NX : nullptr;
     const double* unp = NOM ? a.u_nom + (size_t)prob * (N + 1) * NU : nullptr;
-    double x = a.x0[(size_t)prob * NX + i] - (NOM ? __ldg(xnp + i) : 0.0);
+    double xnk = NOM ? __ldg(xnp + i) : 0.0, unk = NOM ? __ldg(unp + (i < NU ? i : 0)) : 0.0;  // nominal state / input of the current node
+    double x = a.x0[(size_t)prob * NX + i] - xnk;
     bool xfinite = true;
-    // column i of K_k and (lanes < nu) dbias_k: coalesced loads one node ahead
-    double kc[NU], dbk;
-#pragma unroll
-    for (int l = 0; l < NU; ++l) kc[l] = __ldcg(solp + S::oK + l + NU * i);
-    dbk = __ldcg(solp + S::odb + (i < NU ? i : 0));
+    bool jump = EV && __ldg(evp) != 0;  // pre-event node: x+ = A_e x + Hv_e, the input does not enter the jump map
+    int rs = 0;
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
       sm[S::sX + i] = x;
-#pragma unroll
-      for (int l = 0; l < NU; ++l) sm[S::sK + l + NU * i] = kc[l];
+      mbar_wait(&rbar[rs], (rphase >> rs) & 1u);
+      rphase ^= 1u << rs;
       __syncwarp();
+      const double* rec = sm + rs * S::set;
+      const double* pol = rec + S::dyn;
       // u_l = alpha dbias_l + K(l,:) x on lanes l < nu
       {
         const int l = i < NU ? i : NU - 1;
-        double u = a.alpha * dbk;
+        double u = a.alpha * pol[S::odb + l];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) u = fma(sm[S::sK + l + NU * j], sm[S::sX + j], u);
+        for (int j = 0; j < NX; ++j) u = fma(pol[l + NU * j], sm[S::sX + j], u);
         if (i < NU) {
           sm[S::sU + i] = u;
-          if (valid) __stcg(uo + (size_t)k * NU + i, u + (NOM ? __ldg(unp + (size_t)k * NU + i) : 0.0));
+          if (valid) __stcg(uo + (size_t)k * NU + i, u + unk);
         }
       }
-      if (valid) __stcg(xo + (size_t)k * NX + i, x + (NOM ? __ldg(xnp + (size_t)k * NX + i) : 0.0));
+      if (valid) __stcg(xo + (size_t)k * NX + i, x + xnk);
       xfinite = xfinite && finite_bits(x);
-      // gains of node k+1 (node N carries the copy of node N-1)
-      {
-        const double* nsol = solp + (size_t)(k + 1) * S::orec;
-#pragma unroll
-        for (int l = 0; l < NU; ++l) kc[l] = __ldcg(nsol + S::oK + l + NU * i);
-        dbk = __ldcg(nsol + S::odb + (i < NU ? i : 0));
+      if (NOM) {  // next node's nominal values: in flight during the second half of the stage
+        xnk = __ldg(xnp + (size_t)(k + 1) * NX + i);
+        unk = __ldg(unp + (size_t)(k + 1) * NU + (i < NU ? i : 0));
       }
-      mbar_wait(bar, parity);
-      parity ^= 1u;
-      __syncwarp();
-      const double* rec = sm + S::sRec + (k & 1) * S::rec;
-      if (lane == 0 && k + 1 < N) {
-        fence_proxy_async();
-        mbar_expect_tx(bar, dynBytes * nprob);
-        for (int g = 0; g < nprob; ++g)
-          tma_load(wbase + g * S::slot + S::sRec + ((k + 1) & 1) * S::rec, a.lq + ((size_t)(a.begin + base + g) * N + (k + 1)) * S::rec, dynBytes, bar);
-      }
+      const bool jump_next = EV && k + 1 < N && __ldg(evp + k + 1) != 0;
       double xn = rec[S::oHv + i];
 #pragma unroll
       for (int j = 0; j < NX; ++j) xn = fma(rec[S::oA + i + NX * j], sm[S::sX + j], xn);
-      const bool jump = EV && __ldg(evp + k) != 0;  // pre-event node: x+ = A_e x + Hv_e, the input does not enter the jump map
+      __syncwarp();  // u of every lane is in shared memory
       if (!jump) {
 #pragma unroll
         for (int l = 0; l < NU; ++l) xn = fma(rec[S::oB + i + NX * l], sm[S::sU + l], xn);
       }
-      __syncwarp();
+      jump = jump_next;
+      __syncwarp();  // every lane is done with x, u and the stage set
+      if (lane == 0 && k + S::ring < N) {
+        mbar_expect_tx(&rbar[rs], (dynBytes + polBytes) * nprob);
+        for (int g = 0; g < nprob; ++g) {
+          double* dst = wbase + g * S::slot + rs * S::set;
+          tma_load(dst, a.lq + ((size_t)(a.begin + base + g) * N + (k + S::ring)) * S::rec, dynBytes, &rbar[rs]);
+          tma_load(dst + S::dyn, a.sol + ((size_t)(a.begin + base + g) * (N + 1) + (k + S::ring)) * S::orec + S::oK, polBytes, &rbar[rs]);
+        }
+      }
       x = xn;
+      rs = rs + 1 == S::ring ? 0 : rs + 1;
     }
-    // node N: state, and the input of the copied last policy re-evaluated at x_N (TimeTriggeredRollout.cpp:98-102); with nominal
-    // trajectories the copied policy acts on the absolute state: u = bias + alpha dbias + K x
-    const double xabs = x + (NOM ? __ldg(xnp + (size_t)N * NX + i) : 0.0);
+    // node N: state, and the input of the copied last policy (K, dbias of node N-1, still in their ring slot) re-evaluated at x_N
+    // (TimeTriggeredRollout.cpp:98-102); with nominal trajectories the copied policy acts on the absolute state: u = bias + alpha dbias + K x
+    const double xabs = x + xnk;
     sm[S::sX + i] = xabs;
-#pragma unroll
-    for (int l = 0; l < NU; ++l) sm[S::sK + l + NU * i] = kc[l];
     __syncwarp();
     {
+      const double* pol = sm + ((N - 1) % S::ring) * S::set + S::dyn;
       const int l = i < NU ? i : NU - 1;
-      double u = a.alpha * dbk + (NOM ? __ldcg(solp + (size_t)N * S::orec + S::obias + l) : 0.0);
+      double u = a.alpha * pol[S::odb + l] + (NOM ? __ldcg(solp + (size_t)N * S::orec + S::obias + l) : 0.0);
 #pragma unroll
-      for (int j = 0; j < NX; ++j) u = fma(sm[S::sK + l + NU * j], sm[S::sX + j], u);
+      for (int j = 0; j < NX; ++j) u = fma(pol[l + NU * j], sm[S::sX + j], u);
       if (valid && i < NU) __stcg(uo + (size_t)N * NU + i, u);
     }
     if (valid) __stcg(xo + (size_t)N * NX + i, xabs);
