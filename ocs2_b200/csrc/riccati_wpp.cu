@@ -41,15 +41,22 @@
 namespace o2c {
 namespace {
 
-struct __align__(16) WarpSmem {
+// NCB: tiles of 8 state-input equality constraints the kernel instantiation carries (0: unconstrained; nc_max <= 8 NCB)
+template <int NCB>
+struct __align__(16) WarpSmemT {
+  static constexpr int kC8 = NCB > 0 ? 8 * NCB : 2;
   double in[kOperand];   // TMA destination: {A | B | Hv | q | r | c,pad}
   double W[kN * kLd];    // S of node k+1 (both triangles) -> Hm (lower) -> L -> L^-T (upper)
   double Sv[kN], Gv[kN], Yv[kN], xb[kN], ub[kN];
+  double cde[NCB > 0 ? 2 * kC8 * kN + kC8 : 2];  // TMA destination: {C | D | e} as in the record (leading dimension nc_max)
+  double Wm[NCB > 0 ? kC8 * kLd : 2];            // M = Z'Z (lower) -> L_M -> L_M^-T (upper), leading rows of a ld-26 scratch
+  double vw[kC8], vv[kC8];                       // Z'Yv - e -> L_M^-T vv ; vv = L_M^-1 (Z'Yv - e)
   unsigned long long full;   // operand block landed (sweep)
   unsigned long long hfull, hfull2;  // sweep: Q landed in the scratch / P landed in A's slot
-  unsigned long long pad_;
+  unsigned long long cfull;  // {C | D | e} landed
 };
-static_assert(sizeof(WarpSmem) % 16 == 0, "warp slots must keep 16-byte alignment");
+using WarpSmem = WarpSmemT<0>;
+static_assert(sizeof(WarpSmemT<0>) % 16 == 0 && sizeof(WarpSmemT<1>) % 16 == 0 && sizeof(WarpSmemT<2>) % 16 == 0, "warp slots must keep 16-byte alignment");
 
 struct Args {
   const double* lq;
@@ -62,6 +69,9 @@ struct Args {
   double* us;
   int* status;
   const int* event;  // [batch][N] pre-event flags (ILQR.cpp:263-295), or nullptr: kernel instantiation EV
+  const int* nc;     // [batch][N] active constraints per node, or nullptr (nc_max everywhere); constrained instantiations only
+  int rec, oC, cdeD, cdeE, ncmax;  // constrained instantiations: record stride, offset of {C | D | e}, D and e inside that block
+  uint32_t cde_bytes;
   int N;
   int oQf, oqf, ocf, trec;
   int begin, count, with_rollout;
@@ -142,10 +152,15 @@ constexpr int kMaxRingDepth = 4;
 #endif
 constexpr int kRollAhead = O2C_WPP_ROLL_AHEAD;  // rollout: L2 prefetch distance in stages
 
-template <bool NOM, bool EV, int MODE>
-__global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Args a) {
+template <bool NOM, bool EV, int MODE, int NCB>
+// (the constrained instantiations have room for 10 / 8 warps in shared memory: their register budget is that of 320 / 256 threads)
+__global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320 : 256), 1) ilqr_wpp_kernel(const Args a) {
   constexpr bool QPD = true;  // Q and P straight from L2 into the accumulators (the TMA-staged round-1 path is kept for reference only)
   static_assert(!(EV && MODE == kModeLM), "ILQR events under LEVENBERG_MARQUARDT are refused by the API");
+  static_assert(NCB == 0 || (!EV && MODE == kModeLS), "the constrained instantiations serve LINE_SEARCH + DIAGONAL_SHIFT without events");
+  using WarpSmem = WarpSmemT<NCB>;
+  constexpr int NCB_ = NCB > 0 ? NCB : 1;
+  const int rec_stride = NCB > 0 ? a.rec : kRec;  // (a compile-time constant for the unconstrained layout)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // a roller's ring doubles as the WarpSmem of the one sweep it does before its first rollout
@@ -167,12 +182,13 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
       mbar_init(&ws.full, 1);
       mbar_init(&ws.hfull, 1);
       mbar_init(&ws.hfull2, 1);
+      mbar_init(&ws.cfull, 1);
     }
     for (int d = 0; d < kMaxRingDepth; ++d) mbar_init(&ring_full[warp][d], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t phase = 0, hphase = 0, rphase = 0;  // rphase: bit d = parity to wait for on ring_full[warp][d]
+  uint32_t phase = 0, hphase = 0, cphase = 0, rphase = 0;  // rphase: bit d = parity to wait for on ring_full[warp][d]
 
   // Warp roles. Warps [0, nsweep) are SWEEPERS: backward pass after backward pass, the FP64 pipe never waits for a rollout. The
   // remaining warps are ROLLERS: they take finished problems from a queue in shared memory and run the forward rollout, which is
@@ -216,6 +232,7 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
           mbar_inval(&ws.full);
           mbar_inval(&ws.hfull);
           mbar_inval(&ws.hfull2);
+          mbar_inval(&ws.cfull);
         }
         if (lane == 0) {
           __threadfence_block();
@@ -225,18 +242,23 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
     }
     if (sweeping) {
     const int prob = a.begin + pi;
-    const double* lqp = a.lq + (size_t)prob * N * kRec;
+    const double* lqp = a.lq + (size_t)prob * N * rec_stride;
     const double* term = a.term + (size_t)prob * a.trec;
     double* solp = a.sol + (size_t)prob * (N + 1) * kORec;
     const int* evp = EV ? a.event + (size_t)prob * N : nullptr;
+    const int* ncp = (NCB > 0 && a.nc != nullptr) ? a.nc + (size_t)prob * N : nullptr;
 
     // operand block of node N-1 (TMA) and the L2 prefetch of its cost Hessians
     if (lane == 0) {
       fence_proxy_async();
       mbar_expect_tx(&ws.full, opBytes);
-      tma_load(ws.in, lqp + (size_t)(N - 1) * kRec, opBytes, &ws.full);
+      tma_load(ws.in, lqp + (size_t)(N - 1) * rec_stride, opBytes, &ws.full);
+      if (NCB > 0) {
+        mbar_expect_tx(&ws.cfull, a.cde_bytes);
+        tma_load(ws.cde, lqp + (size_t)(N - 1) * rec_stride + a.oC, a.cde_bytes, &ws.cfull);
+      }
     }
-    prefetch_hessians<QPD>(lqp + (size_t)(N - 1) * kRec, a, lo24);
+    prefetch_hessians<QPD>(lqp + (size_t)(N - 1) * rec_stride, a, lo24);
     // terminal condition: valueFunctionTrajectory.back() = finalValueFunction (GaussNewtonDDP.cpp:526)
     {
       double* outN = solp + (size_t)N * kORec;
@@ -254,7 +276,7 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
       if (lane == 0) outN[kOs] = term[a.ocf];
     }
     double sval = term[a.ocf];  // s of node k+1
-    bool pd = true;
+    bool pd = true, rank_ok = true;
     double2 t[6];               // T -> S (lower tiles); after the loop: S of node 0 for the finiteness test
     double svn = 0.0;
     __syncwarp();
@@ -266,7 +288,7 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
       const double* Hv = ws.in + 2 * kMat;
       const double* qv = Hv + kN;
       const double* rv = qv + kN;
-      const double* rec = lqp + (size_t)((kAblate & 2) ? N - 1 : k) * kRec;
+      const double* rec = lqp + (size_t)((kAblate & 2) ? N - 1 : k) * rec_stride;
       double* out = solp + (size_t)((kAblate & 4) ? 0 : k) * kORec;
       // pre-event node (ILQR.cpp:263-295): the staged A, Hv, q, c and Q are the jump map and the pre-jump cost. The value function goes
       // through riccatiTransversalityConditions (S- = Q_e + A_e'S A_e, Sv- = q_e + A_e'(Sv + S Hv), s- = s + c_e + Hv.(Sv + S Hv / 2));
@@ -499,13 +521,13 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
       __syncwarp();  // all lanes are done with the staged operand block: refill it for node k-1 while this stage finishes
       if (MODE != kModeLM && lane == 0 && k >= 1) {  // (LM needs A, B, Hv once more after the gains: its refill follows Acl)
         mbar_expect_tx(&ws.full, opBytes);
-        tma_load(ws.in, lqp + (size_t)((kAblate & 2) ? N - 1 : k - 1) * kRec, opBytes, &ws.full);
+        tma_load(ws.in, lqp + (size_t)((kAblate & 2) ? N - 1 : k - 1) * rec_stride, opBytes, &ws.full);
       }
 
       // ---- blocked Cholesky of Hm and L^-T into the scratch ----
       if (!(kAblate & 1)) pd = factor_hm(ws.W, lane, li, r, c) && pd;
 
-      // ---- Yv = L^-1 Gv, dbias = -L^-T Yv, s ----
+      // ---- Yv = L^-1 Gv ----
       {
         double z[3];
         matvec_cols<kLd, true>(ws.W, ws.Gv, r, c, z);  // (L^-1 Gv)[j] = sum_k (L^-T)[k][j] Gv[k]
@@ -515,6 +537,10 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
           if (!ev) spart = fma(-0.5 * yv, yv, spart);
         }
         __syncwarp();
+      }
+      // ---- dbias = -L^-T Yv, s (with constraints: after the projection, on the constrained Yv) ----
+      auto finish_vectors = [&]() {
+        double z[3];
         // (L^-T Yv)[8jb + r] = sum_{kb >= jb} (L^-T)[8jb+r][8kb+2c..] Yv[8kb+2c..]
         double2 vf[3];
 #pragma unroll
@@ -547,7 +573,8 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
         }
         sval = sval + cval + warp_sum_all(spart);
         if (lane == 0) __stcg(out + kOs, sval);
-      }
+      };
+      if (NCB == 0) finish_vectors();
 
       // ---- Y' = G' L^-T (op fragments of Y); L^-T is block upper triangular ----
       double2 y[3][3];
@@ -563,6 +590,223 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
 #pragma unroll
           for (int ib = 0; ib < 3; ++ib) dmma2(y[ib][jb], g[ib][kb], lf);
         }
+
+      // ---- state-input equality constraints C x + D u + e = 0: the range-space form of the reference's projection
+      //      (LinearAlgebra::computeConstraintProjection, LinearAlgebra.cpp:129-155; GaussNewtonDDP.cpp:751-773), as in riccati_rpl.cu:
+      //      Z = L^-1 D', M = Z'Z = L_M L_M' (L_M' is the R factor of the reference's QR of U^-T D'), Vx = L_M^-1 (Z'Y - C),
+      //      vv = L_M^-1 (Z'Yv - e); the constrained minimiser is Y^ = Y - Z L_M^-T Vx, Yv^ = Yv - Z L_M^-T vv and the value function
+      //      gains + Vx'Vx, + Vx'vv, + 1/2 vv'vv. Everything on 8-row constraint tiles; rows beyond the node's active count are zero rows
+      //      of D, C, e with a unit diagonal in M, which leaves every result untouched (ragged counts cost nothing). ----
+      double zsv[3] = {0.0, 0.0, 0.0};  // Y'Yv - Vx'vv
+      if (NCB > 0) {
+        mbar_wait(&ws.cfull, cphase);
+        cphase ^= 1u;
+        const int ncm = a.ncmax;
+        const int nca = ncp ? __ldg(ncp + k) : ncm;
+        const double* Cc = ws.cde;
+        const double* Dd = ws.cde + a.cdeD;
+        const double* ee = ws.cde + a.cdeE;
+        // op fragment of D' tile (kb, ib): lane (r,c) holds D'[8kb+2c..2c+1][8ib+r] = D[8ib+r][8kb+2c..2c+1]
+        auto dfrag = [&](int ib, int kb) -> double2 {
+          const int row = 8 * ib + r;
+          if (row >= nca) return zero2();
+          const double* q = Dd + row + ncm * (8 * kb + 2 * c);
+          return make_double2(q[0], q[ncm]);
+        };
+        // Z' = D L^-T (accumulators = op fragments of Z)
+        double2 zp[NCB_][3];
+#pragma unroll
+        for (int ib = 0; ib < NCB; ++ib) {
+          double2 df[3];
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) df[kb] = dfrag(ib, kb);
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            zp[ib][jb] = zero2();
+#pragma unroll
+            for (int kb = 0; kb <= jb; ++kb) dmma2(zp[ib][jb], df[kb], ld2(ws.W + lo26 + t26(kb, jb)));
+          }
+        }
+        // M = Z'Z (lower tiles) into its scratch, unit diagonal on the inactive rows; L_M^-T by the blocked factorisation
+#pragma unroll
+        for (int ib = 0; ib < NCB; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) {
+            double2 mm = zero2();
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) dmma2(mm, zp[ib][kb], zp[jb][kb]);
+            if (ib == jb && 8 * ib + r >= nca) {
+              mm.x += (2 * c == r) ? 1.0 : 0.0;
+              mm.y += (2 * c + 1 == r) ? 1.0 : 0.0;
+            }
+            tput(ws.Wm, ib, jb, r, c, mm);
+          }
+        __syncwarp();
+        rank_ok = factor_blocks<NCB_, true>(ws.Wm, lane, r, c) && rank_ok;
+        // R' = Y'Z - C' (n x 8 NCB; accumulators = op fragments of R = Z'Y - C)
+        double2 rp[3][NCB_];
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb < NCB; ++jb) {
+            const int row = 8 * jb + 2 * c;
+            const double* q = Cc + row + ncm * (8 * ib + r);
+            rp[ib][jb] = make_double2(row < nca ? -q[0] : 0.0, row + 1 < nca ? -q[1] : 0.0);
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) dmma2(rp[ib][jb], y[ib][kb], zp[jb][kb]);
+          }
+        // w = Z'Yv - e, vv = L_M^-1 w
+        {
+          double2 yvf[3];
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) yvf[kb] = ld2(ws.Yv + 8 * kb + 2 * c);
+#pragma unroll
+          for (int ib = 0; ib < NCB; ++ib) {
+            double q = 0.0;
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) {
+              q = fma(zp[ib][kb].x, yvf[kb].x, q);
+              q = fma(zp[ib][kb].y, yvf[kb].y, q);
+            }
+            q = quad_sum(q);
+            const int row = 8 * ib + r;
+            if (c == 0) ws.vw[row] = row < nca ? q - ee[row] : 0.0;
+          }
+          __syncwarp();
+          double zz[NCB_];
+          matvec_cols<kLd, true, NCB_>(ws.Wm, ws.vw, r, c, zz);
+          if (c < NCB) {
+            const double v = (NCB_ == 1 || c == 0) ? zz[0] : zz[NCB_ - 1];
+            ws.vv[8 * c + r] = v;
+            spart = fma(0.5 * v, v, spart);
+          }
+          __syncwarp();
+        }
+        // Vx' = R' L_M^-T (accumulators = op fragments of Vx)
+        double2 vx[3][NCB_];
+#pragma unroll
+        for (int jb = 0; jb < NCB; ++jb)
+#pragma unroll
+          for (int kb = 0; kb <= jb; ++kb) {
+            const double2 lf = ld2(ws.Wm + lo26 + t26(kb, jb));
+#pragma unroll
+            for (int ib = 0; ib < 3; ++ib) {
+              if (kb == 0) vx[ib][jb] = zero2();
+              dmma2(vx[ib][jb], rp[ib][kb], lf);
+            }
+          }
+        // the value-function terms take the UNPROJECTED Y: zsv = Y'Yv - Vx'vv ; t = Y'Y - T - Vx'Vx
+        {
+          double2 yvf[3], vvf[NCB_];
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) yvf[kb] = ld2(ws.Yv + 8 * kb + 2 * c);
+#pragma unroll
+          for (int kb = 0; kb < NCB; ++kb) vvf[kb] = ld2(ws.vv + 8 * kb + 2 * c);
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+            double q = 0.0;
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) {
+              q = fma(y[cb][kb].x, yvf[kb].x, q);
+              q = fma(y[cb][kb].y, yvf[kb].y, q);
+            }
+#pragma unroll
+            for (int kb = 0; kb < NCB; ++kb) {
+              q = fma(-vx[cb][kb].x, vvf[kb].x, q);
+              q = fma(-vx[cb][kb].y, vvf[kb].y, q);
+            }
+            zsv[cb] = quad_sum(q);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) t[i] = neg2(t[i]);
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+            for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], y[ib][kb], y[jb][kb]);
+#pragma unroll
+        for (int kb = 0; kb < NCB; ++kb)
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+            const double2 nv = neg2(vx[ib][kb]);
+#pragma unroll
+            for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], nv, vx[jb][kb]);
+          }
+        // U' = Vx' L_M^-1 (accumulators = op fragments of U = L_M^-T Vx)
+        double2 up[3][NCB_];
+#pragma unroll
+        for (int jb = 0; jb < NCB; ++jb)
+#pragma unroll
+          for (int kb = jb; kb < NCB; ++kb) {
+            const double2 lf = tfrag(ws.Wm, jb, kb, r, c);  // L_M^-1[8kb+2c..][8jb+r] = L_M^-T[8jb+r][8kb+2c..]
+#pragma unroll
+            for (int ib = 0; ib < 3; ++ib) {
+              if (kb == jb) up[ib][jb] = zero2();
+              dmma2(up[ib][jb], vx[ib][kb], lf);
+            }
+          }
+        // Z = L^-1 D' (accumulators = op fragments of Z')
+        double2 zq[3][NCB_];
+#pragma unroll
+        for (int jb = 0; jb < NCB; ++jb) {
+          double2 df[3];
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) df[kb] = dfrag(jb, kb);
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+            zq[ib][jb] = zero2();
+#pragma unroll
+            for (int kb = 0; kb <= ib; ++kb) dmma2(zq[ib][jb], ld2(ws.W + lo26 + t26(kb, ib)), df[kb]);
+          }
+        }
+        // Y^' = Y' - U'Z'
+#pragma unroll
+        for (int kb = 0; kb < NCB; ++kb)
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+            const double2 nu = neg2(up[ib][kb]);
+#pragma unroll
+            for (int jb = 0; jb < 3; ++jb) dmma2(y[ib][jb], nu, zq[jb][kb]);
+          }
+        // Yv^ = Yv - Z (L_M^-T vv)
+        {
+          double2 vvf[NCB_];
+#pragma unroll
+          for (int kb = 0; kb < NCB; ++kb) vvf[kb] = ld2(ws.vv + 8 * kb + 2 * c);
+#pragma unroll
+          for (int jb = 0; jb < NCB; ++jb) {
+            double q = 0.0;
+#pragma unroll
+            for (int kb = jb; kb < NCB; ++kb) {
+              const double2 mv = tfrag(ws.Wm, jb, kb, r, c);
+              q = fma(mv.x, vvf[kb].x, q);
+              q = fma(mv.y, vvf[kb].y, q);
+            }
+            q = quad_sum(q);
+            if (c == 0) ws.vw[8 * jb + r] = q;
+          }
+          __syncwarp();
+          double2 tf[NCB_];
+#pragma unroll
+          for (int jb = 0; jb < NCB; ++jb) tf[jb] = ld2(ws.vw + 8 * jb + 2 * c);
+          double zt[3];
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+            double q = 0.0;
+#pragma unroll
+            for (int jb = 0; jb < NCB; ++jb) {
+              q = fma(zq[ib][jb].x, tf[jb].x, q);
+              q = fma(zq[ib][jb].y, tf[jb].y, q);
+            }
+            zt[ib] = quad_sum(q);
+          }
+          if (c < 3) ws.Yv[8 * c + r] -= pick3(zt, c);
+          __syncwarp();
+        }
+        finish_vectors();
+      }
 
       // ---- K' = -Y' L^-1 (op fragments of K -> 16-byte global stores); L^-1 is block lower triangular ----
       double2 zc[3][3];  // LM: -Acl' = -(A + B K)' as accumulators = operand fragments of -Acl
@@ -634,26 +878,31 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
           __syncwarp();  // A, B, Hv are consumed: the operand slot takes node k-1
           if (lane == 0 && k >= 1) {
             mbar_expect_tx(&ws.full, opBytes);
-            tma_load(ws.in, lqp + (size_t)(k - 1) * kRec, opBytes, &ws.full);
+            tma_load(ws.in, lqp + (size_t)(k - 1) * rec_stride, opBytes, &ws.full);
           }
         }
       }
 
-      // ---- Sv = tv - Y'Yv ----
+      // ---- Sv = tv - Y'Yv (+ Vx'vv) ----
       {
-        double2 vf[3];
-#pragma unroll
-        for (int kb = 0; kb < 3; ++kb) vf[kb] = ld2(ws.Yv + 8 * kb + 2 * c);
         double z[3];
+        if (NCB == 0) {
+          double2 vf[3];
 #pragma unroll
-        for (int cb = 0; cb < 3; ++cb) {
-          double p = 0.0;
+          for (int kb = 0; kb < 3; ++kb) vf[kb] = ld2(ws.Yv + 8 * kb + 2 * c);
 #pragma unroll
-          for (int kb = 0; kb < 3; ++kb) {
-            p = fma(y[cb][kb].x, vf[kb].x, p);
-            p = fma(y[cb][kb].y, vf[kb].y, p);
+          for (int cb = 0; cb < 3; ++cb) {
+            double p = 0.0;
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) {
+              p = fma(y[cb][kb].x, vf[kb].x, p);
+              p = fma(y[cb][kb].y, vf[kb].y, p);
+            }
+            z[cb] = quad_sum(p);
           }
-          z[cb] = quad_sum(p);
+        } else {
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) z[cb] = zsv[cb];
         }
         if (MODE == kModeLM) {  // - mu Acl'hcl: the fragments hold -Acl
           double2 hf[3];
@@ -678,10 +927,12 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
         }
       }
 
-      // ---- S = T - Y'Y (lower tiles): accumulate Y'Y - T, flip the sign ----
+      // ---- S = T - Y'Y (+ Vx'Vx) (lower tiles): accumulate Y'Y - T, flip the sign (constrained: done with the unprojected Y above) ----
+      if (NCB == 0) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) t[i] = neg2(t[i]);
-      if (!ev) {
+        for (int i = 0; i < 6; ++i) t[i] = neg2(t[i]);
+      }
+      if (NCB == 0 && !ev) {
 #pragma unroll
         for (int kb = 0; kb < 3; ++kb)
 #pragma unroll
@@ -793,6 +1044,10 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
           }
         }
       __syncwarp();
+      if (NCB > 0 && lane == 0 && k >= 1) {  // every lane is done with this node's {C | D | e}
+        mbar_expect_tx(&ws.cfull, a.cde_bytes);
+        tma_load(ws.cde, lqp + (size_t)(k - 1) * rec_stride + a.oC, a.cde_bytes, &ws.cfull);
+      }
     }
 
     // node N of the controller := node N-1 (GaussNewtonDDP.cpp:609-618)
@@ -811,6 +1066,7 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
       for (int i = 0; i < 6; ++i) finite = finite && finite2(t[i]);
       if (!__all_sync(kFull, pd)) bits |= O2C_STATUS_CHOL_NOT_PD;
       if (!__all_sync(kFull, finite)) bits |= O2C_STATUS_NONFINITE;
+      if (NCB > 0 && !__all_sync(kFull, rank_ok)) bits |= O2C_STATUS_CONSTRAINT_RANK;
     }
     if (lane == 0) a.status[prob] = bits;
 #ifdef O2C_WPP_STATS
@@ -867,7 +1123,7 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
       __threadfence();
     }
     const int prob = a.begin + job;
-    const double* lqp = a.lq + (size_t)prob * N * kRec;
+    const double* lqp = a.lq + (size_t)prob * N * rec_stride;
     double* solp = a.sol + (size_t)prob * (N + 1) * kORec;
     const int* evp = EV ? a.event + (size_t)prob * N : nullptr;
 
@@ -890,7 +1146,7 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
       fence_proxy_async_global();  // K, dbias were written by ordinary stores (this warp or a sweeper of this CTA) and are read by TMA
       for (int d = 0; d < depth && d < N; ++d) {
         mbar_expect_tx(&rfull[d], lqBytes + solBytes);
-        tma_load(ring + (size_t)d * kRing, lqp + (size_t)d * kRec, lqBytes, &rfull[d]);
+        tma_load(ring + (size_t)d * kRing, lqp + (size_t)d * rec_stride, lqBytes, &rfull[d]);
         tma_load(ring + (size_t)d * kRing + kRingK, solp + (size_t)d * kORec + kOK, solBytes, &rfull[d]);
       }
     }
@@ -948,7 +1204,7 @@ __global__ void __launch_bounds__(32 * kMaxCtaWarps, 1) ilqr_wpp_kernel(const Ar
       if (lane < kN) xb[lane] = x;
       if (lane == 0 && k + depth < N) {
         mbar_expect_tx(&rfull[rs], lqBytes + solBytes);
-        tma_load(ring + (size_t)rs * kRing, lqp + (size_t)((kAblate & 16) ? 0 : k + depth) * kRec, lqBytes, &rfull[rs]);
+        tma_load(ring + (size_t)rs * kRing, lqp + (size_t)((kAblate & 16) ? 0 : k + depth) * rec_stride, lqBytes, &rfull[rs]);
         tma_load(ring + (size_t)rs * kRing + kRingK, solp + (size_t)((kAblate & 16) ? 0 : k + depth) * kORec + kOK, solBytes, &rfull[rs]);
       }
       __syncwarp();
@@ -998,8 +1254,12 @@ bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceB
   // K~'G~ + G~'K~ + K~'H~K~ in place of -G~'G~ (H~ = Pu'Hm Pu = I); the reference's own RiccatiTest.cpp:87-105 holds them equal to 1e-9.
   const bool ls = st.strategy == O2C_STRATEGY_LINE_SEARCH && (st.hc == O2C_HC_DIAGONAL_SHIFT || st.hc == O2C_HC_GERSHGORIN_MODIFICATION);
   const bool lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT && buf.event == nullptr;  // (events under LM: refused by the API)
-  return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_ILQR && (ls || lm) &&
-         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && L.rec == kRec && L.oQ == kOQ &&
+  // state-input equality constraints (up to 16, any per-node count): LINE_SEARCH + DIAGONAL_SHIFT without events
+  const bool constrained = L.ncmax > 0;
+  const bool cons_ok = !constrained || (L.ncmax <= 16 && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
+                                        buf.event == nullptr && L.oC == kRec);
+  return L.n == kN && L.m == kN && cons_ok && st.algorithm == O2C_ALG_ILQR && (ls || lm) &&
+         (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && (constrained || L.rec == kRec) && L.oQ == kOQ &&
          L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb && L.obias == kObias && L.oSm == kOSm &&
          L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat;
 }
@@ -1013,9 +1273,10 @@ bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceB
 // minimises the modelled makespan (first round: w sweepers plus one sweep per roller; full rounds of w; the partial last round); only
 // the ratios of tb matter. Batches of many rounds keep the full machine: the dynamic fetch de-synchronises the rounds and the
 // steady-state throughput is what counts.
-int choose_sweepers(int count, int sms, int rollers) {
+int choose_sweepers(int count, int sms, int rollers, int slots) {  // slots: sweepers the shared memory has room for
   static const double tb[kMaxWarps + 1] = {0.0, 0.80, 0.81, 0.83, 0.86, 1.00, 1.03, 1.08, 1.12, 1.30, 1.32, 1.36, 1.40};
-  const int wmax = kMaxCtaWarps - rollers < kMaxWarps ? kMaxCtaWarps - rollers : kMaxWarps;
+  int wmax = kMaxCtaWarps - rollers < kMaxWarps ? kMaxCtaWarps - rollers : kMaxWarps;
+  if (wmax > slots) wmax = slots;
   if (count >= 4L * wmax * sms) return wmax;
   int best = wmax;
   double best_time = 1e300;
@@ -1041,19 +1302,28 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   if (!wpp_ilqr_supported(L, st, buf)) return cudaErrorNotSupported;
   const bool nom = buf.x_nom != nullptr, ev = buf.event != nullptr;
   using Kernel = void (*)(const Args);
+  const int ncb = (L.ncmax + 7) / 8;  // constraint tiles: 0, 1 or 2
+  const size_t slot_bytes = ncb == 0 ? sizeof(WarpSmemT<0>) : (ncb == 1 ? sizeof(WarpSmemT<1>) : sizeof(WarpSmemT<2>));
+  Kernel kernel = nullptr;
 #ifdef O2C_WPP_ONLY_BASE  // profiling builds: one instantiation, seconds to compile
-  const Kernel base = ilqr_wpp_kernel<false, false, kModeLS>;
-  const Kernel kernels[3][4] = {{base, base, base, base}, {base, base, base, base}, {base, base, base, base}};
+  kernel = ilqr_wpp_kernel<false, false, kModeLS, 0>;
+  (void)nom, (void)ev;
 #else
-  const Kernel kernels[3][4] = {
-      {ilqr_wpp_kernel<false, false, kModeLS>, ilqr_wpp_kernel<true, false, kModeLS>, ilqr_wpp_kernel<false, true, kModeLS>,
-       ilqr_wpp_kernel<true, true, kModeLS>},
-      {ilqr_wpp_kernel<false, false, kModeLM>, ilqr_wpp_kernel<true, false, kModeLM>, nullptr, nullptr},
-      {ilqr_wpp_kernel<false, false, kModeGersh>, ilqr_wpp_kernel<true, false, kModeGersh>, ilqr_wpp_kernel<false, true, kModeGersh>,
-       ilqr_wpp_kernel<true, true, kModeGersh>}};
+  if (ncb == 0) {
+    const Kernel kernels[3][4] = {
+        {ilqr_wpp_kernel<false, false, kModeLS, 0>, ilqr_wpp_kernel<true, false, kModeLS, 0>, ilqr_wpp_kernel<false, true, kModeLS, 0>,
+         ilqr_wpp_kernel<true, true, kModeLS, 0>},
+        {ilqr_wpp_kernel<false, false, kModeLM, 0>, ilqr_wpp_kernel<true, false, kModeLM, 0>, nullptr, nullptr},
+        {ilqr_wpp_kernel<false, false, kModeGersh, 0>, ilqr_wpp_kernel<true, false, kModeGersh, 0>, ilqr_wpp_kernel<false, true, kModeGersh, 0>,
+         ilqr_wpp_kernel<true, true, kModeGersh, 0>}};
+    const int mode = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT ? kModeLM : (st.hc == O2C_HC_GERSHGORIN_MODIFICATION ? kModeGersh : kModeLS);
+    kernel = kernels[mode][(nom ? 1 : 0) + (ev ? 2 : 0)];
+  } else if (ncb == 1) {
+    kernel = nom ? ilqr_wpp_kernel<true, false, kModeLS, 1> : ilqr_wpp_kernel<false, false, kModeLS, 1>;
+  } else {
+    kernel = nom ? ilqr_wpp_kernel<true, false, kModeLS, 2> : ilqr_wpp_kernel<false, false, kModeLS, 2>;
+  }
 #endif
-  const int mode = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT ? kModeLM : (st.hc == O2C_HC_GERSHGORIN_MODIFICATION ? kModeGersh : kModeLS);
-  const Kernel kernel = kernels[mode][(nom ? 1 : 0) + (ev ? 2 : 0)];
   if (kernel == nullptr) return cudaErrorNotSupported;
   const int num_sms = device_sm_count();
   if (num_sms <= 0) return cudaErrorInvalidDevice;
@@ -1065,18 +1335,24 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
     const int v = atoi(e);
     if (with_rollout && v >= 0 && v < kMaxCtaWarps) rollers = v;
   }
-  int sweepers = choose_sweepers(count, num_sms, rollers);
+  const size_t smem_cap = 227 * 1024 - 6 * 1024;  // minus the static part (queue, ring barriers, x / u vectors)
+  // sweeper slots the shared memory has room for next to the rollers' rings (two stage sets each at least, and room for the one sweep
+  // a roller does first)
+  const size_t ring_min = 2 * sizeof(double) * kRing > slot_bytes ? 2 * sizeof(double) * kRing : slot_bytes;
+  const int slots = (int)((smem_cap - rollers * ring_min) / slot_bytes);
+  int sweepers = choose_sweepers(count, num_sms, rollers, slots);
   if (const char* e = getenv("O2C_WPP_RESIDENT")) {
     const int v = atoi(e);
     if (v >= 1 && v <= kMaxWarps) sweepers = v;
   }
   if (sweepers + rollers > kMaxCtaWarps) sweepers = kMaxCtaWarps - rollers;
+  if (sweepers > slots) sweepers = slots;
+  if (sweepers < 1) return cudaErrorInvalidConfiguration;
   const int warps = sweepers + rollers;
   // shared memory: the sweepers' slots, then the rollers' rings (as deep as fits, at most kMaxRingDepth stage sets)
-  const size_t smem_cap = 227 * 1024 - 6 * 1024;  // minus the static part (queue, ring barriers, x / u vectors)
   int ring_depth = 0;
   if (rollers > 0) {
-    ring_depth = (int)((smem_cap - sizeof(WarpSmem) * sweepers) / (sizeof(double) * kRing * rollers));
+    ring_depth = (int)((smem_cap - slot_bytes * sweepers) / (sizeof(double) * kRing * rollers));
     if (ring_depth > kMaxRingDepth) ring_depth = kMaxRingDepth;
     if (const char* e = getenv("O2C_WPP_RING")) {
       const int v = atoi(e);
@@ -1086,7 +1362,7 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   }
   bool dynamic = true;
   if (const char* e = getenv("O2C_WPP_DYNAMIC")) dynamic = atoi(e) != 0;
-  const size_t smem = sizeof(WarpSmem) * sweepers + sizeof(double) * kRing * rollers * ring_depth;
+  const size_t smem = slot_bytes * sweepers + sizeof(double) * kRing * rollers * ring_depth;
   // function attributes are per device: set on every launch (sub-microsecond) instead of caching "configured" in a static
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
   if (e != cudaSuccess) return e;
@@ -1103,6 +1379,13 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   a.us = buf.us;
   a.status = buf.status;
   a.event = buf.event;
+  a.nc = buf.nc;
+  a.rec = L.rec;
+  a.oC = L.oC;
+  a.cdeD = L.oD - L.oC;
+  a.cdeE = L.oe - L.oC;
+  a.ncmax = L.ncmax;
+  a.cde_bytes = (uint32_t)((L.oe + ((L.ncmax + 1) & ~1) - L.oC) * sizeof(double));
   a.N = L.N;
   a.oQf = L.oQf;
   a.oqf = L.oqf;
@@ -1122,7 +1405,7 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   // does not fill every warp slot, so a small batch spreads evenly over the SMs
   const int grid = count < num_sms ? count : num_sms;
   // the rollers' initial sweeps: whatever exceeds the sweepers' first static round, at most one problem per roller
-  if (rollers > 0 && sizeof(double) * kRing * ring_depth >= sizeof(WarpSmem) && count > grid * sweepers) {
+  if (rollers > 0 && sizeof(double) * kRing * ring_depth >= slot_bytes && count > grid * sweepers) {
     const int extra = count - grid * sweepers;
     a.sweep_count = count - (extra < grid * rollers ? extra : grid * rollers);
   }

@@ -91,16 +91,16 @@ __device__ __forceinline__ void tput(double* W, int rb, int cb, int r, int c, co
 
 // z[8 jb + r] = sum_k M[k + LD j] v[k] (transposed product) with the operand-fragment access pattern; every lane of quad r gets z[jb].
 // UPPER: M is block upper triangular (only tiles kb <= jb are read).
-template <int LD, bool UPPER>
-__device__ __forceinline__ void matvec_cols(const double* M, const double* v, int r, int c, double (&z)[3]) {
-  double2 vf[3];
+template <int LD, bool UPPER, int NB = 3>
+__device__ __forceinline__ void matvec_cols(const double* M, const double* v, int r, int c, double (&z)[NB]) {
+  double2 vf[NB];
 #pragma unroll
-  for (int kb = 0; kb < 3; ++kb) vf[kb] = ld2(v + 8 * kb + 2 * c);
+  for (int kb = 0; kb < NB; ++kb) vf[kb] = ld2(v + 8 * kb + 2 * c);
 #pragma unroll
-  for (int jb = 0; jb < 3; ++jb) {
+  for (int jb = 0; jb < NB; ++jb) {
     double p = 0.0;
 #pragma unroll
-    for (int kb = 0; kb < (UPPER ? jb + 1 : 3); ++kb) {
+    for (int kb = 0; kb < (UPPER ? jb + 1 : NB); ++kb) {
       const double2 mv = ld2(M + 2 * c + LD * r + 8 * kb + 8 * LD * jb);
       p = fma(mv.x, vf[kb].x, p);
       p = fma(mv.y, vf[kb].y, p);
@@ -133,12 +133,21 @@ __device__ __forceinline__ double matvec_rows(const double* M, const double* v, 
 //     L^-1 follow from three small DMMA chains:  Li10 = -Li11 (L10 Li00),  Li21 = -Li22 (L21 Li11),
 //     Li20 = -Li22 (L20 Li00 + L21 Li10).
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool factor_hm(double* W, int lane, int li, int r, int c) {
+// NB: the matrix is 8 NB x 8 NB (NB = 3: Hm; NB = 1, 2: the Gram matrix M = Z'Z of up to 16 equality constraints, which lives in the
+// leading rows / columns of its own scratch). CLAMP: pivots are floored instead of being tested for positivity — the reference clamps
+// the diagonal of the R factor of its constraint QR, |Rc_jj| = L_M,jj, to 1e-9 (LinearAlgebra.cpp:38-47), i.e. the pivot L_M,jj^2 to
+// 1e-18. The Gram form resolves a pivot only down to rounding of its diagonal entry (a dependent row leaves ~1e-16 M_jj instead of
+// 0), so the floor is max(1e-18, 1e-13 M_jj); the return value then says "no pivot was clamped" (full row rank to working accuracy).
+template <int NB, bool CLAMP>
+__device__ __forceinline__ bool factor_blocks(double* W, int lane, int r, int c) {
+  constexpr int kRows = 8 * NB;
+  const int li = lane < kRows ? lane : kRows - 1;
   bool pd = true;
+  const double dorig = CLAMP ? W[li + kLd * li] : 0.0;  // the lane's own diagonal entry before the elimination
 #pragma unroll 1
-  for (int b = 0; b < 3; ++b) {
+  for (int b = 0; b < NB; ++b) {
     double* col = W + kLd * 8 * b;  // column 8b of the scratch
-    const bool owner = lane >= 8 * b && lane < kN;
+    const bool owner = lane >= 8 * b && lane < kRows;
     double g[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) g[k] = col[li + kLd * k];
@@ -147,13 +156,29 @@ __device__ __forceinline__ bool factor_hm(double* W, int lane, int li, int r, in
     // shared memory instead of one (same conditioning: both forms subtract b^2 (/d0) from (d0) c).
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-      const double d0 = __shfl_sync(kFull, g[j], 8 * b + j);
+      double d0 = __shfl_sync(kFull, g[j], 8 * b + j);
       const double bq = __shfl_sync(kFull, g[j], 8 * b + j + 1);
       const double cq = __shfl_sync(kFull, g[j + 1], 8 * b + j + 1);
-      const double det = fma(d0, cq, -bq * bq);
-      pd = pd && (__double2hiint(d0) > 0) && (__double2hiint(det) > 0);  // integer pipe, off the dependency chain; a non-positive
-      const double rs0 = rsqrt_pivot(d0);                                // pivot makes rs NaN / Inf, which then propagates like the
-      const double rdet = rsqrt_pivot(det);                              // NaNs of the reference's LLT
+      double floor1 = 0.0;
+      if (CLAMP) {
+        const double floor0 = fmax(1e-18, 1e-13 * __shfl_sync(kFull, dorig, 8 * b + j));
+        floor1 = fmax(1e-18, 1e-13 * __shfl_sync(kFull, dorig, 8 * b + j + 1));
+        if (!(d0 >= floor0)) {
+          pd = false;
+          d0 = floor0;
+        }
+      }
+      double det = fma(d0, cq, -bq * bq);
+      if (CLAMP) {
+        if (!(det >= floor1 * d0)) {  // second pivot det / d0 below the floor
+          pd = false;
+          det = floor1 * d0;
+        }
+      } else {
+        pd = pd && (__double2hiint(d0) > 0) && (__double2hiint(det) > 0);  // integer pipe, off the dependency chain; a non-positive
+      }                                                                    // pivot makes rs NaN / Inf, which then propagates like the
+      const double rs0 = rsqrt_pivot(d0);                                  // NaNs of the reference's LLT
+      const double rdet = rsqrt_pivot(det);
       const double rs1 = rdet * (d0 * rs0);
       const double l0 = g[j] * rs0;
       const double lb = bq * rs0;  // L[j+1][j]
@@ -170,17 +195,22 @@ __device__ __forceinline__ bool factor_hm(double* W, int lane, int li, int r, in
       }
     }
     // trailing tiles (in the scratch): Hm_ij -= L_ib L_jb'
-    if (b == 0) {
-      const double2 f1 = tfrag(W, 1, 0, r, c), f2 = tfrag(W, 2, 0, r, c);
-      const double2 n1 = neg2(f1), n2 = neg2(f2);
-      double2 h11 = tfrag(W, 1, 1, r, c), h21 = tfrag(W, 2, 1, r, c), h22 = tfrag(W, 2, 2, r, c);
+    if (NB >= 2 && b == 0) {
+      const double2 f1 = tfrag(W, 1, 0, r, c);
+      const double2 n1 = neg2(f1);
+      double2 h11 = tfrag(W, 1, 1, r, c);
       dmma2(h11, n1, f1);
-      dmma2(h21, n2, f1);
-      dmma2(h22, n2, f2);
       tput(W, 1, 1, r, c, h11);
-      tput(W, 2, 1, r, c, h21);
-      tput(W, 2, 2, r, c, h22);
-    } else if (b == 1) {
+      if (NB == 3) {
+        const double2 f2 = tfrag(W, 2, 0, r, c);
+        const double2 n2 = neg2(f2);
+        double2 h21 = tfrag(W, 2, 1, r, c), h22 = tfrag(W, 2, 2, r, c);
+        dmma2(h21, n2, f1);
+        dmma2(h22, n2, f2);
+        tput(W, 2, 1, r, c, h21);
+        tput(W, 2, 2, r, c, h22);
+      }
+    } else if (NB == 3 && b == 1) {
       const double2 f2 = tfrag(W, 2, 1, r, c);
       double2 h22 = tfrag(W, 2, 2, r, c);
       dmma2(h22, neg2(f2), f2);
@@ -203,36 +233,50 @@ __device__ __forceinline__ bool factor_hm(double* W, int lane, int li, int r, in
       for (int k = j + 1; k < 8; ++k) g[k] = fma(-a, dg[k + kLd * j], g[k]);
     }
     __syncwarp();
-    if (lane < kN) {
+    if (lane < kRows) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) dg[ii + kLd * k] = g[k];
     }
     __syncwarp();
   }
   // off-diagonal blocks of L^-1 (stored transposed into the upper tiles)
-  {
-    const double2 li00 = tfrag(W, 0, 0, r, c), li11 = tfrag(W, 1, 1, r, c);          // op fragments of Li00, Li11
-    const double2 l10 = tfrag(W, 1, 0, r, c), l20 = tfrag(W, 2, 0, r, c), l21 = tfrag(W, 2, 1, r, c);  // op fragments of L10', L20', L21'
-    const double2 lt11 = ld2(W + 2 * c + kLd * r + t26(1, 1)), lt22 = ld2(W + 2 * c + kLd * r + t26(2, 2));  // op fragments of Li11', Li22'
-    double2 x10 = zero2(), x21 = zero2(), x20 = zero2();
+  if (NB >= 2) {
+    const double2 li00 = tfrag(W, 0, 0, r, c);                        // op fragment of Li00
+    const double2 l10 = tfrag(W, 1, 0, r, c);                         // op fragment of L10'
+    const double2 lt11 = ld2(W + 2 * c + kLd * r + t26(1, 1));        // op fragment of Li11'
+    double2 x10 = zero2();
     dmma2(x10, li00, l10);  // (L10 Li00)' as accumulator = op fragment of L10 Li00
-    dmma2(x21, li11, l21);
-    dmma2(x20, li00, l20);
-    double2 i10 = zero2(), i21 = zero2();
+    double2 i10 = zero2();
     dmma2(i10, lt11, x10);
-    dmma2(i21, lt22, x21);
     i10 = neg2(i10);
-    i21 = neg2(i21);
-    st2(W + 2 * c + kLd * r + t26(0, 1), i10);  // acc(Li10) = op fragment of (L^-T) tile (0,1)
-    st2(W + 2 * c + kLd * r + t26(1, 2), i21);
-    __syncwarp();
-    dmma2(x20, tfrag(W, 0, 1, r, c), l21);  // + (L21 Li10)': op fragment of Li10 = transposed read of tile (0,1)
-    double2 i20 = zero2();
-    dmma2(i20, lt22, x20);
-    st2(W + 2 * c + kLd * r + t26(0, 2), neg2(i20));
+    if (NB == 3) {
+      const double2 li11 = tfrag(W, 1, 1, r, c);
+      const double2 l20 = tfrag(W, 2, 0, r, c), l21 = tfrag(W, 2, 1, r, c);  // op fragments of L20', L21'
+      const double2 lt22 = ld2(W + 2 * c + kLd * r + t26(2, 2));             // op fragment of Li22'
+      double2 x21 = zero2(), x20 = zero2();
+      dmma2(x21, li11, l21);
+      dmma2(x20, li00, l20);
+      double2 i21 = zero2();
+      dmma2(i21, lt22, x21);
+      i21 = neg2(i21);
+      st2(W + 2 * c + kLd * r + t26(0, 1), i10);  // acc(Li10) = op fragment of (L^-T) tile (0,1)
+      st2(W + 2 * c + kLd * r + t26(1, 2), i21);
+      __syncwarp();
+      dmma2(x20, tfrag(W, 0, 1, r, c), l21);  // + (L21 Li10)': op fragment of Li10 = transposed read of tile (0,1)
+      double2 i20 = zero2();
+      dmma2(i20, lt22, x20);
+      st2(W + 2 * c + kLd * r + t26(0, 2), neg2(i20));
+    } else {
+      st2(W + 2 * c + kLd * r + t26(0, 1), i10);
+    }
     __syncwarp();
   }
   return pd;
+}
+// Hm (24 x 24). `li` is kept in the signature for the callers' sake (lane clamped to 23).
+__device__ __forceinline__ bool factor_hm(double* W, int lane, int li, int r, int c) {
+  (void)li;
+  return factor_blocks<3, false>(W, lane, r, c);
 }
 
 }  // namespace

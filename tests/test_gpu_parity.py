@@ -60,16 +60,18 @@ SHAPES = {
     "quadrotor": (12, 4, 0),
     "manipulator": (9, 9, 3),
     "legged": (24, 24, 0),
+    "legged_c6": (24, 24, 6),      # one constraint tile of the legged DMMA kernel
+    "legged_c14": (24, 24, 14),    # two tiles (a trot: 2 stance feet x 3 + 2 swing feet x (3 + 1))
     "test32c": (3, 2, 2),
 }
 
 
-@pytest.mark.parametrize("shape", ["cartpole", "ballbot", "manipulator", "legged", "test32c"])
+@pytest.mark.parametrize("shape", ["cartpole", "ballbot", "manipulator", "legged", "legged_c6", "legged_c14", "test32c"])
 @pytest.mark.parametrize("variant", ["ls_reduced_diag", "ls_full_diag", "ls_reduced_gershgorin", "lm_full"])
 def test_ilqr_generated_batch_matches_oracle(shape, variant):
     n, m, nc = SHAPES[shape]
     N, batch, dt, seed = 100, 24, 0.01, 0
-    st = o2.Settings(algorithm=o2.ALG_ILQR, hessianCorrectionMultiple=1e-3 if shape != "legged" else 1e-5, timeStep=dt)
+    st = o2.Settings(algorithm=o2.ALG_ILQR, hessianCorrectionMultiple=1e-3 if not shape.startswith("legged") else 1e-5, timeStep=dt)
     if variant == "ls_full_diag":
         st.preComputeRiccatiTerms = False
     elif variant == "ls_reduced_gershgorin":
@@ -1147,3 +1149,54 @@ def test_device_count_matches_torch():
     count = C.c_int32(-1)
     o2lib.check(o2lib.load_library().o2c_device_count(C.byref(count)))
     assert count.value == torch.cuda.device_count() >= 1
+
+
+@pytest.mark.parametrize("ncmax", [5, 8, 11, 16])
+@pytest.mark.parametrize("nominal", [False, True])
+def test_legged_dmma_kernel_with_ragged_equality_constraints(ncmax, nominal):
+    """The legged DMMA kernel carries up to 16 state-input equality constraints (contact constraints of the reference's legged robot,
+    LeggedRobotInterface.cpp:186-190) as one or two 8-row tiles; the active count changes from node to node (contact switches), incl.
+    nodes without any constraint and nodes with nc_max. Against the oracle's Householder-QR projection."""
+    rng = np.random.default_rng(100 + ncmax)
+    batch, n, m, N = 5, 24, 24, 12
+    lq = _random_batch(rng, batch, n, m, N, ncmax, o2.ALG_ILQR, ragged_nc=True)
+    lq.nc[0, :] = ncmax
+    lq.nc[1, :] = 0
+    if not nominal:
+        lq.x_nom = lq.u_nom = None
+    st = o2.Settings(hessianCorrectionMultiple=1e-5, timeStep=0.02)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=ncmax, has_nominal=nominal, max_alphas=2) as solver:
+        solver.upload(lq)
+        assert solver.kernel_variant == "ilqr_wpp_kernel"
+        solver.solve(alpha=0.7)
+        sol = solver.download()
+        assert (sol.status == 0).all()
+        for i in range(batch):
+            check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, alphas=(0.7,), what=f"legged nc<={ncmax}")
+        # backward pass and rollout as separate calls
+        solver.solveSequentialRiccatiEquations()
+        solver.rolloutTrajectory((1.0, 0.25))
+        sol = solver.download()
+        check_against_oracle(st, _oracle_problem(lq, 3, N), lq.x0[3], sol, 3, alphas=(1.0, 0.25), what="legged constraints, two calls")
+
+
+def test_legged_dmma_kernel_constraint_rank_flag():
+    rng = np.random.default_rng(7)
+    batch, n, m, nc, N = 4, 24, 24, 9, 8
+    lq = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=False)
+    lq.x_nom = lq.u_nom = None
+    lq.nc = None
+    lq.D[1, 3, 8] = lq.D[1, 3, 2]  # a duplicated constraint row (second tile against the first) at node 3 of problem 1
+    lq.C[1, 3, 8] = lq.C[1, 3, 2]
+    lq.e[1, 3, 8] = lq.e[1, 3, 2]
+    st = o2.Settings(hessianCorrectionMultiple=1e-5)
+    with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
+        solver.upload(lq)
+        assert solver.kernel_variant == "ilqr_wpp_kernel"
+        solver.solve()
+        sol = solver.download()
+    assert sol.status[1] & o2.STATUS_CONSTRAINT_RANK
+    assert (np.delete(sol.status, 1) == 0).all()
+    lq.nc = np.full((batch, N), nc, np.int32)
+    for i in (0, 2, 3):
+        check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, what="legged constraints, rank flag")
