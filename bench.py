@@ -37,8 +37,12 @@ WORKLOADS = {
     "quadrotor_slq": (12, 4, 0, 1, 1e-3, 32768),
     "manipulator": (9, 9, 3, 0, 1e-3, 16384),
     "cartpole": (4, 1, 0, 0, 1e-6, 1),
+    # not BASELINE configs: what the reference's own legged example runs on top of config 5 (contact constraints,
+    # LeggedRobotInterface.cpp:186-190; SLQ, ocs2_legged_robot/config/mpc/task.info:85)
+    "legged_constrained": (24, 24, 12, 0, 1e-5, 16384),
+    "legged_slq": (24, 24, 0, 1, 1e-5, 8192),
 }
-TABLE_WORKLOADS = ("ballbot", "quadrotor_slq", "manipulator")
+TABLE_WORKLOADS = ("ballbot", "quadrotor_slq", "manipulator", "legged_constrained", "legged_slq")
 N_STAGES = 100
 DT = 0.01
 METRIC = "LQ solves/s (Riccati backward sweep + LQ rollout)"
