@@ -422,7 +422,8 @@ def main():
             rf = r["roofline"]
             table[name] = {"workload": workload_label(name), "global_batch": r["global_batch"], "batch_per_gpu": r["batch_local"], "value": r["value"],
                            "unit": "solves/s", "ms_per_step": r["ms_per_step"], "steps": 3, "kernel": r["kernel"], "bound": rf["bound"],
-                           "frac": rf["frac"], "achieved": rf["achieved"], "peak": rf["peak"], "roofline_unit": rf["unit"], "traffic": rf["traffic"]}
+                           "frac": rf["frac"], "achieved": rf["achieved"], "peak": rf["peak"], "roofline_unit": rf["unit"], "traffic": rf["traffic"],
+                           "vs_traffic_roofline": rf.get("vs_traffic_roofline")}
 
     cpu_baseline = None
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
