@@ -1200,3 +1200,37 @@ def test_legged_dmma_kernel_constraint_rank_flag():
     lq.nc = np.full((batch, N), nc, np.int32)
     for i in (0, 2, 3):
         check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, what="legged constraints, rank flag")
+
+
+@pytest.mark.parametrize("nc", [0, 10])
+def test_legged_dmma_kernel_schedule_does_not_change_a_bit(nc, monkeypatch):
+    """Sweeper / roller warp roles, ring depth, dynamic problem fetch and the roller's own first sweep are scheduling only: every
+    combination must reproduce the fused schedule (no rollers, static stride) bit for bit, for a batch of several rounds and for one
+    smaller than the machine."""
+    n = m = 24
+    N, dt = 6, 0.01
+    st = o2.Settings(hessianCorrectionMultiple=1e-5, timeStep=dt)
+    knobs = ("O2C_WPP_ROLLERS", "O2C_WPP_RESIDENT", "O2C_WPP_RING", "O2C_WPP_DYNAMIC", "O2C_WPP_ROLLER_SWEEPS")
+    configs = [dict(O2C_WPP_ROLLERS="0", O2C_WPP_DYNAMIC="0"), dict(), dict(O2C_WPP_ROLLERS="2"), dict(O2C_WPP_ROLLERS="3", O2C_WPP_RESIDENT="2"),
+               dict(O2C_WPP_RESIDENT="1"), dict(O2C_WPP_RING="1"), dict(O2C_WPP_ROLLER_SWEEPS="0", O2C_WPP_RESIDENT="5"),
+               dict(O2C_WPP_ROLLERS="0", O2C_WPP_RESIDENT="3")]
+    for batch in (4000, 37):
+        with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
+            solver.generate_synthetic(9, 0, dt)
+            ref = None
+            for cfg in configs:
+                for k in knobs:
+                    monkeypatch.delenv(k, raising=False)
+                for k, v in cfg.items():
+                    monkeypatch.setenv(k, v)
+                solver.solve(alpha=0.9)
+                sol = solver.download()
+                assert (sol.status == 0).all()
+                got = (sol.K, sol.dbias, sol.Sm, sol.Sv, sol.s, sol.x, sol.u)
+                if ref is None:
+                    ref = got
+                    pb, x0 = orc.generate_problem(9, batch - 1, orc.ALG_ILQR, n, m, nc, N, dt)
+                    check_against_oracle(st, pb, x0, sol, batch - 1, alphas=(0.9,), what="schedule reference")
+                else:
+                    for a, b in zip(ref, got):
+                        assert np.array_equal(a, b), f"batch {batch}, {cfg}"
