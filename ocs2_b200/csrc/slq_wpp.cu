@@ -579,7 +579,7 @@ struct Ro24Args {
   double first_alpha;
 };
 
-__global__ void __launch_bounds__(32 * kRoWarps) rollout_cont24_kernel(const Ro24Args a) {
+__global__ void __launch_bounds__(32 * kRoWarps, 1) rollout_cont24_kernel(const Ro24Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   RoSmem& ws = reinterpret_cast<RoSmem*>(smem_raw)[warp];
@@ -628,20 +628,38 @@ __global__ void __launch_bounds__(32 * kRoWarps) rollout_cont24_kernel(const Ro2
       }
     };
     // u(t, x) for the x in shared memory (row i of K per lane), broadcast through shared memory
+    // (a time that sits on a node — w0 = 1 or w0 = 0, i.e. the first and the last stage of every RK4 step on the nodes' own grid — reads
+    //  that node's rows alone: no lerp, half the shared-memory reads)
     auto policy = [&](int idx, double w0) {
       ensure(idx + 1);
       const int hi = idx + 1 < N ? idx + 1 : N;
-      const double* plo = ws.pol[idx % 3];
-      const double* phi = ws.pol[hi % 3];
       const double w1 = 1.0 - w0;
-      double u0 = w0 * (plo[kMat + kN + i] + alpha * plo[kMat + i]) + w1 * (phi[kMat + kN + i] + alpha * phi[kMat + i]), u1 = 0.0;
+      double u0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+      if (w1 == 0.0 || w0 == 0.0) {
+        const double* pn = ws.pol[(w1 == 0.0 ? idx : hi) % 3];
+        u0 = pn[kMat + kN + i] + alpha * pn[kMat + i];
 #pragma unroll
-      for (int j = 0; j < kN; j += 2) {
-        const double2 xv = ld2(ws.x + j);
-        u0 = fma(fma(w0, plo[i + kN * j], w1 * phi[i + kN * j]), xv.x, u0);
-        u1 = fma(fma(w0, plo[i + kN * (j + 1)], w1 * phi[i + kN * (j + 1)]), xv.y, u1);
+        for (int j = 0; j < kN; j += 4) {
+          const double2 xa = ld2(ws.x + j), xb = ld2(ws.x + j + 2);
+          u0 = fma(pn[i + kN * j], xa.x, u0);
+          u1 = fma(pn[i + kN * (j + 1)], xa.y, u1);
+          u2 = fma(pn[i + kN * (j + 2)], xb.x, u2);
+          u3 = fma(pn[i + kN * (j + 3)], xb.y, u3);
+        }
+      } else {
+        const double* plo = ws.pol[idx % 3];
+        const double* phi = ws.pol[hi % 3];
+        u0 = w0 * (plo[kMat + kN + i] + alpha * plo[kMat + i]) + w1 * (phi[kMat + kN + i] + alpha * phi[kMat + i]);
+#pragma unroll
+        for (int j = 0; j < kN; j += 4) {
+          const double2 xa = ld2(ws.x + j), xb = ld2(ws.x + j + 2);
+          u0 = fma(fma(w0, plo[i + kN * j], w1 * phi[i + kN * j]), xa.x, u0);
+          u1 = fma(fma(w0, plo[i + kN * (j + 1)], w1 * phi[i + kN * (j + 1)]), xa.y, u1);
+          u2 = fma(fma(w0, plo[i + kN * (j + 2)], w1 * phi[i + kN * (j + 2)]), xb.x, u2);
+          u3 = fma(fma(w0, plo[i + kN * (j + 3)], w1 * phi[i + kN * (j + 3)]), xb.y, u3);
+        }
       }
-      if (valid) ws.u[lane] = u0 + u1;
+      if (valid) ws.u[lane] = (u0 + u1) + (u2 + u3);
       __syncwarp();
     };
     auto flow = [&](int idx, double w0) -> double {
@@ -665,17 +683,31 @@ __global__ void __launch_bounds__(32 * kRoWarps) rollout_cont24_kernel(const Ro2
         __syncwarp();
         xv = ws.dx;
       }
-      double a0 = fma(w0, dlo[2 * kMat + i], w1 * dhi[2 * kMat + i]), a1 = 0.0;
+      double a0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+      if (w1 == 0.0 || w0 == 0.0) {
+        const double* dn = (w1 == 0.0) ? dlo : dhi;
+        a0 = dn[2 * kMat + i];
 #pragma unroll
-      for (int j = 0; j < kN; j += 2) {
-        const double2 x2 = ld2(xv + j), u2 = ld2(ws.u + j);
-        a0 = fma(fma(w0, dlo[i + kN * j], w1 * dhi[i + kN * j]), x2.x, a0);
-        a1 = fma(fma(w0, dlo[i + kN * (j + 1)], w1 * dhi[i + kN * (j + 1)]), x2.y, a1);
-        a0 = fma(fma(w0, dlo[kMat + i + kN * j], w1 * dhi[kMat + i + kN * j]), u2.x, a0);
-        a1 = fma(fma(w0, dlo[kMat + i + kN * (j + 1)], w1 * dhi[kMat + i + kN * (j + 1)]), u2.y, a1);
+        for (int j = 0; j < kN; j += 2) {
+          const double2 x2 = ld2(xv + j), u2 = ld2(ws.u + j);
+          a0 = fma(dn[i + kN * j], x2.x, a0);
+          a1 = fma(dn[i + kN * (j + 1)], x2.y, a1);
+          b0 = fma(dn[kMat + i + kN * j], u2.x, b0);
+          b1 = fma(dn[kMat + i + kN * (j + 1)], u2.y, b1);
+        }
+      } else {
+        a0 = fma(w0, dlo[2 * kMat + i], w1 * dhi[2 * kMat + i]);
+#pragma unroll
+        for (int j = 0; j < kN; j += 2) {
+          const double2 x2 = ld2(xv + j), u2 = ld2(ws.u + j);
+          a0 = fma(fma(w0, dlo[i + kN * j], w1 * dhi[i + kN * j]), x2.x, a0);
+          a1 = fma(fma(w0, dlo[i + kN * (j + 1)], w1 * dhi[i + kN * (j + 1)]), x2.y, a1);
+          b0 = fma(fma(w0, dlo[kMat + i + kN * j], w1 * dhi[kMat + i + kN * j]), u2.x, b0);
+          b1 = fma(fma(w0, dlo[kMat + i + kN * (j + 1)], w1 * dhi[kMat + i + kN * (j + 1)]), u2.y, b1);
+        }
       }
       __syncwarp();  // x, u in shared memory are dead
-      return a0 + a1;
+      return (a0 + a1) + (b0 + b1);
     };
     double x = a.x0[(size_t)prob * kN + i];
     bool finite = true;
