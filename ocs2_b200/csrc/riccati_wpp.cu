@@ -157,7 +157,7 @@ template <bool NOM, bool EV, int MODE, int NCB>
 __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320 : 256), 1) ilqr_wpp_kernel(const Args a) {
   constexpr bool QPD = true;  // Q and P straight from L2 into the accumulators (the TMA-staged round-1 path is kept for reference only)
   static_assert(!(EV && MODE == kModeLM), "ILQR events under LEVENBERG_MARQUARDT are refused by the API");
-  static_assert(NCB == 0 || (!EV && MODE == kModeLS), "the constrained instantiations serve LINE_SEARCH + DIAGONAL_SHIFT without events");
+  static_assert(NCB == 0 || MODE == kModeLS, "the constrained instantiations serve LINE_SEARCH + DIAGONAL_SHIFT");
   using WarpSmem = WarpSmemT<NCB>;
   constexpr int NCB_ = NCB > 0 ? NCB : 1;
   const int rec_stride = NCB > 0 ? a.rec : kRec;  // (a compile-time constant for the unconstrained layout)
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
           if (c < NCB) {
             const double v = (NCB_ == 1 || c == 0) ? zz[0] : zz[NCB_ - 1];
             ws.vv[8 * c + r] = v;
-            spart = fma(0.5 * v, v, spart);
+            if (!ev) spart = fma(0.5 * v, v, spart);  // (a pre-event node's value function comes from the transversality condition alone)
           }
           __syncwarp();
         }
@@ -720,20 +720,22 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) t[i] = neg2(t[i]);
+        if (!ev) {
 #pragma unroll
-        for (int kb = 0; kb < 3; ++kb)
+          for (int kb = 0; kb < 3; ++kb)
 #pragma unroll
-          for (int ib = 0; ib < 3; ++ib)
+            for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-            for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], y[ib][kb], y[jb][kb]);
+              for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], y[ib][kb], y[jb][kb]);
 #pragma unroll
-        for (int kb = 0; kb < NCB; ++kb)
+          for (int kb = 0; kb < NCB; ++kb)
 #pragma unroll
-          for (int ib = 0; ib < 3; ++ib) {
-            const double2 nv = neg2(vx[ib][kb]);
+            for (int ib = 0; ib < 3; ++ib) {
+              const double2 nv = neg2(vx[ib][kb]);
 #pragma unroll
-            for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], nv, vx[jb][kb]);
-          }
+              for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], nv, vx[jb][kb]);
+            }
+        }
         // U' = Vx' L_M^-1 (accumulators = op fragments of U = L_M^-T Vx)
         double2 up[3][NCB_];
 #pragma unroll
@@ -1254,10 +1256,9 @@ bool wpp_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceB
   // K~'G~ + G~'K~ + K~'H~K~ in place of -G~'G~ (H~ = Pu'Hm Pu = I); the reference's own RiccatiTest.cpp:87-105 holds them equal to 1e-9.
   const bool ls = st.strategy == O2C_STRATEGY_LINE_SEARCH && (st.hc == O2C_HC_DIAGONAL_SHIFT || st.hc == O2C_HC_GERSHGORIN_MODIFICATION);
   const bool lm = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT && buf.event == nullptr;  // (events under LM: refused by the API)
-  // state-input equality constraints (up to 16, any per-node count): LINE_SEARCH + DIAGONAL_SHIFT without events
+  // state-input equality constraints (up to 16, any per-node count, with or without events): LINE_SEARCH + DIAGONAL_SHIFT
   const bool constrained = L.ncmax > 0;
-  const bool cons_ok = !constrained || (L.ncmax <= 16 && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT &&
-                                        buf.event == nullptr && L.oC == kRec);
+  const bool cons_ok = !constrained || (L.ncmax <= 16 && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT && L.oC == kRec);
   return L.n == kN && L.m == kN && cons_ok && st.algorithm == O2C_ALG_ILQR && (ls || lm) &&
          (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 && (constrained || L.rec == kRec) && L.oQ == kOQ &&
          L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb && L.obias == kObias && L.oSm == kOSm &&
@@ -1319,9 +1320,13 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
     const int mode = st.strategy == O2C_STRATEGY_LEVENBERG_MARQUARDT ? kModeLM : (st.hc == O2C_HC_GERSHGORIN_MODIFICATION ? kModeGersh : kModeLS);
     kernel = kernels[mode][(nom ? 1 : 0) + (ev ? 2 : 0)];
   } else if (ncb == 1) {
-    kernel = nom ? ilqr_wpp_kernel<true, false, kModeLS, 1> : ilqr_wpp_kernel<false, false, kModeLS, 1>;
+    const Kernel kernels[4] = {ilqr_wpp_kernel<false, false, kModeLS, 1>, ilqr_wpp_kernel<true, false, kModeLS, 1>, ilqr_wpp_kernel<false, true, kModeLS, 1>,
+                               ilqr_wpp_kernel<true, true, kModeLS, 1>};
+    kernel = kernels[(nom ? 1 : 0) + (ev ? 2 : 0)];
   } else {
-    kernel = nom ? ilqr_wpp_kernel<true, false, kModeLS, 2> : ilqr_wpp_kernel<false, false, kModeLS, 2>;
+    const Kernel kernels[4] = {ilqr_wpp_kernel<false, false, kModeLS, 2>, ilqr_wpp_kernel<true, false, kModeLS, 2>, ilqr_wpp_kernel<false, true, kModeLS, 2>,
+                               ilqr_wpp_kernel<true, true, kModeLS, 2>};
+    kernel = kernels[(nom ? 1 : 0) + (ev ? 2 : 0)];
   }
 #endif
   if (kernel == nullptr) return cudaErrorNotSupported;

@@ -585,7 +585,7 @@ def test_eigenvalue_modification_matches_oracle(algorithm, n, m, nc):
 
 
 @pytest.mark.parametrize("n,m,nc,nominal", [(5, 3, 0, False), (6, 4, 2, True), (24, 24, 0, False), (24, 24, 0, True), (10, 3, 0, True), (10, 3, 0, False),
-                                               (9, 9, 3, True), (9, 9, 3, False), (4, 1, 0, False)])
+                                               (9, 9, 3, True), (9, 9, 3, False), (4, 1, 0, False), (24, 24, 6, True), (24, 24, 13, False)])
 def test_ilqr_events_match_oracle(n, m, nc, nominal):
     """Pre-event nodes (ILQR.cpp:263-295): value function through riccatiTransversalityConditions on the jump model data, controller
     entry from the regular data with Sm = 0, rollout through the jump map."""
