@@ -52,7 +52,6 @@ struct __align__(16) WarpSmemT {
   double Wm[NCB > 0 ? kC8 * kLd : 2];            // M = Z'Z (lower) -> L_M -> L_M^-T (upper), leading rows of a ld-26 scratch
   double vw[kC8], vv[kC8];                       // Z'Yv - e -> L_M^-T vv ; vv = L_M^-1 (Z'Yv - e)
   unsigned long long full;   // operand block landed (sweep)
-  unsigned long long hfull, hfull2;  // sweep: Q landed in the scratch / P landed in A's slot
   unsigned long long cfull;  // {C | D | e} landed
 };
 using WarpSmem = WarpSmemT<0>;
@@ -85,14 +84,13 @@ struct Args {
 
 // L2 prefetch of the cost Hessians a stage reads: all of P and Q (they are copied to shared memory whole by TMA), and the tiles of R on
 // or above the block diagonal (R is symmetric; the sweep reads R[8jb+2c..][8ib+r] for jb <= ib). One 16-byte touch per lane and tile.
-template <bool QPD>
 __device__ __forceinline__ void prefetch_hessians(const double* rec, const Args& a, int lo24) {
 #pragma unroll
   for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
     for (int jb = 0; jb < 3; ++jb) {
       l2_touch(rec + kOP + lo24 + t24(jb, ib));
-      if (!QPD || jb <= ib) l2_touch(rec + kOQ + lo24 + t24(jb, ib));  // QPD reads Q like R: only the tiles on or above the block diagonal
+      if (jb <= ib) l2_touch(rec + kOQ + lo24 + t24(jb, ib));  // Q is read like R: only the tiles on or above the block diagonal
       if (jb <= ib) l2_touch(rec + kOR + lo24 + t24(jb, ib));
     }
 }
@@ -155,7 +153,6 @@ constexpr int kRollAhead = O2C_WPP_ROLL_AHEAD;  // rollout: L2 prefetch distance
 template <bool NOM, bool EV, int MODE, int NCB>
 // (the constrained instantiations have room for 10 / 8 warps in shared memory: their register budget is that of 320 / 256 threads)
 __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320 : 256), 1) ilqr_wpp_kernel(const Args a) {
-  constexpr bool QPD = true;  // Q and P straight from L2 into the accumulators (the TMA-staged round-1 path is kept for reference only)
   static_assert(!(EV && MODE == kModeLM), "ILQR events under LEVENBERG_MARQUARDT are refused by the API");
   static_assert(NCB == 0 || MODE == kModeLS, "the constrained instantiations serve LINE_SEARCH + DIAGONAL_SHIFT");
   using WarpSmem = WarpSmemT<NCB>;
@@ -172,7 +169,6 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
   const int li = lane < kN ? lane : kN - 1;
   const int N = a.N;
   const uint32_t opBytes = kOperand * sizeof(double);
-  const uint32_t matBytes = kMat * sizeof(double);
 
   const int nwarps = blockDim.x >> 5, nsweep = a.nsweep, nroll = nwarps - nsweep;
   __shared__ unsigned long long ring_full[kMaxCtaWarps][kMaxRingDepth];  // rollout ring: stage set landed
@@ -180,15 +176,13 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
   if (lane == 0) {
     if (warp < nsweep || a.sweep_count < a.count) {
       mbar_init(&ws.full, 1);
-      mbar_init(&ws.hfull, 1);
-      mbar_init(&ws.hfull2, 1);
       mbar_init(&ws.cfull, 1);
     }
     for (int d = 0; d < kMaxRingDepth; ++d) mbar_init(&ring_full[warp][d], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t phase = 0, hphase = 0, cphase = 0, rphase = 0;  // rphase: bit d = parity to wait for on ring_full[warp][d]
+  uint32_t phase = 0, cphase = 0, rphase = 0;  // rphase: bit d = parity to wait for on ring_full[warp][d]
 
   // Warp roles. Warps [0, nsweep) are SWEEPERS: backward pass after backward pass, the FP64 pipe never waits for a rollout. The
   // remaining warps are ROLLERS: they take finished problems from a queue in shared memory and run the forward rollout, which is
@@ -230,8 +224,6 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
         __syncwarp();
         if (lane == 0 && warp >= nsweep) {  // the scratch of the roller's own sweep becomes its ring
           mbar_inval(&ws.full);
-          mbar_inval(&ws.hfull);
-          mbar_inval(&ws.hfull2);
           mbar_inval(&ws.cfull);
         }
         if (lane == 0) {
@@ -258,7 +250,7 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
         tma_load(ws.cde, lqp + (size_t)(N - 1) * rec_stride + a.oC, a.cde_bytes, &ws.cfull);
       }
     }
-    prefetch_hessians<QPD>(lqp + (size_t)(N - 1) * rec_stride, a, lo24);
+    prefetch_hessians(lqp + (size_t)(N - 1) * rec_stride, a, lo24);
     // terminal condition: valueFunctionTrajectory.back() = finalValueFunction (GaussNewtonDDP.cpp:526)
     {
       double* outN = solp + (size_t)N * kORec;
@@ -297,7 +289,7 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
       const bool ev = EV && __ldg(evp + k) != 0;
       mbar_wait(&ws.full, phase);
       phase ^= 1u;
-      if (k < N - 1) prefetch_hessians<QPD>(rec, a, lo24);  // this node's Q, P, R into L2 now: first needed a third of a stage from here
+      if (k < N - 1) prefetch_hessians(rec, a, lo24);  // this node's Q, P, R into L2 now: first needed a third of a stage from here
                                                         // (node N-1's were touched in the prologue); prefetching any earlier only
                                                         // loses lines to L2 capacity misses with 1776 problems in flight
 
@@ -376,21 +368,12 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
                                                                    // Gershgorin: dQ is added to S at the end of the stage
       __syncwarp();  // S (scratch) is dead from here on
 
-      // The cost Hessians Q and P ride through shared memory too, each in a slot that is dead for exactly as long as the copy needs:
-      // Q (4.6 KB, one TMA copy) into the scratch while Hm and T are being contracted, P into A's slot while G' is.
-      if (!QPD && lane == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(&ws.hfull, matBytes);
-        tma_load(ws.W, rec + kOQ, matBytes, &ws.hfull);
-      }
-      // QPD: Q (its six tiles on or below the block diagonal) and P go from L2 straight into the accumulators of T and G', each issued
-      // one contraction (576 pipe cycles) ahead of its first use, like R at the top of the stage
-      if (QPD) {
+      // Q (its six tiles on or below the block diagonal) and P go from L2 straight into the accumulators of T and G', each issued one
+      // contraction (576 pipe cycles) ahead of its first use, like R at the top of the stage
 #pragma unroll
-        for (int ib = 0; ib < 3; ++ib)
+      for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb <= ib; ++jb) t[lt(ib, jb)] = ldg2(rec + kOQ + lo24 + t24(jb, ib));  // Q[8ib+r][8jb+2c..] = Q[8jb+2c..][8ib+r]
-      }
+        for (int jb = 0; jb <= ib; ++jb) t[lt(ib, jb)] = ldg2(rec + kOQ + lo24 + t24(jb, ib));  // Q[8ib+r][8jb+2c..] = Q[8jb+2c..][8ib+r]
 
       // ---- Hm = R + SB'B (lower tiles) ----
       if (!ev) {
@@ -408,15 +391,10 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
 
       // ---- T = Q + eps I + SA'A (lower tiles) ----
       double2 g[3][3];
-      if (QPD) {
 #pragma unroll
-        for (int ib = 0; ib < 3; ++ib)
+      for (int ib = 0; ib < 3; ++ib)
 #pragma unroll
-          for (int jb = 0; jb < 3; ++jb) g[ib][jb] = ldg2(rec + kOP + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
-      } else {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) t[i] = zero2();
-      }
+        for (int jb = 0; jb < 3; ++jb) g[ib][jb] = ldg2(rec + kOP + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) {
         double2 af[3];
@@ -427,33 +405,10 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
 #pragma unroll
           for (int jb = 0; jb <= ib; ++jb) dmma2(t[lt(ib, jb)], zA[ib][kb], af[jb]);
       }
-      if (!QPD) {
-        __syncwarp();  // A is dead: its slot takes P
-        if (lane == 0) {
-          mbar_expect_tx(&ws.hfull2, matBytes);
-          tma_load(ws.in, rec + kOP, matBytes, &ws.hfull2);
-        }
-        mbar_wait(&ws.hfull, hphase);
-      }
 #pragma unroll
       for (int ib = 0; ib < 3; ++ib) {
-        if (!QPD) {
-#pragma unroll
-          for (int jb = 0; jb <= ib; ++jb) {
-            const double2 qq = ld2(ws.W + lo24 + t24(jb, ib));  // Q[8ib+r][8jb+2c..] = Q[8jb+2c..][8ib+r], dense ld 24 as copied
-            t[lt(ib, jb)].x += qq.x;
-            t[lt(ib, jb)].y += qq.y;
-          }
-        }
         t[lt(ib, ib)].x += (2 * c == r) ? epsk : 0.0;
         t[lt(ib, ib)].y += (2 * c + 1 == r) ? epsk : 0.0;
-      }
-      if (!QPD) {
-        __syncwarp();  // Q is consumed: the scratch takes Hm (lower triangle)
-#pragma unroll
-        for (int ib = 0; ib < 3; ++ib)
-#pragma unroll
-          for (int jb = 0; jb < 3; ++jb) g[ib][jb] = zero2();
       }
       if (ev) {
         // S- = T and Sv- = tv are final: through the scratch once more for G' = P' + S-B and Gv = r + B'Sv-
@@ -505,18 +460,6 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
 #pragma unroll
             for (int jb = 0; jb < 3; ++jb) dmma2(g[ib][jb], zA[ib][kb], bf[jb]);
         }
-      }
-      if (!QPD) {
-        mbar_wait(&ws.hfull2, hphase);
-        hphase ^= 1u;
-#pragma unroll
-        for (int ib = 0; ib < 3; ++ib)
-#pragma unroll
-          for (int jb = 0; jb < 3; ++jb) {
-            const double2 pp = ld2(ws.in + lo24 + t24(jb, ib));  // P'[8ib+r][8jb+2c..] = P[8jb+2c..][8ib+r]
-            g[ib][jb].x += pp.x;
-            g[ib][jb].y += pp.y;
-          }
       }
       __syncwarp();  // all lanes are done with the staged operand block: refill it for node k-1 while this stage finishes
       if (MODE != kModeLM && lane == 0 && k >= 1) {  // (LM needs A, B, Hv once more after the gains: its refill follows Acl)
