@@ -17,7 +17,7 @@
  *
  * The reference has no FFI for this path (the seam is C++ virtual dispatch inside GaussNewtonDDP, see
  * ocs2_ddp/include/ocs2_ddp/GaussNewtonDDP.h:149-193); INTEGRATION.md shows the ILQR/SLQ subclass a maintainer would add to
- * call this ABI. Inputs are the ModelData fields (ocs2_core/include/ocs2_core/model_data/ModelData.h:43-60) of every time node
+ * call this ABI (built: include/ocs2_ddp_cuda/GaussNewtonDDP_CUDA.h, ocs2::ILQR_CUDA / ocs2::SLQ_CUDA). Inputs are the ModelData fields (ocs2_core/include/ocs2_core/model_data/ModelData.h:43-60) of every time node
  * in a struct-of-arrays batch layout; every matrix block is column-major (Eigen default) and contiguous.
  *
  * Conventions: all functions return an o2c_error (0 = success) and never throw; o2c_last_error() gives the message of the
@@ -30,6 +30,12 @@
  * (preComputeRiccatiTerms = false) is the same map written with K~'G~ + G~'K~ + K~'H~K~ in place of -G~'G~ (H~ = Pu'Hm Pu = I); the
  * reference's own RiccatiTest.cpp:87-105 holds the two equal to 1e-9. They differ only in rounding, which matters when Hm is barely
  * positive definite. Configurations served by the generic kernels (see o2c_kernel_variant) evaluate the form that was asked for.
+ *
+ * Equality constraints: the shape-specialised kernels use the range-space form of the reference's projection (Z = L^-1 D', the
+ * Cholesky factor of Z'Z is the R factor of the reference's QR of U^-T D'); K, dbias, bias and the value function do not depend on the
+ * choice of null-space basis, so the results equal the Householder-QR projection up to rounding. A dependent constraint row sets
+ * O2C_STATUS_CONSTRAINT_RANK (the reference clamps the pivot, LinearAlgebra.cpp:38-47): the results of that problem are then
+ * regularised, not the reference's.
  */
 #ifndef OCS2_DDP_CUDA_H_
 #define OCS2_DDP_CUDA_H_
