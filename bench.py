@@ -59,6 +59,17 @@ def workload_label(name):
     return f"{name} SLQ-RK4 nx={n} nu={m} N={N_STAGES} timeStep={DT}"
 
 
+def config_of(workload, global_batch, shards):
+    """The `config` object of a bench line: the workload, its global batch, how it is split and why no L2 flush is needed. Both arms
+    (ours and --impl reference) print exactly this object for the same command line."""
+    n, m, nc, alg, _, _ = WORKLOADS[workload]
+    bytes_solve, _ = algorithmic_per_solve(n, m, nc, N_STAGES, alg)
+    per_shard = (global_batch + shards - 1) // shards
+    return {"workload": workload_label(workload), "global_batch": global_batch,
+            "sharding": "by problem index (contiguous blocks), no collective on the data path",
+            "l2": "inputs larger than L2 (per-GPU LQ data %.1f GB >> 126 MB), no flush needed" % (bytes_solve * per_shard / 1e9)}
+
+
 def algorithmic_per_solve(n, m, nc, N, alg=0):
     """compulsory bytes (each input read once, each output written once) and flops of one solve
     (ILQR sweep + discrete rollout, or SLQ-RK4 flow map with one step per interval + continuous rollout)."""
@@ -213,8 +224,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_label(args.workload), "global_batch": args.batch or default_batch, "sample_problems_per_step": sample,
-                   "note": "each step solves a bounded sample of the workload's seeded problem family on the host cores; solves/s does not depend on the sample size"},
+        "config": config_of(args.workload, args.batch or default_batch, max(1, args.gpus)),
+        "config_detail": {"sample_problems_per_step": sample,
+                          "note": "each step solves a bounded sample of the workload's seeded problem family on the host cores; solves/s does not depend on the sample size"},
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} problems per step x {args.steps} steps of the same seeded family (oracle/lq_oracle.cpp, one problem per task)"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -443,15 +455,13 @@ def main():
                                   "the reference itself needs Eigen3/Boost which are absent)"}
 
     if ctx.rank == 0:
-        bytes_solve, _ = algorithmic_per_solve(n, m, nc, N_STAGES, alg)
         line = {
             "metric": METRIC, "value": head["value"], "unit": "solves/s", "n_gpus": ctx.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_label(args.workload), "global_batch": head["global_batch"], "batch_per_gpu": head["batch_local"],
-                       "sharding": "by problem index (contiguous blocks), no collective on the data path", "host_numa_node": numa,
-                       "l2": "inputs larger than L2 (per-GPU LQ data %.1f GB >> 126 MB), no flush needed" % (bytes_solve * head["batch_local"] / 1e9),
-                       "kernel": head["kernel"]},
+            # `config` is the same object in both arms (what is solved); how this arm solves it goes to `config_detail`
+            "config": config_of(args.workload, head["global_batch"], ctx.world),
+            "config_detail": {"batch_per_gpu": head["batch_local"], "host_numa_node": numa, "kernel": head["kernel"]},
             "clocks": head["clocks"], "e2e": e2e, "gpu_launches": head["launches"], "roofline": head["roofline"], "cpu_baseline": cpu_baseline,
             "weak": weak, "workloads": table,
         }
