@@ -37,6 +37,7 @@ constexpr int kTail = kOperand - 2 * kMat;  // { Hv | q | r | c, pad } = 80 doub
 constexpr int kSlot = kOperand + kN;        // { A | B~ | Hv | q | r | c, pad | r~ }
 constexpr int kFlowWarps = 8;               // per SM: two 10 KB node slots + the scratch per warp = 25.5 KB
 constexpr int kNodeWarps = 4;
+constexpr int kStepCache = 256;             // RK4 steps of the schedule kept in shared memory (14 KB; longer schedules read the rest from global memory)
 
 struct SlqWppArgs {
   const double* lq;
@@ -160,6 +161,11 @@ __global__ void __launch_bounds__(32 * kFlowWarps, 1) slq_flow_kernel(const SlqW
   __syncwarp();
   uint32_t phase = 0;  // bit q: parity to wait for on full[q]
   const int total_warps = gridDim.x * (blockDim.x >> 5);
+  // the step schedule is read once per step by every warp: from shared memory (a dependent global load at the top of every step
+  // was 5 % of all stall samples, profiles/r02_ncu_slq_flow_summary.txt)
+  __shared__ SlqStep step_cache[kStepCache];
+  for (int i = threadIdx.x; i < a.nsteps && i < kStepCache; i += blockDim.x) step_cache[i] = a.steps[i];
+  __syncthreads();
 
   for (int pi = warp * gridDim.x + blockIdx.x; pi < a.count; pi += total_warps) {
     const int prob = a.begin + pi;
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(32 * kFlowWarps, 1) slq_flow_kernel(const SlqW
 
 #pragma unroll 1
     for (int sidx = 0; sidx < a.nsteps; ++sidx) {
-      const SlqStep sp = a.steps[sidx];
+      const SlqStep sp = sidx < kStepCache ? step_cache[sidx] : a.steps[sidx];
       const int i0 = sp.interval;
       if (i0 < loaded_lo) {  // the interval moved one node down: node i0 takes the slot of node i0 + 2 (dead)
         __syncwarp();
@@ -595,6 +601,9 @@ __global__ void __launch_bounds__(32 * kRoWarps, 1) rollout_cont24_kernel(const 
   __syncwarp();
   uint32_t parity = 0;
   const int warps_total = gridDim.x * kRoWarps;
+  __shared__ RolloutStep step_cache[kStepCache];  // the schedule out of shared memory instead of a dependent global load per step
+  for (int i = threadIdx.x; i < a.nsteps && i < kStepCache; i += blockDim.x) step_cache[i] = a.steps[i];
+  __syncthreads();
   for (int pi = blockIdx.x * kRoWarps + warp; pi < a.count; pi += warps_total) {
     const int prob = a.begin + pi;
     double* xo = a.xs + ((size_t)ia * a.batch + prob) * (size_t)a.out_nodes * kN;
@@ -725,7 +734,7 @@ __global__ void __launch_bounds__(32 * kRoWarps, 1) rollout_cont24_kernel(const 
     observe(0, a.first_idx, a.first_alpha);
 #pragma unroll 1
     for (int sidx = 0; sidx < a.nsteps; ++sidx) {
-      const RolloutStep sp = a.steps[sidx];
+      const RolloutStep sp = sidx < kStepCache ? step_cache[sidx] : a.steps[sidx];
       const double h = sp.h;
       if (sp.jump > 0) {  // an event (TimeTriggeredRollout.cpp:104-108): x+ = x_nom(post) + A_e (x - x_nom(pre)) + Hv_e
         const double* jr = a.jump + ((size_t)prob * a.jump_capacity + (sp.jump - 1)) * jump_rec(kN);
