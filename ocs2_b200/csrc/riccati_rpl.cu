@@ -1226,7 +1226,7 @@ __global__ void __launch_bounds__(128) rollout_cont_rpl_kernel(const RoArgs a) {
       for (int stg = 0; stg < 4; ++stg) {
         sm[S::sX + i] = xs;
         __syncwarp();
-        const double kx = flow(sp.idx[stg], sp.alpha[stg]);
+        const double kx = flow((stg == 0 ? sp.idx[0] : (stg == 1 ? sp.idx[1] : (stg == 2 ? sp.idx[2] : sp.idx[3]))), (stg == 0 ? sp.alpha[0] : (stg == 1 ? sp.alpha[1] : (stg == 2 ? sp.alpha[2] : sp.alpha[3]))));  // (constant indices: the step stays in registers)
         acc = fma(h * ((stg == 0 || stg == 3) ? (1.0 / 6.0) : (1.0 / 3.0)), kx, acc);
         xs = fma(h * ((stg == 2) ? 1.0 : 0.5), kx, x);
       }

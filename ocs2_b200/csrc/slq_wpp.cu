@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(32 * kFlowWarps, 1) slq_flow_kernel(const SlqW
 
 #pragma unroll 1
       for (int stg = 0; stg < 4; ++stg) {
-        const double al = sp.alpha[stg], be = 1.0 - al;
+        // (selects on constant indices keep the step in registers: a run-time index would put it into local memory)
+        const double al = (stg == 0 ? sp.alpha[0] : (stg == 1 ? sp.alpha[1] : (stg == 2 ? sp.alpha[2] : sp.alpha[3]))), be = 1.0 - al;
         // Q (lower tiles, + eps I) and P~' (all tiles) come from L2, lerped; they are issued here and added to the accumulators after the
         // contractions, so that their latency hides behind the first 126 DMMAs
         double2 d[6], g[3][3], qd[6], pg[3][3];
@@ -755,7 +756,7 @@ __global__ void __launch_bounds__(32 * kRoWarps, 1) rollout_cont24_kernel(const 
       for (int stg = 0; stg < 4; ++stg) {
         if (valid) ws.x[lane] = xs;
         __syncwarp();
-        const double kx = flow(sp.idx[stg], sp.alpha[stg]);
+        const double kx = flow((stg == 0 ? sp.idx[0] : (stg == 1 ? sp.idx[1] : (stg == 2 ? sp.idx[2] : sp.idx[3]))), (stg == 0 ? sp.alpha[0] : (stg == 1 ? sp.alpha[1] : (stg == 2 ? sp.alpha[2] : sp.alpha[3]))));  // (constant indices: the step stays in registers)
         acc = fma(h * ((stg == 0 || stg == 3) ? (1.0 / 6.0) : (1.0 / 3.0)), kx, acc);
         xs = fma(h * ((stg == 2) ? 1.0 : 0.5), kx, x);
       }
