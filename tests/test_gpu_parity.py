@@ -1178,6 +1178,12 @@ def test_legged_dmma_kernel_with_ragged_equality_constraints(ncmax, nominal):
         solver.rolloutTrajectory((1.0, 0.25))
         sol = solver.download()
         check_against_oracle(st, _oracle_problem(lq, 3, N), lq.x0[3], sol, 3, alphas=(1.0, 0.25), what="legged constraints, two calls")
+        # the chunked host pipeline (three stream lanes, constraint counts travel with their chunk) equals the resident path bit for bit
+        solver.solve(alpha=0.7)
+        resident = solver.download()
+        piped = solver.solve_host(lq, alpha=0.7, chunk=2)
+        for name in ("K", "dbias", "bias", "Sm", "Sv", "s", "x", "u"):
+            assert np.array_equal(getattr(piped, name), getattr(resident, name)), f"solve_host with constraints: {name}"
 
 
 def test_legged_dmma_kernel_constraint_rank_flag():
