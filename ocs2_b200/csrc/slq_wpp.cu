@@ -48,6 +48,8 @@ struct SlqWppArgs {
   double* sol;
   int* status;
   const SlqStep* steps;
+  const double* jump;  // SLQ jump records [batch][jump_capacity] (events), or nullptr
+  int jump_capacity;
   int nsteps, N, begin, count;
   int oQf, oqf, ocf, trec;
   double eps;
@@ -144,6 +146,8 @@ __device__ __forceinline__ double2 lerp2(double al, double be, const double2& u,
   return make_double2(fma(al, u.x, be * v.x), fma(al, u.y, be * v.y));
 }
 
+// EV: the schedule carries jump steps (events); a template variant because the event-free kernel sits at its register limit
+template <bool EV>
 __global__ void __launch_bounds__(32 * kFlowWarps, 1) slq_flow_kernel(const SlqWppArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -265,6 +269,79 @@ __global__ void __launch_bounds__(32 * kFlowWarps, 1) slq_flow_kernel(const SlqW
         wait_node(i0);
         if (i0 >= 1) touch_node(i0 - 1);
         loaded_lo = i0;
+      }
+      if (EV && sp.jump > 0) {  // (after the node bookkeeping: the step after the event lerps between nodes i0 - 1 and i0)
+        // node i0 is a pre-event node: instead of integrating, the value function crosses the event through
+        // ContinuousTimeRiccatiEquations::computeJumpMap = riccatiTransversalityConditions on the event's jump model data
+        // (SLQ.cpp:286-296, RiccatiTransversalityConditions.h:40-56): S- = Q_e + (S A_e)' A_e, Sv- = q_e + A_e'(Sv + S Hv_e),
+        // s- = s + c_e + Hv_e.(Sv + S Hv_e / 2). S and Sv of the post-event node are in the scratch (stage argument of the last step).
+        const double* jr = a.jump + ((size_t)prob * a.jump_capacity + (sp.jump - 1)) * jump_rec(kN);
+        const double* Ae = jr;
+        const double* Hve = jr + jump_oHv(kN);
+        double2 zA[3][3];
+        double pSH[3] = {0.0, 0.0, 0.0}, pA[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) zA[i][j] = zero2();
+        double2 hvf[3];
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) {
+          hvf[kb] = ldg2(Hve + 8 * kb + 2 * c);
+          const double2 svf = ld2(ws.Sv + 8 * kb + 2 * c);
+          double2 s[3];
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {
+            s[jb] = ld2(ws.W + lo26 + t26(kb, jb));
+            pSH[jb] = fma(s[jb].x, hvf[kb].x, pSH[jb]);
+            pSH[jb] = fma(s[jb].y, hvf[kb].y, pSH[jb]);
+          }
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib) {
+            const double2 af = ldg2(Ae + lo24 + t24(kb, ib));
+            pA[ib] = fma(af.x, svf.x, pA[ib]);
+            pA[ib] = fma(af.y, svf.y, pA[ib]);
+#pragma unroll
+            for (int jb = 0; jb < 3; ++jb) dmma2(zA[ib][jb], af, s[jb]);  // A_e'S = op fragments of S A_e
+          }
+        }
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) {  // + A_e'(S Hv_e) from the accumulators
+            pA[ib] = fma(zA[ib][jb].x, hvf[jb].x, pA[ib]);
+            pA[ib] = fma(zA[ib][jb].y, hvf[jb].y, pA[ib]);
+          }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          pSH[i] = quad_sum(pSH[i]);
+          pA[i] = quad_sum(pA[i]);
+        }
+        double spart = 0.0;
+        if (own) {
+          spart = __ldg(Hve + jv) * (ws.Sv[jv] + 0.5 * pick3(pSH, c));
+          Svj = __ldg(jr + jump_oq(kN) + jv) + pick3(pA, c);
+        }
+        sval = sval + __ldg(jr + jump_oc(kN)) + warp_sum_all(spart);
+        // S- = Q_e + (S A_e)' A_e (lower tiles)
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+          for (int jb = 0; jb <= ib; ++jb) S[lt(ib, jb)] = ldg2(jr + jump_oQ(kN) + lo24 + t24(jb, ib));
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) {
+          double2 af[3];
+#pragma unroll
+          for (int jb = 0; jb < 3; ++jb) af[jb] = ldg2(Ae + lo24 + t24(kb, jb));
+#pragma unroll
+          for (int ib = 0; ib < 3; ++ib)
+#pragma unroll
+            for (int jb = 0; jb <= ib; ++jb) dmma2(S[lt(ib, jb)], zA[ib][kb], af[jb]);
+        }
+        __syncwarp();  // every lane is done reading the post-event value function from the scratch
+        stage_to_scratch(S, Svj);
+        if (sp.observe_node >= 0) write_value(sp.observe_node);
+        continue;
       }
       const double* s0 = ws.slot[i0 & 1];        // node i0
       const double* s1 = ws.slot[(i0 + 1) & 1];  // node i0 + 1
@@ -778,7 +855,7 @@ size_t slq_wpp_workspace_doubles(const Layout& L, int batch) { return (size_t)ba
 
 bool slq_wpp_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   return L.n == kN && L.m == kN && L.ncmax == 0 && st.algorithm == O2C_ALG_SLQ && st.strategy == O2C_STRATEGY_LINE_SEARCH &&
-         st.hc == O2C_HC_DIAGONAL_SHIFT && buf.event == nullptr && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 &&
+         st.hc == O2C_HC_DIAGONAL_SHIFT && (buf.event == nullptr || buf.jump != nullptr) && (buf.x_nom == nullptr) == (buf.u_nom == nullptr) && L.N >= 1 &&
          L.rec == kRec && L.oQ == kOQ && L.oP == kOP && L.oR == kOR && L.orec == kORec && L.oK == kOK && L.odb == kOdb &&
          L.obias == kObias && L.oSm == kOSm && L.oSv == kOSv && L.os == kOs && L.oA == 0 && L.oB == kMat && L.oHv == 2 * kMat &&
          L.oq == 2 * kMat + kN && L.or_ == 2 * kMat + 2 * kN && L.oc == 2 * kMat + 3 * kN;
@@ -798,6 +875,8 @@ cudaError_t launch_slq_wpp(const Layout& L, const SolverSettings& st, const Devi
   a.sol = buf.sol;
   a.status = buf.status;
   a.steps = steps;
+  a.jump = buf.jump;
+  a.jump_capacity = buf.jump_capacity;
   a.nsteps = nsteps;
   a.N = L.N;
   a.begin = begin;
@@ -824,12 +903,13 @@ cudaError_t launch_slq_wpp(const Layout& L, const SolverSettings& st, const Devi
       if (v >= 1 && v <= kFlowWarps) warps = v;
     }
     const size_t smem = sizeof(FlowSmem) * warps;
-    e = cudaFuncSetAttribute(slq_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FlowSmem) * kFlowWarps));
+    void (*flow)(const SlqWppArgs) = (buf.event != nullptr && buf.jump != nullptr) ? slq_flow_kernel<true> : slq_flow_kernel<false>;
+    e = cudaFuncSetAttribute(flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FlowSmem) * kFlowWarps));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(slq_flow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(flow, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     const int grid = count < sms ? count : sms;
-    slq_flow_kernel<<<grid, 32 * warps, smem, stream>>>(a);
+    flow<<<grid, 32 * warps, smem, stream>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {

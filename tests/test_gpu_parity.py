@@ -857,7 +857,8 @@ def test_slq_events_match_oracle(n, m, nc, variant):
                      riccatiMultiple=0.3 if variant == "lm_full" else 0.0)
     with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc, has_nominal=True, max_alphas=2) as solver:
         solver.upload(lq)
-        assert ("slq_rpl" if n in (12, 10, 4) else "generic") in solver.kernel_variant  # the quadrotor shape keeps its row-per-lane kernels
+        # the quadrotor shape keeps its row-per-lane kernels, the legged shape its tensor-pipe kernels (jump map on tiles)
+        assert ("slq_rpl" if n in (12, 10, 4) else ("slq_wpp" if (n == 24 and variant == "ls_reduced") else "generic")) in solver.kernel_variant
         solver.solveSequentialRiccatiEquations()
         solver.rolloutTrajectory((1.0, 0.4))
         sol = solver.download()
