@@ -141,7 +141,8 @@ constexpr int kDefaultRollers = 1;
 #ifndef O2C_WPP_CTA_WARPS
 #define O2C_WPP_CTA_WARPS 12
 #endif
-constexpr int kMaxCtaWarps = O2C_WPP_CTA_WARPS;  // sweepers + rollers of a CTA (the register file holds 12 warps at 168 registers, 13 at 152)
+constexpr int kMaxCtaWarps = O2C_WPP_CTA_WARPS;  // sweepers + rollers of a CTA (the register file holds 12 warps at 168 registers)
+constexpr int kWideWarps = 14;  // the WIDE instantiations: 14 sweepers at 128 registers (register allocation is per 4 warps: 16 x 32 x 128)
 constexpr int kRingK = 2 * kMat + kN;        // stage set of the rollout ring: { A | B | Hv } then { K | dbias }
 constexpr int kRing = kRingK + kMat + kN;    // 1776 doubles = 14.2 KB
 constexpr int kMaxRingDepth = 4;
@@ -150,9 +151,12 @@ constexpr int kMaxRingDepth = 4;
 #endif
 constexpr int kRollAhead = O2C_WPP_ROLL_AHEAD;  // rollout: L2 prefetch distance in stages
 
-template <bool NOM, bool EV, int MODE, int NCB>
+// WIDE: 14 warps per SM at 128 registers (a few spills) instead of 12 at 168. One sweep is ~10 % slower, but a batch of 12 x SMs <
+// count <= 14 x SMs problems — 2048 on 148 SMs, the 8-GPU share of BASELINE config 5 — runs as ONE round of sweeps instead of two:
+// 2.12 ms instead of 2.21 ms (profiles/r02_wpp_wide.jsonl). Every sweeper rolls its own problem out (no room for a roller's ring).
+template <bool NOM, bool EV, int MODE, int NCB, bool WIDE = false>
 // (the constrained instantiations have room for 10 / 8 warps in shared memory: their register budget is that of 320 / 256 threads)
-__global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320 : 256), 1) ilqr_wpp_kernel(const Args a) {
+__global__ void __launch_bounds__(WIDE ? 32 * kWideWarps : (NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320 : 256)), 1) ilqr_wpp_kernel(const Args a) {
   static_assert(!(EV && MODE == kModeLM), "ILQR events under LEVENBERG_MARQUARDT are refused by the API");
   static_assert(NCB == 0 || MODE == kModeLS, "the constrained instantiations serve LINE_SEARCH + DIAGONAL_SHIFT");
   using WarpSmem = WarpSmemT<NCB>;
@@ -171,8 +175,9 @@ __global__ void __launch_bounds__(NCB == 0 ? 32 * kMaxCtaWarps : (NCB == 1 ? 320
   const uint32_t opBytes = kOperand * sizeof(double);
 
   const int nwarps = blockDim.x >> 5, nsweep = a.nsweep, nroll = nwarps - nsweep;
-  __shared__ unsigned long long ring_full[kMaxCtaWarps][kMaxRingDepth];  // rollout ring: stage set landed
-  __shared__ __align__(16) double rvec[kMaxCtaWarps][2][kN];               // rollout: x, u of the current node
+  constexpr int kCtaWarps = WIDE ? kWideWarps : kMaxCtaWarps;
+  __shared__ unsigned long long ring_full[kCtaWarps][kMaxRingDepth];  // rollout ring: stage set landed
+  __shared__ __align__(16) double rvec[kCtaWarps][2][kN];               // rollout: x, u of the current node
   if (lane == 0) {
     if (warp < nsweep || a.sweep_count < a.count) {
       mbar_init(&ws.full, 1);
@@ -1275,15 +1280,28 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   if (kernel == nullptr) return cudaErrorNotSupported;
   const int num_sms = device_sm_count();
   if (num_sms <= 0) return cudaErrorInvalidDevice;
+  // one round of 13 or 14 sweeps per SM instead of a round of 12 and a nearly empty one: the WIDE instantiation
+  bool wide = false;
+#ifndef O2C_WPP_ONLY_BASE
+  if (ncb == 0 && !ev && st.strategy == O2C_STRATEGY_LINE_SEARCH && st.hc == O2C_HC_DIAGONAL_SHIFT && count > kMaxWarps * num_sms &&
+      count <= kWideWarps * num_sms) {
+    wide = true;
+    if (const char* e = getenv("O2C_WPP_WIDE")) wide = atoi(e) != 0;
+    if (wide) kernel = nom ? ilqr_wpp_kernel<true, false, kModeLS, 0, true> : ilqr_wpp_kernel<false, false, kModeLS, 0, true>;
+  }
+#endif
   // profiling knobs, read per launch (no state is cached in statics: launches from several host threads / on several devices are
   // independent): O2C_WPP_RESIDENT = sweeping warps per SM, O2C_WPP_ROLLERS = rollout-only warps per SM (0 = every sweeper rolls its own
   // problem out), O2C_WPP_DYNAMIC = 0 switches the dynamic problem fetch off
-  int rollers = with_rollout ? kDefaultRollers : 0;
+  int rollers = (with_rollout && !wide) ? kDefaultRollers : 0;
   if (const char* e = getenv("O2C_WPP_ROLLERS")) {
     const int v = atoi(e);
-    if (with_rollout && v >= 0 && v < kMaxCtaWarps) rollers = v;
+    if (with_rollout && !wide && v >= 0 && v < kMaxCtaWarps) rollers = v;
   }
-  const size_t smem_cap = 227 * 1024 - 6 * 1024;  // minus the static part (queue, ring barriers, x / u vectors)
+  cudaFuncAttributes fattr{};
+  cudaError_t e = cudaFuncGetAttributes(&fattr, kernel);
+  if (e != cudaSuccess) return e;
+  const size_t smem_cap = (227 * 1024 - fattr.sharedSizeBytes) & ~(size_t)127;  // minus the static part (queue, ring barriers, x / u vectors)
   // sweeper slots the shared memory has room for next to the rollers' rings (two stage sets each at least, and room for the one sweep
   // a roller does first)
   const size_t ring_min = 2 * sizeof(double) * kRing > slot_bytes ? 2 * sizeof(double) * kRing : slot_bytes;
@@ -1291,9 +1309,10 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   int sweepers = choose_sweepers(count, num_sms, rollers, slots);
   if (const char* e = getenv("O2C_WPP_RESIDENT")) {
     const int v = atoi(e);
-    if (v >= 1 && v <= kMaxWarps) sweepers = v;
+    if (v >= 1 && v <= kMaxCtaWarps) sweepers = v;
   }
-  if (sweepers + rollers > kMaxCtaWarps) sweepers = kMaxCtaWarps - rollers;
+  if (wide) sweepers = (count + num_sms - 1) / num_sms;  // 13 or 14: one round
+  if (!wide && sweepers + rollers > kMaxCtaWarps) sweepers = kMaxCtaWarps - rollers;
   if (sweepers > slots) sweepers = slots;
   if (sweepers < 1) return cudaErrorInvalidConfiguration;
   const int warps = sweepers + rollers;
@@ -1312,7 +1331,7 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   if (const char* e = getenv("O2C_WPP_DYNAMIC")) dynamic = atoi(e) != 0;
   const size_t smem = slot_bytes * sweepers + sizeof(double) * kRing * rollers * ring_depth;
   // function attributes are per device: set on every launch (sub-microsecond) instead of caching "configured" in a static
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;

@@ -1217,11 +1217,12 @@ def test_legged_dmma_kernel_schedule_does_not_change_a_bit(nc, monkeypatch):
     n = m = 24
     N, dt = 6, 0.01
     st = o2.Settings(hessianCorrectionMultiple=1e-5, timeStep=dt)
-    knobs = ("O2C_WPP_ROLLERS", "O2C_WPP_RESIDENT", "O2C_WPP_RING", "O2C_WPP_DYNAMIC", "O2C_WPP_ROLLER_SWEEPS")
-    configs = [dict(O2C_WPP_ROLLERS="0", O2C_WPP_DYNAMIC="0"), dict(), dict(O2C_WPP_ROLLERS="2"), dict(O2C_WPP_ROLLERS="3", O2C_WPP_RESIDENT="2"),
+    knobs = ("O2C_WPP_ROLLERS", "O2C_WPP_RESIDENT", "O2C_WPP_RING", "O2C_WPP_DYNAMIC", "O2C_WPP_ROLLER_SWEEPS", "O2C_WPP_WIDE")
+    configs = [dict(O2C_WPP_ROLLERS="0", O2C_WPP_DYNAMIC="0", O2C_WPP_WIDE="0"), dict(), dict(O2C_WPP_ROLLERS="2"), dict(O2C_WPP_ROLLERS="3", O2C_WPP_RESIDENT="2"),
                dict(O2C_WPP_RESIDENT="1"), dict(O2C_WPP_RING="1"), dict(O2C_WPP_ROLLER_SWEEPS="0", O2C_WPP_RESIDENT="5"),
-               dict(O2C_WPP_ROLLERS="0", O2C_WPP_RESIDENT="3")]
-    for batch in (4000, 37):
+               dict(O2C_WPP_ROLLERS="0", O2C_WPP_RESIDENT="3"), dict(O2C_WPP_WIDE="0")]
+    # 2000 problems: one round of 14 sweeps per SM on the 14-warp instantiation (the default there) against the two-round schedules
+    for batch in (4000, 37, 2000):
         with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
             solver.generate_synthetic(9, 0, dt)
             ref = None
