@@ -1,13 +1,18 @@
-// riccati_wpp.cu — warp-per-problem ILQR sweep + fused LQ rollout for nx = nu = 24 (the legged-robot shape), FP64, sm_100a.
+// riccati_wpp.cu — warp-per-problem ILQR sweep + LQ rollout for nx = nu = 24 (the legged-robot shape), FP64, sm_100a.
 //
-// One WARP owns one problem's whole time-sequential sweep and its rollout; a CTA is just four independent warps, there is no CTA
-// barrier after the prologue. Twelve problems are resident per SM (3 CTAs x 4 warps), so while one warp sits in the latency chain
-// of its Cholesky the other warps of the same scheduler keep the FP64 pipe busy with their contractions.
+// One WARP owns one problem's whole time-sequential sweep; one persistent CTA per SM, 12 warps (168 registers per thread fill the
+// register file), no CTA barrier after the prologue. The warps of a CTA have roles: SWEEPERS run backward pass after backward pass,
+// ROLLERS run the forward rollouts of finished problems, which reach them through a ticketed queue in shared memory (see the kernel
+// for why: fused behind each sweep the rollout took 21 % of the time for 1.6 % of the flops). While one sweeper sits in the latency
+// chain of its Cholesky the other warps of the same scheduler keep the FP64 pipe busy with their contractions. Template variants:
+// nominal trajectories, events, the Riccati modification (line search / Levenberg-Marquardt / Gershgorin), up to 16 state-input
+// equality constraints as 8-row tiles, and a 14-warp / 128-register instantiation for batches of one round.
 //
 //   * The per-node operand block {A | B | Hv | q | r | c} (9.8 KB) is staged into the warp's shared-memory slot by ONE TMA bulk copy
-//     (cp.async.bulk + a per-warp mbarrier), issued half a stage ahead (the second half of a stage does not touch A, B); the block
-//     was pulled into L2 one stage earlier by cp.async.bulk.prefetch.L2, as were the cost Hessians Q, P, R, which are only ever
-//     added to accumulators and are therefore read straight from L2 into registers.
+//     (cp.async.bulk + a per-warp mbarrier), issued half a stage ahead (the second half of a stage does not touch A, B). The cost
+//     Hessians Q, P, R are only ever added to accumulators: they are touched into L2 per lane at the top of the stage and read
+//     straight from L2 into the accumulator registers, one contraction ahead of their first use. {C | D | e} of a constrained node
+//     arrive by their own bulk copy. A rollout stage reads {A | B | Hv} and {K | dbias} out of a TMA ring of stage sets.
 //   * Every 24x24x24 contraction runs on the FP64 tensor pipe (mma.sync m8n8k4 f64 = DMMA; tcgen05 has no FP64 kind) in the form
 //     Z = X'Y, for which both operand fragments have the same register layout ("op": lane (r,c) holds M[8kb+2c..2c+1][8jb+r]) and the
 //     accumulator fragment of Z ("acc": lane holds Z[8ib+r][8jb+2c..2c+1]) IS the operand fragment of Z'. The sweep is arranged so
@@ -30,7 +35,7 @@
 //   K  = Pu K~ = -L^-T Y ;  dbias = -L^-T Yv ;  bias = 0 (deviation coordinates)        ILQR::calculateControllerWorker ILQR.cpp:162-181
 //   dQ = eps I: the reference forms (M + eps I) - M with M = Q~ - P~'P~ (LineSearchStrategy.cpp:294-312), which equals eps I up
 //   to one rounding of M_ii + eps (<= 1e-16 |M_ii|).
-// Rollout (fused, same warp): du_k = K_k dx_k + alpha dbias_k ; dx_{k+1} = A_k dx_k + B_k du_k + Hv_k
+// Rollout (roller warps): du_k = K_k dx_k + alpha dbias_k ; dx_{k+1} = A_k dx_k + B_k du_k + Hv_k
 //                                            DDP_HelperFunctions.cpp:125-138, 296-304; LinearController.cpp:79-87
 #include <cstdio>
 #include <cstdlib>
