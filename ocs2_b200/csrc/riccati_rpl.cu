@@ -20,7 +20,8 @@
 // riccati_wpp.cu: Y = L^-1 G, S = T - Y'Y, K = -L^-T Y). The stage records of the P problems arrive by TMA bulk copies
 // (cp.async.bulk + one mbarrier per warp), double buffered, node k-1 in flight while node k is processed; outputs are written once.
 // The forward rollout of the LQ model (DDP_HelperFunctions.cpp:125-138, 296-304; LinearController.cpp:79-87) is fused behind the
-// sweep and streams the same records forwards through the same two buffers.
+// sweep: { A | B | Hv } of the records and { K | dbias } of the solution stream forwards through a TMA ring of 3-6 stage sets laid over
+// the part of the slot the sweep no longer needs.
 #include "o2c_common.cuh"
 
 namespace o2c {
