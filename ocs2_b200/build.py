@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libocs2_ddp_cuda.so")
-SOURCES = ["api.cu", "stability.cu", "riccati_generic.cu", "riccati_wpp.cu", "slq_wpp.cu", "riccati_rpl.cu", "rollout.cu", "line_search.cu", "synthetic.cu", "pack.cu"]
+SOURCES = ["api.cu", "stability.cu", "riccati_generic.cu", "riccati_generic_p1.cu", "riccati_generic_p2.cu", "riccati_generic_p3.cu", "riccati_generic_p4.cu", "riccati_wpp.cu", "slq_wpp.cu", "riccati_rpl.cu", "rollout.cu", "line_search.cu", "synthetic.cu", "pack.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
               "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -1102,6 +1102,42 @@ cudaError_t run_slq(const Layout& L, const SolverSettings& st, const DeviceBuffe
 }
 }  // namespace
 
+// The kernel instantiations are spread over several translation units that nvcc compiles in parallel (one instantiation with
+// compile-time dimensions takes about a minute): riccati_generic_p1.cu ... p3.cu include this file with O2C_GENERIC_PART set and
+// define the named-shape runners declared here; this file (part 0) keeps the run-time-dimension kernels and the public launchers.
+#ifndef O2C_GENERIC_PART
+#define O2C_GENERIC_PART 0
+#endif
+cudaError_t run_ilqr_generic_10_3_0(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count, int warp_doubles, cudaStream_t stream);
+cudaError_t run_ilqr_generic_4_1_0(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count, int warp_doubles, cudaStream_t stream);
+cudaError_t run_ilqr_generic_9_9_3(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count, int warp_doubles, cudaStream_t stream);
+cudaError_t run_slq_generic_12_4_0(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin, int count,
+                                   int warp_doubles, cudaStream_t stream);
+cudaError_t run_slq_generic_any(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin, int count,
+                                int warp_doubles, cudaStream_t stream);
+
+#if O2C_GENERIC_PART == 1
+cudaError_t run_ilqr_generic_10_3_0(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count, int warp_doubles, cudaStream_t stream) {
+  return run_ilqr<10, 3, 0, true>(L, st, buf, begin, count, warp_doubles, stream);
+}
+cudaError_t run_ilqr_generic_4_1_0(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count, int warp_doubles, cudaStream_t stream) {
+  return run_ilqr<4, 1, 0, true>(L, st, buf, begin, count, warp_doubles, stream);
+}
+#elif O2C_GENERIC_PART == 2
+cudaError_t run_ilqr_generic_9_9_3(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, int begin, int count, int warp_doubles, cudaStream_t stream) {
+  return run_ilqr<9, 9, 3, true>(L, st, buf, begin, count, warp_doubles, stream);
+}
+#elif O2C_GENERIC_PART == 4
+cudaError_t run_slq_generic_any(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin, int count,
+                                int warp_doubles, cudaStream_t stream) {
+  return run_slq<0, 0, 0, false>(L, st, buf, steps, nsteps, begin, count, warp_doubles, stream);
+}
+#elif O2C_GENERIC_PART == 3
+cudaError_t run_slq_generic_12_4_0(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf, const SlqStep* steps, int nsteps, int begin, int count,
+                                   int warp_doubles, cudaStream_t stream) {
+  return run_slq<12, 4, 0, true>(L, st, buf, steps, nsteps, begin, count, warp_doubles, stream);
+}
+#else
 // which compiled variant serves this configuration (diagnostics: o2c_kernel_variant)
 const char* generic_variant_name(const Layout& L, const SolverSettings& st) {
   const bool s = std_settings(st);
@@ -1119,9 +1155,9 @@ cudaError_t launch_ilqr_generic(const Layout& L, const SolverSettings& st, const
   const int wd = work_doubles(L, full, lm, gersh) + 2 * L.n * L.n + 2 * L.n;
   const int warp_doubles = (wd + 1) & ~1;
   if (std_settings(st)) {  // the named BASELINE shapes get compile-time dimensions
-    if (L.n == 10 && L.m == 3 && L.ncmax == 0) return run_ilqr<10, 3, 0, true>(L, st, buf, begin, count, warp_doubles, stream);
-    if (L.n == 9 && L.m == 9 && L.ncmax == 3) return run_ilqr<9, 9, 3, true>(L, st, buf, begin, count, warp_doubles, stream);
-    if (L.n == 4 && L.m == 1 && L.ncmax == 0) return run_ilqr<4, 1, 0, true>(L, st, buf, begin, count, warp_doubles, stream);
+    if (L.n == 10 && L.m == 3 && L.ncmax == 0) return run_ilqr_generic_10_3_0(L, st, buf, begin, count, warp_doubles, stream);
+    if (L.n == 9 && L.m == 9 && L.ncmax == 3) return run_ilqr_generic_9_9_3(L, st, buf, begin, count, warp_doubles, stream);
+    if (L.n == 4 && L.m == 1 && L.ncmax == 0) return run_ilqr_generic_4_1_0(L, st, buf, begin, count, warp_doubles, stream);
   }
   return run_ilqr<0, 0, 0, false>(L, st, buf, begin, count, warp_doubles, stream);
 }
@@ -1132,8 +1168,10 @@ cudaError_t launch_slq_generic(const Layout& L, const SolverSettings& st, const 
   const bool gersh = !lm && (st.hc == O2C_HC_GERSHGORIN_MODIFICATION || st.hc == O2C_HC_EIGENVALUE_MODIFICATION);  // full dQ matrix
   const int warp_doubles = slq_warp_doubles(L, full, lm, gersh);
   if (std_settings(st) && L.n == 12 && L.m == 4 && L.ncmax == 0)
-    return run_slq<12, 4, 0, true>(L, st, buf, steps, nsteps, begin, count, warp_doubles, stream);
-  return run_slq<0, 0, 0, false>(L, st, buf, steps, nsteps, begin, count, warp_doubles, stream);
+    return run_slq_generic_12_4_0(L, st, buf, steps, nsteps, begin, count, warp_doubles, stream);
+  return run_slq_generic_any(L, st, buf, steps, nsteps, begin, count, warp_doubles, stream);
 }
+
+#endif  // O2C_GENERIC_PART
 
 }  // namespace o2c

@@ -1,0 +1,3 @@
+// Part 3 of the generic kernels' instantiations (see the end of riccati_generic.cu): compiled in parallel with the other parts.
+#define O2C_GENERIC_PART 3
+#include "riccati_generic.cu"
