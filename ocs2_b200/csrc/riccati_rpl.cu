@@ -64,6 +64,7 @@ struct Args {
   double* us;
   int* status;
   const int* event;  // [batch][N] pre-event flags (ILQR.cpp:263-295), or nullptr: kernel instantiation EV
+  const int* nc;     // [batch][N] active constraints per node (<= NC), or nullptr: NC everywhere
   int N, begin, count, with_rollout;
   double eps, alpha;
 };
@@ -276,12 +277,16 @@ __global__ void __launch_bounds__(64, (NX == 10 ? 6 : 1)) ilqr_rpl_kernel(const 
         yvh[l] = yv[l];
       }
       if (NC > 0) {
+        // rows beyond the node's active count are zero rows of D, C, e with a unit diagonal in M: they leave every result untouched, so
+        // per-node (ragged) counts run the same code
+        const int nca = a.nc ? __ldg(a.nc + (size_t)prob * N + k) : NC;
         {  // lane c < nc: column c of Z by forward substitution
           const int cc = i < NC ? i : NC - 1;
+          const double keep = cc < nca ? 1.0 : 0.0;
           double z[NU];
 #pragma unroll
           for (int l = 0; l < NU; ++l) {
-            double v = rec[S::oD + cc + NC * l];
+            double v = keep * rec[S::oD + cc + NC * l];
 #pragma unroll
             for (int l2 = 0; l2 < l; ++l2) v = fma(-Lm[l + NU * l2], z[l2], v);
             z[l] = v * Lm[l + NU * l];
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(64, (NX == 10 ? 6 : 1)) ilqr_rpl_kernel(const 
             double v = 0.0;
 #pragma unroll
             for (int l = 0; l < NU; ++l) v = fma(Z[l + NU * c1], Z[l + NU * c2], v);
-            lm[c1][c2] = v;
+            lm[c1][c2] = (c1 == c2 && c1 >= nca) ? 1.0 : v;
           }
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(64, (NX == 10 ? 6 : 1)) ilqr_rpl_kernel(const 
         // Vx(:,i) = L_M^-1 (Z'Y(:,i) - C(:,i)),  vv = L_M^-1 (Z'Yv - e)
 #pragma unroll
         for (int c1 = 0; c1 < NC; ++c1) {
-          double v = -rec[S::oC + c1 + NC * i], w2 = -rec[S::oe + c1];
+          double v = c1 < nca ? -rec[S::oC + c1 + NC * i] : 0.0, w2 = c1 < nca ? -rec[S::oe + c1] : 0.0;
 #pragma unroll
           for (int l = 0; l < NU; ++l) {
             v = fma(Z[l + NU * c1], yt[l], v);
@@ -1372,7 +1377,6 @@ cudaError_t launch_rollout_cont_rpl(const Layout& L, const SolverSettings& st, c
 
 bool rpl_ilqr_supported(const Layout& L, const SolverSettings& st, const DeviceBuffers& buf) {
   if (!settings_match(st, buf, L)) return false;
-  if (L.ncmax > 0 && buf.nc != nullptr) return false;  // ragged per-node constraint counts: the generic kernel handles those
   return layout_matches<10, 3, 0>(L) || layout_matches<4, 1, 0>(L) || layout_matches<9, 9, 3>(L) || layout_matches<12, 4, 0>(L);
 }
 
@@ -1390,6 +1394,7 @@ cudaError_t launch_ilqr_rpl(const Layout& L, const SolverSettings& st, const Dev
   a.us = buf.us;
   a.status = buf.status;
   a.event = buf.event;
+  a.nc = buf.nc;
   a.N = L.N;
   a.begin = begin;
   a.count = count;

@@ -396,7 +396,7 @@ int main(int argc, char** argv) {
       {"legged ilqr nominal", ORC_ALG_ILQR, 24, 24, 0, 20, 5, true, false, false, "ilqr_wpp"},
       {"ballbot ilqr", ORC_ALG_ILQR, 10, 3, 0, 30, 7, true, false, false, "ilqr_rpl"},
       {"manipulator ilqr nc=3", ORC_ALG_ILQR, 9, 9, 3, 25, 7, false, false, false, "ilqr_rpl"},
-      {"manipulator ragged nc", ORC_ALG_ILQR, 9, 9, 3, 25, 4, true, true, false, "generic"},
+      {"manipulator ragged nc", ORC_ALG_ILQR, 9, 9, 3, 25, 4, true, true, false, "ilqr_rpl"},
       {"quadrotor slq", ORC_ALG_SLQ, 12, 4, 0, 20, 5, true, false, false, "slq_rpl"},
       {"generic slq nc=2", ORC_ALG_SLQ, 6, 4, 2, 16, 3, false, false, false, "generic"},
       {"ilqr events", ORC_ALG_ILQR, 6, 4, 0, 14, 6, true, false, true, "generic"},

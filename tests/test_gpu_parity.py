@@ -419,7 +419,7 @@ def test_rpl_kernels_partial_warps_and_subranges(shape, algorithm, variant, batc
 
 def test_rpl_constraints_rank_deficient_flag_and_ragged_fallback():
     """Manipulator shape through the range-space constraint path: a duplicated constraint row sets CONSTRAINT_RANK on that problem
-    only; per-node (ragged) constraint counts make the handle fall back to the generic kernel, with the same results."""
+    only; per-node (ragged) constraint counts stay on the row-per-lane kernel (inactive rows are masked), with the oracle's results."""
     rng = np.random.default_rng(5)
     batch, n, m, nc, N = 6, 9, 9, 3, 10
     lq = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=False)
@@ -439,17 +439,17 @@ def test_rpl_constraints_rank_deficient_flag_and_ragged_fallback():
     lq.nc = np.full((batch, N), nc, np.int32)
     for i in (0, 1, 3, 5):
         check_against_oracle(st, _oracle_problem(lq, i, N), lq.x0[i], sol, i, what="rpl constraints uploaded")
-    # ragged counts: generic kernel
+    # ragged counts: the same kernel (rows beyond a node's active count are masked)
     lq2 = _random_batch(rng, batch, n, m, N, nc, o2.ALG_ILQR, ragged_nc=True)
     lq2.x_nom = lq2.u_nom = None
     with o2.BatchedLqSolver(st, n, m, N, batch, nc_max=nc) as solver:
         solver.upload(lq2)
-        assert solver.kernel_variant.startswith("ilqr_generic_kernel")
+        assert solver.kernel_variant == "ilqr_rpl_kernel"
         solver.solve()
         sol2 = solver.download()
     assert (sol2.status == 0).all()
-    for i in (0, batch - 1):
-        check_against_oracle(st, _oracle_problem(lq2, i, N), lq2.x0[i], sol2, i, what="ragged fallback")
+    for i in range(batch):
+        check_against_oracle(st, _oracle_problem(lq2, i, N), lq2.x0[i], sol2, i, what="ragged counts on the row-per-lane kernel")
 
 
 # ---- the step after the backward pass: batched Armijo line search on the LQ model (o2c_line_search) ----
