@@ -1298,7 +1298,9 @@ cudaError_t launch_ilqr_wpp(const Layout& L, const SolverSettings& st, const Dev
   // profiling knobs, read per launch (no state is cached in statics: launches from several host threads / on several devices are
   // independent): O2C_WPP_RESIDENT = sweeping warps per SM, O2C_WPP_ROLLERS = rollout-only warps per SM (0 = every sweeper rolls its own
   // problem out), O2C_WPP_DYNAMIC = 0 switches the dynamic problem fetch off
-  int rollers = (with_rollout && !wide) ? kDefaultRollers : 0;
+  // (two constraint tiles: shared memory has room for 8 sweepers or for 7 and a roller — 8 sweepers rolling their own problems out
+  //  are 3 % faster, profiles/r02_legged_constraints.jsonl)
+  int rollers = (with_rollout && !wide && ncb < 2) ? kDefaultRollers : 0;
   if (const char* e = getenv("O2C_WPP_ROLLERS")) {
     const int v = atoi(e);
     if (with_rollout && !wide && v >= 0 && v < kMaxCtaWarps) rollers = v;
